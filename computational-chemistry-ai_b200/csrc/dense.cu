@@ -1,0 +1,776 @@
+// Dense-side kernels: BatchNorm statistics / backward, LayerNorm+ReLU+dropout, K7 fused
+// sigmoid+MSE+cosine loss, column sums, K8 flat AdamW, and the CUDA-core fp32 GEMM that is the
+// parity check path for the tcgen05 GEMM (gemm_tc.cu).
+#include "common.cuh"
+#include "launchers.h"
+
+namespace eims {
+
+// =========================================================================== fp32 SIMT GEMM
+// C[M,N] = op(A) op(B); 64x64x16 tiles, 256 threads, 4x4 micro-tiles.  Check path only.
+struct GemmArgs {
+  const float* A; const float* B; float* C;
+  int lda, ldb, ldc, a_mn, b_mn;
+  int M, N, K;
+  const int* m_dev; const int* k_dev;
+  const float* row_scale; const float* bias;
+  int relu, accumulate;
+};
+
+__global__ void __launch_bounds__(256) sgemm_simt_kernel(GemmArgs g) {
+  const int M = g.m_dev ? *g.m_dev : g.M;
+  const int K = g.k_dev ? *g.k_dev : g.K;
+  const int N = g.N;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  if (m0 >= M || n0 >= N) return;
+  int kchunk = (K + gridDim.z - 1) / gridDim.z;
+  kchunk = (kchunk + 15) & ~15;
+  const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+  if (kbeg >= kend && (g.accumulate || blockIdx.z > 0)) return;
+  __shared__ float As[16][65];
+  __shared__ float Bs[16][65];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  float acc[4][4] = {};
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int kk, mm;
+      if (g.a_mn) { mm = t & 63; kk = (t >> 6) + 4 * i; } else { kk = t & 15; mm = (t >> 4) + 16 * i; }
+      int m = m0 + mm, k = k0 + kk;
+      float v = 0.f;
+      if (m < M && k < kend) v = g.a_mn ? g.A[(int64_t)k * g.lda + m] : g.A[(int64_t)m * g.lda + k];
+      As[kk][mm] = v;
+      int nn;
+      if (g.b_mn) { nn = t & 63; kk = (t >> 6) + 4 * i; } else { kk = t & 15; nn = (t >> 4) + 16 * i; }
+      int n = n0 + nn;
+      k = k0 + kk;
+      v = 0.f;
+      if (n < N && k < kend) v = g.b_mn ? g.B[(int64_t)k * g.ldb + n] : g.B[(int64_t)n * g.ldb + k];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    float rs = g.row_scale ? g.row_scale[m] : 1.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] * rs + ((g.bias && blockIdx.z == 0) ? g.bias[n] : 0.f);
+      if (g.relu) v = fmaxf(v, 0.f);
+      if (g.accumulate) atomicAdd(g.C + (int64_t)m * g.ldc + n, v); else g.C[(int64_t)m * g.ldc + n] = v;
+    }
+  }
+}
+
+int launch_gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
+                     int N, int K, const int* m_dev, const int* k_dev, const float* row_scale, const float* bias,
+                     int relu, int accumulate, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return EIMS_ERR_ARG;
+  GemmArgs g{A, B, C, lda, ldb, ldc, a_mn, b_mn, M, N, K, m_dev, k_dev, row_scale, bias, relu, accumulate};
+  int splits = 1;
+  if (accumulate) {  // split-K for the weight gradients (K = atoms or graphs)
+    int tiles = ((M + 63) / 64) * ((N + 63) / 64);
+    splits = (148 * 4 + tiles - 1) / tiles;
+    int maxs = (K + 63) / 64;
+    if (splits > maxs) splits = maxs;
+    if (splits < 1) splits = 1;
+  }
+  dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
+  sgemm_simt_kernel<<<grid, 256, 0, st>>>(g);
+  return 0;
+}
+
+// =========================================================================== BatchNorm stats
+// Block = kBnRows rows x all columns.  Per-thread shifted sums -> per-block (n, mean, M2) ->
+// the last block combines blocks with Chan's formula in double, writes mean / invstd /
+// scale / shift and updates the running buffers (nn.BatchNorm1d, momentum 0.1).
+constexpr int kBnRows = 64;
+
+static inline int bn_blocks(int max_nodes) { int b = (max_nodes + kBnRows - 1) / kBnRows; return b < 1 ? 1 : b; }
+
+int64_t bn_scratch_floats(int H, int max_nodes) { return (int64_t)bn_blocks(max_nodes) * (2 * H + 4) + 64; }
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const int* __restrict__ dims, const float* __restrict__ z, int H,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                       float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                                       float* __restrict__ scale_out, float* __restrict__ shift_out,
+                                                       float* __restrict__ partials) {
+  extern __shared__ float smem[];  // [rows_in_flight][H] x {mean, M2, n}
+  const int N = dims[DIM_N];
+  const int cols4 = H >> 2;
+  const int rif = max(1, (int)blockDim.x / cols4);  // rows in flight
+  const int nblk = gridDim.x;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partials);
+  float* pn = partials + 16;                      // [nblk]
+  float* pmean = pn + ((nblk + 3) & ~3);          // [nblk][H]
+  float* pm2 = pmean + (int64_t)nblk * H;         // [nblk][H]
+  const int r0 = blockIdx.x * kBnRows, r1 = min(N, r0 + kBnRows);
+  float* s_mean = smem;
+  float* s_m2 = smem + rif * H;
+  float* s_n = smem + 2 * rif * H;
+  for (int cg = threadIdx.x % cols4; cg < cols4; cg += (blockDim.x >= cols4 ? cols4 : blockDim.x)) {
+    const int rs = blockDim.x >= cols4 ? threadIdx.x / cols4 : 0;
+    if (rs >= rif) continue;
+    float4 K4 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = K4, s2 = K4;
+    int cnt = 0;
+    for (int r = r0 + rs; r < r1; r += rif) {
+      float4 v = ldg4(z + (int64_t)r * H + 4 * cg);
+      if (cnt == 0) K4 = v;
+      float dx = v.x - K4.x, dy = v.y - K4.y, dz = v.z - K4.z, dw = v.w - K4.w;
+      s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
+      s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
+      ++cnt;
+    }
+    const float inv = cnt ? 1.f / cnt : 0.f;
+    float* m = s_mean + rs * H + 4 * cg;
+    float* q = s_m2 + rs * H + 4 * cg;
+    m[0] = K4.x + s1.x * inv; m[1] = K4.y + s1.y * inv; m[2] = K4.z + s1.z * inv; m[3] = K4.w + s1.w * inv;
+    q[0] = s2.x - s1.x * s1.x * inv; q[1] = s2.y - s1.y * s1.y * inv;
+    q[2] = s2.z - s1.z * s1.z * inv; q[3] = s2.w - s1.w * s1.w * inv;
+    if (cg == 0) s_n[rs] = (float)cnt;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float n = 0.f, mean = 0.f, m2 = 0.f;
+    for (int rs = 0; rs < rif; ++rs) {
+      float nb = s_n[rs];
+      if (nb > 0.f) {
+        float mb = s_mean[rs * H + c], qb = s_m2[rs * H + c];
+        float tot = n + nb, d = mb - mean;
+        mean += d * (nb / tot);
+        m2 += qb + d * d * (n * nb / tot);
+        n = tot;
+      }
+    }
+    pmean[(int64_t)blockIdx.x * H + c] = mean;
+    pm2[(int64_t)blockIdx.x * H + c] = m2;
+    if (c == 0) pn[blockIdx.x] = n;
+  }
+  if (!last_block_ticket(counter, nblk)) return;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+      double nb = (double)__ldcg(pn + b);
+      if (nb > 0.0) {
+        double mb = (double)__ldcg(pmean + (int64_t)b * H + c), qb = (double)__ldcg(pm2 + (int64_t)b * H + c);
+        double tot = n + nb, d = mb - mean;
+        mean += d * (nb / tot);
+        m2 += qb + d * d * (n * nb / tot);
+        n = tot;
+      }
+    }
+    if (n <= 0.0) continue;
+    const double var = m2 / n;
+    const float mean_f = (float)mean;
+    const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
+    mean_out[c] = mean_f;
+    invstd_out[c] = invstd;
+    const float sc = gamma[c] * invstd;
+    scale_out[c] = sc;
+    shift_out[c] = fmaf(-mean_f, sc, beta[c]);
+    if (running_mean) {
+      const float unbiased = (float)(n > 1.0 ? m2 / (n - 1.0) : var);
+      running_mean[c] = (1.f - kBnMomentum) * running_mean[c] + kBnMomentum * mean_f;
+      running_var[c] = (1.f - kBnMomentum) * running_var[c] + kBnMomentum * unbiased;
+    }
+  }
+}
+
+int launch_bn_stats(const int* dims, const float* z, int H, const float* gamma, const float* beta, float* rmean,
+                    float* rvar, float* mean, float* invstd, float* scale, float* shift, float* partials,
+                    int max_nodes, cudaStream_t st) {
+  if (H % 4 || H > 4096) return EIMS_ERR_ARG;
+  const int cols4 = H / 4;
+  const int rif = 256 / cols4 > 0 ? 256 / cols4 : 1;
+  size_t smem = (size_t)(2 * rif * H + rif + 4) * sizeof(float);
+  bn_stats_kernel<<<bn_blocks(max_nodes), 256, smem, st>>>(dims, z, H, gamma, beta, rmean, rvar, mean, invstd, scale,
+                                                           shift, partials);
+  return 0;
+}
+
+// eval-mode coefficients from the running buffers (GCN:442, model.eval()):
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rmean, const float* __restrict__ rvar, int H,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < H; c += gridDim.x * blockDim.x) {
+    float invstd = 1.f / sqrtf(rvar[c] + kBnEps);
+    float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = fmaf(-rmean[c], sc, beta[c]);
+  }
+}
+int launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* rmean, const float* rvar, int H,
+                          float* scale, float* shift, cudaStream_t st) {
+  bn_eval_coeffs_kernel<<<(H + 255) / 256, 256, 0, st>>>(gamma, beta, rmean, rvar, H, scale, shift);
+  return 0;
+}
+
+// =========================================================================== BatchNorm backward
+// dh source: either a materialised [N,H] buffer, or the readout backward computed on the fly
+// from dG[B,pool_dim] (SumPooling/AvgPooling: broadcast; MaxPooling: first arg-max only).
+struct DhSrc {
+  const float* dh;       // [N,H] or null
+  const float* dG;       // [B,pool_dim]
+  const int* gid;        // [N]
+  const int* gptr;       // [B+1]
+  const int* argmax;     // [B,H]
+  int pooling;
+};
+
+__device__ __forceinline__ float4 load_dh(const DhSrc& s, int i, int c, int H) {
+  if (s.dh) return ldg4(s.dh + (int64_t)i * H + c);
+  const int g = __ldg(s.gid + i);
+  const int pd = s.pooling == EIMS_POOL_COMBINED ? 2 * H : H;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s.pooling != EIMS_POOL_MAX) {
+    v = ldg4(s.dG + (int64_t)g * pd + c);
+    if (s.pooling == EIMS_POOL_MEAN) {
+      float n = (float)(__ldg(s.gptr + g + 1) - __ldg(s.gptr + g));
+      v.x /= n; v.y /= n; v.z /= n; v.w /= n;
+    }
+  }
+  if (s.pooling == EIMS_POOL_MAX || s.pooling == EIMS_POOL_COMBINED) {
+    const int4 a = *reinterpret_cast<const int4*>(s.argmax + (int64_t)g * H + c);
+    const float4 m = ldg4(s.dG + (int64_t)g * pd + (s.pooling == EIMS_POOL_COMBINED ? H : 0) + c);
+    if (a.x == i) v.x += m.x;
+    if (a.y == i) v.y += m.y;
+    if (a.z == i) v.z += m.z;
+    if (a.w == i) v.w += m.w;
+  }
+  return v;
+}
+
+// pass 1: column sums of dh and dh*xhat -> dgamma, dbeta (into grads) and the two means.
+__global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const int* __restrict__ dims, DhSrc src,
+                                                           const float* __restrict__ z, int H,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           float* __restrict__ means /*[2][H]*/, float* __restrict__ partials) {
+  extern __shared__ float smem[];
+  const int N = dims[DIM_N];
+  const int cols4 = H >> 2;
+  const int rif = max(1, (int)blockDim.x / cols4);
+  const int nblk = gridDim.x;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(partials);
+  float* p1 = partials + 16;
+  float* p2 = p1 + (int64_t)nblk * H;
+  const int r0 = blockIdx.x * kBnRows, r1 = min(N, r0 + kBnRows);
+  float* s_1 = smem;
+  float* s_2 = smem + rif * H;
+  for (int cg = threadIdx.x % cols4; cg < cols4; cg += (blockDim.x >= cols4 ? cols4 : blockDim.x)) {
+    const int rs = blockDim.x >= cols4 ? threadIdx.x / cols4 : 0;
+    if (rs >= rif) continue;
+    const float4 mu = ldg4(mean + 4 * cg), is = ldg4(invstd + 4 * cg);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    for (int r = r0 + rs; r < r1; r += rif) {
+      float4 d = load_dh(src, r, 4 * cg, H);
+      float4 v = ldg4(z + (int64_t)r * H + 4 * cg);
+      a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+      b.x = fmaf(d.x, (v.x - mu.x) * is.x, b.x); b.y = fmaf(d.y, (v.y - mu.y) * is.y, b.y);
+      b.z = fmaf(d.z, (v.z - mu.z) * is.z, b.z); b.w = fmaf(d.w, (v.w - mu.w) * is.w, b.w);
+    }
+    st4(s_1 + rs * H + 4 * cg, a);
+    st4(s_2 + rs * H + 4 * cg, b);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int rs = 0; rs < rif; ++rs) { a += s_1[rs * H + c]; b += s_2[rs * H + c]; }
+    p1[(int64_t)blockIdx.x * H + c] = a;
+    p2[(int64_t)blockIdx.x * H + c] = b;
+  }
+  if (!last_block_ticket(counter, nblk)) return;
+  const int used = (N + kBnRows - 1) / kBnRows;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < used; ++k) { a += (double)__ldcg(p1 + (int64_t)k * H + c); b += (double)__ldcg(p2 + (int64_t)k * H + c); }
+    dbeta[c] += (float)a;
+    dgamma[c] += (float)b;
+    means[c] = N > 0 ? (float)(a / N) : 0.f;
+    means[H + c] = N > 0 ? (float)(b / N) : 0.f;
+  }
+}
+
+// pass 2: q = gamma*invstd*(dh - mean(dh) - xhat*mean(dh*xhat)) * [z>0] * c_i ;  dbias += colsum(dr)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const int* __restrict__ dims, DhSrc src,
+                                                           const float* __restrict__ z, int H,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ means,
+                                                           const float* __restrict__ norm, float* __restrict__ q,
+                                                           float* __restrict__ dbias) {
+  extern __shared__ float smem[];
+  const int N = dims[DIM_N];
+  const int cols4 = H >> 2;
+  const int rif = max(1, (int)blockDim.x / cols4);
+  for (int r0 = blockIdx.x * kBnRows; r0 < N; r0 += gridDim.x * kBnRows) {
+    const int r1 = min(N, r0 + kBnRows);
+    __syncthreads();
+    for (int cg = threadIdx.x % cols4; cg < cols4; cg += (blockDim.x >= cols4 ? cols4 : blockDim.x)) {
+      const int rs = blockDim.x >= cols4 ? threadIdx.x / cols4 : 0;
+      if (rs >= rif) continue;
+      const float4 mu = ldg4(mean + 4 * cg), is = ldg4(invstd + 4 * cg), ga = ldg4(gamma + 4 * cg);
+      const float4 m1 = ldg4(means + 4 * cg), m2 = ldg4(means + H + 4 * cg);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = r0 + rs; r < r1; r += rif) {
+        float4 d = load_dh(src, r, 4 * cg, H);
+        float4 v = ldg4(z + (int64_t)r * H + 4 * cg);
+        const float ci = __ldg(norm + r);
+        float4 o;
+        o.x = v.x > 0.f ? ga.x * is.x * (d.x - m1.x - (v.x - mu.x) * is.x * m2.x) : 0.f;
+        o.y = v.y > 0.f ? ga.y * is.y * (d.y - m1.y - (v.y - mu.y) * is.y * m2.y) : 0.f;
+        o.z = v.z > 0.f ? ga.z * is.z * (d.z - m1.z - (v.z - mu.z) * is.z * m2.z) : 0.f;
+        o.w = v.w > 0.f ? ga.w * is.w * (d.w - m1.w - (v.w - mu.w) * is.w * m2.w) : 0.f;
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        o.x *= ci; o.y *= ci; o.z *= ci; o.w *= ci;
+        st4(q + (int64_t)r * H + 4 * cg, o);
+      }
+      st4(smem + rs * H + 4 * cg, acc);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {
+      float a = 0.f;
+      for (int rs = 0; rs < rif; ++rs) a += smem[rs * H + c];
+      atomicAdd(dbias + c, a);
+    }
+  }
+}
+
+int launch_bn_bwd(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr, const int* argmax,
+                  int pooling, const float* z, int H, const float* mean, const float* invstd, const float* gamma,
+                  const float* norm, float* dgamma, float* dbeta, float* dbias, float* means, float* partials,
+                  float* q, int max_nodes, cudaStream_t st) {
+  if (H % 4 || H > 4096) return EIMS_ERR_ARG;
+  DhSrc src{dh, dG, gid, gptr, argmax, pooling};
+  const int cols4 = H / 4;
+  const int rif = 256 / cols4 > 0 ? 256 / cols4 : 1;
+  size_t smem = (size_t)(2 * rif * H) * sizeof(float);
+  const int blocks = bn_blocks(max_nodes);
+  bn_bwd_stats_kernel<<<blocks, 256, smem, st>>>(dims, src, z, H, mean, invstd, dgamma, dbeta, means, partials);
+  bn_bwd_apply_kernel<<<blocks, 256, smem / 2, st>>>(dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias);
+  return 0;
+}
+
+// =========================================================================== LayerNorm + ReLU + dropout
+// Warp per row (GCN:343-345, 347-349).  Row kept in registers: NV float4 per lane, width <= 2048.
+template <int NV>
+__global__ void __launch_bounds__(256) ln_relu_drop_fwd_kernel(const int* __restrict__ dims, const float* __restrict__ u,
+                                                               int W, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, DropCfg drop,
+                                                               float* __restrict__ y, float* __restrict__ stats) {
+  const int B = dims[DIM_B];
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nv4 = W >> 2;
+  for (int r = warp; r < B; r += nwarps) {
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < nv4) {
+        v[i] = ldg4(u + (int64_t)r * W + 4 * c4);
+        s += v[i].x + v[i].y + v[i].z + v[i].w;
+      }
+    }
+    const float mean = warp_sum(s) / (float)W;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (i * 32 + lane < nv4) {
+        float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        ss += a * a + b * b + c * c + d * d;
+      }
+    const float rstd = 1.f / sqrtf(warp_sum(ss) / (float)W + kLnEps);
+    if (stats && lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nv4) {
+        const int c = 4 * c4;
+        float4 g = ldg4(gamma + c), b = ldg4(beta + c), o;
+        o.x = fmaxf(fmaf((v[i].x - mean) * rstd, g.x, b.x), 0.f);
+        o.y = fmaxf(fmaf((v[i].y - mean) * rstd, g.y, b.y), 0.f);
+        o.z = fmaxf(fmaf((v[i].z - mean) * rstd, g.z, b.z), 0.f);
+        o.w = fmaxf(fmaf((v[i].w - mean) * rstd, g.w, b.w), 0.f);
+        if (drop.active()) {
+          float4 m = drop_mask4(drop, (uint64_t)r * W + c);
+          o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
+        }
+        st4(y + (int64_t)r * W + c, o);
+      }
+    }
+  }
+}
+
+static inline int ln_nv(int W) {
+  int nv = (W + 127) / 128, p = 1;
+  while (p < nv) p <<= 1;
+  return p;
+}
+
+int launch_ln_fwd(const int* dims, const float* u, int W, const float* gamma, const float* beta, DropCfg drop, float* y,
+                  float* stats, int max_graphs, cudaStream_t st) {
+  if (W % 4 || W > 2048 || W < 4) return EIMS_ERR_ARG;
+  int blocks = (max_graphs + 7) / 8;
+  if (blocks < 1) blocks = 1;
+  switch (ln_nv(W)) {
+#define EIMS_LN_F(NV) case NV: ln_relu_drop_fwd_kernel<NV><<<blocks, 256, 0, st>>>(dims, u, W, gamma, beta, drop, y, stats); break;
+    EIMS_LN_F(1) EIMS_LN_F(2) EIMS_LN_F(4) EIMS_LN_F(8) EIMS_LN_F(16)
+#undef EIMS_LN_F
+    default: return EIMS_ERR_ARG;
+  }
+  return 0;
+}
+
+// backward: dy (grad w.r.t. the post-dropout output y) -> du (may alias dy); dgamma/dbeta += .
+template <int NV>
+__global__ void __launch_bounds__(256) ln_relu_drop_bwd_kernel(const int* __restrict__ dims, const float* __restrict__ u,
+                                                               const float* __restrict__ y, const float* dy, int W,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ stats, float drop_scale,
+                                                               float* du, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta) {
+  extern __shared__ float smem[];  // [8 warps][2][W] : per-warp column partials of dgamma / dbeta
+  const int B = dims[DIM_B];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nv4 = W >> 2;
+  float* sg = smem + (wib * 2 + 0) * W;
+  float* sb = smem + (wib * 2 + 1) * W;
+  for (int c = lane; c < W; c += 32) { sg[c] = 0.f; sb[c] = 0.f; }
+  __syncwarp();
+  for (int r = warp; r < B; r += nwarps) {
+    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+    float4 xh[NV], g[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      xh[i] = g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c4 < nv4) {
+        const int c = 4 * c4;
+        float4 uu = ldg4(u + (int64_t)r * W + c), yy = ldg4(y + (int64_t)r * W + c);
+        float4 d = *reinterpret_cast<const float4*>(dy + (int64_t)r * W + c);
+        float4 ga = ldg4(gamma + c);
+        float4 dt;
+        dt.x = yy.x > 0.f ? d.x * drop_scale : 0.f; dt.y = yy.y > 0.f ? d.y * drop_scale : 0.f;
+        dt.z = yy.z > 0.f ? d.z * drop_scale : 0.f; dt.w = yy.w > 0.f ? d.w * drop_scale : 0.f;
+        xh[i].x = (uu.x - mean) * rstd; xh[i].y = (uu.y - mean) * rstd;
+        xh[i].z = (uu.z - mean) * rstd; xh[i].w = (uu.w - mean) * rstd;
+        float4 a = *reinterpret_cast<float4*>(sg + c), b = *reinterpret_cast<float4*>(sb + c);
+        a.x = fmaf(dt.x, xh[i].x, a.x); a.y = fmaf(dt.y, xh[i].y, a.y);
+        a.z = fmaf(dt.z, xh[i].z, a.z); a.w = fmaf(dt.w, xh[i].w, a.w);
+        b.x += dt.x; b.y += dt.y; b.z += dt.z; b.w += dt.w;
+        *reinterpret_cast<float4*>(sg + c) = a;
+        *reinterpret_cast<float4*>(sb + c) = b;
+        g[i].x = dt.x * ga.x; g[i].y = dt.y * ga.y; g[i].z = dt.z * ga.z; g[i].w = dt.w * ga.w;
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+      }
+    }
+    const float m1 = warp_sum(s1) / (float)W, m2 = warp_sum(s2) / (float)W;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c4 = i * 32 + lane;
+      if (c4 < nv4) {
+        float4 o;
+        o.x = rstd * (g[i].x - m1 - xh[i].x * m2); o.y = rstd * (g[i].y - m1 - xh[i].y * m2);
+        o.z = rstd * (g[i].z - m1 - xh[i].z * m2); o.w = rstd * (g[i].w - m1 - xh[i].w * m2);
+        st4(du + (int64_t)r * W + 4 * c4, o);
+      }
+    }
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < nw; ++w) { a += smem[(w * 2) * W + c]; b += smem[(w * 2 + 1) * W + c]; }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, b);
+  }
+}
+
+int launch_ln_bwd(const int* dims, const float* u, const float* y, const float* dy, int W, const float* gamma,
+                  const float* stats, float drop_scale, float* du, float* dgamma, float* dbeta, int max_graphs,
+                  cudaStream_t st) {
+  if (W % 4 || W > 2048 || W < 4) return EIMS_ERR_ARG;
+  int blocks = (max_graphs + 31) / 32;  // ~4 rows per warp
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148) blocks = 148;
+  size_t smem = (size_t)8 * 2 * W * sizeof(float);
+  switch (ln_nv(W)) {
+#define EIMS_LN_B(NV)                                                                                              \
+  case NV:                                                                                                         \
+    if (smem > 48 * 1024)                                                                                          \
+      cudaFuncSetAttribute(ln_relu_drop_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    ln_relu_drop_bwd_kernel<NV><<<blocks, 256, smem, st>>>(dims, u, y, dy, W, gamma, stats, drop_scale, du, dgamma, dbeta); \
+    break;
+    EIMS_LN_B(1) EIMS_LN_B(2) EIMS_LN_B(4) EIMS_LN_B(8) EIMS_LN_B(16)
+#undef EIMS_LN_B
+    default: return EIMS_ERR_ARG;
+  }
+  return 0;
+}
+
+// =========================================================================== K7 loss
+// Block (128 threads) per graph: prob = sigmoid(logits); MSE and cosine terms; dlogits.
+constexpr int kLossMaxV4 = 8;  // max_mz <= 4096
+
+__device__ __forceinline__ float block_sum_128(float v, float* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return sh[0] + sh[1] + sh[2] + sh[3];
+}
+
+__global__ void __launch_bounds__(128) loss_kernel(const int* __restrict__ dims, const float* __restrict__ logits,
+                                                   const float* __restrict__ targets, const int* __restrict__ target_rows,
+                                                   int M, int loss_kind, float* __restrict__ prob,
+                                                   float* __restrict__ dlogits, float* __restrict__ row_loss,
+                                                   float* __restrict__ row_cos) {
+  __shared__ float sh[4];
+  const int B = dims[DIM_B];
+  const int nv4 = M >> 2;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const int64_t trow = target_rows ? (int64_t)target_rows[b] : (int64_t)b;
+    const float* t = targets + trow * M;
+    float4 p[kLossMaxV4], tt[kLossMaxV4];
+    float se = 0.f, pp = 0.f, tq = 0.f, pt = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLossMaxV4; ++i) {
+      const int c4 = i * 128 + threadIdx.x;
+      if (c4 < nv4) {
+        float4 u = ldg4(logits + (int64_t)b * M + 4 * c4);
+        tt[i] = ldg4(t + 4 * c4);
+        p[i].x = 1.f / (1.f + expf(-u.x)); p[i].y = 1.f / (1.f + expf(-u.y));
+        p[i].z = 1.f / (1.f + expf(-u.z)); p[i].w = 1.f / (1.f + expf(-u.w));
+        float dx = p[i].x - tt[i].x, dy = p[i].y - tt[i].y, dz = p[i].z - tt[i].z, dw = p[i].w - tt[i].w;
+        se += dx * dx + dy * dy + dz * dz + dw * dw;
+        pp += p[i].x * p[i].x + p[i].y * p[i].y + p[i].z * p[i].z + p[i].w * p[i].w;
+        tq += tt[i].x * tt[i].x + tt[i].y * tt[i].y + tt[i].z * tt[i].z + tt[i].w * tt[i].w;
+        pt += p[i].x * tt[i].x + p[i].y * tt[i].y + p[i].z * tt[i].z + p[i].w * tt[i].w;
+        if (prob) st4(prob + (int64_t)b * M + 4 * c4, p[i]);
+      }
+    }
+    se = block_sum_128(se, sh);
+    pp = block_sum_128(pp, sh);
+    tq = block_sum_128(tq, sh);
+    pt = block_sum_128(pt, sh);
+    const float np = sqrtf(pp) + kCosEps, nt = sqrtf(tq) + kCosEps;
+    const float cosv = pt / (np * nt);
+    if (threadIdx.x == 0) { row_loss[b] = se; row_cos[b] = cosv; }
+    if (dlogits) {
+      const float k_mse = 2.f / ((float)B * (float)M);
+      // d(1-mean cos)/dp = -(1/B) * ( t/(nt*np) - cos * p / (||p|| * np) )
+      const float ka = -1.f / ((float)B * nt * np);
+      const float kb = cosv / ((float)B * fmaxf(sqrtf(pp), 1e-30f) * np);
+#pragma unroll
+      for (int i = 0; i < kLossMaxV4; ++i) {
+        const int c4 = i * 128 + threadIdx.x;
+        if (c4 < nv4) {
+          float4 d;
+          if (loss_kind == EIMS_LOSS_MSE) {
+            d.x = k_mse * (p[i].x - tt[i].x); d.y = k_mse * (p[i].y - tt[i].y);
+            d.z = k_mse * (p[i].z - tt[i].z); d.w = k_mse * (p[i].w - tt[i].w);
+          } else {
+            d.x = ka * tt[i].x + kb * p[i].x; d.y = ka * tt[i].y + kb * p[i].y;
+            d.z = ka * tt[i].z + kb * p[i].z; d.w = ka * tt[i].w + kb * p[i].w;
+          }
+          d.x *= p[i].x * (1.f - p[i].x); d.y *= p[i].y * (1.f - p[i].y);
+          d.z *= p[i].z * (1.f - p[i].z); d.w *= p[i].w * (1.f - p[i].w);
+          st4(dlogits + (int64_t)b * M + 4 * c4, d);
+        }
+      }
+    }
+  }
+}
+
+int launch_loss(const int* dims, const float* logits, const float* targets, const int* target_rows, int M,
+                int loss_kind, float* prob, float* dlogits, float* row_loss, float* row_cos, int max_graphs,
+                cudaStream_t st) {
+  if (M % 4 || M > 4 * 128 * kLossMaxV4) return EIMS_ERR_ARG;
+  int blocks = max_graphs < 1 ? 1 : max_graphs;
+  loss_kernel<<<blocks, 128, 0, st>>>(dims, logits, targets, target_rows, M, loss_kind, prob, dlogits, row_loss, row_cos);
+  return 0;
+}
+
+// prob = sigmoid(logits) (inference) ; dlogits = dprob * p * (1-p) (autograd entry)
+__global__ void sigmoid_kernel(const int* __restrict__ dims, const float* __restrict__ logits, int M,
+                               float* __restrict__ prob) {
+  const int64_t n4 = (int64_t)dims[DIM_B] * M / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 u = ldg4(logits + 4 * i), p;
+    p.x = 1.f / (1.f + expf(-u.x)); p.y = 1.f / (1.f + expf(-u.y));
+    p.z = 1.f / (1.f + expf(-u.z)); p.w = 1.f / (1.f + expf(-u.w));
+    st4(prob + 4 * i, p);
+  }
+}
+__global__ void dprob_to_dlogits_kernel(const int* __restrict__ dims, const float* __restrict__ prob,
+                                        const float* __restrict__ dprob, int M, float* __restrict__ dlogits) {
+  const int64_t n4 = (int64_t)dims[DIM_B] * M / 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 p = ldg4(prob + 4 * i), d = ldg4(dprob + 4 * i);
+    d.x *= p.x * (1.f - p.x); d.y *= p.y * (1.f - p.y); d.z *= p.z * (1.f - p.z); d.w *= p.w * (1.f - p.w);
+    st4(dlogits + 4 * i, d);
+  }
+}
+static inline int ew_blocks(int64_t n4) {
+  int64_t b = (n4 + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  return b < 1 ? 1 : (int)b;
+}
+int launch_sigmoid(const int* dims, const float* logits, int M, float* prob, int max_graphs, cudaStream_t st) {
+  sigmoid_kernel<<<ew_blocks((int64_t)max_graphs * M / 4), 256, 0, st>>>(dims, logits, M, prob);
+  return 0;
+}
+int launch_dprob_to_dlogits(const int* dims, const float* prob, const float* dprob, int M, float* dlogits,
+                            int max_graphs, cudaStream_t st) {
+  dprob_to_dlogits_kernel<<<ew_blocks((int64_t)max_graphs * M / 4), 256, 0, st>>>(dims, prob, dprob, M, dlogits);
+  return 0;
+}
+
+// metrics += {mean loss, mean cos, 1}; one block, fixed summation order (deterministic).
+__global__ void __launch_bounds__(256) metrics_kernel(const int* __restrict__ dims, const float* __restrict__ row_loss,
+                                                      const float* __restrict__ row_cos, int M,
+                                                      float* __restrict__ metrics) {
+  __shared__ double s1[256], s2[256];
+  const int B = dims[DIM_B];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < B; i += 256) { a += (double)row_loss[i]; b += (double)row_cos[i]; }
+  s1[threadIdx.x] = a; s2[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && B > 0) {
+    const float loss = (float)(s1[0] / ((double)B * (double)M));
+    const float cosm = (float)(s2[0] / (double)B);
+    metrics[0] += loss; metrics[1] += cosm; metrics[2] += 1.f;
+    metrics[4] = loss; metrics[5] = cosm;  // last step's values
+  }
+}
+int launch_metrics(const int* dims, const float* row_loss, const float* row_cos, int M, float* metrics, cudaStream_t st) {
+  metrics_kernel<<<1, 256, 0, st>>>(dims, row_loss, row_cos, M, metrics);
+  return 0;
+}
+
+// =========================================================================== column sums (bias grads)
+// out[c] += sum_r in[r,c]  for r < dims[dim_slot]
+__global__ void __launch_bounds__(256) colsum_kernel(const int* __restrict__ dims, int dim_slot,
+                                                     const float* __restrict__ in, int C, int ld, float* __restrict__ out) {
+  __shared__ float4 sh[4][64];
+  const int R = dims[dim_slot];
+  const int cg = blockIdx.x * 64 + (threadIdx.x & 63), rs = threadIdx.x >> 6;
+  const int rows_per = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (4 * cg < C)
+    for (int r = r0 + rs; r < r1; r += 4) {
+      float4 v = ldg4(in + (int64_t)r * ld + 4 * cg);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  sh[rs][threadIdx.x & 63] = a;
+  __syncthreads();
+  if (rs == 0 && 4 * cg < C && r0 < r1) {
+    for (int k = 1; k < 4; ++k) { float4 v = sh[k][threadIdx.x]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+    atomicAdd(out + 4 * cg + 0, a.x); atomicAdd(out + 4 * cg + 1, a.y);
+    atomicAdd(out + 4 * cg + 2, a.z); atomicAdd(out + 4 * cg + 3, a.w);
+  }
+}
+int launch_colsum(const int* dims, int dim_slot, const float* in, int C, int ld, float* out, int max_rows, cudaStream_t st) {
+  if (C % 4) return EIMS_ERR_ARG;
+  int gy = (max_rows + 31) / 32;
+  if (gy > 64) gy = 64;
+  if (gy < 1) gy = 1;
+  dim3 grid((C / 4 + 63) / 64, gy);
+  colsum_kernel<<<grid, 256, 0, st>>>(dims, dim_slot, in, C, ld, out);
+  return 0;
+}
+
+// =========================================================================== K8 AdamW
+struct AdamK { float decay, one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps, grad_scale; };
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, int64_t n, AdamK k) {
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = *reinterpret_cast<float4*>(p + 4 * i), gg = *reinterpret_cast<float4*>(g + 4 * i);
+    float4 mm = *reinterpret_cast<float4*>(m + 4 * i), vv = *reinterpret_cast<float4*>(v + 4 * i);
+#define EIMS_ADAM1(P, G, Mm, V)                                       \
+  {                                                                   \
+    float gr = G * k.grad_scale;                                      \
+    P *= k.decay;                                                     \
+    Mm = Mm + (gr - Mm) * k.one_minus_b1;                             \
+    V = V * k.b2 + k.one_minus_b2 * gr * gr;                          \
+    float den = sqrtf(V) * k.inv_bc2_sqrt + k.eps;                    \
+    P = P - k.step_size * (Mm / den);                                 \
+  }
+    EIMS_ADAM1(pp.x, gg.x, mm.x, vv.x) EIMS_ADAM1(pp.y, gg.y, mm.y, vv.y)
+    EIMS_ADAM1(pp.z, gg.z, mm.z, vv.z) EIMS_ADAM1(pp.w, gg.w, mm.w, vv.w)
+    *reinterpret_cast<float4*>(p + 4 * i) = pp;
+    *reinterpret_cast<float4*>(m + 4 * i) = mm;
+    *reinterpret_cast<float4*>(v + 4 * i) = vv;
+    *reinterpret_cast<float4*>(g + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);  // optimizer.zero_grad (GCN:414)
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      float P = p[i], G = g[i], Mm = m[i], V = v[i];
+      EIMS_ADAM1(P, G, Mm, V)
+      p[i] = P; m[i] = Mm; v[i] = V; g[i] = 0.f;
+    }
+}
+
+int launch_adamw(float* p, float* g, float* m, float* v, int64_t n, const eims_step* s, cudaStream_t st) {
+  if (!s || s->step < 1) return EIMS_ERR_ARG;
+  const double b1 = s->beta1, b2 = s->beta2;
+  const double bc1 = 1.0 - pow(b1, (double)s->step), bc2 = 1.0 - pow(b2, (double)s->step);
+  AdamK k;
+  k.decay = (float)(1.0 - (double)s->lr * (double)s->weight_decay);
+  k.one_minus_b1 = (float)(1.0 - b1);
+  k.b2 = (float)b2;
+  k.one_minus_b2 = (float)(1.0 - b2);
+  k.step_size = (float)((double)s->lr / bc1);
+  k.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  k.eps = s->eps;
+  k.grad_scale = s->grad_scale;
+  adamw_kernel<<<ew_blocks(n / 4), 256, 0, st>>>(p, g, m, v, n, k);
+  return 0;
+}
+
+// =========================================================================== dropout mask (tests)
+__global__ void dropout_mask_kernel(DropCfg d, int64_t n4, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 m = drop_mask4(d, (uint64_t)i * 4);
+    m.x = m.x != 0.f; m.y = m.y != 0.f; m.z = m.z != 0.f; m.w = m.w != 0.f;
+    st4(out + 4 * i, m);
+  }
+}
+int launch_dropout_mask(DropCfg d, int rows, int W, float* out, cudaStream_t st) {
+  if (W % 4) return EIMS_ERR_ARG;
+  int64_t n4 = (int64_t)rows * W / 4;
+  dropout_mask_kernel<<<ew_blocks(n4), 256, 0, st>>>(d, n4, out);
+  return 0;
+}
+
+}  // namespace eims

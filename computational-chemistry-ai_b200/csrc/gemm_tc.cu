@@ -1,0 +1,330 @@
+// K3/K6: fp32-grade GEMM on the 5th-generation tensor cores (tcgen05.mma kind::tf32, fp32
+// accumulators in TMEM), 3xTF32 split:  x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi)
+//   A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi       (the dropped lo*lo term is ~2^-22 relative)
+// which is what the 1e-4 spectrum / gradient bar needs (single-pass TF32 gives 3e-3).
+//
+// Structure of one CTA (288 threads), one 128 x BN output tile:
+//   warps 0-7  producers: 128-bit global loads of the fp32 A / B tiles (either storage order),
+//              hi/lo split in registers, st.shared into the canonical UMMA SWIZZLE_128B layout
+//              (K-major or MN-major, so no transposes anywhere), fence.proxy.async, mbarrier
+//              arrive.  Two groups of 4 warps alternate k-blocks so two are in flight.
+//   warp  8    one elected lane issues 12 tcgen05.mma per k-block (4 k-steps x 3 products) and
+//              tcgen05.commit's the stage back to the producers.
+//   warps 0-7  epilogue: tcgen05.ld the accumulator (lane quarter = warp%4, column half =
+//              warp/4), apply row scale / bias / ReLU, store or red.add (split-K).
+// Sizes M and K may live in device memory (atoms in the current batch) so a captured step
+// can be replayed; tiles past the live range exit before touching barriers or TMEM.
+#include "common.cuh"
+#include "launchers.h"
+
+namespace eims {
+
+namespace tc {
+
+constexpr int BM = 128, BK = 32, STAGES = 3;
+constexpr int kProducerWarps = 8, kThreads = (kProducerWarps + 1) * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a protocol bug must not hang the GPU
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor (sm_100 format, version 1, SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // layout type: SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+  float r = x - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+struct Args {
+  const float* A; const float* B; float* C;
+  int lda, ldb, ldc, a_mn, b_mn;
+  int M, N, K;
+  const int* m_dev; const int* k_dev;
+  const float* row_scale; const float* bias;
+  int relu, accumulate, vec_a, vec_b;
+};
+
+// Load one 16-byte chunk (4 consecutive floats) with zero fill outside [0, lim) of the
+// contiguous dimension; `ok` gates the whole chunk (strided dimension in range).
+__device__ __forceinline__ float4 load_chunk(const float* base, int64_t off, int pos, int lim, bool ok, int vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!ok || pos >= lim) return v;
+  const float* p = base + off;
+  if (vec && pos + 3 < lim) return ldg4(p);
+  v.x = __ldg(p);
+  if (pos + 1 < lim) v.y = __ldg(p + 1);
+  if (pos + 2 < lim) v.z = __ldg(p + 2);
+  if (pos + 3 < lim) v.w = __ldg(p + 3);
+  return v;
+}
+
+__device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float4 v) {
+  uint4 h, l;
+  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+  *reinterpret_cast<uint4*>(hi_tile + off) = h;
+  *reinterpret_cast<uint4*>(lo_tile + off) = l;
+}
+
+// Tile of an operand with ROWS "MN" rows and BK k-columns, written by one producer group
+// (128 threads).  mn_major = 0: memory is [mn][k] (k contiguous) -> canonical K-major layout
+//   offset(r, c) = (r/8)*1024 + (r%8)*128 + ((c ^ (r%8))*16)          c = 16-byte chunk along k
+// mn_major = 1: memory is [k][mn] (mn contiguous) -> canonical MN-major layout
+//   offset(k, c) = (k/8)*(ROWS/32*1024) + (c/8)*1024 + (k%8)*128 + (((c%8) ^ (k%8))*16)   c = chunk along mn
+template <int ROWS>
+__device__ __forceinline__ void produce_tile(const float* __restrict__ base, int ld, int mn_major, int vec, int mn0,
+                                             int mn_lim, int k0, int k_lim, uint8_t* hi_tile, uint8_t* lo_tile,
+                                             int t /*0..127*/) {
+  constexpr int CHUNKS = ROWS * BK / 4;   // 16-byte chunks in the tile
+  constexpr int PER = CHUNKS / 128;
+  float4 v[PER];
+  uint32_t off[PER];
+  if (!mn_major) {
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const int idx = it * 128 + t, r = idx >> 3, c = idx & 7;
+      const int mn = mn0 + r, k = k0 + 4 * c;
+      v[it] = load_chunk(base, (int64_t)mn * ld + k, k, k_lim, mn < mn_lim, vec);
+      off[it] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+    }
+  } else {
+    constexpr int CPR = ROWS / 4;  // chunks per k-row
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const int idx = it * 128 + t, kk = idx / CPR, c = idx % CPR;
+      const int k = k0 + kk, mn = mn0 + 4 * c;
+      v[it] = load_chunk(base, (int64_t)k * ld + mn, mn, mn_lim, k < k_lim, vec);
+      off[it] = (uint32_t)((kk >> 3) * (ROWS / 32 * 1024) + (c >> 3) * 1024 + (kk & 7) * 128 + (((c & 7) ^ (kk & 7)) << 4));
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < PER; ++it) store_split(hi_tile, lo_tile, off[it], v[it]);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
+  constexpr int A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;
+  constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int M = g.m_dev ? *g.m_dev : g.M;
+  const int K = g.k_dev ? *g.k_dev : g.K;
+  const int N = g.N;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (m0 >= M || n0 >= N) return;
+  const int kblocks = (K + BK - 1) / BK;
+  const int per_split = (kblocks + gridDim.z - 1) / gridDim.z;
+  const int kb0 = blockIdx.z * per_split;
+  const int kb1 = min(kblocks, kb0 + per_split);
+  const int nkb = kb1 - kb0;
+  if (nkb <= 0) return;  // only possible for split-K slices past the live K (accumulate mode)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kProducerWarps) tmem_alloc(smem_u32(&tmem_base_slot), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < kProducerWarps) {
+    // ---------------------------------------------------------------- producers
+    const int group = warp >> 2, t = threadIdx.x & 127;
+    for (int i = group; i < nkb; i += 2) {
+      const int s = i % STAGES;
+      const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+      mbar_wait(empty0 + 8 * s, ph ^ 1u);
+      uint8_t* st = smem + s * STAGE_BYTES;
+      const int k0 = (kb0 + i) * BK;
+      produce_tile<BM>(g.A, g.lda, g.a_mn, g.vec_a, m0, M, k0, K, st, st + A_TILE, t);
+      produce_tile<BN>(g.B, g.ldb, g.b_mn, g.vec_b, n0, N, k0, K, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, t);
+      fence_proxy_async();
+      mbar_arrive(full0 + 8 * s);
+    }
+    // ---------------------------------------------------------------- epilogue
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int m = m0 + q * 32 + lane;
+    const float rs = (g.row_scale && m < M) ? __ldg(g.row_scale + m) : 1.f;
+    const bool add_bias = g.bias && (!g.accumulate || blockIdx.z == 0);
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 2; cb += 32) {
+      const int col0 = half * (BN / 2) + cb;
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
+      if (m < M) {
+        float* crow = g.C + (int64_t)m * g.ldc;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + col0 + j;
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v = __uint_as_float(r[j + e]) * rs;
+            if (add_bias && n + e < N) v += __ldg(g.bias + n + e);
+            if (g.relu) v = fmaxf(v, 0.f);
+            o[e] = v;
+          }
+          if (g.accumulate) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < N) atomicAdd(crow + n + e, o[e]);
+          } else if (n + 3 < N && ((g.ldc & 3) == 0)) {
+            st4(crow + n, make_float4(o[0], o[1], o[2], o[3]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < N) crow[n + e] = o[e];
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // K-major: 8-row groups 1024 B apart (SBO); k-step = +32 B inside the 128-B swizzle row.
+    // MN-major: 32-element MN atoms 1024 B apart (LBO); k-groups ROWS/32*1024 B apart (SBO).
+    const uint32_t a_lbo = g.a_mn ? 1024u : 16u, a_sbo = g.a_mn ? (uint32_t)(BM / 32 * 1024) : 1024u;
+    const uint32_t b_lbo = g.b_mn ? 1024u : 16u, b_sbo = g.b_mn ? (uint32_t)(BN / 32 * 1024) : 1024u;
+    const uint32_t a_kstep = g.a_mn ? (uint32_t)(BM / 32 * 1024) : 32u;
+    const uint32_t b_kstep = g.b_mn ? (uint32_t)(BN / 32 * 1024) : 32u;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+      mbar_wait(full0 + 8 * s, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t a_hi = sa, a_lo = sa + A_TILE, b_hi = sa + 2 * A_TILE, b_lo = b_hi + B_TILE;
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          const uint64_t dah = make_desc(a_hi + ks * a_kstep, a_lbo, a_sbo);
+          const uint64_t dal = make_desc(a_lo + ks * a_kstep, a_lbo, a_sbo);
+          const uint64_t dbh = make_desc(b_hi + ks * b_kstep, b_lbo, b_sbo);
+          const uint64_t dbl = make_desc(b_lo + ks * b_kstep, b_lbo, b_sbo);
+          umma_tf32(tmem_base, dal, dbh, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        umma_commit(empty0 + 8 * s);                 // frees the stage when these MMAs retire
+        if (i == nkb - 1) umma_commit(accum_bar);    // accumulator complete
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+}  // namespace tc
+
+int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
+                   int N, int K, const int* m_dev, const int* k_dev, const float* row_scale, const float* bias,
+                   int relu, int accumulate, cudaStream_t st) {
+  using namespace tc;
+  if (M <= 0 || N <= 0 || K <= 0) return EIMS_ERR_ARG;
+  Args g{A, B, C, lda, ldb, ldc, a_mn, b_mn, M, N, K, m_dev, k_dev, row_scale, bias, relu, accumulate, 0, 0};
+  g.vec_a = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 4 == 0);
+  g.vec_b = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 4 == 0);
+  constexpr int BN = 128;
+  constexpr int smem_bytes = STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return EIMS_ERR_CUDA;
+    attr_done = true;
+  }
+  const int mt = (M + BM - 1) / BM, nt = (N + BN - 1) / BN;
+  int splits = 1;
+  if (accumulate) {  // split-K: weight gradients reduce over atoms / graphs
+    const int kblocks = (K + BK - 1) / BK;
+    splits = (148 + mt * nt - 1) / (mt * nt);
+    const int maxs = (kblocks + 3) / 4;  // at least 4 k-blocks per slice
+    if (splits > maxs) splits = maxs;
+    if (splits < 1) splits = 1;
+  }
+  dim3 grid(nt, mt, splits);
+  gemm_3xtf32_kernel<BN><<<grid, kThreads, smem_bytes, st>>>(g);
+  return 0;
+}
+
+}  // namespace eims

@@ -1,0 +1,61 @@
+// Host-side launchers shared between the translation units (internal; the public ABI is
+// include/eims_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/eims_b200.h"
+#include "common.cuh"
+
+namespace eims {
+
+// graph.cu
+int launch_csr_build(const eims_dataset* ds, const int32_t* ids, int B, int F, int max_nodes, int max_edges,
+                     int* gptr, int* eptr, int* gid, int* src, int* dst, int* rowptr, int* col, float* norm,
+                     float* x, int* dims, cudaStream_t st);
+int launch_layer0_fwd(const int* dims, const int* rowptr, const int* col, const float* norm, const float* x, int F,
+                      const float* W, const float* bias, int H, float* a0, float* z, int max_nodes, cudaStream_t st);
+int launch_layer0_wgrad(const int* dims, const float* a0, int F, const float* q, int H, float* dW, int max_nodes,
+                        cudaStream_t st);
+int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const float* norm, const float* h, int H,
+                     const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
+                     int max_nodes, cudaStream_t st);
+int launch_readout(const int* dims, const int* gptr, const float* z, int H, const float* bn_scale,
+                   const float* bn_shift, int pooling, float* out, int* argmax, int max_graphs, cudaStream_t st);
+
+// dense.cu
+int launch_gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
+                     int N, int K, const int* m_dev, const int* k_dev, const float* row_scale, const float* bias,
+                     int relu, int accumulate, cudaStream_t st);
+int64_t bn_scratch_floats(int H, int max_nodes);
+int launch_bn_stats(const int* dims, const float* z, int H, const float* gamma, const float* beta, float* rmean,
+                    float* rvar, float* mean, float* invstd, float* scale, float* shift, float* partials,
+                    int max_nodes, cudaStream_t st);
+int launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* rmean, const float* rvar, int H,
+                          float* scale, float* shift, cudaStream_t st);
+int launch_bn_bwd(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr, const int* argmax,
+                  int pooling, const float* z, int H, const float* mean, const float* invstd, const float* gamma,
+                  const float* norm, float* dgamma, float* dbeta, float* dbias, float* means, float* partials,
+                  float* q, int max_nodes, cudaStream_t st);
+int launch_ln_fwd(const int* dims, const float* u, int W, const float* gamma, const float* beta, DropCfg drop, float* y,
+                  float* stats, int max_graphs, cudaStream_t st);
+int launch_ln_bwd(const int* dims, const float* u, const float* y, const float* dy, int W, const float* gamma,
+                  const float* stats, float drop_scale, float* du, float* dgamma, float* dbeta, int max_graphs,
+                  cudaStream_t st);
+int launch_loss(const int* dims, const float* logits, const float* targets, const int* target_rows, int M,
+                int loss_kind, float* prob, float* dlogits, float* row_loss, float* row_cos, int max_graphs,
+                cudaStream_t st);
+int launch_sigmoid(const int* dims, const float* logits, int M, float* prob, int max_graphs, cudaStream_t st);
+int launch_dprob_to_dlogits(const int* dims, const float* prob, const float* dprob, int M, float* dlogits,
+                            int max_graphs, cudaStream_t st);
+int launch_metrics(const int* dims, const float* row_loss, const float* row_cos, int M, float* metrics, cudaStream_t st);
+int launch_colsum(const int* dims, int dim_slot, const float* in, int C, int ld, float* out, int max_rows, cudaStream_t st);
+int launch_adamw(float* p, float* g, float* m, float* v, int64_t n, const eims_step* s, cudaStream_t st);
+int launch_dropout_mask(DropCfg d, int rows, int W, float* out, cudaStream_t st);
+
+// gemm_tc.cu  (tcgen05 / TMEM, 3xTF32)
+int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
+                   int N, int K, const int* m_dev, const int* k_dev, const float* row_scale, const float* bias,
+                   int relu, int accumulate, cudaStream_t st);
+
+}  // namespace eims

@@ -1,0 +1,472 @@
+// The C ABI (include/eims_b200.h): parameter layout, workspace plan, and the whole-step
+// orchestration  batch build -> GCNSpectrum.forward -> loss -> backward -> AdamW
+// (reference: templates/ms-pred-gcn-eims-cupy.py:292-297, 354-376, 410-431).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "launchers.h"
+
+using namespace eims;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define EIMS_TRY(expr)                      \
+  do {                                      \
+    int _rc = (expr);                       \
+    if (_rc != 0) return _rc < 0 ? fail(_rc, "%s failed (%d) at %s:%d", #expr, _rc, __FILE__, __LINE__) : _rc; \
+  } while (0)
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(EIMS_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+int check_dims(const eims_dims* d) {
+  if (!d) return fail(EIMS_ERR_ARG, "dims is NULL");
+  if (d->node_feat_dim < 1 || d->node_feat_dim > 8) return fail(EIMS_ERR_ARG, "node_feat_dim must be in [1,8]");
+  if (d->hidden_dim < 64 || d->hidden_dim % 64 || d->hidden_dim > 1024)
+    return fail(EIMS_ERR_ARG, "hidden_dim must be a multiple of 64 in [64,1024]");
+  if (d->num_gcn_layers < 1 || d->num_gcn_layers > 16) return fail(EIMS_ERR_ARG, "num_gcn_layers must be in [1,16]");
+  if (d->max_mz < 4 || d->max_mz % 4 || d->max_mz > 4096) return fail(EIMS_ERR_ARG, "max_mz must be a multiple of 4 in [4,4096]");
+  if (d->pooling < 0 || d->pooling > 3) return fail(EIMS_ERR_ARG, "pooling must be one of EIMS_POOL_*");
+  if (!(d->dropout >= 0.f && d->dropout < 1.f)) return fail(EIMS_ERR_ARG, "dropout must be in [0,1)");
+  return 0;
+}
+
+// tensor sizes in model.parameters() order
+std::vector<int64_t> param_sizes(const eims_dims* d) {
+  const int64_t F = d->node_feat_dim, H = d->hidden_dim, M = d->max_mz, L = d->num_gcn_layers;
+  const int64_t P = d->pooling == EIMS_POOL_COMBINED ? 2 * H : H;
+  std::vector<int64_t> s;
+  for (int l = 0; l < L; ++l) { s.push_back((l == 0 ? F : H) * H); s.push_back(H); }
+  for (int l = 0; l < L; ++l) { s.push_back(H); s.push_back(H); }
+  s.push_back(2 * H * P); s.push_back(2 * H); s.push_back(2 * H); s.push_back(2 * H);
+  s.push_back(H * 2 * H); s.push_back(H); s.push_back(H); s.push_back(H);
+  s.push_back(M * H); s.push_back(M);
+  return s;
+}
+
+struct Buf { void* ptr; int64_t bytes; };
+
+}  // namespace
+
+struct eims_plan {
+  eims_dims d;
+  int Bc, Nc, Ec;  // capacities
+  int gemm_backend;
+  int64_t ws_bytes;
+  bool bound;
+  std::vector<int64_t> poff;  // parameter offsets
+  std::vector<std::pair<std::string, int64_t>> order;  // name -> bytes (carve order)
+  std::map<std::string, Buf> buf;
+  int state;  // 0 none, 1 batch built, 2 forward(train) done, 3 loss grad ready
+  int last_training;
+  eims_step last_step;
+  int pool_dim() const { return d.pooling == EIMS_POOL_COMBINED ? 2 * d.hidden_dim : d.hidden_dim; }
+  template <class T> T* get(const std::string& n) { return reinterpret_cast<T*>(buf[n].ptr); }
+  float* f(const std::string& n) { return get<float>(n); }
+  int* i(const std::string& n) { return get<int>(n); }
+  // parameter accessors (flat buffer)
+  int64_t off_gcn_w(int l) const { return poff[2 * l]; }
+  int64_t off_gcn_b(int l) const { return poff[2 * l + 1]; }
+  int64_t off_bn_g(int l) const { return poff[2 * d.num_gcn_layers + 2 * l]; }
+  int64_t off_bn_b(int l) const { return poff[2 * d.num_gcn_layers + 2 * l + 1]; }
+  int64_t off_head(int k) const { return poff[4 * d.num_gcn_layers + k]; }  // 0..9
+};
+
+namespace {
+
+int gemm(eims_plan* p, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
+         int N, int K, const int* m_dev, const int* k_dev, const float* rs, const float* bias, int relu, int acc,
+         cudaStream_t st) {
+  if (p->gemm_backend == EIMS_GEMM_FP32_SIMT)
+    return launch_gemm_simt(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, m_dev, k_dev, rs, bias, relu, acc, st);
+  return launch_gemm_tc(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, m_dev, k_dev, rs, bias, relu, acc, st);
+}
+
+void add(eims_plan* p, const std::string& name, int64_t bytes) {
+  bytes = (bytes + 255) & ~(int64_t)255;
+  p->order.emplace_back(name, bytes);
+  p->ws_bytes += bytes;
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int eims_version(void) { return 100; }
+const char* eims_last_error(void) { return g_err; }
+
+int eims_device_check(void) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    return fail(EIMS_ERR_CUDA, "no CUDA device");
+  if (prop.major != 10) return fail(EIMS_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  return 0;
+}
+
+int64_t eims_param_count(const eims_dims* d) {
+  if (check_dims(d)) return -1;
+  int64_t n = 0;
+  for (int64_t s : param_sizes(d)) n += s;
+  return n;
+}
+int eims_param_num_tensors(const eims_dims* d) { return check_dims(d) ? -1 : 4 * d->num_gcn_layers + 10; }
+int eims_param_layout(const eims_dims* d, int64_t* offsets, int32_t n_entries) {
+  EIMS_TRY(check_dims(d));
+  auto s = param_sizes(d);
+  if (!offsets || n_entries != (int)s.size() + 1) return fail(EIMS_ERR_ARG, "offsets must have %d entries", (int)s.size() + 1);
+  int64_t o = 0;
+  for (size_t k = 0; k < s.size(); ++k) { offsets[k] = o; o += s[k]; }
+  offsets[s.size()] = o;
+  return 0;
+}
+
+// ------------------------------------------------------------------ stand-alone kernels
+int eims_csr_build(const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs, int32_t node_feat_dim,
+                   int32_t max_nodes, int32_t max_edges, int32_t* gptr, int32_t* eptr, int32_t* gid, int32_t* src,
+                   int32_t* dst, int32_t* rowptr, int32_t* col, float* norm, float* x, int32_t* dims,
+                   eims_stream_t stream) {
+  if (!ds || num_graphs < 0) return fail(EIMS_ERR_ARG, "bad dataset / num_graphs");
+  EIMS_TRY(launch_csr_build(ds, mol_ids, num_graphs, node_feat_dim, max_nodes, max_edges, gptr, eptr, gid, src, dst,
+                            rowptr, col, norm, x, dims, (cudaStream_t)stream));
+  return check_launch("eims_csr_build");
+}
+
+int eims_spmm_norm(const int32_t* dims, const int32_t* rowptr, const int32_t* col, const float* norm, const float* h,
+                   int32_t width, const float* bn_scale, const float* bn_shift, float drop_p, uint64_t seed,
+                   int32_t step, int32_t site, int32_t out_scale_norm, float* out, int32_t max_nodes,
+                   eims_stream_t stream) {
+  EIMS_TRY(launch_spmm_norm(dims, rowptr, col, norm, h, width, bn_scale, bn_shift, make_drop(drop_p, seed, step, site),
+                            out_scale_norm ? 1 : 0, out, max_nodes, (cudaStream_t)stream));
+  return check_launch("eims_spmm_norm");
+}
+
+int eims_gemm(int32_t backend, const float* A, int32_t lda, int32_t a_mn_major, const float* B, int32_t ldb,
+              int32_t b_mn_major, float* C, int32_t ldc, int32_t M, int32_t N, int32_t K, const int32_t* m_dev,
+              const int32_t* k_dev, const float* row_scale, const float* bias, int32_t relu, int32_t accumulate,
+              eims_stream_t stream) {
+  if (backend == EIMS_GEMM_FP32_SIMT)
+    EIMS_TRY(launch_gemm_simt(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, m_dev, k_dev, row_scale, bias,
+                              relu, accumulate, (cudaStream_t)stream));
+  else
+    EIMS_TRY(launch_gemm_tc(A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, m_dev, k_dev, row_scale, bias,
+                            relu, accumulate, (cudaStream_t)stream));
+  return check_launch("eims_gemm");
+}
+
+int64_t eims_bn_scratch_floats(int32_t width, int32_t max_nodes) { return bn_scratch_floats(width, max_nodes); }
+
+int eims_bn_stats(const int32_t* dims, const float* z, int32_t width, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float* mean, float* invstd, float* scale, float* shift,
+                  float* partials, int32_t max_nodes, eims_stream_t stream) {
+  EIMS_TRY(launch_bn_stats(dims, z, width, gamma, beta, running_mean, running_var, mean, invstd, scale, shift, partials,
+                           max_nodes, (cudaStream_t)stream));
+  return check_launch("eims_bn_stats");
+}
+
+int eims_readout(const int32_t* dims, const int32_t* gptr, const float* z, int32_t width, const float* bn_scale,
+                 const float* bn_shift, int32_t pooling, float* out, int32_t* argmax, int32_t max_graphs,
+                 eims_stream_t stream) {
+  EIMS_TRY(launch_readout(dims, gptr, z, width, bn_scale, bn_shift, pooling, out, argmax, max_graphs, (cudaStream_t)stream));
+  return check_launch("eims_readout");
+}
+
+int eims_loss_mse_cos(const int32_t* dims, const float* logits, const float* targets, const int32_t* target_rows,
+                      int32_t max_mz, int32_t loss_kind, float* prob, float* dlogits, float* row_loss, float* row_cos,
+                      int32_t max_graphs, eims_stream_t stream) {
+  EIMS_TRY(launch_loss(dims, logits, targets, target_rows, max_mz, loss_kind, prob, dlogits, row_loss, row_cos,
+                       max_graphs, (cudaStream_t)stream));
+  return check_launch("eims_loss_mse_cos");
+}
+
+int eims_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const eims_step* s, eims_stream_t stream) {
+  EIMS_TRY(launch_adamw(p, g, m, v, n, s, (cudaStream_t)stream));
+  return check_launch("eims_adamw_flat");
+}
+
+int eims_dropout_mask(float drop_p, uint64_t seed, int32_t step, int32_t site, int32_t rows, int32_t width, float* out,
+                      eims_stream_t stream) {
+  EIMS_TRY(launch_dropout_mask(make_drop(drop_p, seed, step, site), rows, width, out, (cudaStream_t)stream));
+  return check_launch("eims_dropout_mask");
+}
+
+// ------------------------------------------------------------------ plan
+int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, int32_t max_edges, eims_plan** out) {
+  EIMS_TRY(check_dims(d));
+  if (!out || max_graphs < 1 || max_nodes < 1 || max_edges < 0) return fail(EIMS_ERR_ARG, "bad capacities");
+  eims_plan* p = new eims_plan();
+  p->d = *d;
+  p->Bc = max_graphs; p->Nc = max_nodes; p->Ec = max_edges > 0 ? max_edges : 1;
+  p->gemm_backend = EIMS_GEMM_TCGEN05;
+  p->ws_bytes = 0; p->bound = false; p->state = 0; p->last_training = 0;
+  memset(&p->last_step, 0, sizeof(p->last_step));
+  auto s = param_sizes(d);
+  int64_t o = 0;
+  for (int64_t v : s) { p->poff.push_back(o); o += v; }
+  p->poff.push_back(o);
+  const int64_t B = p->Bc, N = p->Nc, E = p->Ec, H = d->hidden_dim, F = d->node_feat_dim, M = d->max_mz, L = d->num_gcn_layers;
+  const int64_t P = p->pool_dim();
+  add(p, "dims", 16 * 4); add(p, "flags", 16 * 4);
+  add(p, "gptr", (B + 1) * 4); add(p, "eptr", (B + 1) * 4); add(p, "gid", N * 4);
+  add(p, "src", E * 4); add(p, "dst", E * 4); add(p, "rowptr", (N + 1) * 4); add(p, "col", E * 4);
+  add(p, "argmax", B * H * 4);
+  add(p, "norm", N * 4); add(p, "x", N * F * 4); add(p, "a0", N * F * 4);
+  for (int l = 1; l < L; ++l) add(p, "a" + std::to_string(l), N * H * 4);
+  for (int l = 0; l < L; ++l) add(p, "z" + std::to_string(l), N * H * 4);
+  for (int l = 0; l < L; ++l) {
+    add(p, "bn_mean" + std::to_string(l), H * 4); add(p, "bn_invstd" + std::to_string(l), H * 4);
+    add(p, "bn_scale" + std::to_string(l), H * 4); add(p, "bn_shift" + std::to_string(l), H * 4);
+  }
+  add(p, "bn_means2", 2 * H * 4);
+  add(p, "bn_partials", bn_scratch_floats(d->hidden_dim, p->Nc) * 4);
+  add(p, "readout", B * P * 4);
+  add(p, "u1", B * 2 * H * 4); add(p, "y1", B * 2 * H * 4); add(p, "ln1", B * 2 * 4);
+  add(p, "u2", B * H * 4); add(p, "y2", B * H * 4); add(p, "ln2", B * 2 * 4);
+  add(p, "logits", B * M * 4); add(p, "prob", B * M * 4); add(p, "dlogits", B * M * 4);
+  add(p, "row_loss", B * 4); add(p, "row_cos", B * 4);
+  add(p, "dy2", B * H * 4); add(p, "dy1", B * 2 * H * 4); add(p, "dG", B * P * 4);
+  add(p, "dh", N * H * 4); add(p, "q", N * H * 4); add(p, "da", N * H * 4);
+  *out = p;
+  return 0;
+}
+
+int eims_plan_destroy(eims_plan* p) { delete p; return 0; }
+int64_t eims_plan_workspace_bytes(const eims_plan* p) { return p ? p->ws_bytes : -1; }
+
+int eims_plan_bind(eims_plan* p, void* workspace, int64_t bytes) {
+  if (!p || !workspace) return fail(EIMS_ERR_ARG, "plan / workspace is NULL");
+  if (bytes < p->ws_bytes) return fail(EIMS_ERR_ARG, "workspace too small: %lld < %lld", (long long)bytes, (long long)p->ws_bytes);
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(EIMS_ERR_ARG, "workspace must be 256-byte aligned");
+  char* c = reinterpret_cast<char*>(workspace);
+  for (auto& kv : p->order) { p->buf[kv.first] = Buf{c, kv.second}; c += kv.second; }
+  // counters / flags / dims start at zero (the ticket counter in bn_partials must be 0)
+  if (cudaMemset(p->buf["dims"].ptr, 0, p->buf["dims"].bytes) != cudaSuccess ||
+      cudaMemset(p->buf["flags"].ptr, 0, p->buf["flags"].bytes) != cudaSuccess ||
+      cudaMemset(p->buf["bn_partials"].ptr, 0, p->buf["bn_partials"].bytes) != cudaSuccess)
+    return fail(EIMS_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(cudaGetLastError()));
+  p->bound = true;
+  p->state = 0;
+  return 0;
+}
+
+int eims_plan_set_gemm_backend(eims_plan* p, int32_t backend) {
+  if (!p || (backend != EIMS_GEMM_TCGEN05 && backend != EIMS_GEMM_FP32_SIMT)) return fail(EIMS_ERR_ARG, "bad backend");
+  p->gemm_backend = backend;
+  return 0;
+}
+
+int eims_plan_buffer(eims_plan* p, const char* name, void** ptr, int64_t* bytes) {
+  if (!p || !p->bound || !name) return fail(EIMS_ERR_STATE, "plan not bound");
+  auto it = p->buf.find(name);
+  if (it == p->buf.end()) return fail(EIMS_ERR_ARG, "no workspace buffer named '%s'", name);
+  if (ptr) *ptr = it->second.ptr;
+  if (bytes) *bytes = it->second.bytes;
+  return 0;
+}
+
+int eims_batch_build(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
+                     eims_stream_t stream) {
+  if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
+  if (!ds || num_graphs < 0) return fail(EIMS_ERR_ARG, "bad dataset / num_graphs");
+  if (num_graphs > p->Bc) return fail(EIMS_ERR_CAPACITY, "num_graphs %d exceeds plan max_graphs %d", num_graphs, p->Bc);
+  EIMS_TRY(launch_csr_build(ds, mol_ids, num_graphs, p->d.node_feat_dim, p->Nc, p->Ec, p->i("gptr"), p->i("eptr"),
+                            p->i("gid"), p->i("src"), p->i("dst"), p->i("rowptr"), p->i("col"), p->f("norm"),
+                            p->f("x"), p->i("dims"), (cudaStream_t)stream));
+  p->state = 1;
+  return check_launch("eims_batch_build");
+}
+
+int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t training, const eims_step* s,
+                 eims_stream_t stream) {
+  if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
+  if (p->state < 1) return fail(EIMS_ERR_STATE, "eims_forward before eims_batch_build");
+  if (!params || !bn_running) return fail(EIMS_ERR_ARG, "params / bn_running is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const eims_dims& d = p->d;
+  const int H = d.hidden_dim, F = d.node_feat_dim, L = d.num_gcn_layers, M = d.max_mz, P = p->pool_dim();
+  const int* dims = p->i("dims");
+  const float drop_p = (training && d.dropout > 0.f) ? d.dropout : 0.f;
+  const uint64_t seed = s ? s->seed : 0;
+  const int step = s ? s->step : 0;
+  if (s) p->last_step = *s;
+  auto L_ = [&](const char* b, int l) { return std::string(b) + std::to_string(l); };
+  auto bn = [&](int l) -> int {
+    float* rm = bn_running + (int64_t)l * 2 * H;
+    float* rv = rm + H;
+    if (training)
+      return launch_bn_stats(dims, p->f(L_("z", l)), H, params + p->off_bn_g(l), params + p->off_bn_b(l), rm, rv,
+                             p->f(L_("bn_mean", l)), p->f(L_("bn_invstd", l)), p->f(L_("bn_scale", l)),
+                             p->f(L_("bn_shift", l)), p->f("bn_partials"), p->Nc, st);
+    return launch_bn_eval_coeffs(params + p->off_bn_g(l), params + p->off_bn_b(l), rm, rv, H, p->f(L_("bn_scale", l)),
+                                 p->f(L_("bn_shift", l)), st);
+  };
+  EIMS_TRY(launch_layer0_fwd(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("x"), F, params + p->off_gcn_w(0),
+                             params + p->off_gcn_b(0), H, p->f("a0"), p->f("z0"), p->Nc, st));
+  EIMS_TRY(bn(0));
+  for (int l = 1; l < L; ++l) {
+    EIMS_TRY(launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f(L_("z", l - 1)), H,
+                              p->f(L_("bn_scale", l - 1)), p->f(L_("bn_shift", l - 1)),
+                              make_drop(drop_p, seed, step, l - 1), 0, p->f(L_("a", l)), p->Nc, st));
+    EIMS_TRY(gemm(p, p->f(L_("a", l)), H, 0, params + p->off_gcn_w(l), H, 1, p->f(L_("z", l)), H, p->Nc, H, H,
+                  dims + DIM_N, nullptr, p->f("norm"), params + p->off_gcn_b(l), 1, 0, st));
+    EIMS_TRY(bn(l));
+  }
+  EIMS_TRY(launch_readout(dims, p->i("gptr"), p->f(L_("z", L - 1)), H, p->f(L_("bn_scale", L - 1)),
+                          p->f(L_("bn_shift", L - 1)), d.pooling, p->f("readout"), p->i("argmax"), p->Bc, st));
+  EIMS_TRY(gemm(p, p->f("readout"), P, 0, params + p->off_head(0), P, 0, p->f("u1"), 2 * H, p->Bc, 2 * H, P,
+                dims + DIM_B, nullptr, nullptr, params + p->off_head(1), 0, 0, st));
+  EIMS_TRY(launch_ln_fwd(dims, p->f("u1"), 2 * H, params + p->off_head(2), params + p->off_head(3),
+                         make_drop(drop_p, seed, step, L), p->f("y1"), p->f("ln1"), p->Bc, st));
+  EIMS_TRY(gemm(p, p->f("y1"), 2 * H, 0, params + p->off_head(4), 2 * H, 0, p->f("u2"), H, p->Bc, H, 2 * H,
+                dims + DIM_B, nullptr, nullptr, params + p->off_head(5), 0, 0, st));
+  EIMS_TRY(launch_ln_fwd(dims, p->f("u2"), H, params + p->off_head(6), params + p->off_head(7),
+                         make_drop(drop_p, seed, step, L + 1), p->f("y2"), p->f("ln2"), p->Bc, st));
+  EIMS_TRY(gemm(p, p->f("y2"), H, 0, params + p->off_head(8), H, 0, p->f("logits"), M, p->Bc, M, H, dims + DIM_B,
+                nullptr, nullptr, params + p->off_head(9), 0, 0, st));
+  p->state = training ? 2 : 1;
+  p->last_training = training;
+  return check_launch("eims_forward");
+}
+
+int eims_sigmoid(eims_plan* p, eims_stream_t stream) {
+  if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
+  EIMS_TRY(launch_sigmoid(p->i("dims"), p->f("logits"), p->d.max_mz, p->f("prob"), p->Bc, (cudaStream_t)stream));
+  return check_launch("eims_sigmoid");
+}
+
+int eims_loss(eims_plan* p, const float* targets, const int32_t* target_rows, int32_t loss_kind, int32_t want_grad,
+              eims_stream_t stream) {
+  if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
+  if (!targets) return fail(EIMS_ERR_ARG, "targets is NULL");
+  EIMS_TRY(launch_loss(p->i("dims"), p->f("logits"), targets, target_rows, p->d.max_mz, loss_kind, p->f("prob"),
+                       want_grad ? p->f("dlogits") : nullptr, p->f("row_loss"), p->f("row_cos"), p->Bc,
+                       (cudaStream_t)stream));
+  if (want_grad && p->state == 2) p->state = 3;
+  return check_launch("eims_loss");
+}
+
+int eims_backward(eims_plan* p, const float* params, const float* dprob, float* grads, eims_stream_t stream) {
+  if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
+  if (p->state < 2 || !p->last_training) return fail(EIMS_ERR_STATE, "eims_backward needs a training-mode eims_forward first");
+  if (!dprob && p->state != 3) return fail(EIMS_ERR_STATE, "eims_backward without dprob needs eims_loss(want_grad=1) first");
+  if (!params || !grads) return fail(EIMS_ERR_ARG, "params / grads is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const eims_dims& d = p->d;
+  const int H = d.hidden_dim, F = d.node_feat_dim, L = d.num_gcn_layers, M = d.max_mz, P = p->pool_dim();
+  const int* dims = p->i("dims");
+  const float drop_p = d.dropout > 0.f ? d.dropout : 0.f;
+  const float drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const uint64_t seed = p->last_step.seed;
+  const int step = p->last_step.step;
+  auto L_ = [&](const char* b, int l) { return std::string(b) + std::to_string(l); };
+  if (dprob) EIMS_TRY(launch_dprob_to_dlogits(dims, p->f("prob"), dprob, M, p->f("dlogits"), p->Bc, st));
+  float* dl = p->f("dlogits");
+  // ---- head (GCN:341-352 backwards)
+  EIMS_TRY(gemm(p, dl, M, 1, p->f("y2"), H, 1, grads + p->off_head(8), H, M, H, p->Bc, nullptr, dims + DIM_B, nullptr,
+                nullptr, 0, 1, st));
+  EIMS_TRY(launch_colsum(dims, DIM_B, dl, M, M, grads + p->off_head(9), p->Bc, st));
+  EIMS_TRY(gemm(p, dl, M, 0, params + p->off_head(8), H, 1, p->f("dy2"), H, p->Bc, H, M, dims + DIM_B, nullptr, nullptr,
+                nullptr, 0, 0, st));
+  EIMS_TRY(launch_ln_bwd(dims, p->f("u2"), p->f("y2"), p->f("dy2"), H, params + p->off_head(6), p->f("ln2"), drop_scale,
+                         p->f("dy2"), grads + p->off_head(6), grads + p->off_head(7), p->Bc, st));
+  EIMS_TRY(gemm(p, p->f("dy2"), H, 1, p->f("y1"), 2 * H, 1, grads + p->off_head(4), 2 * H, H, 2 * H, p->Bc, nullptr,
+                dims + DIM_B, nullptr, nullptr, 0, 1, st));
+  EIMS_TRY(launch_colsum(dims, DIM_B, p->f("dy2"), H, H, grads + p->off_head(5), p->Bc, st));
+  EIMS_TRY(gemm(p, p->f("dy2"), H, 0, params + p->off_head(4), 2 * H, 1, p->f("dy1"), 2 * H, p->Bc, 2 * H, H,
+                dims + DIM_B, nullptr, nullptr, nullptr, 0, 0, st));
+  EIMS_TRY(launch_ln_bwd(dims, p->f("u1"), p->f("y1"), p->f("dy1"), 2 * H, params + p->off_head(2), p->f("ln1"),
+                         drop_scale, p->f("dy1"), grads + p->off_head(2), grads + p->off_head(3), p->Bc, st));
+  EIMS_TRY(gemm(p, p->f("dy1"), 2 * H, 1, p->f("readout"), P, 1, grads + p->off_head(0), P, 2 * H, P, p->Bc, nullptr,
+                dims + DIM_B, nullptr, nullptr, 0, 1, st));
+  EIMS_TRY(launch_colsum(dims, DIM_B, p->f("dy1"), 2 * H, 2 * H, grads + p->off_head(1), p->Bc, st));
+  EIMS_TRY(gemm(p, p->f("dy1"), 2 * H, 0, params + p->off_head(0), P, 1, p->f("dG"), P, p->Bc, P, 2 * H, dims + DIM_B,
+                nullptr, nullptr, nullptr, 0, 0, st));
+  // ---- GCN layers, last to first (GCN:358-363 backwards)
+  for (int l = L - 1; l >= 0; --l) {
+    const bool from_readout = (l == L - 1);
+    EIMS_TRY(launch_bn_bwd(dims, from_readout ? nullptr : p->f("dh"), p->f("dG"), p->i("gid"), p->i("gptr"),
+                           p->i("argmax"), d.pooling, p->f(L_("z", l)), H, p->f(L_("bn_mean", l)),
+                           p->f(L_("bn_invstd", l)), params + p->off_bn_g(l), p->f("norm"), grads + p->off_bn_g(l),
+                           grads + p->off_bn_b(l), grads + p->off_gcn_b(l), p->f("bn_means2"), p->f("bn_partials"),
+                           p->f("q"), p->Nc, st));
+    if (l > 0) {
+      EIMS_TRY(gemm(p, p->f(L_("a", l)), H, 1, p->f("q"), H, 1, grads + p->off_gcn_w(l), H, H, H, p->Nc, nullptr,
+                    dims + DIM_N, nullptr, nullptr, 0, 1, st));
+      EIMS_TRY(gemm(p, p->f("q"), H, 0, params + p->off_gcn_w(l), H, 0, p->f("da"), H, p->Nc, H, H, dims + DIM_N,
+                    nullptr, nullptr, nullptr, 0, 0, st));
+      EIMS_TRY(launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("da"), H, nullptr, nullptr,
+                                make_drop(drop_p, seed, step, l - 1), 1, p->f("dh"), p->Nc, st));
+    } else {
+      EIMS_TRY(launch_layer0_wgrad(dims, p->f("a0"), F, p->f("q"), H, grads + p->off_gcn_w(0), p->Nc, st));
+    }
+  }
+  p->state = 1;
+  return check_launch("eims_backward");
+}
+
+int eims_metrics_accumulate(eims_plan* p, float* metrics, eims_stream_t stream) {
+  if (!p || !p->bound || !metrics) return fail(EIMS_ERR_STATE, "plan not bound / metrics NULL");
+  EIMS_TRY(launch_metrics(p->i("dims"), p->f("row_loss"), p->f("row_cos"), p->d.max_mz, metrics, (cudaStream_t)stream));
+  return check_launch("eims_metrics_accumulate");
+}
+
+int eims_train_step(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs, float* params,
+                    float* grads, float* adam_m, float* adam_v, float* bn_running, int32_t loss_kind,
+                    const eims_step* s, float* metrics, eims_stream_t stream) {
+  if (!s) return fail(EIMS_ERR_ARG, "step scalars are NULL");
+  if (!ds || !ds->targets) return fail(EIMS_ERR_ARG, "training needs dataset targets");
+  EIMS_TRY(eims_batch_build(p, ds, mol_ids, num_graphs, stream));
+  EIMS_TRY(eims_forward(p, params, bn_running, 1, s, stream));
+  EIMS_TRY(eims_loss(p, ds->targets, mol_ids, loss_kind, 1, stream));
+  if (metrics) EIMS_TRY(eims_metrics_accumulate(p, metrics, stream));
+  EIMS_TRY(eims_backward(p, params, nullptr, grads, stream));
+  if (adam_m && adam_v) EIMS_TRY(eims_adamw_flat(params, grads, adam_m, adam_v, p->poff.back(), s, stream));
+  return 0;
+}
+
+int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
+                     const float* params, const float* bn_running, float* prob_out, eims_stream_t stream) {
+  EIMS_TRY(eims_batch_build(p, ds, mol_ids, num_graphs, stream));
+  EIMS_TRY(eims_forward(p, params, const_cast<float*>(bn_running), 0, nullptr, stream));
+  EIMS_TRY(launch_sigmoid(p->i("dims"), p->f("logits"), p->d.max_mz, prob_out ? prob_out : p->f("prob"), p->Bc,
+                          (cudaStream_t)stream));
+  return check_launch("eims_infer_batch");
+}
+
+int eims_plan_check(eims_plan* p, int32_t* num_nodes, int32_t* num_edges, eims_stream_t stream) {
+  if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
+  int h[8];
+  if (cudaMemcpyAsync(h, p->i("dims"), sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess ||
+      cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
+    return fail(EIMS_ERR_CUDA, "dims read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (num_nodes) *num_nodes = h[DIM_N];
+  if (num_edges) *num_edges = h[DIM_E];
+  if (h[DIM_OVERFLOW]) return fail(EIMS_ERR_CAPACITY, "batch exceeds plan capacity (max_nodes %d, max_edges %d)", p->Nc, p->Ec);
+  if (h[DIM_ZERO_DEG]) return fail(EIMS_ERR_ZERO_DEGREE, "There are 0-in-degree nodes in the graph (DGL GraphConv would raise)");
+  return 0;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,112 @@
+"""ctypes binding of libeims_b200.so (the C ABI declared in include/eims_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or the device is not a
+B200-class (sm_100) GPU, importing / using this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeims_b200.so")
+
+POOLING = {"sum": 0, "mean": 1, "max": 2, "combined": 3}
+LOSS = {"mse": 0, "cosine": 1}
+GEMM_TCGEN05, GEMM_FP32_SIMT = 0, 1
+
+ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_ZERO_DEGREE, ERR_STATE = -1, -2, -3, -4, -5
+
+
+class EimsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"eims_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ZeroInDegreeError(EimsError):
+    """Mirrors DGLError('There are 0-in-degree nodes in the graph ...') raised by GraphConv."""
+
+
+class Dims(C.Structure):
+    _fields_ = [("node_feat_dim", C.c_int32), ("hidden_dim", C.c_int32), ("num_gcn_layers", C.c_int32),
+                ("max_mz", C.c_int32), ("pooling", C.c_int32), ("dropout", C.c_float)]
+
+
+class Dataset(C.Structure):
+    _fields_ = [("node_ptr", C.c_void_p), ("bond_ptr", C.c_void_p), ("feat", C.c_void_p),
+                ("bond_begin", C.c_void_p), ("bond_end", C.c_void_p), ("targets", C.c_void_p),
+                ("num_mols", C.c_int64)]
+
+
+class Step(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("grad_scale", C.c_float), ("step", C.c_int32), ("seed", C.c_uint64)]
+
+
+_vp, _i32, _i64, _f32, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
+_SIGS = {
+    "eims_version": (C.c_int, []),
+    "eims_last_error": (C.c_char_p, []),
+    "eims_device_check": (C.c_int, []),
+    "eims_param_count": (_i64, [C.POINTER(Dims)]),
+    "eims_param_num_tensors": (C.c_int, [C.POINTER(Dims)]),
+    "eims_param_layout": (C.c_int, [C.POINTER(Dims), C.POINTER(_i64), _i32]),
+    "eims_csr_build": (C.c_int, [C.POINTER(Dataset), _vp, _i32, _i32, _i32, _i32] + [_vp] * 10 + [_vp]),
+    "eims_spmm_norm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "eims_gemm": (C.c_int, [_i32, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "eims_bn_scratch_floats": (_i64, [_i32, _i32]),
+    "eims_bn_stats": (C.c_int, [_vp, _vp, _i32] + [_vp] * 9 + [_i32, _vp]),
+    "eims_readout": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
+    "eims_loss_mse_cos": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "eims_adamw_flat": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.POINTER(Step), _vp]),
+    "eims_dropout_mask": (C.c_int, [_f32, _u64, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "eims_plan_create": (C.c_int, [C.POINTER(Dims), _i32, _i32, _i32, C.POINTER(_vp)]),
+    "eims_plan_destroy": (C.c_int, [_vp]),
+    "eims_plan_workspace_bytes": (_i64, [_vp]),
+    "eims_plan_bind": (C.c_int, [_vp, _vp, _i64]),
+    "eims_plan_set_gemm_backend": (C.c_int, [_vp, _i32]),
+    "eims_plan_buffer": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_i64)]),
+    "eims_batch_build": (C.c_int, [_vp, C.POINTER(Dataset), _vp, _i32, _vp]),
+    "eims_forward": (C.c_int, [_vp, _vp, _vp, _i32, C.POINTER(Step), _vp]),
+    "eims_sigmoid": (C.c_int, [_vp, _vp]),
+    "eims_loss": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "eims_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "eims_metrics_accumulate": (C.c_int, [_vp, _vp, _vp]),
+    "eims_train_step": (C.c_int, [_vp, C.POINTER(Dataset), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(Step), _vp, _vp]),
+    "eims_infer_batch": (C.c_int, [_vp, C.POINTER(Dataset), _vp, _i32, _vp, _vp, _vp, _vp]),
+    "eims_plan_check": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), _vp]),
+}
+
+EXPORTS = tuple(_SIGS)
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (no device needed for this; compute calls need a B200)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing. Build it with `python computational-chemistry-ai_b200/build.py` "
+                "(nvcc, sm_100a). There is no CPU or other-GPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc == 0:
+        return
+    msg = load().eims_last_error().decode(errors="replace")
+    if rc == ERR_ZERO_DEGREE:
+        raise ZeroInDegreeError(rc, msg)
+    raise EimsError(rc, msg)
+
+
+def ptr(t):
+    """Device / host pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

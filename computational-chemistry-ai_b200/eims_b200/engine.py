@@ -1,0 +1,304 @@
+"""Thin host-side objects over the C ABI: device-resident molecule tables, the workspace
+plan and the flat parameter buffer.  torch is used for device memory and streams only."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Dataset, Dims, Step, check, ptr
+from .synth import MolTable
+
+
+@dataclass(frozen=True)
+class ModelDims:
+    node_feat_dim: int = 6
+    hidden_dim: int = 256
+    num_gcn_layers: int = 3
+    max_mz: int = 500
+    pooling: str = "combined"
+    dropout: float = 0.2
+
+    @property
+    def pool_dim(self):
+        return self.hidden_dim * (2 if self.pooling == "combined" else 1)
+
+    def c(self) -> Dims:
+        return Dims(self.node_feat_dim, self.hidden_dim, self.num_gcn_layers, self.max_mz,
+                    _lib.POOLING[self.pooling], float(self.dropout))
+
+    @classmethod
+    def from_config(cls, config, node_feat_dim=6):
+        return cls(node_feat_dim, config.hidden_dim, config.num_gcn_layers, config.max_mz, config.pooling, config.dropout)
+
+
+def param_spec(d: ModelDims):
+    """(state-dict name, shape) of the trainable tensors in `model.parameters()` order
+    (SURVEY Appendix A.6); offsets come from the library (eims_param_layout)."""
+    H, L, M, P = d.hidden_dim, d.num_gcn_layers, d.max_mz, d.pool_dim
+    spec = []
+    for l in range(L):
+        spec += [(f"gcn_layers.{l}.weight", (d.node_feat_dim if l == 0 else H, H)), (f"gcn_layers.{l}.bias", (H,))]
+    for l in range(L):
+        spec += [(f"batch_norms.{l}.weight", (H,)), (f"batch_norms.{l}.bias", (H,))]
+    sp = "spectrum_predictor"
+    spec += [(f"{sp}.0.weight", (2 * H, P)), (f"{sp}.0.bias", (2 * H,)), (f"{sp}.1.weight", (2 * H,)), (f"{sp}.1.bias", (2 * H,)),
+             (f"{sp}.4.weight", (H, 2 * H)), (f"{sp}.4.bias", (H,)), (f"{sp}.5.weight", (H,)), (f"{sp}.5.bias", (H,)),
+             (f"{sp}.8.weight", (M, H)), (f"{sp}.8.bias", (M,))]
+    return spec
+
+
+def param_offsets(d: ModelDims):
+    lib = _lib.load()
+    cd = d.c()
+    n = lib.eims_param_num_tensors(C.byref(cd))
+    if n < 0:
+        check(_lib.ERR_ARG)
+    arr = (C.c_int64 * (n + 1))()
+    check(lib.eims_param_layout(C.byref(cd), arr, n + 1))
+    return list(arr)
+
+
+def state_dict_order(d: ModelDims):
+    """Full state_dict key order of the reference GCNSpectrum (parameters + BN buffers)."""
+    names = []
+    for l in range(d.num_gcn_layers):
+        names += [f"gcn_layers.{l}.weight", f"gcn_layers.{l}.bias"]
+    for l in range(d.num_gcn_layers):
+        names += [f"batch_norms.{l}.{k}" for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")]
+    names += [n for n, _ in param_spec(d)[4 * d.num_gcn_layers:]]
+    return names
+
+
+class FlatParams:
+    """Flat fp32 parameter / gradient / Adam-state buffers with named views, plus the
+    BatchNorm buffers [L,2,H] (running_mean, running_var) and num_batches_tracked."""
+
+    def __init__(self, d: ModelDims, device):
+        self.d, self.device = d, torch.device(device)
+        self.spec = param_spec(d)
+        self.offsets = param_offsets(d)
+        self.numel = self.offsets[-1]
+        self.params = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros_like(self.params)
+        self.adam_m = None
+        self.adam_v = None
+        self.bn_running = torch.zeros(d.num_gcn_layers, 2, d.hidden_dim, dtype=torch.float32, device=self.device)
+        self.bn_running[:, 1].fill_(1.0)
+        self.num_batches_tracked = [0] * d.num_gcn_layers
+
+    def ensure_adam(self):
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.params)
+            self.adam_v = torch.zeros_like(self.params)
+
+    def views(self, flat):
+        out = OrderedDict()
+        for (name, shape), o in zip(self.spec, self.offsets):
+            out[name] = flat[o:o + int(np.prod(shape))].view(shape)
+        return out
+
+    def named_params(self):
+        return self.views(self.params)
+
+    def named_grads(self):
+        return self.views(self.grads)
+
+    def state_dict(self):
+        sd = OrderedDict()
+        p = self.named_params()
+        for name in state_dict_order(self.d):
+            if name in p:
+                sd[name] = p[name].detach().clone()
+            else:
+                l = int(name.split(".")[1])
+                if name.endswith("running_mean"):
+                    sd[name] = self.bn_running[l, 0].clone()
+                elif name.endswith("running_var"):
+                    sd[name] = self.bn_running[l, 1].clone()
+                else:
+                    sd[name] = torch.tensor(self.num_batches_tracked[l], dtype=torch.int64, device=self.device)
+        return sd
+
+    def load_state_dict(self, sd, strict=True):
+        p = self.named_params()
+        missing = [n for n in state_dict_order(self.d) if n not in sd]
+        unexpected = [n for n in sd if n not in state_dict_order(self.d)]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing {missing}, unexpected {unexpected}")
+        with torch.no_grad():
+            for name, t in sd.items():
+                t = torch.as_tensor(t)
+                if name in p:
+                    if tuple(t.shape) != tuple(p[name].shape):
+                        raise RuntimeError(f"size mismatch for {name}: {tuple(t.shape)} vs {tuple(p[name].shape)}")
+                    p[name].copy_(t.to(self.device, torch.float32))
+                elif name.endswith("running_mean"):
+                    self.bn_running[int(name.split(".")[1]), 0].copy_(t.to(self.device, torch.float32))
+                elif name.endswith("running_var"):
+                    self.bn_running[int(name.split(".")[1]), 1].copy_(t.to(self.device, torch.float32))
+                elif name.endswith("num_batches_tracked"):
+                    self.num_batches_tracked[int(name.split(".")[1])] = int(t)
+
+
+class DeviceDataset:
+    """A MolTable (+ dense target spectra) resident in HBM: ~1 KB of graph data and
+    4*max_mz bytes of targets per molecule."""
+
+    def __init__(self, table: MolTable, targets=None, device="cuda", pinned_stage=False):
+        self.device = torch.device(device)
+        self.num_mols = table.num_mols
+        self.host_num_atoms = np.diff(table.node_ptr).astype(np.int64)
+        self.host_num_bonds = np.diff(table.bond_ptr).astype(np.int64)
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(self.device, non_blocking=False)
+        self.node_ptr = up(table.node_ptr, torch.int64)
+        self.bond_ptr = up(table.bond_ptr, torch.int64)
+        self.feat = up(table.feat.reshape(-1), torch.float32) if table.feat.size else torch.zeros(1, device=self.device)
+        self.bond_begin = up(table.bond_begin, torch.int32) if table.bond_begin.size else torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.bond_end = up(table.bond_end, torch.int32) if table.bond_end.size else torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.targets = None if targets is None else up(np.asarray(targets, np.float32), torch.float32)
+        self._struct = Dataset(self.node_ptr.data_ptr(), self.bond_ptr.data_ptr(), self.feat.data_ptr(),
+                               self.bond_begin.data_ptr(), self.bond_end.data_ptr(),
+                               0 if self.targets is None else self.targets.data_ptr(), self.num_mols)
+
+    @property
+    def struct(self) -> Dataset:
+        return self._struct
+
+    def batch_counts(self, ids):
+        ids = np.asarray(ids)
+        return int(self.host_num_atoms[ids].sum()), int(2 * self.host_num_bonds[ids].sum())
+
+
+def make_step(lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-4, grad_scale=1.0, step=1, seed=0) -> Step:
+    return Step(lr, beta1, beta2, eps, weight_decay, grad_scale, int(step), int(seed))
+
+
+def onecycle_schedule(total_steps, max_lr=1e-3, pct_start=0.3, div_factor=25.0, final_div_factor=1e4,
+                      base_momentum=0.85, max_momentum=0.95):
+    """(lr, beta1) seen by optimiser step k = 0..total-1: torch.optim.lr_scheduler.OneCycleLR
+    (cos anneal, two phases) as the reference configures it (GCN:386-391), scheduler stepped
+    after the optimiser (GCN:429-431).  Checked against torch in tests/test_host_logic.py."""
+    initial_lr = max_lr / div_factor
+    min_lr = initial_lr / final_div_factor
+    phase1_end = float(pct_start * total_steps) - 1
+    phase2_end = float(total_steps) - 1
+
+    def cos(start, end, pct):
+        return end + (start - end) / 2.0 * (math.cos(math.pi * pct) + 1)
+
+    out = []
+    for k in range(total_steps):
+        if k <= phase1_end:
+            pct = k / phase1_end if phase1_end != 0 else 0.0
+            out.append((cos(initial_lr, max_lr, pct), cos(max_momentum, base_momentum, pct)))
+        else:
+            pct = (k - phase1_end) / (phase2_end - phase1_end)
+            out.append((cos(max_lr, min_lr, pct), cos(base_momentum, max_momentum, pct)))
+    return out
+
+
+class Plan:
+    """Workspace plan for batches of up to (max_graphs, max_nodes, max_edges)."""
+
+    def __init__(self, d: ModelDims, max_graphs, max_nodes, max_edges, device="cuda", gemm_backend=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("eims_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.d, self.device = d, torch.device(device)
+        with torch.cuda.device(self.device):
+            check(self.lib.eims_device_check())
+        self.max_graphs, self.max_nodes, self.max_edges = int(max_graphs), int(max_nodes), int(max_edges)
+        h = C.c_void_p()
+        cd = d.c()
+        check(self.lib.eims_plan_create(C.byref(cd), self.max_graphs, self.max_nodes, self.max_edges, C.byref(h)))
+        self.h = h
+        nbytes = self.lib.eims_plan_workspace_bytes(self.h)
+        self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+        self._base = (self.workspace.data_ptr() + 255) // 256 * 256
+        with torch.cuda.device(self.device):
+            check(self.lib.eims_plan_bind(self.h, C.c_void_p(self._base), nbytes))
+            torch.cuda.synchronize()
+        if gemm_backend is not None:
+            self.set_gemm_backend(gemm_backend)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.eims_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_gemm_backend(self, backend):
+        b = {"tcgen05": _lib.GEMM_TCGEN05, "simt": _lib.GEMM_FP32_SIMT}.get(backend, backend)
+        check(self.lib.eims_plan_set_gemm_backend(self.h, int(b)))
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def buffer(self, name, dtype=torch.float32, shape=None):
+        p, n = C.c_void_p(), C.c_int64()
+        check(self.lib.eims_plan_buffer(self.h, name.encode(), C.byref(p), C.byref(n)))
+        off = p.value - self.workspace.data_ptr()
+        t = self.workspace[off:off + n.value].view(dtype)
+        if shape is not None:
+            t = t[: int(np.prod(shape))].view(shape)
+        return t
+
+    # -- stages ---------------------------------------------------------------------
+    def batch_build(self, ds: DeviceDataset, ids, num_graphs=None):
+        n = int(num_graphs if num_graphs is not None else (len(ids) if ids is not None else ds.num_mols))
+        check(self.lib.eims_batch_build(self.h, C.byref(ds.struct), ptr(ids), n, self.stream))
+        self.num_graphs = n
+
+    def check(self):
+        nn, ne = C.c_int32(), C.c_int32()
+        check(self.lib.eims_plan_check(self.h, C.byref(nn), C.byref(ne), self.stream))
+        return nn.value, ne.value
+
+    def forward(self, fp: FlatParams, training: bool, step: Step | None = None):
+        check(self.lib.eims_forward(self.h, ptr(fp.params), ptr(fp.bn_running), int(training),
+                                    C.byref(step) if step is not None else None, self.stream))
+
+    def sigmoid(self):
+        check(self.lib.eims_sigmoid(self.h, self.stream))
+
+    def loss(self, targets, target_rows=None, loss_kind="mse", want_grad=True):
+        check(self.lib.eims_loss(self.h, ptr(targets), ptr(target_rows), _lib.LOSS[loss_kind], int(want_grad), self.stream))
+
+    def backward(self, fp: FlatParams, dprob=None):
+        check(self.lib.eims_backward(self.h, ptr(fp.params), ptr(dprob), ptr(fp.grads), self.stream))
+
+    def metrics_accumulate(self, metrics):
+        check(self.lib.eims_metrics_accumulate(self.h, ptr(metrics), self.stream))
+
+    def adamw(self, fp: FlatParams, step: Step):
+        fp.ensure_adam()
+        check(self.lib.eims_adamw_flat(ptr(fp.params), ptr(fp.grads), ptr(fp.adam_m), ptr(fp.adam_v), fp.numel,
+                                       C.byref(step), self.stream))
+
+    def train_step(self, ds: DeviceDataset, ids, fp: FlatParams, step: Step, metrics=None, loss_kind="mse",
+                   optimizer=True, num_graphs=None):
+        n = int(num_graphs if num_graphs is not None else (len(ids) if ids is not None else ds.num_mols))
+        if optimizer:
+            fp.ensure_adam()
+        check(self.lib.eims_train_step(self.h, C.byref(ds.struct), ptr(ids), n, ptr(fp.params), ptr(fp.grads),
+                                       ptr(fp.adam_m) if optimizer else None, ptr(fp.adam_v) if optimizer else None,
+                                       ptr(fp.bn_running), _lib.LOSS[loss_kind], C.byref(step), ptr(metrics), self.stream))
+        self.num_graphs = n
+        for l in range(self.d.num_gcn_layers):
+            fp.num_batches_tracked[l] += 1
+
+    def infer_batch(self, ds: DeviceDataset, ids, fp: FlatParams, out=None, num_graphs=None):
+        n = int(num_graphs if num_graphs is not None else (len(ids) if ids is not None else ds.num_mols))
+        check(self.lib.eims_infer_batch(self.h, C.byref(ds.struct), ptr(ids), n, ptr(fp.params), ptr(fp.bn_running),
+                                        ptr(out), self.stream))
+        self.num_graphs = n
+        return out if out is not None else self.buffer("prob", torch.float32, (n, self.d.max_mz))

@@ -1,0 +1,209 @@
+/*
+ * eims_b200.h - C ABI of the B200-native GCN EI-MS hot path.
+ *
+ * The reference (turnDeep/Computational-Chemistry-AI, templates/ms-pred-gcn-eims-cupy.py,
+ * "GCN:n" below) has no FFI: the path is ordinary Python calls into DGL / torch / CuPy.
+ * Each entry point here names the reference call(s) it replaces.  The Python host layer
+ * (computational-chemistry-ai_b200/eims_b200) binds these with ctypes and mirrors the
+ * script's own interface (Config, collate_fn, GCNSpectrum, train_model, predict_spectrum).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device pointer is caller-owned (torch allocates);
+ *   - every function returns 0 on success, <0 on error (never throws); eims_last_error()
+ *     gives the message for the calling thread;
+ *   - all work is enqueued on the given cudaStream_t and is asynchronous; the library
+ *     allocates no device memory (the workspace size comes from eims_plan_workspace_bytes);
+ *   - a plan may be used from one thread at a time;
+ *   - built for sm_100a only: there is no CPU path and no other GPU path.
+ */
+#ifndef EIMS_B200_H_
+#define EIMS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* eims_stream_t; /* == cudaStream_t */
+typedef struct eims_plan eims_plan;
+
+enum {
+  EIMS_OK = 0,
+  EIMS_ERR_ARG = -1,       /* bad argument / unsupported dimension */
+  EIMS_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+  EIMS_ERR_CAPACITY = -3,  /* batch exceeds the plan's max_graphs / max_nodes / max_edges */
+  EIMS_ERR_ZERO_DEGREE = -4, /* an atom without bonds: DGL GraphConv raises (GCN:316,359) */
+  EIMS_ERR_STATE = -5      /* call order (e.g. backward before forward, plan not bound) */
+};
+
+enum { EIMS_POOL_SUM = 0, EIMS_POOL_MEAN = 1, EIMS_POOL_MAX = 2, EIMS_POOL_COMBINED = 3 };
+enum { EIMS_LOSS_MSE = 0 /* GCN:393 */, EIMS_LOSS_COSINE = 1 /* north-star variant */ };
+enum { EIMS_GEMM_TCGEN05 = 0 /* 3xTF32 tensor-core path */, EIMS_GEMM_FP32_SIMT = 1 /* CUDA-core check path */ };
+
+/* Model hyper-parameters: `Config` GCN:73-101 + node_feat_dim (GCN:580,603). */
+typedef struct {
+  int32_t node_feat_dim;  /* 6 */
+  int32_t hidden_dim;     /* multiple of 64 */
+  int32_t num_gcn_layers; /* >= 1 */
+  int32_t max_mz;         /* multiple of 4 */
+  int32_t pooling;        /* EIMS_POOL_* (GCN:325-338) */
+  float dropout;          /* GCN:88 */
+} eims_dims;
+
+/* A packed set of molecules in device memory (a whole data set, or one uploaded batch).
+ * Molecule g owns atoms [node_ptr[g], node_ptr[g+1]) and bonds [bond_ptr[g], bond_ptr[g+1]);
+ * bond ends are molecule-local atom indices in RDKit bond order (GCN:139-143).
+ * `targets` is the dense [num_mols, max_mz] spectrum matrix of GCN:256 (may be NULL for
+ * inference). */
+typedef struct {
+  const int64_t* node_ptr;
+  const int64_t* bond_ptr;
+  const float* feat; /* [total atoms, node_feat_dim], get_atom_features order GCN:113-122 */
+  const int32_t* bond_begin;
+  const int32_t* bond_end;
+  const float* targets;
+  int64_t num_mols;
+} eims_dataset;
+
+/* Per-step optimiser scalars, computed on the host exactly as torch's AdamW + OneCycleLR
+ * do (GCN:385-391, 429-431): lr and beta1 follow the one-cycle schedule. */
+typedef struct {
+  float lr, beta1, beta2, eps, weight_decay;
+  float grad_scale;  /* 1/world_size for data-parallel training, else 1 */
+  int32_t step;      /* 1-based optimiser step count t */
+  uint64_t seed;     /* dropout stream seed; the mask is a function of (seed, step, site, element) */
+} eims_step;
+
+/* ---------------------------------------------------------------- misc */
+int eims_version(void);
+const char* eims_last_error(void);
+int eims_device_check(void); /* 0 iff the current device is sm_100 */
+
+/* Flat parameter buffer: the 4L+10 trainable tensors in `model.parameters()` order
+ * (= state_dict order without BN buffers).  offsets has n_tensors+1 entries. */
+int64_t eims_param_count(const eims_dims* d);
+int eims_param_num_tensors(const eims_dims* d);
+int eims_param_layout(const eims_dims* d, int64_t* offsets, int32_t n_entries);
+
+/* ---------------------------------------------------------------- stand-alone kernels
+ * (each is also a stage of eims_train_step; exposed for per-kernel parity tests) */
+
+/* K1  replaces collate_fn -> dgl.batch (GCN:292-297), the in-degree pass and the
+ * degree normalisation of DGL GraphConv.  Outputs (all int32 / fp32, device):
+ *   gptr[B+1] node offset per graph, eptr[B+1] edge offset per graph, gid[N],
+ *   src[E], dst[E] (reference edge order), rowptr[N+1], col[E] (CSR by destination,
+ *   ascending edge id inside a row), norm[N] = fl(1/fl(sqrt(max(deg,1)))), x[N,F],
+ *   dims[8] = {B, N, E, zero_degree_flag, overflow_flag, 0,0,0}. */
+int eims_csr_build(const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
+                   int32_t node_feat_dim, int32_t max_nodes, int32_t max_edges,
+                   int32_t* gptr, int32_t* eptr, int32_t* gid, int32_t* src, int32_t* dst,
+                   int32_t* rowptr, int32_t* col, float* norm, float* x, int32_t* dims,
+                   eims_stream_t stream);
+
+/* K2  replaces DGL update_all(copy_u, sum) with the source-side normalisation
+ * (GraphConv, GCN:359):  out[i,:] = sum_{j in row i} fl(f(h[j,:]) * norm[j])  where
+ * f(x) = x*scale+shift (BatchNorm apply, may be NULL) followed by the dropout mask of
+ * `site` (skipped when drop_p == 0).  With out_scale_norm != 0 the result row is scaled by
+ * norm[i] (the backward form: dh = (A da) * c) and by the same dropout mask. */
+int eims_spmm_norm(const int32_t* dims, const int32_t* rowptr, const int32_t* col, const float* norm,
+                   const float* h, int32_t width, const float* bn_scale, const float* bn_shift,
+                   float drop_p, uint64_t seed, int32_t step, int32_t site,
+                   int32_t out_scale_norm, float* out, int32_t max_nodes, eims_stream_t stream);
+
+/* K3/K6  C[M,N] = op(A)[M,K] * op(B)[K,N] in fp32-grade arithmetic.
+ * a_mn_major: 0 -> A stored [M,K] row-major (lda), 1 -> stored [K,M] row-major (lda).
+ * b_mn_major: 0 -> B stored [N,K] row-major (ldb) (nn.Linear weight), 1 -> stored [K,N]
+ * row-major (GraphConv weight).  Epilogue: C = act(acc * row_scale[m] + bias[n]);
+ * row_scale / bias may be NULL; relu != 0 applies max(.,0); accumulate != 0 adds into C
+ * atomically (split-K weight gradients).  m_dev / k_dev (may be NULL) override M / K with
+ * a device-side int (the number of atoms of the current batch).
+ * backend: EIMS_GEMM_TCGEN05 or EIMS_GEMM_FP32_SIMT. */
+int eims_gemm(int32_t backend, const float* A, int32_t lda, int32_t a_mn_major,
+              const float* B, int32_t ldb, int32_t b_mn_major, float* C, int32_t ldc,
+              int32_t M, int32_t N, int32_t K, const int32_t* m_dev, const int32_t* k_dev,
+              const float* row_scale, const float* bias, int32_t relu, int32_t accumulate,
+              eims_stream_t stream);
+
+/* BatchNorm1d training statistics over the N atoms of the batch (GCN:361):
+ * mean / biased var per column -> scale = gamma*invstd, shift = beta - mean*scale,
+ * saved mean & invstd, running stats update (momentum 0.1, unbiased var).  `partials`
+ * is scratch of eims_bn_scratch_floats(width, max_nodes) floats. */
+int64_t eims_bn_scratch_floats(int32_t width, int32_t max_nodes);
+int eims_bn_stats(const int32_t* dims, const float* z, int32_t width, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float* mean, float* invstd,
+                  float* scale, float* shift, float* partials, int32_t max_nodes, eims_stream_t stream);
+
+/* K5  replaces SumPooling / AvgPooling / MaxPooling (+ torch.cat) GCN:366-371 with the
+ * last layer's BatchNorm apply fused in.  out[B, pool_dim]; argmax[B,H] = first maximum. */
+int eims_readout(const int32_t* dims, const int32_t* gptr, const float* z, int32_t width,
+                 const float* bn_scale, const float* bn_shift, int32_t pooling,
+                 float* out, int32_t* argmax, int32_t max_graphs, eims_stream_t stream);
+
+/* K7  replaces Sigmoid (GCN:351) + nn.MSELoss (GCN:393,427) + cosine_similarity_batch
+ * (GCN:213-215) and their gradient.  logits[B,M] -> prob[B,M]; target row of graph b is
+ * targets[target_rows ? target_rows[b] : b].  row_loss[b] = sum_m (p-t)^2, row_cos[b];
+ * dlogits (may be NULL) = dLoss/dlogits for loss_kind, mean over the batch. */
+int eims_loss_mse_cos(const int32_t* dims, const float* logits, const float* targets,
+                      const int32_t* target_rows, int32_t max_mz, int32_t loss_kind,
+                      float* prob, float* dlogits, float* row_loss, float* row_cos,
+                      int32_t max_graphs, eims_stream_t stream);
+
+/* K8  replaces optimizer.zero_grad + AdamW.step (GCN:414,429) over the flat buffers.
+ * g is scaled by s->grad_scale first and zeroed afterwards. */
+int eims_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const eims_step* s,
+                    eims_stream_t stream);
+
+/* Materialise the dropout keep-mask (0/1 floats) of a site, for tests. */
+int eims_dropout_mask(float drop_p, uint64_t seed, int32_t step, int32_t site,
+                      int32_t rows, int32_t width, float* out, eims_stream_t stream);
+
+/* ---------------------------------------------------------------- plan: the whole path */
+int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, int32_t max_edges,
+                     eims_plan** out);
+int eims_plan_destroy(eims_plan* p);
+int64_t eims_plan_workspace_bytes(const eims_plan* p);
+int eims_plan_bind(eims_plan* p, void* workspace, int64_t bytes);
+int eims_plan_set_gemm_backend(eims_plan* p, int32_t backend);
+
+/* Named views into the bound workspace (tests / host layer).  Names: "dims","gptr","eptr",
+ * "gid","src","dst","rowptr","col","norm","x","prob","logits","row_loss","row_cos",
+ * "readout","argmax","a<l>","z<l>","bn_mean<l>","bn_invstd<l>". */
+int eims_plan_buffer(eims_plan* p, const char* name, void** ptr, int64_t* bytes);
+
+/* K1 on the plan's buffers. */
+int eims_batch_build(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids,
+                     int32_t num_graphs, eims_stream_t stream);
+
+/* GCNSpectrum.forward (GCN:354-376) on the batch built last.  training != 0: batch
+ * statistics + dropout + everything backward needs is kept; bn_running [L][2][H]
+ * (running_mean, running_var) is updated.  Result: "logits" and (after eims_loss or
+ * eims_sigmoid) "prob". */
+int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t training,
+                 const eims_step* s, eims_stream_t stream);
+int eims_sigmoid(eims_plan* p, eims_stream_t stream); /* prob = sigmoid(logits), inference */
+int eims_loss(eims_plan* p, const float* targets, const int32_t* target_rows, int32_t loss_kind,
+              int32_t want_grad, eims_stream_t stream);
+/* dprob: optional [B,M] gradient w.r.t. the spectrum (autograd use); NULL = use the
+ * dlogits left by eims_loss(want_grad=1).  Gradients are ADDED into grads (flat, zeroed by
+ * eims_adamw_flat / the caller). */
+int eims_backward(eims_plan* p, const float* params, const float* dprob, float* grads,
+                  eims_stream_t stream);
+/* metrics[4] (device) += {sum_b row_loss/(B*M), mean_b row_cos, 1, 0}  - the per-step
+ * `loss.item()` / `cos_sim.mean().item()` of GCN:436-437 without the host syncs. */
+int eims_metrics_accumulate(eims_plan* p, float* metrics, eims_stream_t stream);
+
+/* One optimiser step: batch build + forward + loss + backward [+ AdamW when adam_m != NULL]. */
+int eims_train_step(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
+                    float* params, float* grads, float* adam_m, float* adam_v, float* bn_running,
+                    int32_t loss_kind, const eims_step* s, float* metrics, eims_stream_t stream);
+/* predict_spectrum (GCN:494-511) for a batch: batch build + eval forward + sigmoid. */
+int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
+                     const float* params, const float* bn_running, float* prob_out, eims_stream_t stream);
+/* Reads dims[] back (one small synchronous copy) and maps flags to error codes. */
+int eims_plan_check(eims_plan* p, int32_t* num_nodes, int32_t* num_edges, eims_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EIMS_B200_H_ */

@@ -1,0 +1,224 @@
+"""End-to-end parity of the CUDA path (through the C ABI) against the oracle and against the
+golden fixtures recorded from the reference script.  Needs a B200 (`-m gpu`).
+
+Tolerances (north star): integer/index work bit-exact (test_gpu_kernels.py); spectra, loss
+and gradients within 1e-4 relative (max-abs error over max-abs value per tensor)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from eims_b200 import _lib
+from eims_b200._lib import check, ptr
+from eims_b200.engine import DeviceDataset, FlatParams, ModelDims, Plan, make_step, onecycle_schedule
+from eims_b200.synth import dense_spectra, peaks_as_lists, synth_molecules, synth_peaks
+from oracle import gcn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+REL = 1e-4
+BACKENDS = os.environ.get("EIMS_TEST_BACKENDS", "tcgen05,simt").split(",")
+
+
+def rel_err(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def odims(d: ModelDims, dropout=None):
+    return O.Dims(d.node_feat_dim, d.hidden_dim, d.num_gcn_layers, d.max_mz, d.pooling, d.dropout if dropout is None else dropout)
+
+
+def setup(d, n_mols, max_atoms, seed, backend, wseed=0):
+    table = synth_molecules(n_mols, max_atoms=max_atoms, seed=seed)
+    targets = dense_spectra(*synth_peaks(n_mols, d.max_mz, seed=seed + 1), d.max_mz)
+    N, E = int(table.node_ptr[-1]), int(2 * table.bond_ptr[-1])
+    plan = Plan(d, n_mols, N, E, DEV, gemm_backend=backend)
+    ds = DeviceDataset(table, targets, DEV)
+    fp = FlatParams(d, DEV)
+    sd = O.init_params(odims(d), wseed)
+    fp.load_state_dict(sd)
+    return table, targets, plan, ds, fp, sd
+
+
+def gpu_fwd_bwd(plan, ds, fp, ids, step, loss_kind="mse"):
+    plan.batch_build(ds, ids, None if ids is not None else ds.num_mols)
+    plan.forward(fp, True, step)
+    plan.loss(ds.targets, ids, loss_kind, True)
+    fp.grads.zero_()
+    plan.backward(fp)
+    plan.check()
+    B = plan.num_graphs
+    prob = plan.buffer("prob", torch.float32, (B, plan.d.max_mz)).cpu().numpy()
+    loss = plan.buffer("row_loss")[:B].double().sum().item() / (B * plan.d.max_mz)
+    cos = plan.buffer("row_cos")[:B].cpu().numpy()
+    return prob, loss, cos, {k: v.cpu().numpy() for k, v in fp.named_grads().items()}
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("name,H,M", [("fwd_bwd_small.npz", 64, 100), ("fwd_bwd_full.npz", 256, 1000)])
+def test_golden_forward_backward(golden_dir, backend, name, H, M):
+    """Same inputs and weights as the reference-script run in tests/golden/make_golden.py."""
+    g = dict(np.load(os.path.join(golden_dir, name)))
+    d = ModelDims(hidden_dim=H, max_mz=M, dropout=0.0)
+    table, targets, plan, ds, fp, sd = setup(d, int(g["n_mols"]), int(g["max_atoms"]), int(g["seed"]), backend)
+    assert np.array_equal(targets, g["target"])
+    prob, loss, cos, grads = gpu_fwd_bwd(plan, ds, fp, None, make_step())
+    E = len(g["src"])
+    assert np.array_equal(plan.buffer("src", torch.int32)[:E].cpu().numpy(), g["src"])
+    assert np.array_equal(plan.buffer("dst", torch.int32)[:E].cpu().numpy(), g["dst"])
+    assert rel_err(prob, g["pred_train"]) < REL
+    assert abs(loss - float(g["loss"])) < REL * float(g["loss"])
+    for l in range(3):
+        assert rel_err(fp.bn_running[l, 0].cpu().numpy(), g[f"rm{l}"]) < REL
+        assert rel_err(fp.bn_running[l, 1].cpu().numpy(), g[f"rv{l}"]) < REL
+    worst = {}
+    for n, gr in grads.items():
+        if f"grad:{n}" in g:
+            worst[n] = rel_err(gr, g[f"grad:{n}"])
+        else:
+            worst[n] = rel_err(gr.reshape(-1)[:: max(1, gr.size // 256)][:256], g[f"gslice:{n}"])
+        gn = float(np.sqrt((gr.astype(np.float64) ** 2).sum()))
+        assert abs(gn - float(g[f"gnorm:{n}"])) < REL * float(g[f"gnorm:{n}"]) + 1e-12, n
+    assert max(worst.values()) < REL, worst
+    # eval mode (running statistics, no dropout) + torch-branch cosine of the reference
+    out = plan.infer_batch(ds, None, fp).cpu().numpy()
+    assert rel_err(out, g["pred_eval"]) < REL
+    ref_cos = O.cosine_similarity_batch(torch.from_numpy(prob), torch.from_numpy(targets), "cupy")
+    np.testing.assert_allclose(cos, ref_cos, rtol=1e-5)
+    np.testing.assert_allclose(cos, g["cos_torch"], rtol=1e-4)  # the two eps conventions agree to ~1e-8
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("pooling", ["sum", "mean", "max", "combined"])
+def test_pooling_modes_vs_oracle(backend, pooling):
+    d = ModelDims(hidden_dim=128, max_mz=200, pooling=pooling, dropout=0.0)
+    table, targets, plan, ds, fp, sd = setup(d, 24, 30, 21, backend, wseed=2)
+    ids = torch.tensor(np.random.default_rng(0).permutation(24)[:17].astype(np.int32), device=DEV)
+    prob, loss, cos, grads = gpu_fwd_bwd(plan, ds, fp, ids, make_step())
+    idl = ids.cpu().numpy()
+    graph, feat = O.Graph.from_mols([table.mol(int(i)) for i in idl])
+    pred, oloss, ograds, _ = O.loss_and_grads(sd, graph, feat, torch.from_numpy(targets[idl]), odims(d))
+    assert rel_err(prob, pred.numpy()) < REL
+    assert abs(loss - float(oloss)) < REL * float(oloss)
+    worst = {n: rel_err(grads[n], ograds[n].numpy()) for n in grads}
+    assert max(worst.values()) < REL, worst
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_dropout_and_cosine_loss_vs_oracle(backend):
+    """Dropout on (p = 0.2): the oracle is fed the masks the GPU's Philox stream produces."""
+    d = ModelDims(hidden_dim=128, max_mz=200, dropout=0.2)
+    table, targets, plan, ds, fp, sd = setup(d, 20, 40, 33, backend, wseed=4)
+    step = make_step(step=7, seed=99)
+    for loss_kind in ("mse", "cosine"):
+        prob, loss, cos, grads = gpu_fwd_bwd(plan, ds, fp, None, step, loss_kind)
+        N, B, H = int(table.node_ptr[-1]), 20, d.hidden_dim
+        lib = _lib.load()
+        masks = {}
+        for key, site, rows, width in [(("gcn", 0), 0, N, H), (("gcn", 1), 1, N, H), (("head", 0), 3, B, 2 * H), (("head", 1), 4, B, H)]:
+            m = torch.empty(rows, width, device=DEV)
+            check(lib.eims_dropout_mask(0.2, 99, 7, site, rows, width, ptr(m), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            masks[key] = m.cpu()
+        graph, feat = O.Graph.from_mols([table.mol(i) for i in range(20)])
+        pred, oloss, ograds, _ = O.loss_and_grads(sd, graph, feat, torch.from_numpy(targets), odims(d), dropout_masks=masks, loss_kind=loss_kind)
+        assert rel_err(prob, pred.numpy()) < REL
+        if loss_kind == "cosine":
+            assert abs((1.0 - cos.mean()) - float(oloss)) < REL
+        else:
+            assert abs(loss - float(oloss)) < REL * float(oloss)
+        worst = {n: rel_err(grads[n], ograds[n].numpy()) for n in grads}
+        assert max(worst.values()) < REL, (loss_kind, worst)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_training_loop_golden(golden_dir, backend):
+    """Two epochs of AdamW + OneCycleLR on 12 molecules == the reference's train_model."""
+    g = dict(np.load(os.path.join(golden_dir, "train_small.npz")))
+    d = ModelDims(hidden_dim=64, max_mz=100, dropout=0.0)
+    n_train, n_val, bs, epochs = (int(g[k]) for k in ("n_train", "n_val", "batch_size", "epochs"))
+    table = synth_molecules(n_train + n_val, max_atoms=12, seed=2024)
+    spectra = dense_spectra(*synth_peaks(n_train + n_val, d.max_mz, seed=2025), d.max_mz)
+    assert np.array_equal(spectra, g["spectra"].astype(np.float32))
+    plan = Plan(d, bs, int(table.node_ptr[-1]), int(2 * table.bond_ptr[-1]), DEV, gemm_backend=backend)
+    ds = DeviceDataset(table, spectra, DEV)
+    fp = FlatParams(d, DEV)
+    fp.load_state_dict(O.init_params(odims(d), 1))
+    spe = (n_train + bs - 1) // bs
+    sched = onecycle_schedule(epochs * spe)
+    hist = {k: [] for k in ("train_loss", "val_loss", "train_cosine", "val_cosine")}
+    k = 0
+    for _ in range(epochs):
+        metrics = torch.zeros(8, device=DEV)
+        for s in range(0, n_train, bs):
+            ids = torch.arange(s, min(s + bs, n_train), dtype=torch.int32, device=DEV)
+            plan.train_step(ds, ids, fp, make_step(lr=sched[k][0], beta1=sched[k][1], step=k + 1), metrics)
+            k += 1
+        m = metrics.cpu().numpy()
+        hist["train_loss"].append(m[0] / m[2])
+        hist["train_cosine"].append(m[1] / m[2])
+        vm = torch.zeros(8, device=DEV)
+        for s in range(n_train, n_train + n_val, bs):
+            ids = torch.arange(s, min(s + bs, n_train + n_val), dtype=torch.int32, device=DEV)
+            plan.batch_build(ds, ids)
+            plan.forward(fp, False)
+            plan.loss(ds.targets, ids, "mse", False)
+            plan.metrics_accumulate(vm)
+        vm = vm.cpu().numpy()
+        hist["val_loss"].append(vm[0] / vm[2])
+        hist["val_cosine"].append(vm[1] / vm[2])
+    for key, v in hist.items():
+        np.testing.assert_allclose(v, g[f"hist:{key}"], rtol=2e-4)
+    sd = fp.state_dict()
+    worst = {}
+    for n, t in sd.items():
+        ref = g[f"sd:{n}"]
+        if n.endswith("num_batches_tracked"):
+            assert int(t) == int(ref)
+        else:
+            worst[n] = rel_err(t.cpu().numpy(), ref)
+    assert max(worst.values()) < 3e-4, worst  # 6 optimiser steps of accumulated fp32 differences
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_batched_inference_equals_single(backend):
+    """predict_spectrum (GCN:494-511) is one molecule per call; eval mode couples nothing
+    across molecules, so the batched predictor must reproduce the looped result."""
+    d = ModelDims(hidden_dim=64, max_mz=100, dropout=0.2)
+    table, targets, plan, ds, fp, sd = setup(d, 9, 20, 55, backend, wseed=6)
+    fp.bn_running[:, 0].normal_(0, 0.1)
+    fp.bn_running[:, 1].uniform_(0.5, 2.0)
+    batched = plan.infer_batch(ds, None, fp).cpu().numpy().copy()
+    for i in range(9):
+        one = plan.infer_batch(ds, torch.tensor([i], dtype=torch.int32, device=DEV), fp).cpu().numpy()
+        assert rel_err(one[0], batched[i]) < 1e-5
+    sdo = fp.state_dict()
+    graph, feat = O.Graph.from_mols([table.mol(i) for i in range(9)])
+    ref, _ = O.forward({k: v.cpu() for k, v in sdo.items()}, graph, feat, odims(d), False)
+    assert rel_err(batched, ref.numpy()) < REL
+
+
+def test_full_size_properties():
+    """BASELINE cfg-2 shapes (batch 512, H 256, M 1000): size-independent properties -
+    tcgen05 and CUDA-core GEMM paths agree, gradients are replay-stable, loss decreases."""
+    d = ModelDims(hidden_dim=256, max_mz=1000, dropout=0.0)
+    table, targets, plan, ds, fp, sd = setup(d, 512, 64, 1234, "tcgen05")
+    ids = torch.arange(512, dtype=torch.int32, device=DEV)
+    p1, l1, c1, g1 = gpu_fwd_bwd(plan, ds, fp, ids, make_step())
+    plan.set_gemm_backend("simt")
+    p2, l2, c2, g2 = gpu_fwd_bwd(plan, ds, fp, ids, make_step())
+    assert rel_err(p1, p2) < REL and abs(l1 - l2) < REL * l2
+    worst = {n: rel_err(g1[n], g2[n]) for n in g1}
+    assert max(worst.values()) < 2e-3, worst  # ReLU sign flips between two fp32 paths
+    assert np.median(list(worst.values())) < REL
+    plan.set_gemm_backend("tcgen05")
+    sched = onecycle_schedule(30)
+    losses = []
+    for k in range(30):
+        m = torch.zeros(8, device=DEV)
+        plan.train_step(ds, ids, fp, make_step(lr=sched[k][0], beta1=sched[k][1], step=k + 1), m)
+        losses.append(float(m[4]))
+    assert losses[-1] < losses[0]
+    assert np.isfinite(losses).all()
