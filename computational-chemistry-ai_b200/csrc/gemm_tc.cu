@@ -83,14 +83,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// UMMA shared-memory matrix descriptor (sm_100 format, version 1, SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// UMMA shared-memory matrix descriptor (sm_100 format, version 1).
+// layout_type: 2 = SWIZZLE_128B (16-byte swizzle units), 1 = SWIZZLE_128B with 32-byte base
+// (the only swizzled layout the hardware accepts for MN-major 32-bit / tf32 operands).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // layout type: SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -131,10 +133,13 @@ __device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, 
 }
 
 // Tile of an operand with ROWS "MN" rows and BK k-columns, written by one producer group
-// (128 threads).  mn_major = 0: memory is [mn][k] (k contiguous) -> canonical K-major layout
+// (128 threads).  mn_major = 0: memory is [mn][k] (k contiguous) -> canonical K-major
+// SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XOR row%8):
 //   offset(r, c) = (r/8)*1024 + (r%8)*128 + ((c ^ (r%8))*16)          c = 16-byte chunk along k
-// mn_major = 1: memory is [k][mn] (mn contiguous) -> canonical MN-major layout
-//   offset(k, c) = (k/8)*(ROWS/32*1024) + (c/8)*1024 + (k%8)*128 + (((c%8) ^ (k%8))*16)   c = chunk along mn
+// mn_major = 1: memory is [k][mn] (mn contiguous) -> canonical MN-major SWIZZLE_128B_BASE32B
+// layout (atoms of 4 k-rows x 128 bytes = 32 mn elements; 32-byte chunk index XOR k%4):
+//   offset(k, c) = (k/4)*(ROWS/32*512) + (c/8)*512 + (k%4)*128 + ((((c%8)>>1) ^ (k%4))*32) + (c&1)*16
+//   with c = 16-byte chunk along mn;  LBO = 512 (next 32 mn), SBO = ROWS/32*512 (next 4 k)
 template <int ROWS>
 __device__ __forceinline__ void produce_tile(const float* __restrict__ base, int ld, int mn_major, int vec, int mn0,
                                              int mn_lim, int k0, int k_lim, uint8_t* hi_tile, uint8_t* lo_tile,
@@ -158,7 +163,8 @@ __device__ __forceinline__ void produce_tile(const float* __restrict__ base, int
       const int idx = it * 128 + t, kk = idx / CPR, c = idx % CPR;
       const int k = k0 + kk, mn = mn0 + 4 * c;
       v[it] = load_chunk(base, (int64_t)k * ld + mn, mn, mn_lim, k < k_lim, vec);
-      off[it] = (uint32_t)((kk >> 3) * (ROWS / 32 * 1024) + (c >> 3) * 1024 + (kk & 7) * 128 + (((c & 7) ^ (kk & 7)) << 4));
+      off[it] = (uint32_t)((kk >> 2) * (ROWS / 32 * 512) + (c >> 3) * 512 + (kk & 3) * 128 +
+                           ((((c & 7) >> 1) ^ (kk & 3)) << 5) + ((c & 1) << 4));
     }
   }
 #pragma unroll
@@ -257,12 +263,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
     // ---------------------------------------------------------------- MMA issuer
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    // K-major: 8-row groups 1024 B apart (SBO); k-step = +32 B inside the 128-B swizzle row.
-    // MN-major: 32-element MN atoms 1024 B apart (LBO); k-groups ROWS/32*1024 B apart (SBO).
-    const uint32_t a_lbo = g.a_mn ? 1024u : 16u, a_sbo = g.a_mn ? (uint32_t)(BM / 32 * 1024) : 1024u;
-    const uint32_t b_lbo = g.b_mn ? 1024u : 16u, b_sbo = g.b_mn ? (uint32_t)(BN / 32 * 1024) : 1024u;
+    // K-major: 8-row groups 1024 B apart (SBO); k-step (8 tf32) = +32 B inside the 128-B swizzle row.
+    // MN-major: 32-element MN atoms 512 B apart (LBO); 4-row k-groups ROWS/32*512 B apart (SBO);
+    //           k-step (8 k-rows = 2 k-groups) = +ROWS/32*1024 B.
+    const uint32_t a_lbo = g.a_mn ? 512u : 16u, a_sbo = g.a_mn ? (uint32_t)(BM / 32 * 512) : 1024u;
+    const uint32_t b_lbo = g.b_mn ? 512u : 16u, b_sbo = g.b_mn ? (uint32_t)(BN / 32 * 512) : 1024u;
     const uint32_t a_kstep = g.a_mn ? (uint32_t)(BM / 32 * 1024) : 32u;
     const uint32_t b_kstep = g.b_mn ? (uint32_t)(BN / 32 * 1024) : 32u;
+    const uint32_t a_lt = g.a_mn ? 1u : 2u, b_lt = g.b_mn ? 1u : 2u;
     for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES;
       const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
@@ -273,10 +281,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
         const uint32_t a_hi = sa, a_lo = sa + A_TILE, b_hi = sa + 2 * A_TILE, b_lo = b_hi + B_TILE;
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
-          const uint64_t dah = make_desc(a_hi + ks * a_kstep, a_lbo, a_sbo);
-          const uint64_t dal = make_desc(a_lo + ks * a_kstep, a_lbo, a_sbo);
-          const uint64_t dbh = make_desc(b_hi + ks * b_kstep, b_lbo, b_sbo);
-          const uint64_t dbl = make_desc(b_lo + ks * b_kstep, b_lbo, b_sbo);
+          const uint64_t dah = make_desc(a_hi + ks * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t dal = make_desc(a_lo + ks * a_kstep, a_lbo, a_sbo, a_lt);
+          const uint64_t dbh = make_desc(b_hi + ks * b_kstep, b_lbo, b_sbo, b_lt);
+          const uint64_t dbl = make_desc(b_lo + ks * b_kstep, b_lbo, b_sbo, b_lt);
           umma_tf32(tmem_base, dal, dbh, idesc, (i > 0 || ks > 0) ? 1u : 0u);
           umma_tf32(tmem_base, dah, dbl, idesc, 1u);
           umma_tf32(tmem_base, dah, dbh, idesc, 1u);

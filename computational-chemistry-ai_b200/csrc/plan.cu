@@ -80,6 +80,12 @@ struct eims_plan {
   std::map<std::string, Buf> buf;
   int state;  // 0 none, 1 batch built, 2 forward(train) done, 3 loss grad ready
   int last_training;
+  // per-stage CUDA-event profiling (bench.py's roofline pass) and launch accounting
+  bool prof = false;
+  struct ProfRec { int stage; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  size_t prof_used = 0;
+  int64_t launches = 0;
   eims_step last_step;
   int pool_dim() const { return d.pooling == EIMS_POOL_COMBINED ? 2 * d.hidden_dim : d.hidden_dim; }
   template <class T> T* get(const std::string& n) { return reinterpret_cast<T*>(buf[n].ptr); }
@@ -102,6 +108,41 @@ int gemm(eims_plan* p, const float* A, int lda, int a_mn, const float* B, int ld
     return launch_gemm_simt(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, m_dev, k_dev, rs, bias, relu, acc, st);
   return launch_gemm_tc(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, m_dev, k_dev, rs, bias, relu, acc, st);
 }
+
+enum Stage {
+  ST_K1 = 0, ST_LAYER0_FWD, ST_BN_STATS, ST_SPMM_FWD, ST_GEMM_GCN_FWD, ST_READOUT, ST_GEMM_HEAD_FWD, ST_LN_FWD, ST_LOSS,
+  ST_METRICS, ST_GEMM_HEAD_WGRAD, ST_COLSUM, ST_GEMM_HEAD_DGRAD, ST_LN_BWD, ST_BN_BWD, ST_GEMM_GCN_WGRAD,
+  ST_GEMM_GCN_DGRAD, ST_SPMM_BWD, ST_LAYER0_WGRAD, ST_ADAMW, ST_ELEMENTWISE, ST_COUNT
+};
+const char* kStageNames[ST_COUNT] = {
+  "k1_batch_build", "layer0_fwd", "bn_stats", "spmm_fwd", "gemm_gcn_fwd", "readout", "gemm_head_fwd", "ln_fwd", "loss",
+  "metrics", "gemm_head_wgrad", "colsum", "gemm_head_dgrad", "ln_bwd", "bn_bwd", "gemm_gcn_wgrad",
+  "gemm_gcn_dgrad", "spmm_bwd", "layer0_wgrad", "adamw", "elementwise"};
+
+void prof_begin(eims_plan* p, int stage, int nkernels, cudaStream_t st) {
+  p->launches += nkernels;
+  if (!p->prof) return;
+  if (p->prof_used == p->prof_recs.size()) {
+    eims_plan::ProfRec r;
+    r.stage = stage;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    p->prof_recs.push_back(r);
+  }
+  p->prof_recs[p->prof_used].stage = stage;
+  cudaEventRecord(p->prof_recs[p->prof_used].a, st);
+}
+void prof_end(eims_plan* p, cudaStream_t st) {
+  if (!p->prof) return;
+  cudaEventRecord(p->prof_recs[p->prof_used].b, st);
+  ++p->prof_used;
+}
+#define STAGE(id, nk, expr)          \
+  do {                               \
+    prof_begin(p, id, nk, st);       \
+    EIMS_TRY(expr);                  \
+    prof_end(p, st);                 \
+  } while (0)
 
 void add(eims_plan* p, const std::string& name, int64_t bytes) {
   bytes = (bytes + 255) & ~(int64_t)255;
@@ -252,7 +293,11 @@ int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, 
   return 0;
 }
 
-int eims_plan_destroy(eims_plan* p) { delete p; return 0; }
+int eims_plan_destroy(eims_plan* p) {
+  if (p) for (auto& r : p->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  delete p;
+  return 0;
+}
 int64_t eims_plan_workspace_bytes(const eims_plan* p) { return p ? p->ws_bytes : -1; }
 
 int eims_plan_bind(eims_plan* p, void* workspace, int64_t bytes) {
@@ -291,9 +336,10 @@ int eims_batch_build(eims_plan* p, const eims_dataset* ds, const int32_t* mol_id
   if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
   if (!ds || num_graphs < 0) return fail(EIMS_ERR_ARG, "bad dataset / num_graphs");
   if (num_graphs > p->Bc) return fail(EIMS_ERR_CAPACITY, "num_graphs %d exceeds plan max_graphs %d", num_graphs, p->Bc);
-  EIMS_TRY(launch_csr_build(ds, mol_ids, num_graphs, p->d.node_feat_dim, p->Nc, p->Ec, p->i("gptr"), p->i("eptr"),
+  cudaStream_t st = (cudaStream_t)stream;
+  STAGE(ST_K1, num_graphs > 0 ? 2 : 1, launch_csr_build(ds, mol_ids, num_graphs, p->d.node_feat_dim, p->Nc, p->Ec, p->i("gptr"), p->i("eptr"),
                             p->i("gid"), p->i("src"), p->i("dst"), p->i("rowptr"), p->i("col"), p->f("norm"),
-                            p->f("x"), p->i("dims"), (cudaStream_t)stream));
+                            p->f("x"), p->i("dims"), st));
   p->state = 1;
   return check_launch("eims_batch_build");
 }
@@ -322,28 +368,28 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
     return launch_bn_eval_coeffs(params + p->off_bn_g(l), params + p->off_bn_b(l), rm, rv, H, p->f(L_("bn_scale", l)),
                                  p->f(L_("bn_shift", l)), st);
   };
-  EIMS_TRY(launch_layer0_fwd(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("x"), F, params + p->off_gcn_w(0),
+  STAGE(ST_LAYER0_FWD, 1, launch_layer0_fwd(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("x"), F, params + p->off_gcn_w(0),
                              params + p->off_gcn_b(0), H, p->f("a0"), p->f("z0"), p->Nc, st));
-  EIMS_TRY(bn(0));
+  STAGE(ST_BN_STATS, 1, bn(0));
   for (int l = 1; l < L; ++l) {
-    EIMS_TRY(launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f(L_("z", l - 1)), H,
+    STAGE(ST_SPMM_FWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f(L_("z", l - 1)), H,
                               p->f(L_("bn_scale", l - 1)), p->f(L_("bn_shift", l - 1)),
                               make_drop(drop_p, seed, step, l - 1), 0, p->f(L_("a", l)), p->Nc, st));
-    EIMS_TRY(gemm(p, p->f(L_("a", l)), H, 0, params + p->off_gcn_w(l), H, 1, p->f(L_("z", l)), H, p->Nc, H, H,
+    STAGE(ST_GEMM_GCN_FWD, 1, gemm(p, p->f(L_("a", l)), H, 0, params + p->off_gcn_w(l), H, 1, p->f(L_("z", l)), H, p->Nc, H, H,
                   dims + DIM_N, nullptr, p->f("norm"), params + p->off_gcn_b(l), 1, 0, st));
-    EIMS_TRY(bn(l));
+    STAGE(ST_BN_STATS, 1, bn(l));
   }
-  EIMS_TRY(launch_readout(dims, p->i("gptr"), p->f(L_("z", L - 1)), H, p->f(L_("bn_scale", L - 1)),
+  STAGE(ST_READOUT, 1, launch_readout(dims, p->i("gptr"), p->f(L_("z", L - 1)), H, p->f(L_("bn_scale", L - 1)),
                           p->f(L_("bn_shift", L - 1)), d.pooling, p->f("readout"), p->i("argmax"), p->Bc, st));
-  EIMS_TRY(gemm(p, p->f("readout"), P, 0, params + p->off_head(0), P, 0, p->f("u1"), 2 * H, p->Bc, 2 * H, P,
+  STAGE(ST_GEMM_HEAD_FWD, 1, gemm(p, p->f("readout"), P, 0, params + p->off_head(0), P, 0, p->f("u1"), 2 * H, p->Bc, 2 * H, P,
                 dims + DIM_B, nullptr, nullptr, params + p->off_head(1), 0, 0, st));
-  EIMS_TRY(launch_ln_fwd(dims, p->f("u1"), 2 * H, params + p->off_head(2), params + p->off_head(3),
+  STAGE(ST_LN_FWD, 1, launch_ln_fwd(dims, p->f("u1"), 2 * H, params + p->off_head(2), params + p->off_head(3),
                          make_drop(drop_p, seed, step, L), p->f("y1"), p->f("ln1"), p->Bc, st));
-  EIMS_TRY(gemm(p, p->f("y1"), 2 * H, 0, params + p->off_head(4), 2 * H, 0, p->f("u2"), H, p->Bc, H, 2 * H,
+  STAGE(ST_GEMM_HEAD_FWD, 1, gemm(p, p->f("y1"), 2 * H, 0, params + p->off_head(4), 2 * H, 0, p->f("u2"), H, p->Bc, H, 2 * H,
                 dims + DIM_B, nullptr, nullptr, params + p->off_head(5), 0, 0, st));
-  EIMS_TRY(launch_ln_fwd(dims, p->f("u2"), H, params + p->off_head(6), params + p->off_head(7),
+  STAGE(ST_LN_FWD, 1, launch_ln_fwd(dims, p->f("u2"), H, params + p->off_head(6), params + p->off_head(7),
                          make_drop(drop_p, seed, step, L + 1), p->f("y2"), p->f("ln2"), p->Bc, st));
-  EIMS_TRY(gemm(p, p->f("y2"), H, 0, params + p->off_head(8), H, 0, p->f("logits"), M, p->Bc, M, H, dims + DIM_B,
+  STAGE(ST_GEMM_HEAD_FWD, 1, gemm(p, p->f("y2"), H, 0, params + p->off_head(8), H, 0, p->f("logits"), M, p->Bc, M, H, dims + DIM_B,
                 nullptr, nullptr, params + p->off_head(9), 0, 0, st));
   p->state = training ? 2 : 1;
   p->last_training = training;
@@ -352,7 +398,8 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
 
 int eims_sigmoid(eims_plan* p, eims_stream_t stream) {
   if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
-  EIMS_TRY(launch_sigmoid(p->i("dims"), p->f("logits"), p->d.max_mz, p->f("prob"), p->Bc, (cudaStream_t)stream));
+  cudaStream_t st = (cudaStream_t)stream;
+  STAGE(ST_ELEMENTWISE, 1, launch_sigmoid(p->i("dims"), p->f("logits"), p->d.max_mz, p->f("prob"), p->Bc, (cudaStream_t)stream));
   return check_launch("eims_sigmoid");
 }
 
@@ -360,7 +407,8 @@ int eims_loss(eims_plan* p, const float* targets, const int32_t* target_rows, in
               eims_stream_t stream) {
   if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
   if (!targets) return fail(EIMS_ERR_ARG, "targets is NULL");
-  EIMS_TRY(launch_loss(p->i("dims"), p->f("logits"), targets, target_rows, p->d.max_mz, loss_kind, p->f("prob"),
+  cudaStream_t st = (cudaStream_t)stream;
+  STAGE(ST_LOSS, 1, launch_loss(p->i("dims"), p->f("logits"), targets, target_rows, p->d.max_mz, loss_kind, p->f("prob"),
                        want_grad ? p->f("dlogits") : nullptr, p->f("row_loss"), p->f("row_cos"), p->Bc,
                        (cudaStream_t)stream));
   if (want_grad && p->state == 2) p->state = 3;
@@ -381,45 +429,45 @@ int eims_backward(eims_plan* p, const float* params, const float* dprob, float* 
   const uint64_t seed = p->last_step.seed;
   const int step = p->last_step.step;
   auto L_ = [&](const char* b, int l) { return std::string(b) + std::to_string(l); };
-  if (dprob) EIMS_TRY(launch_dprob_to_dlogits(dims, p->f("prob"), dprob, M, p->f("dlogits"), p->Bc, st));
+  if (dprob) STAGE(ST_ELEMENTWISE, 1, launch_dprob_to_dlogits(dims, p->f("prob"), dprob, M, p->f("dlogits"), p->Bc, st));
   float* dl = p->f("dlogits");
   // ---- head (GCN:341-352 backwards)
-  EIMS_TRY(gemm(p, dl, M, 1, p->f("y2"), H, 1, grads + p->off_head(8), H, M, H, p->Bc, nullptr, dims + DIM_B, nullptr,
+  STAGE(ST_GEMM_HEAD_WGRAD, 1, gemm(p, dl, M, 1, p->f("y2"), H, 1, grads + p->off_head(8), H, M, H, p->Bc, nullptr, dims + DIM_B, nullptr,
                 nullptr, 0, 1, st));
-  EIMS_TRY(launch_colsum(dims, DIM_B, dl, M, M, grads + p->off_head(9), p->Bc, st));
-  EIMS_TRY(gemm(p, dl, M, 0, params + p->off_head(8), H, 1, p->f("dy2"), H, p->Bc, H, M, dims + DIM_B, nullptr, nullptr,
+  STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, dl, M, M, grads + p->off_head(9), p->Bc, st));
+  STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, dl, M, 0, params + p->off_head(8), H, 1, p->f("dy2"), H, p->Bc, H, M, dims + DIM_B, nullptr, nullptr,
                 nullptr, 0, 0, st));
-  EIMS_TRY(launch_ln_bwd(dims, p->f("u2"), p->f("y2"), p->f("dy2"), H, params + p->off_head(6), p->f("ln2"), drop_scale,
+  STAGE(ST_LN_BWD, 1, launch_ln_bwd(dims, p->f("u2"), p->f("y2"), p->f("dy2"), H, params + p->off_head(6), p->f("ln2"), drop_scale,
                          p->f("dy2"), grads + p->off_head(6), grads + p->off_head(7), p->Bc, st));
-  EIMS_TRY(gemm(p, p->f("dy2"), H, 1, p->f("y1"), 2 * H, 1, grads + p->off_head(4), 2 * H, H, 2 * H, p->Bc, nullptr,
+  STAGE(ST_GEMM_HEAD_WGRAD, 1, gemm(p, p->f("dy2"), H, 1, p->f("y1"), 2 * H, 1, grads + p->off_head(4), 2 * H, H, 2 * H, p->Bc, nullptr,
                 dims + DIM_B, nullptr, nullptr, 0, 1, st));
-  EIMS_TRY(launch_colsum(dims, DIM_B, p->f("dy2"), H, H, grads + p->off_head(5), p->Bc, st));
-  EIMS_TRY(gemm(p, p->f("dy2"), H, 0, params + p->off_head(4), 2 * H, 1, p->f("dy1"), 2 * H, p->Bc, 2 * H, H,
+  STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, p->f("dy2"), H, H, grads + p->off_head(5), p->Bc, st));
+  STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, p->f("dy2"), H, 0, params + p->off_head(4), 2 * H, 1, p->f("dy1"), 2 * H, p->Bc, 2 * H, H,
                 dims + DIM_B, nullptr, nullptr, nullptr, 0, 0, st));
-  EIMS_TRY(launch_ln_bwd(dims, p->f("u1"), p->f("y1"), p->f("dy1"), 2 * H, params + p->off_head(2), p->f("ln1"),
+  STAGE(ST_LN_BWD, 1, launch_ln_bwd(dims, p->f("u1"), p->f("y1"), p->f("dy1"), 2 * H, params + p->off_head(2), p->f("ln1"),
                          drop_scale, p->f("dy1"), grads + p->off_head(2), grads + p->off_head(3), p->Bc, st));
-  EIMS_TRY(gemm(p, p->f("dy1"), 2 * H, 1, p->f("readout"), P, 1, grads + p->off_head(0), P, 2 * H, P, p->Bc, nullptr,
+  STAGE(ST_GEMM_HEAD_WGRAD, 1, gemm(p, p->f("dy1"), 2 * H, 1, p->f("readout"), P, 1, grads + p->off_head(0), P, 2 * H, P, p->Bc, nullptr,
                 dims + DIM_B, nullptr, nullptr, 0, 1, st));
-  EIMS_TRY(launch_colsum(dims, DIM_B, p->f("dy1"), 2 * H, 2 * H, grads + p->off_head(1), p->Bc, st));
-  EIMS_TRY(gemm(p, p->f("dy1"), 2 * H, 0, params + p->off_head(0), P, 1, p->f("dG"), P, p->Bc, P, 2 * H, dims + DIM_B,
+  STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, p->f("dy1"), 2 * H, 2 * H, grads + p->off_head(1), p->Bc, st));
+  STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, p->f("dy1"), 2 * H, 0, params + p->off_head(0), P, 1, p->f("dG"), P, p->Bc, P, 2 * H, dims + DIM_B,
                 nullptr, nullptr, nullptr, 0, 0, st));
   // ---- GCN layers, last to first (GCN:358-363 backwards)
   for (int l = L - 1; l >= 0; --l) {
     const bool from_readout = (l == L - 1);
-    EIMS_TRY(launch_bn_bwd(dims, from_readout ? nullptr : p->f("dh"), p->f("dG"), p->i("gid"), p->i("gptr"),
+    STAGE(ST_BN_BWD, 2, launch_bn_bwd(dims, from_readout ? nullptr : p->f("dh"), p->f("dG"), p->i("gid"), p->i("gptr"),
                            p->i("argmax"), d.pooling, p->f(L_("z", l)), H, p->f(L_("bn_mean", l)),
                            p->f(L_("bn_invstd", l)), params + p->off_bn_g(l), p->f("norm"), grads + p->off_bn_g(l),
                            grads + p->off_bn_b(l), grads + p->off_gcn_b(l), p->f("bn_means2"), p->f("bn_partials"),
                            p->f("q"), p->Nc, st));
     if (l > 0) {
-      EIMS_TRY(gemm(p, p->f(L_("a", l)), H, 1, p->f("q"), H, 1, grads + p->off_gcn_w(l), H, H, H, p->Nc, nullptr,
+      STAGE(ST_GEMM_GCN_WGRAD, 1, gemm(p, p->f(L_("a", l)), H, 1, p->f("q"), H, 1, grads + p->off_gcn_w(l), H, H, H, p->Nc, nullptr,
                     dims + DIM_N, nullptr, nullptr, 0, 1, st));
-      EIMS_TRY(gemm(p, p->f("q"), H, 0, params + p->off_gcn_w(l), H, 0, p->f("da"), H, p->Nc, H, H, dims + DIM_N,
+      STAGE(ST_GEMM_GCN_DGRAD, 1, gemm(p, p->f("q"), H, 0, params + p->off_gcn_w(l), H, 0, p->f("da"), H, p->Nc, H, H, dims + DIM_N,
                     nullptr, nullptr, nullptr, 0, 0, st));
-      EIMS_TRY(launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("da"), H, nullptr, nullptr,
+      STAGE(ST_SPMM_BWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("da"), H, nullptr, nullptr,
                                 make_drop(drop_p, seed, step, l - 1), 1, p->f("dh"), p->Nc, st));
     } else {
-      EIMS_TRY(launch_layer0_wgrad(dims, p->f("a0"), F, p->f("q"), H, grads + p->off_gcn_w(0), p->Nc, st));
+      STAGE(ST_LAYER0_WGRAD, 1, launch_layer0_wgrad(dims, p->f("a0"), F, p->f("q"), H, grads + p->off_gcn_w(0), p->Nc, st));
     }
   }
   p->state = 1;
@@ -428,7 +476,8 @@ int eims_backward(eims_plan* p, const float* params, const float* dprob, float* 
 
 int eims_metrics_accumulate(eims_plan* p, float* metrics, eims_stream_t stream) {
   if (!p || !p->bound || !metrics) return fail(EIMS_ERR_STATE, "plan not bound / metrics NULL");
-  EIMS_TRY(launch_metrics(p->i("dims"), p->f("row_loss"), p->f("row_cos"), p->d.max_mz, metrics, (cudaStream_t)stream));
+  cudaStream_t st = (cudaStream_t)stream;
+  STAGE(ST_METRICS, 1, launch_metrics(p->i("dims"), p->f("row_loss"), p->f("row_cos"), p->d.max_mz, metrics, (cudaStream_t)stream));
   return check_launch("eims_metrics_accumulate");
 }
 
@@ -442,7 +491,10 @@ int eims_train_step(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids
   EIMS_TRY(eims_loss(p, ds->targets, mol_ids, loss_kind, 1, stream));
   if (metrics) EIMS_TRY(eims_metrics_accumulate(p, metrics, stream));
   EIMS_TRY(eims_backward(p, params, nullptr, grads, stream));
-  if (adam_m && adam_v) EIMS_TRY(eims_adamw_flat(params, grads, adam_m, adam_v, p->poff.back(), s, stream));
+  if (adam_m && adam_v) {
+    cudaStream_t st = (cudaStream_t)stream;
+    STAGE(ST_ADAMW, 1, launch_adamw(params, grads, adam_m, adam_v, p->poff.back(), s, st));
+  }
   return 0;
 }
 
@@ -450,10 +502,39 @@ int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_id
                      const float* params, const float* bn_running, float* prob_out, eims_stream_t stream) {
   EIMS_TRY(eims_batch_build(p, ds, mol_ids, num_graphs, stream));
   EIMS_TRY(eims_forward(p, params, const_cast<float*>(bn_running), 0, nullptr, stream));
-  EIMS_TRY(launch_sigmoid(p->i("dims"), p->f("logits"), p->d.max_mz, prob_out ? prob_out : p->f("prob"), p->Bc,
+  cudaStream_t st = (cudaStream_t)stream;
+  STAGE(ST_ELEMENTWISE, 1, launch_sigmoid(p->i("dims"), p->f("logits"), p->d.max_mz, prob_out ? prob_out : p->f("prob"), p->Bc,
                           (cudaStream_t)stream));
   return check_launch("eims_infer_batch");
 }
+
+int eims_plan_profile(eims_plan* p, int32_t enable) {
+  if (!p) return fail(EIMS_ERR_ARG, "plan is NULL");
+  p->prof = enable != 0;
+  p->prof_used = 0;
+  p->launches = 0;
+  return 0;
+}
+
+int eims_plan_profile_read(eims_plan* p, float* stage_ms, int32_t* stage_launches, int32_t n_stages, int64_t* total_launches) {
+  if (!p) return fail(EIMS_ERR_ARG, "plan is NULL");
+  if (n_stages != ST_COUNT) return fail(EIMS_ERR_ARG, "n_stages must be %d", (int)ST_COUNT);
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail(EIMS_ERR_CUDA, "sync failed: %s", cudaGetErrorString(cudaGetLastError()));
+  for (int k = 0; k < ST_COUNT; ++k) { if (stage_ms) stage_ms[k] = 0.f; if (stage_launches) stage_launches[k] = 0; }
+  for (size_t k = 0; k < p->prof_used; ++k) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p->prof_recs[k].a, p->prof_recs[k].b) != cudaSuccess)
+      return fail(EIMS_ERR_CUDA, "cudaEventElapsedTime failed");
+    if (stage_ms) stage_ms[p->prof_recs[k].stage] += ms;
+    if (stage_launches) stage_launches[p->prof_recs[k].stage] += 1;
+  }
+  if (total_launches) *total_launches = p->launches;
+  p->prof_used = 0;
+  return 0;
+}
+
+int eims_plan_num_stages(void) { return ST_COUNT; }
+const char* eims_plan_stage_name(int32_t k) { return (k >= 0 && k < ST_COUNT) ? kStageNames[k] : ""; }
 
 int eims_plan_check(eims_plan* p, int32_t* num_nodes, int32_t* num_edges, eims_stream_t stream) {
   if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");

@@ -75,6 +75,10 @@ _SIGS = {
     "eims_metrics_accumulate": (C.c_int, [_vp, _vp, _vp]),
     "eims_train_step": (C.c_int, [_vp, C.POINTER(Dataset), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(Step), _vp, _vp]),
     "eims_infer_batch": (C.c_int, [_vp, C.POINTER(Dataset), _vp, _i32, _vp, _vp, _vp, _vp]),
+    "eims_plan_profile": (C.c_int, [_vp, _i32]),
+    "eims_plan_profile_read": (C.c_int, [_vp, C.POINTER(_f32), C.POINTER(_i32), _i32, C.POINTER(_i64)]),
+    "eims_plan_num_stages": (C.c_int, []),
+    "eims_plan_stage_name": (C.c_char_p, [_i32]),
     "eims_plan_check": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), _vp]),
 }
 

@@ -296,6 +296,18 @@ class Plan:
         for l in range(self.d.num_gcn_layers):
             fp.num_batches_tracked[l] += 1
 
+    # -- per-stage profiling (bench.py) ------------------------------------------------
+    def profile(self, enable: bool):
+        check(self.lib.eims_plan_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        """{stage: (total ms, brackets)} and the kernel-launch count since profile() was called."""
+        n = self.lib.eims_plan_num_stages()
+        ms, cnt, tot = (C.c_float * n)(), (C.c_int32 * n)(), C.c_int64()
+        check(self.lib.eims_plan_profile_read(self.h, ms, cnt, n, C.byref(tot)))
+        names = [self.lib.eims_plan_stage_name(k).decode() for k in range(n)]
+        return {names[k]: (float(ms[k]), int(cnt[k])) for k in range(n)}, int(tot.value)
+
     def infer_batch(self, ds: DeviceDataset, ids, fp: FlatParams, out=None, num_graphs=None):
         n = int(num_graphs if num_graphs is not None else (len(ids) if ids is not None else ds.num_mols))
         check(self.lib.eims_infer_batch(self.h, C.byref(ds.struct), ptr(ids), n, ptr(fp.params), ptr(fp.bn_running),

@@ -104,8 +104,9 @@ int eims_csr_build(const eims_dataset* ds, const int32_t* mol_ids, int32_t num_g
 /* K2  replaces DGL update_all(copy_u, sum) with the source-side normalisation
  * (GraphConv, GCN:359):  out[i,:] = sum_{j in row i} fl(f(h[j,:]) * norm[j])  where
  * f(x) = x*scale+shift (BatchNorm apply, may be NULL) followed by the dropout mask of
- * `site` (skipped when drop_p == 0).  With out_scale_norm != 0 the result row is scaled by
- * norm[i] (the backward form: dh = (A da) * c) and by the same dropout mask. */
+ * `site` (skipped when drop_p == 0).  With out_scale_norm != 0 (the backward form,
+ * dh = (A da) * c) the gathered rows are summed unscaled and the result row is scaled by
+ * norm[i] and by the dropout mask of row i. */
 int eims_spmm_norm(const int32_t* dims, const int32_t* rowptr, const int32_t* col, const float* norm,
                    const float* h, int32_t width, const float* bn_scale, const float* bn_shift,
                    float drop_p, uint64_t seed, int32_t step, int32_t site,
@@ -189,7 +190,7 @@ int eims_loss(eims_plan* p, const float* targets, const int32_t* target_rows, in
  * eims_adamw_flat / the caller). */
 int eims_backward(eims_plan* p, const float* params, const float* dprob, float* grads,
                   eims_stream_t stream);
-/* metrics[4] (device) += {sum_b row_loss/(B*M), mean_b row_cos, 1, 0}  - the per-step
+/* metrics[8] (device): [0..2] += {sum_b row_loss/(B*M), mean_b row_cos, 1}; [4],[5] = this step's loss / cosine  - the per-step
  * `loss.item()` / `cos_sim.mean().item()` of GCN:436-437 without the host syncs. */
 int eims_metrics_accumulate(eims_plan* p, float* metrics, eims_stream_t stream);
 
@@ -200,6 +201,16 @@ int eims_train_step(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids
 /* predict_spectrum (GCN:494-511) for a batch: batch build + eval forward + sigmoid. */
 int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
                      const float* params, const float* bn_running, float* prob_out, eims_stream_t stream);
+/* Per-stage device timing for the roofline report (bench.py): when enabled every kernel
+ * launch of the plan is bracketed by CUDA events on the launching stream.  _read
+ * synchronises, sums the elapsed ms and the bracket count per stage (eims_plan_num_stages()
+ * entries, names from eims_plan_stage_name) and returns the number of kernels launched
+ * since _profile was last called. */
+int eims_plan_profile(eims_plan* p, int32_t enable);
+int eims_plan_profile_read(eims_plan* p, float* stage_ms, int32_t* stage_launches, int32_t n_stages,
+                           int64_t* total_launches);
+int eims_plan_num_stages(void);
+const char* eims_plan_stage_name(int32_t k);
 /* Reads dims[] back (one small synchronous copy) and maps flags to error codes. */
 int eims_plan_check(eims_plan* p, int32_t* num_nodes, int32_t* num_edges, eims_stream_t stream);
 
