@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py - GCN EI-MS training throughput (molecules/s) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 200 --warmup 20          # our arm (default N=1)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 10 --warmup 1    # the reference path on host cores
+
+A "step" is one optimiser step of the reference's hot path (GCN:410-431) over one batch of
+512 synthetic molecules: batch build (K1) -> GCNSpectrum forward -> MSE loss + cosine metric
+-> backward -> AdamW, with H=256, L=3, 1000 m/z bins, dropout 0.2, fp32 (BASELINE.json
+configs[1]; at N>1 configs[3]: 1 M molecules sharded over the ranks, batch 512 per GPU,
+gradient all-reduce over NCCL).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "computational-chemistry-ai_b200"))
+
+METRIC = "gcn_eims_train_molecules_per_sec"
+UNIT = "molecules/s"
+BATCH, H, L, M, F0, DROPOUT, MAX_ATOMS = 512, 256, 3, 1000, 6, 0.2, 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--molecules", type=int, default=0, help="molecules per rank (0 = BASELINE config)")
+    ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=20)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm_gbs=float(j["hbm_gbs"]), bf16_tflops=float(j["bf16_tflops"]),
+                    bf16_tflops_sustained=float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic bytes / flops per stage and step (fp32 values, int32 indices)
+# ------------------------------------------------------------------------------------------
+def stage_work(N, E, B, P):
+    pd = 2 * H
+    nb = E // 2
+    gemm_head = 2 * B * (pd * 2 * H + 2 * H * H + H * M)
+    return {
+        # name: (bound, work per STEP in bytes or flops)
+        "k1_batch_build": ("hbm", 2 * N * F0 * 4 + nb * 8 + B * 16 + 3 * E * 4 + 3 * N * 4 + 2 * B * 4),
+        "layer0_fwd": ("hbm", 2 * N * F0 * 4 + 4 * E + 8 * N + 4 * N * H),
+        "bn_stats": ("hbm", L * 4 * N * H),
+        "spmm_fwd": ("hbm", (L - 1) * (8 * N * H + 4 * E + 8 * N)),
+        "gemm_gcn_fwd": ("tensor", (L - 1) * 2 * N * H * H),
+        "readout": ("hbm", 4 * N * H + 12 * B * H),
+        "gemm_head_fwd": ("tensor", gemm_head),
+        "ln_fwd": ("hbm", 8 * B * (2 * H + H)),
+        "loss": ("hbm", 16 * B * M),
+        "metrics": ("hbm", 8 * B),
+        "gemm_head_wgrad": ("tensor", gemm_head),
+        "colsum": ("hbm", 4 * B * (M + H + 2 * H)),
+        "gemm_head_dgrad": ("tensor", gemm_head),
+        "ln_bwd": ("hbm", 16 * B * (2 * H + H)),
+        "bn_bwd": ("hbm", L * 20 * N * H - 8 * N * H),
+        "gemm_gcn_wgrad": ("tensor", (L - 1) * 2 * N * H * H),
+        "gemm_gcn_dgrad": ("tensor", (L - 1) * 2 * N * H * H),
+        "spmm_bwd": ("hbm", (L - 1) * (8 * N * H + 4 * E + 8 * N)),
+        "layer0_wgrad": ("hbm", 4 * N * H + 4 * N * F0),
+        "adamw": ("hbm", 28 * P),
+        "elementwise": ("hbm", 0),
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# the reference path on host cores (oracle port of the script's train step)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, batch, n_mols=4096, time_budget=None):
+    import torch
+    from eims_b200.synth import dense_spectra, synth_molecules, synth_peaks
+    from oracle import gcn_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    d = O.Dims(F0, H, L, M, "combined", DROPOUT)
+    n_mols = max(n_mols, batch)
+    table = synth_molecules(n_mols, max_atoms=MAX_ATOMS, seed=1234)
+    spectra = torch.from_numpy(dense_spectra(*synth_peaks(n_mols, M, seed=4321), M))
+    tr = O.Trainer(O.init_params(d, 0), d, total_steps=max(steps + warmup, 4))
+    rng = np.random.default_rng(0)
+
+    def one():
+        ids = rng.choice(n_mols, size=batch, replace=False)
+        sub = table.select(ids)  # host-side collate (dgl.batch equivalent, vectorised)
+        src, dst = O.mol_edges(sub.bond_begin.astype(np.int64), sub.bond_end.astype(np.int64))
+        off = np.repeat(sub.node_ptr[:-1], 2 * np.diff(sub.bond_ptr))
+        g = O.Graph(src + off, dst + off, np.diff(sub.node_ptr))
+        pred, loss = tr.step(g, torch.from_numpy(sub.feat), spectra[ids])
+        O.cosine_similarity_batch(pred, spectra[ids], "cupy")  # the per-step metric (GCN:435)
+        return loss
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        one()
+        done += 1
+        if time_budget and time.perf_counter() - t0 > time_budget and done >= 3:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=done * batch / dt, steps=done, seconds=dt, cores=torch.get_num_threads(), batch=batch)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = BATCH if args.steps <= 300 else 128
+    r = cpu_reference_run(args.steps, max(args.warmup, 1), batch)
+    sample = f"{r['steps']} optimiser steps of batch {batch} drawn from 4096 synthetic molecules (same generator, H={H}, L={L}, M={M}, dropout {DROPOUT})"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * r["seconds"] / r["steps"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle/gcn_oracle.py (torch-CPU restatement of the reference script; dgl/cupy/rdkit are not installable offline) on the box's host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    if n_gpus == 1:
+        wl = "BASELINE configs[1]: GCN EI-MS training, 100k synthetic molecules (<=64 heavy atoms), batch 512, 3 GCN layers, hidden 256, 1000 m/z bins, fp32, single B200"
+    else:
+        wl = f"BASELINE configs[3]: data-parallel GCN EI-MS training, 1M synthetic molecules sharded over {n_gpus} B200, batch 512/GPU, NCCL gradient all-reduce"
+    return {"workload": wl, "batch_per_gpu": BATCH, "hidden_dim": H, "num_gcn_layers": L, "max_mz": M,
+            "dropout": DROPOUT, "loss": "mse", "optimizer": "AdamW+OneCycleLR",
+            "l2_policy": "no explicit flush: every step reads a fresh batch from a device-resident set (graph tables + 4 KB/molecule targets, >= 0.5 GB) larger than the 126 MB L2; activations are produced and consumed inside the step",
+            "parallelism": f"dp{n_gpus}"}
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from eims_b200.engine import DeviceDataset, FlatParams, ModelDims, Plan, make_step, onecycle_schedule
+    from eims_b200.hostpath import HostBatchRunner, PackedHostBatch
+    from eims_b200.synth import dense_spectra, synth_molecules, synth_peaks
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_mols = args.molecules or (100_000 if world == 1 else 1_000_000 // world)
+    steps_total = args.warmup + args.steps
+    n_mols = max(n_mols, BATCH)
+
+    # ---- synthetic data, device resident
+    table = synth_molecules(n_mols, max_atoms=MAX_ATOMS, seed=1234 + 7919 * rank)
+    pk = synth_peaks(n_mols, M, seed=4321 + 7919 * rank)
+    targets = dense_spectra(*pk, M)
+    ds = DeviceDataset(table, targets, dev)
+    d = ModelDims(F0, H, L, M, "combined", DROPOUT)
+    rng = np.random.default_rng(99 + rank)
+    perm_host = np.concatenate([rng.permutation(n_mols) for _ in range((steps_total * BATCH) // n_mols + 2)]).astype(np.int32)
+    cap_nodes = BATCH * MAX_ATOMS
+    cap_edges = 2 * (cap_nodes + 3 * BATCH)
+    plan = Plan(d, BATCH, cap_nodes, cap_edges, dev, gemm_backend=args.gemm)
+    fp = FlatParams(d, dev)
+    init_weights(fp, d)
+    if world > 1:
+        dist.broadcast(fp.params, 0)
+    perm = torch.from_numpy(perm_host).to(dev)
+    sched = onecycle_schedule(max(steps_total * 4, 100))
+    metrics = torch.zeros(8, device=dev)
+    gscale = 1.0 / world
+
+    def step_fn(i, k):
+        ids = perm[i * BATCH:(i + 1) * BATCH]
+        st = make_step(lr=sched[k][0], beta1=sched[k][1], grad_scale=gscale, step=k + 1, seed=2024 + rank)
+        if world == 1:
+            plan.train_step(ds, ids, fp, st, metrics)
+        else:
+            plan.train_step(ds, ids, fp, st, metrics, optimizer=False)
+            dist.all_reduce(fp.grads)
+            plan.adamw(fp, st)
+
+    k = 0
+    for i in range(args.warmup):
+        step_fn(i, k)
+        k += 1
+    plan.check()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    plan.profile(False)  # resets the launch counter
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.warmup, steps_total):
+        step_fn(i, k)
+        k += 1
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    _, launches = plan.profile_read()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    plan.check()
+    value = args.steps * BATCH * world / (ms * 1e-3)
+    final_loss = float(metrics[4].item())
+
+    # ---- per-stage pass (same steps, CUDA events around every launch, not used for `value`)
+    roofline, stages_out = None, None
+    if rank == 0 and args.profile_steps > 0:
+        pk_ = peaks()
+        plan.profile(True)
+        Ns, Es = [], []
+        for j in range(args.profile_steps):
+            i = (steps_total + j) % (len(perm_host) // BATCH)
+            ids_h = perm_host[i * BATCH:(i + 1) * BATCH]
+            n_, e_ = ds.batch_counts(ids_h)
+            Ns.append(n_)
+            Es.append(e_)
+            st = make_step(lr=sched[k][0], beta1=sched[k][1], grad_scale=gscale, step=k + 1, seed=2024)
+            plan.train_step(ds, perm[i * BATCH:(i + 1) * BATCH], fp, st, metrics)
+            k += 1
+        prof, _ = plan.profile_read()
+        plan.profile(False)
+        work = stage_work(float(np.mean(Ns)), float(np.mean(Es)), BATCH, fp.numel)
+        tot_ms = sum(v[0] for v in prof.values())
+        stages_out = {}
+        for name, (tms, cnt) in prof.items():
+            if cnt == 0:
+                continue
+            bound, w = work[name]
+            per_step_ms = tms / args.profile_steps
+            ach = w / (per_step_ms * 1e-3) / (1e9 if bound == "hbm" else 1e12) if per_step_ms > 0 else 0.0
+            peak = pk_["hbm_gbs"] if bound == "hbm" else pk_["bf16_tflops"]
+            stages_out[name] = {"ms_per_step": round(per_step_ms, 5), "share": round(tms / tot_ms, 4), "launches_per_step": cnt / args.profile_steps,
+                                "bound": bound, "achieved": round(ach, 3), "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                                "frac": round(ach / peak, 4)}
+        dom = max(stages_out, key=lambda n: stages_out[n]["ms_per_step"])
+        s = stages_out[dom]
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom)
+        roofline = {"kernel": dom, "bound": s["bound"], "achieved": s["achieved"], "peak": peaks()["hbm_gbs"] if s["bound"] == "hbm" else peaks()["bf16_tflops"],
+                    "unit": s["unit"], "frac": s["frac"], "traffic": traffic,
+                    "peak_source": f"{pk_['source']} ({'copy bandwidth' if s['bound'] == 'hbm' else 'cuBLAS bf16 burst; tf32 is half of it and the kernel runs 3 tf32 passes, so 1/6 is the ceiling'})",
+                    "launch_ms": round(s["ms_per_step"] / s["launches_per_step"], 5)}
+
+    # ---- e2e: the same step through the host-buffer call (H2D of inputs + D2H of loss inside)
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = min(args.steps, 100)
+        hbs = []
+        for j in range(n_e2e + 3):
+            ids_h = perm_host[j * BATCH:(j + 1) * BATCH]
+            hbs.append(PackedHostBatch(table.select(ids_h), targets[ids_h]))
+        runner = HostBatchRunner(plan, fp, max(h.nbytes for h in hbs) + 4096)
+
+        def e2e_step(j, slot_next):
+            st = make_step(lr=sched[k + j][0], beta1=sched[k + j][1], grad_scale=gscale, step=k + j + 1, seed=2024 + rank)
+            slot = slot_next
+            nxt = runner.upload(hbs[j + 1]) if j + 1 < len(hbs) else None
+            if world == 1:
+                runner.train_step(slot, hbs[j], st)
+            else:
+                raise NotImplementedError
+            return nxt
+
+        if world == 1:
+            slot = runner.upload(hbs[0])
+            for j in range(3):
+                slot = e2e_step(j, slot)
+            torch.cuda.synchronize()
+            runner.h2d_bytes = runner.d2h_bytes = 0
+            t0 = time.perf_counter()
+            e0.record()
+            for j in range(3, 3 + n_e2e):
+                slot = e2e_step(j, slot)
+                if j > 3:
+                    _ = runner.host_metrics[4].item()  # read the previous step's loss on the host
+            loss_e2e, _ = runner.result()
+            e1.record()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            e2e = {"value": n_e2e * BATCH / wall, "unit": UNIT, "h2d_bytes_per_step": int(runner.h2d_bytes / n_e2e),
+                   "d2h_bytes_per_step": int(runner.d2h_bytes / n_e2e), "steps": n_e2e,
+                   "timing": "host wall clock around the loop (device events agree: %.1f ms)" % e0.elapsed_time(e1),
+                   "last_loss": loss_e2e}
+        else:
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "note": "e2e is measured on the N=1 run"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(40, 1, BATCH, time_budget=20.0)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"{r['steps']} optimiser steps of batch {BATCH} from 4096 synthetic molecules in {r['seconds']:.1f} s (oracle/gcn_oracle.py, torch-CPU fp32, all host threads)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(world), "gemm": args.gemm,
+        "gpu_launches": int(launches), "clocks": clocks, "final_loss": final_loss,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "stages": stages_out,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def init_weights(fp, d):
+    """Reference initial distributions (GraphConv xavier-uniform / zero bias; nn.Linear
+    U(+-1/sqrt(fan_in)); norm layers 1/0) from a NumPy stream - same on every rank."""
+    import math
+    import torch
+    rng = np.random.Generator(np.random.PCG64(0))
+    with torch.no_grad():
+        for name, t in fp.named_params().items():
+            if name.startswith("gcn_layers") and name.endswith("weight"):
+                b = math.sqrt(6.0 / (t.shape[0] + t.shape[1]))
+                t.copy_(torch.from_numpy(rng.uniform(-b, b, size=tuple(t.shape)).astype(np.float32)))
+            elif name.startswith("spectrum_predictor") and int(name.split(".")[1]) in (0, 4, 8):
+                fan_in = dict(fp.spec)[name.rsplit(".", 1)[0] + ".weight"][1]
+                b = 1.0 / math.sqrt(fan_in)
+                t.copy_(torch.from_numpy(rng.uniform(-b, b, size=tuple(t.shape)).astype(np.float32)))
+            elif name.endswith("weight"):
+                t.fill_(1.0)
+            else:
+                t.zero_()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -81,6 +81,7 @@ int launch_gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb,
                      int N, int K, const int* m_dev, const int* k_dev, const float* row_scale, const float* bias,
                      int relu, int accumulate, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return EIMS_ERR_ARG;
+  if (accumulate == 2) accumulate = 0;  // split-K-allowed store: plain store on this path
   GemmArgs g{A, B, C, lda, ldb, ldc, a_mn, b_mn, M, N, K, m_dev, k_dev, row_scale, bias, relu, accumulate};
   int splits = 1;
   if (accumulate) {  // split-K for the weight gradients (K = atoms or graphs)
@@ -96,87 +97,90 @@ int launch_gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb,
 }
 
 // =========================================================================== BatchNorm stats
-// Block = kBnRows rows x all columns.  Per-thread shifted sums -> per-block (n, mean, M2) ->
-// the last block combines blocks with Chan's formula in double, writes mean / invstd /
-// scale / shift and updates the running buffers (nn.BatchNorm1d, momentum 0.1).
-constexpr int kBnRows = 64;
+// Persistent blocks; every thread owns one float4 column group and strides over rows with
+// fp64 accumulators (sum x, sum x^2 - exact enough that var = E[x^2]-mean^2 has no
+// cancellation problem even for nearly constant columns), block reduce in shared memory,
+// fp64 atomics into 2H global accumulators, and the last block (ticket) writes mean /
+// invstd / scale / shift, updates the running buffers (nn.BatchNorm1d, momentum 0.1) and
+// re-zeroes the accumulators so the kernel can be replayed.
+constexpr int kBnMaxBlocks = 2 * 148;
 
-static inline int bn_blocks(int max_nodes) { int b = (max_nodes + kBnRows - 1) / kBnRows; return b < 1 ? 1 : b; }
+static inline int bn_rif(int H) { int c4 = H / 4; return 256 / c4 > 0 ? 256 / c4 : 1; }
+static inline int bn_blocks(int H, int max_nodes) {
+  int rif = bn_rif(H);
+  int b = (max_nodes + 4 * rif - 1) / (4 * rif);  // >= 4 rows per thread
+  if (b > kBnMaxBlocks) b = kBnMaxBlocks;
+  return b < 1 ? 1 : b;
+}
 
-int64_t bn_scratch_floats(int H, int max_nodes) { return (int64_t)bn_blocks(max_nodes) * (2 * H + 4) + 64; }
+// scratch: [16 floats: ticket counter] [2H doubles: accumulators]
+int64_t bn_scratch_floats(int H, int max_nodes) { (void)max_nodes; return 16 + 4 * (int64_t)H + 16; }
+
+__device__ __forceinline__ void bn_block_reduce_atomic(double (&a)[4], double (&b)[4], double* smem, int H, int rif,
+                                                       int cg, int rs, bool active, double* acc) {
+  // smem layout [rif][2][H] doubles
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      smem[(rs * 2 + 0) * H + 4 * cg + e] = a[e];
+      smem[(rs * 2 + 1) * H + 4 * cg + e] = b[e];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * H; c += blockDim.x) {
+    const int which = c / H, col = c % H;
+    double t = 0.0;
+    for (int r = 0; r < rif; ++r) t += smem[(r * 2 + which) * H + col];
+    atomicAdd(acc + which * H + col, t);
+  }
+}
 
 __global__ void __launch_bounds__(256) bn_stats_kernel(const int* __restrict__ dims, const float* __restrict__ z, int H,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float* __restrict__ running_mean, float* __restrict__ running_var,
                                                        float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                                        float* __restrict__ scale_out, float* __restrict__ shift_out,
-                                                       float* __restrict__ partials) {
-  extern __shared__ float smem[];  // [rows_in_flight][H] x {mean, M2, n}
+                                                       float* __restrict__ scratch) {
+  extern __shared__ double smem_d[];
   const int N = dims[DIM_N];
   const int cols4 = H >> 2;
-  const int rif = max(1, (int)blockDim.x / cols4);  // rows in flight
-  const int nblk = gridDim.x;
-  unsigned int* counter = reinterpret_cast<unsigned int*>(partials);
-  float* pn = partials + 16;                      // [nblk]
-  float* pmean = pn + ((nblk + 3) & ~3);          // [nblk][H]
-  float* pm2 = pmean + (int64_t)nblk * H;         // [nblk][H]
-  const int r0 = blockIdx.x * kBnRows, r1 = min(N, r0 + kBnRows);
-  float* s_mean = smem;
-  float* s_m2 = smem + rif * H;
-  float* s_n = smem + 2 * rif * H;
-  for (int cg = threadIdx.x % cols4; cg < cols4; cg += (blockDim.x >= cols4 ? cols4 : blockDim.x)) {
-    const int rs = blockDim.x >= cols4 ? threadIdx.x / cols4 : 0;
-    if (rs >= rif) continue;
-    float4 K4 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = K4, s2 = K4;
-    int cnt = 0;
-    for (int r = r0 + rs; r < r1; r += rif) {
-      float4 v = ldg4(z + (int64_t)r * H + 4 * cg);
-      if (cnt == 0) K4 = v;
-      float dx = v.x - K4.x, dy = v.y - K4.y, dz = v.z - K4.z, dw = v.w - K4.w;
-      s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
-      s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
-      ++cnt;
-    }
-    const float inv = cnt ? 1.f / cnt : 0.f;
-    float* m = s_mean + rs * H + 4 * cg;
-    float* q = s_m2 + rs * H + 4 * cg;
-    m[0] = K4.x + s1.x * inv; m[1] = K4.y + s1.y * inv; m[2] = K4.z + s1.z * inv; m[3] = K4.w + s1.w * inv;
-    q[0] = s2.x - s1.x * s1.x * inv; q[1] = s2.y - s1.y * s1.y * inv;
-    q[2] = s2.z - s1.z * s1.z * inv; q[3] = s2.w - s1.w * s1.w * inv;
-    if (cg == 0) s_n[rs] = (float)cnt;
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    float n = 0.f, mean = 0.f, m2 = 0.f;
-    for (int rs = 0; rs < rif; ++rs) {
-      float nb = s_n[rs];
-      if (nb > 0.f) {
-        float mb = s_mean[rs * H + c], qb = s_m2[rs * H + c];
-        float tot = n + nb, d = mb - mean;
-        mean += d * (nb / tot);
-        m2 += qb + d * d * (n * nb / tot);
-        n = tot;
+  const bool wide = (int)blockDim.x < cols4;            // H > 1024: threads loop over column groups
+  const int rif = wide ? 1 : (int)blockDim.x / cols4;   // rows in flight per block
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
+  double* acc = reinterpret_cast<double*>(scratch + 16);
+  for (int cg0 = 0; cg0 < cols4; cg0 += blockDim.x) {
+    const int cg = wide ? cg0 + threadIdx.x : threadIdx.x % cols4;
+    const int rs = wide ? 0 : threadIdx.x / cols4;
+    const bool active = cg < cols4 && rs < rif;
+    double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+    if (active) {
+#pragma unroll 4
+      for (int r = blockIdx.x * rif + rs; r < N; r += gridDim.x * rif) {
+        const float4 v = ldg4(z + (int64_t)r * H + 4 * cg);
+        const double x0 = v.x, x1 = v.y, x2 = v.z, x3 = v.w;
+        a[0] += x0; a[1] += x1; a[2] += x2; a[3] += x3;
+        b[0] = fma(x0, x0, b[0]); b[1] = fma(x1, x1, b[1]); b[2] = fma(x2, x2, b[2]); b[3] = fma(x3, x3, b[3]);
       }
     }
-    pmean[(int64_t)blockIdx.x * H + c] = mean;
-    pm2[(int64_t)blockIdx.x * H + c] = m2;
-    if (c == 0) pn[blockIdx.x] = n;
-  }
-  if (!last_block_ticket(counter, nblk)) return;
-  for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    double n = 0.0, mean = 0.0, m2 = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-      double nb = (double)__ldcg(pn + b);
-      if (nb > 0.0) {
-        double mb = (double)__ldcg(pmean + (int64_t)b * H + c), qb = (double)__ldcg(pm2 + (int64_t)b * H + c);
-        double tot = n + nb, d = mb - mean;
-        mean += d * (nb / tot);
-        m2 += qb + d * d * (n * nb / tot);
-        n = tot;
-      }
+    if (wide) {  // no cross-thread reduction needed: one thread per column group
+      if (active)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { atomicAdd(acc + 4 * cg + e, a[e]); atomicAdd(acc + H + 4 * cg + e, b[e]); }
+    } else {
+      bn_block_reduce_atomic(a, b, smem_d, H, rif, cg, rs, active, acc);
+      break;
     }
-    if (n <= 0.0) continue;
-    const double var = m2 / n;
+  }
+  if (!last_block_ticket(counter, gridDim.x)) return;
+  const double n = (double)N;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    const double s1 = __ldcg(acc + c), s2 = __ldcg(acc + H + c);
+    acc[c] = 0.0;
+    acc[H + c] = 0.0;
+    if (N <= 0) continue;
+    const double mean = s1 / n;
+    double var = s2 / n - mean * mean;
+    if (var < 0.0) var = 0.0;
     const float mean_f = (float)mean;
     const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
     mean_out[c] = mean_f;
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const int* __restrict__ d
     scale_out[c] = sc;
     shift_out[c] = fmaf(-mean_f, sc, beta[c]);
     if (running_mean) {
-      const float unbiased = (float)(n > 1.0 ? m2 / (n - 1.0) : var);
+      const float unbiased = (float)(N > 1 ? var * n / (n - 1.0) : var);
       running_mean[c] = (1.f - kBnMomentum) * running_mean[c] + kBnMomentum * mean_f;
       running_var[c] = (1.f - kBnMomentum) * running_var[c] + kBnMomentum * unbiased;
     }
@@ -196,11 +200,9 @@ int launch_bn_stats(const int* dims, const float* z, int H, const float* gamma, 
                     float* rvar, float* mean, float* invstd, float* scale, float* shift, float* partials,
                     int max_nodes, cudaStream_t st) {
   if (H % 4 || H > 4096) return EIMS_ERR_ARG;
-  const int cols4 = H / 4;
-  const int rif = 256 / cols4 > 0 ? 256 / cols4 : 1;
-  size_t smem = (size_t)(2 * rif * H + rif + 4) * sizeof(float);
-  bn_stats_kernel<<<bn_blocks(max_nodes), 256, smem, st>>>(dims, z, H, gamma, beta, rmean, rvar, mean, invstd, scale,
-                                                           shift, partials);
+  size_t smem = (size_t)bn_rif(H) * 2 * H * sizeof(double);
+  bn_stats_kernel<<<bn_blocks(H, max_nodes), 256, smem, st>>>(dims, z, H, gamma, beta, rmean, rvar, mean, invstd,
+                                                              scale, shift, partials);
   return 0;
 }
 
@@ -256,50 +258,50 @@ __device__ __forceinline__ float4 load_dh(const DhSrc& s, int i, int c, int H) {
   return v;
 }
 
-// pass 1: column sums of dh and dh*xhat -> dgamma, dbeta (into grads) and the two means.
+// pass 1: column sums of dh and dh*xhat (fp64 accumulators + atomics, ticketed finalize)
+//         -> dgamma, dbeta (into grads) and the two column means.
 __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const int* __restrict__ dims, DhSrc src,
                                                            const float* __restrict__ z, int H,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           float* __restrict__ means /*[2][H]*/, float* __restrict__ partials) {
-  extern __shared__ float smem[];
+                                                           float* __restrict__ means /*[2][H]*/, float* __restrict__ scratch) {
+  extern __shared__ double smem_d[];
   const int N = dims[DIM_N];
   const int cols4 = H >> 2;
-  const int rif = max(1, (int)blockDim.x / cols4);
-  const int nblk = gridDim.x;
-  unsigned int* counter = reinterpret_cast<unsigned int*>(partials);
-  float* p1 = partials + 16;
-  float* p2 = p1 + (int64_t)nblk * H;
-  const int r0 = blockIdx.x * kBnRows, r1 = min(N, r0 + kBnRows);
-  float* s_1 = smem;
-  float* s_2 = smem + rif * H;
-  for (int cg = threadIdx.x % cols4; cg < cols4; cg += (blockDim.x >= cols4 ? cols4 : blockDim.x)) {
-    const int rs = blockDim.x >= cols4 ? threadIdx.x / cols4 : 0;
-    if (rs >= rif) continue;
-    const float4 mu = ldg4(mean + 4 * cg), is = ldg4(invstd + 4 * cg);
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    for (int r = r0 + rs; r < r1; r += rif) {
-      float4 d = load_dh(src, r, 4 * cg, H);
-      float4 v = ldg4(z + (int64_t)r * H + 4 * cg);
-      a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
-      b.x = fmaf(d.x, (v.x - mu.x) * is.x, b.x); b.y = fmaf(d.y, (v.y - mu.y) * is.y, b.y);
-      b.z = fmaf(d.z, (v.z - mu.z) * is.z, b.z); b.w = fmaf(d.w, (v.w - mu.w) * is.w, b.w);
+  const bool wide = (int)blockDim.x < cols4;
+  const int rif = wide ? 1 : (int)blockDim.x / cols4;
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
+  double* acc = reinterpret_cast<double*>(scratch + 16);
+  for (int cg0 = 0; cg0 < cols4; cg0 += blockDim.x) {
+    const int cg = wide ? cg0 + threadIdx.x : threadIdx.x % cols4;
+    const int rs = wide ? 0 : threadIdx.x / cols4;
+    const bool active = cg < cols4 && rs < rif;
+    double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+    if (active) {
+      const float4 mu = ldg4(mean + 4 * cg), is = ldg4(invstd + 4 * cg);
+#pragma unroll 2
+      for (int r = blockIdx.x * rif + rs; r < N; r += gridDim.x * rif) {
+        const float4 d = load_dh(src, r, 4 * cg, H);
+        const float4 v = ldg4(z + (int64_t)r * H + 4 * cg);
+        a[0] += (double)d.x; a[1] += (double)d.y; a[2] += (double)d.z; a[3] += (double)d.w;
+        b[0] += (double)(d.x * ((v.x - mu.x) * is.x)); b[1] += (double)(d.y * ((v.y - mu.y) * is.y));
+        b[2] += (double)(d.z * ((v.z - mu.z) * is.z)); b[3] += (double)(d.w * ((v.w - mu.w) * is.w));
+      }
     }
-    st4(s_1 + rs * H + 4 * cg, a);
-    st4(s_2 + rs * H + 4 * cg, b);
+    if (wide) {
+      if (active)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { atomicAdd(acc + 4 * cg + e, a[e]); atomicAdd(acc + H + 4 * cg + e, b[e]); }
+    } else {
+      bn_block_reduce_atomic(a, b, smem_d, H, rif, cg, rs, active, acc);
+      break;
+    }
   }
-  __syncthreads();
+  if (!last_block_ticket(counter, gridDim.x)) return;
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int rs = 0; rs < rif; ++rs) { a += s_1[rs * H + c]; b += s_2[rs * H + c]; }
-    p1[(int64_t)blockIdx.x * H + c] = a;
-    p2[(int64_t)blockIdx.x * H + c] = b;
-  }
-  if (!last_block_ticket(counter, nblk)) return;
-  const int used = (N + kBnRows - 1) / kBnRows;
-  for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    double a = 0.0, b = 0.0;
-    for (int k = 0; k < used; ++k) { a += (double)__ldcg(p1 + (int64_t)k * H + c); b += (double)__ldcg(p2 + (int64_t)k * H + c); }
+    const double a = __ldcg(acc + c), b = __ldcg(acc + H + c);
+    acc[c] = 0.0;
+    acc[H + c] = 0.0;
     dbeta[c] += (float)a;
     dgamma[c] += (float)b;
     means[c] = N > 0 ? (float)(a / N) : 0.f;
@@ -317,19 +319,20 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const int* __restrict
   extern __shared__ float smem[];
   const int N = dims[DIM_N];
   const int cols4 = H >> 2;
-  const int rif = max(1, (int)blockDim.x / cols4);
-  for (int r0 = blockIdx.x * kBnRows; r0 < N; r0 += gridDim.x * kBnRows) {
-    const int r1 = min(N, r0 + kBnRows);
-    __syncthreads();
-    for (int cg = threadIdx.x % cols4; cg < cols4; cg += (blockDim.x >= cols4 ? cols4 : blockDim.x)) {
-      const int rs = blockDim.x >= cols4 ? threadIdx.x / cols4 : 0;
-      if (rs >= rif) continue;
+  const bool wide = (int)blockDim.x < cols4;
+  const int rif = wide ? 1 : (int)blockDim.x / cols4;
+  for (int cg0 = 0; cg0 < cols4; cg0 += blockDim.x) {
+    const int cg = wide ? cg0 + threadIdx.x : threadIdx.x % cols4;
+    const int rs = wide ? 0 : threadIdx.x / cols4;
+    const bool active = cg < cols4 && rs < rif;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
       const float4 mu = ldg4(mean + 4 * cg), is = ldg4(invstd + 4 * cg), ga = ldg4(gamma + 4 * cg);
       const float4 m1 = ldg4(means + 4 * cg), m2 = ldg4(means + H + 4 * cg);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = r0 + rs; r < r1; r += rif) {
-        float4 d = load_dh(src, r, 4 * cg, H);
-        float4 v = ldg4(z + (int64_t)r * H + 4 * cg);
+#pragma unroll 2
+      for (int r = blockIdx.x * rif + rs; r < N; r += gridDim.x * rif) {
+        const float4 d = load_dh(src, r, 4 * cg, H);
+        const float4 v = ldg4(z + (int64_t)r * H + 4 * cg);
         const float ci = __ldg(norm + r);
         float4 o;
         o.x = v.x > 0.f ? ga.x * is.x * (d.x - m1.x - (v.x - mu.x) * is.x * m2.x) : 0.f;
@@ -340,13 +343,21 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const int* __restrict
         o.x *= ci; o.y *= ci; o.z *= ci; o.w *= ci;
         st4(q + (int64_t)r * H + 4 * cg, o);
       }
-      st4(smem + rs * H + 4 * cg, acc);
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < H; c += blockDim.x) {
-      float a = 0.f;
-      for (int rs = 0; rs < rif; ++rs) a += smem[rs * H + c];
-      atomicAdd(dbias + c, a);
+    if (wide) {
+      if (active) {
+        atomicAdd(dbias + 4 * cg + 0, acc.x); atomicAdd(dbias + 4 * cg + 1, acc.y);
+        atomicAdd(dbias + 4 * cg + 2, acc.z); atomicAdd(dbias + 4 * cg + 3, acc.w);
+      }
+    } else {
+      if (active) st4(smem + rs * H + 4 * cg, acc);
+      __syncthreads();
+      for (int c = threadIdx.x; c < H; c += blockDim.x) {
+        float a = 0.f;
+        for (int r = 0; r < rif; ++r) a += smem[r * H + c];
+        atomicAdd(dbias + c, a);
+      }
+      break;
     }
   }
 }
@@ -357,12 +368,12 @@ int launch_bn_bwd(const int* dims, const float* dh, const float* dG, const int* 
                   float* q, int max_nodes, cudaStream_t st) {
   if (H % 4 || H > 4096) return EIMS_ERR_ARG;
   DhSrc src{dh, dG, gid, gptr, argmax, pooling};
-  const int cols4 = H / 4;
-  const int rif = 256 / cols4 > 0 ? 256 / cols4 : 1;
-  size_t smem = (size_t)(2 * rif * H) * sizeof(float);
-  const int blocks = bn_blocks(max_nodes);
-  bn_bwd_stats_kernel<<<blocks, 256, smem, st>>>(dims, src, z, H, mean, invstd, dgamma, dbeta, means, partials);
-  bn_bwd_apply_kernel<<<blocks, 256, smem / 2, st>>>(dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias);
+  const int rif = bn_rif(H);
+  const int blocks = bn_blocks(H, max_nodes);
+  bn_bwd_stats_kernel<<<blocks, 256, (size_t)rif * 2 * H * sizeof(double), st>>>(dims, src, z, H, mean, invstd, dgamma,
+                                                                                 dbeta, means, partials);
+  bn_bwd_apply_kernel<<<blocks, 256, (size_t)rif * H * sizeof(float), st>>>(dims, src, z, H, mean, invstd, gamma, means,
+                                                                            norm, q, dbias);
   return 0;
 }
 

@@ -141,20 +141,23 @@ __device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, 
 //   offset(k, c) = (k/4)*(ROWS/32*512) + (c/8)*512 + (k%4)*128 + ((((c%8)>>1) ^ (k%4))*32) + (c&1)*16
 //   with c = 16-byte chunk along mn;  LBO = 512 (next 32 mn), SBO = ROWS/32*512 (next 4 k)
 template <int ROWS>
-__device__ __forceinline__ void produce_tile(const float* __restrict__ base, int ld, int mn_major, int vec, int mn0,
-                                             int mn_lim, int k0, int k_lim, uint8_t* hi_tile, uint8_t* lo_tile,
-                                             int t /*0..127*/) {
-  constexpr int CHUNKS = ROWS * BK / 4;   // 16-byte chunks in the tile
-  constexpr int PER = CHUNKS / 128;
+struct TileRegs {
+  static constexpr int PER = ROWS * BK / 4 / 128;  // 16-byte chunks per producer thread
   float4 v[PER];
-  uint32_t off[PER];
+};
+
+// global -> registers (issued early: the loads of a group's next k-block are in flight while
+// it waits for the stage to be released)
+template <int ROWS>
+__device__ __forceinline__ void tile_load(TileRegs<ROWS>& r, const float* __restrict__ base, int ld, int mn_major,
+                                          int vec, int mn0, int mn_lim, int k0, int k_lim, int t /*0..127*/) {
+  constexpr int PER = TileRegs<ROWS>::PER;
   if (!mn_major) {
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
-      const int idx = it * 128 + t, r = idx >> 3, c = idx & 7;
-      const int mn = mn0 + r, k = k0 + 4 * c;
-      v[it] = load_chunk(base, (int64_t)mn * ld + k, k, k_lim, mn < mn_lim, vec);
-      off[it] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+      const int idx = it * 128 + t, row = idx >> 3, c = idx & 7;
+      const int mn = mn0 + row, k = k0 + 4 * c;
+      r.v[it] = load_chunk(base, (int64_t)mn * ld + k, k, k_lim, mn < mn_lim, vec);
     }
   } else {
     constexpr int CPR = ROWS / 4;  // chunks per k-row
@@ -162,13 +165,33 @@ __device__ __forceinline__ void produce_tile(const float* __restrict__ base, int
     for (int it = 0; it < PER; ++it) {
       const int idx = it * 128 + t, kk = idx / CPR, c = idx % CPR;
       const int k = k0 + kk, mn = mn0 + 4 * c;
-      v[it] = load_chunk(base, (int64_t)k * ld + mn, mn, mn_lim, k < k_lim, vec);
-      off[it] = (uint32_t)((kk >> 2) * (ROWS / 32 * 512) + (c >> 3) * 512 + (kk & 3) * 128 +
-                           ((((c & 7) >> 1) ^ (kk & 3)) << 5) + ((c & 1) << 4));
+      r.v[it] = load_chunk(base, (int64_t)k * ld + mn, mn, mn_lim, k < k_lim, vec);
     }
   }
+}
+
+// registers -> hi/lo split -> canonical UMMA shared-memory layout
+template <int ROWS>
+__device__ __forceinline__ void tile_store(const TileRegs<ROWS>& r, int mn_major, uint8_t* hi_tile, uint8_t* lo_tile,
+                                           int t) {
+  constexpr int PER = TileRegs<ROWS>::PER;
+  if (!mn_major) {
 #pragma unroll
-  for (int it = 0; it < PER; ++it) store_split(hi_tile, lo_tile, off[it], v[it]);
+    for (int it = 0; it < PER; ++it) {
+      const int idx = it * 128 + t, row = idx >> 3, c = idx & 7;
+      store_split(hi_tile, lo_tile, (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4)), r.v[it]);
+    }
+  } else {
+    constexpr int CPR = ROWS / 4;
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const int idx = it * 128 + t, kk = idx / CPR, c = idx % CPR;
+      store_split(hi_tile, lo_tile,
+                  (uint32_t)((kk >> 2) * (ROWS / 32 * 512) + (c >> 3) * 512 + (kk & 3) * 128 +
+                             ((((c & 7) >> 1) ^ (kk & 3)) << 5) + ((c & 1) << 4)),
+                  r.v[it]);
+    }
+  }
 }
 
 template <int BN>
@@ -208,16 +231,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
   if (warp < kProducerWarps) {
     // ---------------------------------------------------------------- producers
     const int group = warp >> 2, t = threadIdx.x & 127;
+    TileRegs<BM> ra;
+    TileRegs<BN> rb;
+    if (group < nkb) {
+      const int k0 = (kb0 + group) * BK;
+      tile_load<BM>(ra, g.A, g.lda, g.a_mn, g.vec_a, m0, M, k0, K, t);
+      tile_load<BN>(rb, g.B, g.ldb, g.b_mn, g.vec_b, n0, N, k0, K, t);
+    }
     for (int i = group; i < nkb; i += 2) {
       const int s = i % STAGES;
       const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
       mbar_wait(empty0 + 8 * s, ph ^ 1u);
       uint8_t* st = smem + s * STAGE_BYTES;
-      const int k0 = (kb0 + i) * BK;
-      produce_tile<BM>(g.A, g.lda, g.a_mn, g.vec_a, m0, M, k0, K, st, st + A_TILE, t);
-      produce_tile<BN>(g.B, g.ldb, g.b_mn, g.vec_b, n0, N, k0, K, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, t);
+      tile_store<BM>(ra, g.a_mn, st, st + A_TILE, t);
+      tile_store<BN>(rb, g.b_mn, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, t);
       fence_proxy_async();
       mbar_arrive(full0 + 8 * s);
+      if (i + 2 < nkb) {  // prefetch this group's next k-block while the tensor core works
+        const int k0 = (kb0 + i + 2) * BK;
+        tile_load<BM>(ra, g.A, g.lda, g.a_mn, g.vec_a, m0, M, k0, K, t);
+        tile_load<BN>(rb, g.B, g.ldb, g.b_mn, g.vec_b, n0, N, k0, K, t);
+      }
     }
     // ---------------------------------------------------------------- epilogue
     mbar_wait(accum_bar, 0);
@@ -322,13 +356,28 @@ int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, i
     attr_done = true;
   }
   const int mt = (M + BM - 1) / BM, nt = (N + BN - 1) / BN;
+  const int kblocks = (K + BK - 1) / BK;
   int splits = 1;
-  if (accumulate) {  // split-K: weight gradients reduce over atoms / graphs
-    const int kblocks = (K + BK - 1) / BK;
+  if (accumulate == 1) {  // split-K: weight gradients reduce over atoms / graphs
     splits = (148 + mt * nt - 1) / (mt * nt);
     const int maxs = (kblocks + 3) / 4;  // at least 4 k-blocks per slice
     if (splits > maxs) splits = maxs;
     if (splits < 1) splits = 1;
+  } else if (accumulate == 2) {
+    // store semantics, but the caller tolerates atomic accumulation order (backward dgrads of the
+    // 512-row head): when the tile grid cannot fill the chip, split K and add into a zeroed C.
+    g.accumulate = 0;
+    if (!relu && !row_scale && mt * nt <= 37 && kblocks >= 8 && ldc == N) {
+      splits = 148 / (mt * nt);
+      const int maxs = kblocks / 4;
+      if (splits > maxs) splits = maxs;
+      if (splits > 1) {
+        if (cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st) != cudaSuccess) return EIMS_ERR_CUDA;
+        g.accumulate = 1;
+      } else {
+        splits = 1;
+      }
+    }
   }
   dim3 grid(nt, mt, splits);
   gemm_3xtf32_kernel<BN><<<grid, kThreads, smem_bytes, st>>>(g);

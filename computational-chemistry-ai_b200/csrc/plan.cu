@@ -436,21 +436,21 @@ int eims_backward(eims_plan* p, const float* params, const float* dprob, float* 
                 nullptr, 0, 1, st));
   STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, dl, M, M, grads + p->off_head(9), p->Bc, st));
   STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, dl, M, 0, params + p->off_head(8), H, 1, p->f("dy2"), H, p->Bc, H, M, dims + DIM_B, nullptr, nullptr,
-                nullptr, 0, 0, st));
+                nullptr, 0, 2, st));
   STAGE(ST_LN_BWD, 1, launch_ln_bwd(dims, p->f("u2"), p->f("y2"), p->f("dy2"), H, params + p->off_head(6), p->f("ln2"), drop_scale,
                          p->f("dy2"), grads + p->off_head(6), grads + p->off_head(7), p->Bc, st));
   STAGE(ST_GEMM_HEAD_WGRAD, 1, gemm(p, p->f("dy2"), H, 1, p->f("y1"), 2 * H, 1, grads + p->off_head(4), 2 * H, H, 2 * H, p->Bc, nullptr,
                 dims + DIM_B, nullptr, nullptr, 0, 1, st));
   STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, p->f("dy2"), H, H, grads + p->off_head(5), p->Bc, st));
   STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, p->f("dy2"), H, 0, params + p->off_head(4), 2 * H, 1, p->f("dy1"), 2 * H, p->Bc, 2 * H, H,
-                dims + DIM_B, nullptr, nullptr, nullptr, 0, 0, st));
+                dims + DIM_B, nullptr, nullptr, nullptr, 0, 2, st));
   STAGE(ST_LN_BWD, 1, launch_ln_bwd(dims, p->f("u1"), p->f("y1"), p->f("dy1"), 2 * H, params + p->off_head(2), p->f("ln1"),
                          drop_scale, p->f("dy1"), grads + p->off_head(2), grads + p->off_head(3), p->Bc, st));
   STAGE(ST_GEMM_HEAD_WGRAD, 1, gemm(p, p->f("dy1"), 2 * H, 1, p->f("readout"), P, 1, grads + p->off_head(0), P, 2 * H, P, p->Bc, nullptr,
                 dims + DIM_B, nullptr, nullptr, 0, 1, st));
   STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, p->f("dy1"), 2 * H, 2 * H, grads + p->off_head(1), p->Bc, st));
   STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, p->f("dy1"), 2 * H, 0, params + p->off_head(0), P, 1, p->f("dG"), P, p->Bc, P, 2 * H, dims + DIM_B,
-                nullptr, nullptr, nullptr, 0, 0, st));
+                nullptr, nullptr, nullptr, 0, 2, st));
   // ---- GCN layers, last to first (GCN:358-363 backwards)
   for (int l = L - 1; l >= 0; --l) {
     const bool from_readout = (l == L - 1);

@@ -224,19 +224,42 @@ def test_batched_inference_equals_single(backend):
 
 
 def test_full_size_properties():
-    """BASELINE cfg-2 shapes (batch 512, H 256, M 1000): size-independent properties -
-    tcgen05 and CUDA-core GEMM paths agree, gradients are replay-stable, loss decreases."""
+    """BASELINE cfg-2 shapes (batch 512, H 256, M 1000, N ~ 17k atoms).
+
+    At this size gradient parity is limited by conditioning, not by the kernels: 40 % of the
+    layer-0 BatchNorm columns are nearly dead (invstd up to 316) and one ReLU sign flip among
+    ~4 M pre-activations moves the early-layer gradients by ~1e-3.  So the bar
+    is set by the reference arithmetic itself: the fp32 oracle's distance from the fp64 oracle.
+    Spectra and loss must still meet 1e-4; each gradient tensor must be within
+    max(1e-4, 4 x the fp32 oracle's own error) of the fp64 oracle.  Plus: both GEMM paths
+    agree on spectra, a replay gives bit-identical spectra, the loss goes down."""
+    import json
     d = ModelDims(hidden_dim=256, max_mz=1000, dropout=0.0)
     table, targets, plan, ds, fp, sd = setup(d, 512, 64, 1234, "tcgen05")
     ids = torch.arange(512, dtype=torch.int32, device=DEV)
-    p1, l1, c1, g1 = gpu_fwd_bwd(plan, ds, fp, ids, make_step())
-    plan.set_gemm_backend("simt")
-    p2, l2, c2, g2 = gpu_fwd_bwd(plan, ds, fp, ids, make_step())
-    assert rel_err(p1, p2) < REL and abs(l1 - l2) < REL * l2
-    worst = {n: rel_err(g1[n], g2[n]) for n in g1}
-    assert max(worst.values()) < 2e-3, worst  # ReLU sign flips between two fp32 paths (SURVEY 7.3-2)
-    assert np.median(list(worst.values())) < REL
+    graph, feat = O.Graph.from_mols([table.mol(i) for i in range(512)])
+    tt = torch.from_numpy(targets)
+    p64, l64, g64, _ = O.loss_and_grads(sd, graph, feat, tt, odims(d), dtype=torch.float64)
+    p32, l32, g32, _ = O.loss_and_grads(sd, graph, feat, tt, odims(d))
+    report = {"oracle_fp32_vs_fp64": {n: rel_err(g32[n].numpy(), g64[n].numpy()) for n in g64}}
+    preds = {}
+    for backend in ("tcgen05", "simt"):
+        plan.set_gemm_backend(backend)
+        prob, loss, cos, grads = gpu_fwd_bwd(plan, ds, fp, ids, make_step())
+        preds[backend] = prob
+        assert rel_err(prob, p64.numpy()) < REL
+        assert abs(loss - float(l64)) < REL * float(l64)
+        errs = {n: rel_err(grads[n], g64[n].numpy()) for n in grads}
+        report[f"{backend}_vs_fp64"] = errs
+        for n, e in errs.items():
+            assert e < max(REL, 4 * report["oracle_fp32_vs_fp64"][n]), (backend, n, e, report["oracle_fp32_vs_fp64"][n])
+    assert rel_err(preds["tcgen05"], preds["simt"]) < REL
     plan.set_gemm_backend("tcgen05")
+    prob2, _, _, _ = gpu_fwd_bwd(plan, ds, fp, ids, make_step())
+    assert np.array_equal(prob2, preds["tcgen05"])  # forward is deterministic (no float atomics on that path)
+    os.makedirs(os.path.join(os.path.dirname(golden_path()), "..", "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(golden_path()), "..", "gpurun_out", "fullsize_grad_errors.json"), "w") as fh:
+        json.dump(report, fh, indent=1)
     sched = onecycle_schedule(30)
     losses = []
     for k in range(30):
@@ -245,3 +268,7 @@ def test_full_size_properties():
         losses.append(float(m[4]))
     assert losses[-1] < losses[0]
     assert np.isfinite(losses).all()
+
+
+def golden_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
