@@ -21,7 +21,7 @@ namespace eims {
 
 namespace tc {
 
-constexpr int BM = 128, BK = 32, STAGES = 3;
+constexpr int BM = 128, BK = 32;
 constexpr int kProducerWarps = 8, kThreads = (kProducerWarps + 1) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -160,10 +160,11 @@ __device__ __forceinline__ void tile_load(TileRegs<ROWS>& r, const float* __rest
       r.v[it] = load_chunk(base, (int64_t)mn * ld + k, k, k_lim, mn < mn_lim, vec);
     }
   } else {
-    constexpr int CPR = ROWS / 4;  // chunks per k-row
+    // one warp = one 512-byte atom (4 k-rows x 32 mn): lanes 0-7 -> k-row 0, 8-15 -> k-row 1, ...
+    constexpr int MNA = ROWS / 32;  // mn atoms per tile row
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
-      const int idx = it * 128 + t, kk = idx / CPR, c = idx % CPR;
+      const int atom = it * 4 + (t >> 5), kk = (atom / MNA) * 4 + ((t >> 3) & 3), c = (atom % MNA) * 8 + (t & 7);
       const int k = k0 + kk, mn = mn0 + 4 * c;
       r.v[it] = load_chunk(base, (int64_t)k * ld + mn, mn, mn_lim, k < k_lim, vec);
     }
@@ -182,10 +183,10 @@ __device__ __forceinline__ void tile_store(const TileRegs<ROWS>& r, int mn_major
       store_split(hi_tile, lo_tile, (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4)), r.v[it]);
     }
   } else {
-    constexpr int CPR = ROWS / 4;
+    constexpr int MNA = ROWS / 32;
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
-      const int idx = it * 128 + t, kk = idx / CPR, c = idx % CPR;
+      const int atom = it * 4 + (t >> 5), kk = (atom / MNA) * 4 + ((t >> 3) & 3), c = (atom % MNA) * 8 + (t & 7);
       store_split(hi_tile, lo_tile,
                   (uint32_t)((kk >> 2) * (ROWS / 32 * 512) + (c >> 3) * 512 + (kk & 3) * 128 +
                              ((((c & 7) >> 1) ^ (kk & 3)) << 5) + ((c & 1) << 4)),
@@ -194,7 +195,7 @@ __device__ __forceinline__ void tile_store(const TileRegs<ROWS>& r, int mn_major
   }
 }
 
-template <int BN>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
   constexpr int A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;
   constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
@@ -254,45 +255,66 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
       }
     }
     // ---------------------------------------------------------------- epilogue
+    // TMEM -> registers (row scale) -> shared staging tile (the pipeline stages are free once
+    // the accumulator barrier has fired) -> bias / ReLU -> coalesced 512-byte row stores.
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
-    const int m = m0 + q * 32 + lane;
-    const float rs = (g.row_scale && m < M) ? __ldg(g.row_scale + m) : 1.f;
-    const bool add_bias = g.bias && (!g.accumulate || blockIdx.z == 0);
+    constexpr int LDS = BN + 4;  // padded row stride (floats): conflict-free float4 row writes
+    float* stage = reinterpret_cast<float*>(smem);
+    {
+      const int q = warp & 3, half = warp >> 2;
+      const int row = q * 32 + lane, m = m0 + row;
+      const float rs = (g.row_scale && m < M) ? __ldg(g.row_scale + m) : 1.f;
 #pragma unroll 1
-    for (int cb = 0; cb < BN / 2; cb += 32) {
-      const int col0 = half * (BN / 2) + cb;
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
-      if (m < M) {
-        float* crow = g.C + (int64_t)m * g.ldc;
+      for (int cb = 0; cb < BN / 2; cb += 32) {
+        const int col0 = half * (BN / 2) + cb;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
+        float* dst = stage + row * LDS + col0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + col0 + j;
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float v = __uint_as_float(r[j + e]) * rs;
-            if (add_bias && n + e < N) v += __ldg(g.bias + n + e);
-            if (g.relu) v = fmaxf(v, 0.f);
-            o[e] = v;
-          }
+        for (int j = 0; j < 32; j += 4)
+          st4(dst + j, make_float4(__uint_as_float(r[j]) * rs, __uint_as_float(r[j + 1]) * rs,
+                                   __uint_as_float(r[j + 2]) * rs, __uint_as_float(r[j + 3]) * rs));
+      }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+    {
+      const bool add_bias = g.bias && (!g.accumulate || blockIdx.z == 0);
+      const bool vec_out = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
+      for (int c = 4 * lane; c < BN; c += 128) {
+        const int n = n0 + c;
+        if (n >= N) break;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (add_bias) {
+          b4.x = __ldg(g.bias + n);
+          if (n + 1 < N) b4.y = __ldg(g.bias + n + 1);
+          if (n + 2 < N) b4.z = __ldg(g.bias + n + 2);
+          if (n + 3 < N) b4.w = __ldg(g.bias + n + 3);
+        }
+        for (int row = warp; row < BM; row += kProducerWarps) {
+          const int m = m0 + row;
+          if (m >= M) break;
+          float4 v = *reinterpret_cast<const float4*>(stage + row * LDS + c);
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          float* dst = g.C + (int64_t)m * g.ldc + n;
           if (g.accumulate) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n + e < N) atomicAdd(crow + n + e, o[e]);
-          } else if (n + 3 < N && ((g.ldc & 3) == 0)) {
-            st4(crow + n, make_float4(o[0], o[1], o[2], o[3]));
+            atomicAdd(dst, v.x);
+            if (n + 1 < N) atomicAdd(dst + 1, v.y);
+            if (n + 2 < N) atomicAdd(dst + 2, v.z);
+            if (n + 3 < N) atomicAdd(dst + 3, v.w);
+          } else if (vec_out && n + 3 < N) {
+            st4(dst, v);
           } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n + e < N) crow[n + e] = o[e];
+            dst[0] = v.x;
+            if (n + 1 < N) dst[1] = v.y;
+            if (n + 2 < N) dst[2] = v.z;
+            if (n + 3 < N) dst[3] = v.w;
           }
         }
       }
     }
-    tc_fence_before();
   } else {
     // ---------------------------------------------------------------- MMA issuer
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) |
@@ -347,12 +369,17 @@ int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, i
   Args g{A, B, C, lda, ldb, ldc, a_mn, b_mn, M, N, K, m_dev, k_dev, row_scale, bias, relu, accumulate, 0, 0};
   g.vec_a = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 4 == 0);
   g.vec_b = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 4 == 0);
-  constexpr int BN = 128;
-  constexpr int smem_bytes = STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
+  // 128 x 256 tiles (A read once per row block, 2 stages) when the problem is tall enough to
+  // fill the chip with them; 128 x 128 tiles (3 stages) otherwise.
+  const bool wide = (N % 256 == 0) && ((int64_t)((M + BM - 1) / BM) * (N / 256) >= 64 || (accumulate == 1 && K >= 4096));
+  const int BN = wide ? 256 : 128;
+  const int stages = wide ? 2 : 3;
+  const int smem_bytes = stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return EIMS_ERR_CUDA;
+    cudaError_t e1 = cudaFuncSetAttribute(gemm_3xtf32_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * BM * BK * 4 + 2 * 128 * BK * 4) + 1024);
+    cudaError_t e2 = cudaFuncSetAttribute(gemm_3xtf32_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * BM * BK * 4 + 2 * 256 * BK * 4) + 1024);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return EIMS_ERR_CUDA;
     attr_done = true;
   }
   const int mt = (M + BM - 1) / BM, nt = (N + BN - 1) / BN;
@@ -380,7 +407,8 @@ int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, i
     }
   }
   dim3 grid(nt, mt, splits);
-  gemm_3xtf32_kernel<BN><<<grid, kThreads, smem_bytes, st>>>(g);
+  if (wide) gemm_3xtf32_kernel<256, 2><<<grid, kThreads, smem_bytes, st>>>(g);
+  else gemm_3xtf32_kernel<128, 3><<<grid, kThreads, smem_bytes, st>>>(g);
   return 0;
 }
 
