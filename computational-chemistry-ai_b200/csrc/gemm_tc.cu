@@ -3,15 +3,18 @@
 //   A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi       (the dropped lo*lo term is ~2^-22 relative)
 // which is what the 1e-4 spectrum / gradient bar needs (single-pass TF32 gives 3e-3).
 //
-// Structure of one CTA (288 threads), one 128 x BN output tile:
-//   warps 0-7  producers: 128-bit global loads of the fp32 A / B tiles (either storage order),
+// Structure of one CTA (544 threads), one 128 x BN output tile:
+//   warps 0-15 producers: 128-bit global loads of the fp32 A / B tiles (either storage order),
 //              hi/lo split in registers, st.shared into the canonical UMMA SWIZZLE_128B layout
-//              (K-major or MN-major, so no transposes anywhere), fence.proxy.async, mbarrier
-//              arrive.  Two groups of 4 warps alternate k-blocks so two are in flight.
-//   warp  8    one elected lane issues 12 tcgen05.mma per k-block (4 k-steps x 3 products) and
+//              (K-major or MN-major, so no transposes anywhere), fence.proxy.async, one mbarrier
+//              arrive per warp.  Two groups of 8 warps alternate k-blocks so two are in flight.
+//              Interior tiles take a predicate-free path (thread-constant global / shared offsets,
+//              one pointer bump per k-block); edge tiles and the K tail take the checked path.
+//   warp  16   one elected lane issues 12 tcgen05.mma per k-block (4 k-steps x 3 products) and
 //              tcgen05.commit's the stage back to the producers.
-//   warps 0-7  epilogue: tcgen05.ld the accumulator (lane quarter = warp%4, column half =
-//              warp/4), apply row scale / bias / ReLU, store or red.add (split-K).
+//   warps 0-15 epilogue: tcgen05.ld the accumulator (lane quarter = warp%4, 32-column slices by
+//              warp/4) -> row scale -> shared staging tile -> bias / ReLU -> coalesced row stores
+//              or red.global.add.v4.f32 (split-K).
 // Sizes M and K may live in device memory (atoms in the current batch) so a captured step
 // can be replayed; tiles past the live range exit before touching barriers or TMEM.
 #include "common.cuh"
@@ -22,7 +25,7 @@ namespace eims {
 namespace tc {
 
 constexpr int BM = 128, BK = 32;
-constexpr int kProducerWarps = 8, kThreads = (kProducerWarps + 1) * 32;
+constexpr int kProducerWarps = 16, kGroupThreads = 256, kThreads = (kProducerWarps + 1) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -96,10 +99,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi).  cvt.rna.tf32.f32 has no SASS
+// instruction on sm_100 (it expands to a NaN/Inf test, an add, a select and a mask), so the
+// round-to-nearest-away is done directly on the magnitude bits: +2^12, clear the 13 low bits.
+// Identical to cvt.rna for every finite input (Inf stays Inf, NaN stays NaN).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  const float r = x - __uint_as_float(hi);
+  lo = (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
 }
 
 struct Args {
@@ -125,74 +132,121 @@ __device__ __forceinline__ float4 load_chunk(const float* base, int64_t off, int
   return v;
 }
 
-__device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, uint32_t off, float4 v) {
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void store_split(uint32_t hi_saddr, uint32_t lo_saddr, float4 v) {
   uint4 h, l;
   split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-  *reinterpret_cast<uint4*>(hi_tile + off) = h;
-  *reinterpret_cast<uint4*>(lo_tile + off) = l;
+  sts128(hi_saddr, h);
+  sts128(lo_saddr, l);
 }
 
 // Tile of an operand with ROWS "MN" rows and BK k-columns, written by one producer group
-// (128 threads).  mn_major = 0: memory is [mn][k] (k contiguous) -> canonical K-major
+// (256 threads).  mn_major = 0: memory is [mn][k] (k contiguous) -> canonical K-major
 // SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index XOR row%8):
 //   offset(r, c) = (r/8)*1024 + (r%8)*128 + ((c ^ (r%8))*16)          c = 16-byte chunk along k
 // mn_major = 1: memory is [k][mn] (mn contiguous) -> canonical MN-major SWIZZLE_128B_BASE32B
 // layout (atoms of 4 k-rows x 128 bytes = 32 mn elements; 32-byte chunk index XOR k%4):
 //   offset(k, c) = (k/4)*(ROWS/32*512) + (c/8)*512 + (k%4)*128 + ((((c%8)>>1) ^ (k%4))*32) + (c&1)*16
 //   with c = 16-byte chunk along mn;  LBO = 512 (next 32 mn), SBO = ROWS/32*512 (next 4 k)
+// Work split: chunk `it` of thread t.  K-major: chunk index it*256+t -> row = it*32 + t/8,
+// c = t%8.  MN-major: one warp = one 512-byte atom (lanes 0-7 -> k-row 0, 8-15 -> k-row 1, ..),
+// atom = it*8 + t/32.  In both layouts the shared offset is  soff(t) + it*4096  and the global
+// element offset is  goff(t) + it*gstride,  which is what the predicate-free path uses.
 template <int ROWS>
 struct TileRegs {
-  static constexpr int PER = ROWS * BK / 4 / 128;  // 16-byte chunks per producer thread
+  static constexpr int PER = ROWS * BK / 4 / kGroupThreads;  // 16-byte chunks per producer thread
   float4 v[PER];
 };
 
-// global -> registers (issued early: the loads of a group's next k-block are in flight while
-// it waits for the stage to be released)
+// (k, mn) element coordinates inside the tile of chunk `it` of thread t
 template <int ROWS>
-__device__ __forceinline__ void tile_load(TileRegs<ROWS>& r, const float* __restrict__ base, int ld, int mn_major,
-                                          int vec, int mn0, int mn_lim, int k0, int k_lim, int t /*0..127*/) {
-  constexpr int PER = TileRegs<ROWS>::PER;
+__device__ __forceinline__ void chunk_coords(int mn_major, int it, int t, int& mn, int& k) {
   if (!mn_major) {
-#pragma unroll
-    for (int it = 0; it < PER; ++it) {
-      const int idx = it * 128 + t, row = idx >> 3, c = idx & 7;
-      const int mn = mn0 + row, k = k0 + 4 * c;
-      r.v[it] = load_chunk(base, (int64_t)mn * ld + k, k, k_lim, mn < mn_lim, vec);
-    }
+    const int idx = it * kGroupThreads + t;
+    mn = idx >> 3;
+    k = (idx & 7) * 4;
   } else {
-    // one warp = one 512-byte atom (4 k-rows x 32 mn): lanes 0-7 -> k-row 0, 8-15 -> k-row 1, ...
-    constexpr int MNA = ROWS / 32;  // mn atoms per tile row
-#pragma unroll
-    for (int it = 0; it < PER; ++it) {
-      const int atom = it * 4 + (t >> 5), kk = (atom / MNA) * 4 + ((t >> 3) & 3), c = (atom % MNA) * 8 + (t & 7);
-      const int k = k0 + kk, mn = mn0 + 4 * c;
-      r.v[it] = load_chunk(base, (int64_t)k * ld + mn, mn, mn_lim, k < k_lim, vec);
-    }
+    constexpr int MNA = ROWS / 32;  // mn atoms per 4-k-row group
+    const int atom = it * 8 + (t >> 5);
+    k = (atom / MNA) * 4 + ((t >> 3) & 3);
+    mn = ((atom % MNA) * 8 + (t & 7)) * 4;
   }
 }
 
-// registers -> hi/lo split -> canonical UMMA shared-memory layout
+// shared-memory byte offset of chunk 0 of thread t (chunk `it` is 4096 bytes further)
 template <int ROWS>
-__device__ __forceinline__ void tile_store(const TileRegs<ROWS>& r, int mn_major, uint8_t* hi_tile, uint8_t* lo_tile,
-                                           int t) {
-  constexpr int PER = TileRegs<ROWS>::PER;
+__device__ __forceinline__ uint32_t chunk_soff(int mn_major, int t) {
   if (!mn_major) {
-#pragma unroll
-    for (int it = 0; it < PER; ++it) {
-      const int idx = it * 128 + t, row = idx >> 3, c = idx & 7;
-      store_split(hi_tile, lo_tile, (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4)), r.v[it]);
-    }
-  } else {
-    constexpr int MNA = ROWS / 32;
-#pragma unroll
-    for (int it = 0; it < PER; ++it) {
-      const int atom = it * 4 + (t >> 5), kk = (atom / MNA) * 4 + ((t >> 3) & 3), c = (atom % MNA) * 8 + (t & 7);
-      store_split(hi_tile, lo_tile,
-                  (uint32_t)((kk >> 2) * (ROWS / 32 * 512) + (c >> 3) * 512 + (kk & 3) * 128 +
-                             ((((c & 7) >> 1) ^ (kk & 3)) << 5) + ((c & 1) << 4)),
-                  r.v[it]);
-    }
+    const int row = t >> 3, c = t & 7;
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
   }
+  const int kk = (t >> 3) & 3, c = t & 7;
+  return (uint32_t)((t >> 5) * 512 + kk * 128 + (((c >> 1) ^ kk) << 5) + ((c & 1) << 4));
+}
+
+// One operand as seen by one producer thread.
+template <int ROWS>
+struct Operand {
+  const float* base;   // matrix origin
+  const float* fast;   // pointer of chunk 0 of this thread in the group's current k-block
+  int64_t kadv;        // elements between successive k-blocks of this group (2*BK or 2*BK*ld)
+  int64_t gstride;     // elements between chunks it and it+1
+  int ld, mn_major, vec, mn0, mn_lim, full;
+  uint32_t soff;
+
+  __device__ __forceinline__ void init(const float* b, int ld_, int mn_major_, int vec_, int mn0_, int mn_lim_, int kbeg,
+                                       int t) {
+    base = b; ld = ld_; mn_major = mn_major_; vec = vec_; mn0 = mn0_; mn_lim = mn_lim_;
+    full = vec_ && (mn0_ + ROWS <= mn_lim_);
+    int mn, k, mn1, k1;
+    chunk_coords<ROWS>(mn_major_, 0, t, mn, k);
+    chunk_coords<ROWS>(mn_major_, 1, t, mn1, k1);
+    if (!mn_major_) {
+      fast = b + (int64_t)(mn0_ + mn) * ld_ + kbeg + k;
+      gstride = (int64_t)(mn1 - mn) * ld_;
+      kadv = 2 * BK;
+    } else {
+      fast = b + (int64_t)(kbeg + k) * ld_ + mn0_ + mn;
+      gstride = (int64_t)(k1 - k) * ld_ + (mn1 - mn);
+      kadv = (int64_t)2 * BK * ld_;
+    }
+    soff = chunk_soff<ROWS>(mn_major_, t);
+  }
+
+  // global -> registers for the k-block starting at k0 (issued early: the loads of a group's
+  // next k-block are in flight while it waits for the stage to be released)
+  __device__ __forceinline__ void load(TileRegs<ROWS>& r, int k0, int k_lim, int t) {
+    constexpr int PER = TileRegs<ROWS>::PER;
+    if (full && k0 + BK <= k_lim) {
+#pragma unroll
+      for (int it = 0; it < PER; ++it) r.v[it] = ldg4(fast + it * gstride);
+    } else {
+#pragma unroll
+      for (int it = 0; it < PER; ++it) {
+        int mn, k;
+        chunk_coords<ROWS>(mn_major, it, t, mn, k);
+        mn += mn0;
+        k += k0;
+        if (!mn_major) r.v[it] = load_chunk(base, (int64_t)mn * ld + k, k, k_lim, mn < mn_lim, vec);
+        else r.v[it] = load_chunk(base, (int64_t)k * ld + mn, mn, mn_lim, k < k_lim, vec);
+      }
+    }
+    fast += kadv;
+  }
+
+  // registers -> hi/lo split -> canonical UMMA shared-memory layout
+  __device__ __forceinline__ void store(const TileRegs<ROWS>& r, uint32_t hi_tile, uint32_t lo_tile) const {
+    constexpr int PER = TileRegs<ROWS>::PER;
+#pragma unroll
+    for (int it = 0; it < PER; ++it) store_split(hi_tile + soff + it * 4096u, lo_tile + soff + it * 4096u, r.v[it]);
+  }
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 template <int BN, int STAGES>
@@ -219,39 +273,45 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, kGroupThreads / 32); mbar_init(empty0 + 8 * s, 1); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kProducerWarps) tmem_alloc(smem_u32(&tmem_base_slot), BN);
+  if (warp == kProducerWarps) tmem_alloc(smem_u32(&tmem_base_slot), BN < 32 ? 32 : BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t smem_base = smem_u32(smem);
 
   if (warp < kProducerWarps) {
     // ---------------------------------------------------------------- producers
-    const int group = warp >> 2, t = threadIdx.x & 127;
+    const int group = warp >> 3, t = threadIdx.x & (kGroupThreads - 1);
     TileRegs<BM> ra;
     TileRegs<BN> rb;
+    Operand<BM> oa;
+    Operand<BN> ob;
+    oa.init(g.A, g.lda, g.a_mn, g.vec_a, m0, M, (kb0 + group) * BK, t);
+    ob.init(g.B, g.ldb, g.b_mn, g.vec_b, n0, N, (kb0 + group) * BK, t);
     if (group < nkb) {
       const int k0 = (kb0 + group) * BK;
-      tile_load<BM>(ra, g.A, g.lda, g.a_mn, g.vec_a, m0, M, k0, K, t);
-      tile_load<BN>(rb, g.B, g.ldb, g.b_mn, g.vec_b, n0, N, k0, K, t);
+      oa.load(ra, k0, K, t);
+      ob.load(rb, k0, K, t);
     }
     for (int i = group; i < nkb; i += 2) {
       const int s = i % STAGES;
       const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
       mbar_wait(empty0 + 8 * s, ph ^ 1u);
-      uint8_t* st = smem + s * STAGE_BYTES;
-      tile_store<BM>(ra, g.a_mn, st, st + A_TILE, t);
-      tile_store<BN>(rb, g.b_mn, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE, t);
+      const uint32_t st = smem_base + s * STAGE_BYTES;
+      oa.store(ra, st, st + A_TILE);
+      ob.store(rb, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE);
       fence_proxy_async();
-      mbar_arrive(full0 + 8 * s);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full0 + 8 * s);
       if (i + 2 < nkb) {  // prefetch this group's next k-block while the tensor core works
         const int k0 = (kb0 + i + 2) * BK;
-        tile_load<BM>(ra, g.A, g.lda, g.a_mn, g.vec_a, m0, M, k0, K, t);
-        tile_load<BN>(rb, g.B, g.ldb, g.b_mn, g.vec_b, n0, N, k0, K, t);
+        oa.load(ra, k0, K, t);
+        ob.load(rb, k0, K, t);
       }
     }
     // ---------------------------------------------------------------- epilogue
@@ -262,12 +322,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
     constexpr int LDS = BN + 4;  // padded row stride (floats): conflict-free float4 row writes
     float* stage = reinterpret_cast<float*>(smem);
     {
-      const int q = warp & 3, half = warp >> 2;
+      const int q = warp & 3;
       const int row = q * 32 + lane, m = m0 + row;
       const float rs = (g.row_scale && m < M) ? __ldg(g.row_scale + m) : 1.f;
 #pragma unroll 1
-      for (int cb = 0; cb < BN / 2; cb += 32) {
-        const int col0 = half * (BN / 2) + cb;
+      for (int col0 = (warp >> 2) * 32; col0 < BN; col0 += 128) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
         float* dst = stage + row * LDS + col0;
@@ -278,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
       }
     }
     tc_fence_before();
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+    asm volatile("bar.sync 1, 512;" ::: "memory");  // the 16 epilogue warps only
     {
       const bool add_bias = g.bias && (!g.accumulate || blockIdx.z == 0);
       const bool vec_out = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
@@ -292,6 +351,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
           if (n + 2 < N) b4.z = __ldg(g.bias + n + 2);
           if (n + 3 < N) b4.w = __ldg(g.bias + n + 3);
         }
+        const bool v4 = vec_out && n + 3 < N;
+#pragma unroll 4
         for (int row = warp; row < BM; row += kProducerWarps) {
           const int m = m0 + row;
           if (m >= M) break;
@@ -300,11 +361,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
           if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
           float* dst = g.C + (int64_t)m * g.ldc + n;
           if (g.accumulate) {
-            atomicAdd(dst, v.x);
-            if (n + 1 < N) atomicAdd(dst + 1, v.y);
-            if (n + 2 < N) atomicAdd(dst + 2, v.z);
-            if (n + 3 < N) atomicAdd(dst + 3, v.w);
-          } else if (vec_out && n + 3 < N) {
+            if (v4) {
+              red_add_v4(dst, v);
+            } else {
+              atomicAdd(dst, v.x);
+              if (n + 1 < N) atomicAdd(dst + 1, v.y);
+              if (n + 2 < N) atomicAdd(dst + 2, v.z);
+              if (n + 3 < N) atomicAdd(dst + 3, v.w);
+            }
+          } else if (v4) {
             st4(dst, v);
           } else {
             dst[0] = v.x;
@@ -333,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
       mbar_wait(full0 + 8 * s, ph);
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t a_hi = sa, a_lo = sa + A_TILE, b_hi = sa + 2 * A_TILE, b_lo = b_hi + B_TILE;
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
@@ -355,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
   __syncthreads();
   if (warp == kProducerWarps) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
   }
 }
 
