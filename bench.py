@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one-shot all-reduce after backward instead of two overlapped buckets")
     ap.add_argument("--profile-steps", type=int, default=20)
     return ap.parse_args()
 
@@ -200,6 +201,7 @@ def workload_config(n_gpus):
 def run_ours(args):
     import torch
     import torch.distributed as dist
+    from eims_b200.dist import GradReducer, broadcast_params, train_step_dp
     from eims_b200.engine import DeviceDataset, FlatParams, ModelDims, Plan, make_step, onecycle_schedule
     from eims_b200.hostpath import HostBatchRunner, PackedHostBatch
     from eims_b200.synth import dense_spectra, synth_molecules, synth_peaks
@@ -230,8 +232,8 @@ def run_ours(args):
     plan = Plan(d, BATCH, cap_nodes, cap_edges, dev, gemm_backend=args.gemm)
     fp = FlatParams(d, dev)
     init_weights(fp, d)
-    if world > 1:
-        dist.broadcast(fp.params, 0)
+    broadcast_params(fp)
+    reducer = GradReducer(fp.offsets, L, overlap=not args.no_overlap)
     perm = torch.from_numpy(perm_host).to(dev)
     sched = onecycle_schedule(max(steps_total * 4, 100))
     metrics = torch.zeros(8, device=dev)
@@ -240,12 +242,7 @@ def run_ours(args):
     def step_fn(i, k):
         ids = perm[i * BATCH:(i + 1) * BATCH]
         st = make_step(lr=sched[k][0], beta1=sched[k][1], grad_scale=gscale, step=k + 1, seed=2024 + rank)
-        if world == 1:
-            plan.train_step(ds, ids, fp, st, metrics)
-        else:
-            plan.train_step(ds, ids, fp, st, metrics, optimizer=False)
-            dist.all_reduce(fp.grads)
-            plan.adamw(fp, st)
+        train_step_dp(plan, ds, ids, fp, st, reducer, metrics)
 
     k = 0
     for i in range(args.warmup):

@@ -78,7 +78,7 @@ struct eims_plan {
   std::vector<int64_t> poff;  // parameter offsets
   std::vector<std::pair<std::string, int64_t>> order;  // name -> bytes (carve order)
   std::map<std::string, Buf> buf;
-  int state;  // 0 none, 1 batch built, 2 forward(train) done, 3 loss grad ready
+  int state;  // 0 none, 1 batch built, 2 forward(train) done, 3 loss grad ready, 4 head backward done
   int last_training;
   // per-stage CUDA-event profiling (bench.py's roofline pass) and launch accounting
   bool prof = false;
@@ -415,10 +415,16 @@ int eims_loss(eims_plan* p, const float* targets, const int32_t* target_rows, in
   return check_launch("eims_loss");
 }
 
-int eims_backward(eims_plan* p, const float* params, const float* dprob, float* grads, eims_stream_t stream) {
+int eims_backward_part(eims_plan* p, const float* params, const float* dprob, float* grads, int32_t part,
+                       eims_stream_t stream) {
   if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
+  if (part < EIMS_BWD_ALL || part > EIMS_BWD_GCN) return fail(EIMS_ERR_ARG, "part must be one of EIMS_BWD_*");
   if (p->state < 2 || !p->last_training) return fail(EIMS_ERR_STATE, "eims_backward needs a training-mode eims_forward first");
-  if (!dprob && p->state != 3) return fail(EIMS_ERR_STATE, "eims_backward without dprob needs eims_loss(want_grad=1) first");
+  if (part == EIMS_BWD_GCN) {
+    if (p->state != 4) return fail(EIMS_ERR_STATE, "EIMS_BWD_GCN needs EIMS_BWD_HEAD first");
+  } else if (!dprob && p->state != 3) {
+    return fail(EIMS_ERR_STATE, "eims_backward without dprob needs eims_loss(want_grad=1) first");
+  }
   if (!params || !grads) return fail(EIMS_ERR_ARG, "params / grads is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   const eims_dims& d = p->d;
@@ -429,6 +435,7 @@ int eims_backward(eims_plan* p, const float* params, const float* dprob, float* 
   const uint64_t seed = p->last_step.seed;
   const int step = p->last_step.step;
   auto L_ = [&](const char* b, int l) { return std::string(b) + std::to_string(l); };
+  if (part != EIMS_BWD_GCN) {
   if (dprob) STAGE(ST_ELEMENTWISE, 1, launch_dprob_to_dlogits(dims, p->f("prob"), dprob, M, p->f("dlogits"), p->Bc, st));
   float* dl = p->f("dlogits");
   // ---- head (GCN:341-352 backwards)
@@ -451,6 +458,9 @@ int eims_backward(eims_plan* p, const float* params, const float* dprob, float* 
   STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, p->f("dy1"), 2 * H, 2 * H, grads + p->off_head(1), p->Bc, st));
   STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, p->f("dy1"), 2 * H, 0, params + p->off_head(0), P, 1, p->f("dG"), P, p->Bc, P, 2 * H, dims + DIM_B,
                 nullptr, nullptr, nullptr, 0, 2, st));
+  p->state = 4;  // head gradients final (the data-parallel reducer may start on that bucket)
+  }
+  if (part == EIMS_BWD_HEAD) return check_launch("eims_backward_part");
   // ---- GCN layers, last to first (GCN:358-363 backwards)
   for (int l = L - 1; l >= 0; --l) {
     const bool from_readout = (l == L - 1);
@@ -471,7 +481,11 @@ int eims_backward(eims_plan* p, const float* params, const float* dprob, float* 
     }
   }
   p->state = 1;
-  return check_launch("eims_backward");
+  return check_launch("eims_backward_part");
+}
+
+int eims_backward(eims_plan* p, const float* params, const float* dprob, float* grads, eims_stream_t stream) {
+  return eims_backward_part(p, params, dprob, grads, EIMS_BWD_ALL, stream);
 }
 
 int eims_metrics_accumulate(eims_plan* p, float* metrics, eims_stream_t stream) {

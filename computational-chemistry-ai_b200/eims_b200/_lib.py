@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libeims_b200.so")
 POOLING = {"sum": 0, "mean": 1, "max": 2, "combined": 3}
 LOSS = {"mse": 0, "cosine": 1}
 GEMM_TCGEN05, GEMM_FP32_SIMT = 0, 1
+BWD_ALL, BWD_HEAD, BWD_GCN = 0, 1, 2
 
 ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_ZERO_DEGREE, ERR_STATE = -1, -2, -3, -4, -5
 
@@ -72,6 +73,7 @@ _SIGS = {
     "eims_sigmoid": (C.c_int, [_vp, _vp]),
     "eims_loss": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "eims_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "eims_backward_part": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "eims_metrics_accumulate": (C.c_int, [_vp, _vp, _vp]),
     "eims_train_step": (C.c_int, [_vp, C.POINTER(Dataset), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(Step), _vp, _vp]),
     "eims_infer_batch": (C.c_int, [_vp, C.POINTER(Dataset), _vp, _i32, _vp, _vp, _vp, _vp]),

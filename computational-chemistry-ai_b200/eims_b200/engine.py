@@ -296,6 +296,23 @@ class Plan:
         for l in range(self.d.num_gcn_layers):
             fp.num_batches_tracked[l] += 1
 
+    def train_step_split(self, ds: DeviceDataset, ids, fp: FlatParams, step: Step, metrics=None, loss_kind="mse",
+                         on_head_grads=None, num_graphs=None):
+        """K1 + forward + loss + backward without the optimiser, with a host callback between the
+        head and the GCN part of the backward pass (data-parallel bucket overlap, dist.py)."""
+        n = int(num_graphs if num_graphs is not None else (len(ids) if ids is not None else ds.num_mols))
+        self.batch_build(ds, ids, n)
+        self.forward(fp, True, step)
+        self.loss(ds.targets, ids, loss_kind, True)
+        if metrics is not None:
+            self.metrics_accumulate(metrics)
+        check(self.lib.eims_backward_part(self.h, ptr(fp.params), None, ptr(fp.grads), _lib.BWD_HEAD, self.stream))
+        if on_head_grads is not None:
+            on_head_grads()
+        check(self.lib.eims_backward_part(self.h, ptr(fp.params), None, ptr(fp.grads), _lib.BWD_GCN, self.stream))
+        for l in range(self.d.num_gcn_layers):
+            fp.num_batches_tracked[l] += 1
+
     # -- per-stage profiling (bench.py) ------------------------------------------------
     def profile(self, enable: bool):
         check(self.lib.eims_plan_profile(self.h, int(enable)))

@@ -39,6 +39,7 @@ enum {
 
 enum { EIMS_POOL_SUM = 0, EIMS_POOL_MEAN = 1, EIMS_POOL_MAX = 2, EIMS_POOL_COMBINED = 3 };
 enum { EIMS_LOSS_MSE = 0 /* GCN:393 */, EIMS_LOSS_COSINE = 1 /* north-star variant */ };
+enum { EIMS_BWD_ALL = 0, EIMS_BWD_HEAD = 1 /* spectrum_predictor + readout */, EIMS_BWD_GCN = 2 /* GCN layers */ };
 enum { EIMS_GEMM_TCGEN05 = 0 /* 3xTF32 tensor-core path */, EIMS_GEMM_FP32_SIMT = 1 /* CUDA-core check path */ };
 
 /* Model hyper-parameters: `Config` GCN:73-101 + node_feat_dim (GCN:580,603). */
@@ -191,6 +192,12 @@ int eims_loss(eims_plan* p, const float* targets, const int32_t* target_rows, in
  * eims_adamw_flat / the caller). */
 int eims_backward(eims_plan* p, const float* params, const float* dprob, float* grads,
                   eims_stream_t stream);
+/* The same in two parts, EIMS_BWD_HEAD then EIMS_BWD_GCN: after the head part the gradients of
+ * the 10 spectrum_predictor tensors (the tail of the flat buffer, 84 % of its bytes) are final,
+ * so a data-parallel caller can start reducing that bucket while the GCN layers are
+ * differentiated (new functionality: the reference is single-GPU, GCN:63). */
+int eims_backward_part(eims_plan* p, const float* params, const float* dprob, float* grads, int32_t part,
+                       eims_stream_t stream);
 /* metrics[8] (device): [0..2] += {sum_b row_loss/(B*M), mean_b row_cos, 1}; [4],[5] = this step's loss / cosine  - the per-step
  * `loss.item()` / `cos_sim.mean().item()` of GCN:436-437 without the host syncs. */
 int eims_metrics_accumulate(eims_plan* p, float* metrics, eims_stream_t stream);
