@@ -5,8 +5,7 @@
 
 #include "../../include/eims_b200.h"
 
-#ifndef __CUDA_ARCH_LIST__
-#endif
+#include <cstdlib>
 
 namespace eims {
 
@@ -20,49 +19,42 @@ constexpr float kLnEps = 1e-5f;       // nn.LayerNorm default (GCN:343)
 constexpr float kCosEps = 1e-8f;      // GCN:213-214
 
 // Dropout sites: GCN layer l -> site l (GCN:362-363); head dropouts -> L, L+1 (GCN:345,349).
+// torch's generator cannot be bit-matched, so the keep-mask is a counter-based stream of our
+// own: one SplitMix64 output (Steele et al. 2014) per 4 consecutive elements, keyed by
+// (seed, step, site), 16 random bits per element compared with p * 2^16.  It is a pure
+// function of the element index, so the forward gather, the backward scatter and
+// eims_dropout_mask all see the same mask without storing it.
 struct DropCfg {
-  uint32_t threshold;  // keep iff philox word >= threshold ; threshold = p * 2^32
+  uint32_t threshold;  // keep iff 16-bit word >= threshold ; threshold = round(p * 65536)
   float scale;         // 1/(1-p)
-  uint32_t seed_lo, seed_hi, step, site;
+  uint64_t key;
   __host__ __device__ bool active() const { return threshold != 0; }
 };
 
-static inline DropCfg make_drop(float p, uint64_t seed, int step, int site) {
-  DropCfg d;
-  double t = (double)p * 4294967296.0;
-  d.threshold = p <= 0.f ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
-  d.scale = p <= 0.f ? 1.f : 1.f / (1.f - p);
-  d.seed_lo = (uint32_t)seed;
-  d.seed_hi = (uint32_t)(seed >> 32);
-  d.step = (uint32_t)step;
-  d.site = (uint32_t)site;
-  return d;
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
 }
 
-// Philox4x32-10 (Salmon et al. 2011): counter = (element/4 lo, element/4 hi, site, step).
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-    uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += W0;
-    k.y += W1;
-  }
-  return c;
+static inline DropCfg make_drop(float p, uint64_t seed, int step, int site) {
+  DropCfg d;
+  double t = (double)p * 65536.0 + 0.5;
+  d.threshold = p <= 0.f ? 0u : (t >= 65535.0 ? 65535u : (uint32_t)t);
+  d.scale = p <= 0.f ? 1.f : 1.f / (1.f - p);
+  d.key = mix64(mix64(seed) ^ (((uint64_t)(uint32_t)step << 32) | (uint32_t)site));
+  return d;
 }
 
 // keep-mask (scaled) for the 4 consecutive elements starting at flat index `elem` (elem % 4 == 0)
 __device__ __forceinline__ float4 drop_mask4(const DropCfg& d, uint64_t elem) {
-  uint64_t q = elem >> 2;
-  uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), d.site, d.step),
-                          make_uint2(d.seed_lo, d.seed_hi));
+  const uint64_t r = mix64(d.key + (elem >> 2) * 0x9E3779B97F4A7C15ULL);
+  const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
   float4 m;
-  m.x = r.x >= d.threshold ? d.scale : 0.f;
-  m.y = r.y >= d.threshold ? d.scale : 0.f;
-  m.z = r.z >= d.threshold ? d.scale : 0.f;
-  m.w = r.w >= d.threshold ? d.scale : 0.f;
+  m.x = (lo & 0xffffu) >= d.threshold ? d.scale : 0.f;
+  m.y = (lo >> 16) >= d.threshold ? d.scale : 0.f;
+  m.z = (hi & 0xffffu) >= d.threshold ? d.scale : 0.f;
+  m.w = (hi >> 16) >= d.threshold ? d.scale : 0.f;
   return m;
 }
 
@@ -100,6 +92,81 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigne
   __syncthreads();
   if (is_last) __threadfence();
   return is_last;
+}
+
+// Programmatic dependent launch.  A step is a chain of ~35 short kernels (3-30 us each), so the
+// launch latency and the prologue of kernel k+1 are overlapped with the tail of kernel k: every
+// kernel is launched with the programmatic-stream-serialization attribute and starts with
+// pdl_sync(): `griddepcontrol.wait` blocks until the preceding kernel has completed and its
+// writes are visible (nothing - not even the device-side sizes in dims[] - is read before it),
+// then `griddepcontrol.launch_dependents` lets the next kernel's blocks be scheduled as soon as
+// this grid leaves room.  EIMS_PDL=0 in the environment turns the attribute off.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("EIMS_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// Training-mode BatchNorm1d statistics (GCN:361) fused into the kernel that produces z: the
+// producer adds per-column sums of z and z^2 (fp64) into `acc`, and the last block to finish
+// (ticket) turns them into mean / invstd / scale / shift, updates the running buffers
+// (momentum 0.1, unbiased variance) and re-zeroes `acc` so the launch can be replayed.
+struct BnFuse {
+  double* acc;            // [2][H]; null = no fusion
+  unsigned int* ticket;
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var;   // may be null
+  float* mean; float* invstd; float* scale; float* shift;
+  int H;
+};
+
+// executed by every thread of the finalizing block; n = rows the sums run over
+__device__ __forceinline__ void bn_finalize(const BnFuse& f, int n_rows) {
+  const double n = (double)n_rows;
+  for (int c = threadIdx.x; c < f.H; c += blockDim.x) {
+    const double s1 = __ldcg(f.acc + c), s2 = __ldcg(f.acc + f.H + c);
+    f.acc[c] = 0.0;
+    f.acc[f.H + c] = 0.0;
+    if (n_rows <= 0) continue;
+    const double mean = s1 / n;
+    double var = s2 / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float mean_f = (float)mean;
+    const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
+    f.mean[c] = mean_f;
+    f.invstd[c] = invstd;
+    const float sc = f.gamma[c] * invstd;
+    f.scale[c] = sc;
+    f.shift[c] = fmaf(-mean_f, sc, f.beta[c]);
+    if (f.running_mean) {
+      const float unbiased = (float)(n_rows > 1 ? var * n / (n - 1.0) : var);
+      f.running_mean[c] = (1.f - kBnMomentum) * f.running_mean[c] + kBnMomentum * mean_f;
+      f.running_var[c] = (1.f - kBnMomentum) * f.running_var[c] + kBnMomentum * unbiased;
+    }
+  }
 }
 
 }  // namespace eims

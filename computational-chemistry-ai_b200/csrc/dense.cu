@@ -18,6 +18,7 @@ struct GemmArgs {
 };
 
 __global__ void __launch_bounds__(256) sgemm_simt_kernel(GemmArgs g) {
+  pdl_sync();
   const int M = g.m_dev ? *g.m_dev : g.M;
   const int K = g.k_dev ? *g.k_dev : g.K;
   const int N = g.N;
@@ -92,46 +93,45 @@ int launch_gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb,
     if (splits < 1) splits = 1;
   }
   dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
-  sgemm_simt_kernel<<<grid, 256, 0, st>>>(g);
+  launch_pdl(sgemm_simt_kernel, dim3(grid), dim3(256), 0, st, g);
   return 0;
 }
 
-// =========================================================================== BatchNorm stats
-// Persistent blocks; every thread owns one float4 column group and strides over rows with
-// fp64 accumulators (sum x, sum x^2 - exact enough that var = E[x^2]-mean^2 has no
-// cancellation problem even for nearly constant columns), block reduce in shared memory,
-// fp64 atomics into 2H global accumulators, and the last block (ticket) writes mean /
-// invstd / scale / shift, updates the running buffers (nn.BatchNorm1d, momentum 0.1) and
-// re-zeroes the accumulators so the kernel can be replayed.
-constexpr int kBnMaxBlocks = 2 * 148;
+// =========================================================================== BatchNorm column kernels
+// Decomposition shared by the three kernels below: grid = (column slabs of 64, row groups),
+// 256 threads = 16 float4 column lanes x 16 row lanes.  A thread strides over the rows of its
+// row lane with its loads unrolled (memory-level parallelism is what these L2-resident passes
+// need), the 16 row lanes are combined in shared memory, and each block issues one atomic per
+// column and statistic - fp64 sums, so var = E[x^2]-mean^2 has no cancellation problem even for
+// nearly constant columns.  The last block (ticket) finalises and re-zeroes the accumulators so
+// the launch can be replayed.
+constexpr int kSlab = 64, kRowLanes = 16;
 
-static inline int bn_rif(int H) { int c4 = H / 4; return 256 / c4 > 0 ? 256 / c4 : 1; }
-static inline int bn_blocks(int H, int max_nodes) {
-  int rif = bn_rif(H);
-  int b = (max_nodes + 4 * rif - 1) / (4 * rif);  // >= 4 rows per thread
-  if (b > kBnMaxBlocks) b = kBnMaxBlocks;
-  return b < 1 ? 1 : b;
+static inline dim3 bn_grid(int H, int max_nodes) {
+  const int slabs = (H + kSlab - 1) / kSlab;
+  int rg = (148 * 4 + slabs - 1) / slabs;                       // ~4 blocks per SM in total
+  const int need = (max_nodes + 4 * kRowLanes - 1) / (4 * kRowLanes);  // >= 4 rows per thread
+  if (rg > need) rg = need;
+  if (rg < 1) rg = 1;
+  return dim3(slabs, rg);
 }
 
 // scratch: [16 floats: ticket counter] [2H doubles: accumulators]
 int64_t bn_scratch_floats(int H, int max_nodes) { (void)max_nodes; return 16 + 4 * (int64_t)H + 16; }
 
-__device__ __forceinline__ void bn_block_reduce_atomic(double (&a)[4], double (&b)[4], double* smem, int H, int rif,
-                                                       int cg, int rs, bool active, double* acc) {
-  // smem layout [rif][2][H] doubles
-  if (active) {
+// combine the 16 row lanes of a block and add into acc[which*H + col] (fp64)
+__device__ __forceinline__ void slab_reduce_atomic(const double (&a)[4], const double (&b)[4], int H, int c0, int cl,
+                                                   int rl, double* acc) {
+  __shared__ double red[kRowLanes][2][kSlab];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      smem[(rs * 2 + 0) * H + 4 * cg + e] = a[e];
-      smem[(rs * 2 + 1) * H + 4 * cg + e] = b[e];
-    }
-  }
+  for (int e = 0; e < 4; ++e) { red[rl][0][cl * 4 + e] = a[e]; red[rl][1][cl * 4 + e] = b[e]; }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * H; c += blockDim.x) {
-    const int which = c / H, col = c % H;
+  if (threadIdx.x < 2 * kSlab) {
+    const int which = threadIdx.x / kSlab, c = threadIdx.x % kSlab;
     double t = 0.0;
-    for (int r = 0; r < rif; ++r) t += smem[(r * 2 + which) * H + col];
-    atomicAdd(acc + which * H + col, t);
+#pragma unroll
+    for (int r = 0; r < kRowLanes; ++r) t += red[r][which][c];
+    if (c0 + c < H) atomicAdd(acc + which * H + c0 + c, t);
   }
 }
 
@@ -141,68 +141,35 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const int* __restrict__ d
                                                        float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                                        float* __restrict__ scale_out, float* __restrict__ shift_out,
                                                        float* __restrict__ scratch) {
-  extern __shared__ double smem_d[];
+  pdl_sync();
   const int N = dims[DIM_N];
-  const int cols4 = H >> 2;
-  const bool wide = (int)blockDim.x < cols4;            // H > 1024: threads loop over column groups
-  const int rif = wide ? 1 : (int)blockDim.x / cols4;   // rows in flight per block
   unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
   double* acc = reinterpret_cast<double*>(scratch + 16);
-  for (int cg0 = 0; cg0 < cols4; cg0 += blockDim.x) {
-    const int cg = wide ? cg0 + threadIdx.x : threadIdx.x % cols4;
-    const int rs = wide ? 0 : threadIdx.x / cols4;
-    const bool active = cg < cols4 && rs < rif;
-    double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
-    if (active) {
+  const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int c0 = blockIdx.x * kSlab, c = c0 + cl * 4;
+  double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < H) {
+    const int stride = gridDim.y * kRowLanes;
 #pragma unroll 4
-      for (int r = blockIdx.x * rif + rs; r < N; r += gridDim.x * rif) {
-        const float4 v = ldg4(z + (int64_t)r * H + 4 * cg);
-        const double x0 = v.x, x1 = v.y, x2 = v.z, x3 = v.w;
-        a[0] += x0; a[1] += x1; a[2] += x2; a[3] += x3;
-        b[0] = fma(x0, x0, b[0]); b[1] = fma(x1, x1, b[1]); b[2] = fma(x2, x2, b[2]); b[3] = fma(x3, x3, b[3]);
-      }
-    }
-    if (wide) {  // no cross-thread reduction needed: one thread per column group
-      if (active)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { atomicAdd(acc + 4 * cg + e, a[e]); atomicAdd(acc + H + 4 * cg + e, b[e]); }
-    } else {
-      bn_block_reduce_atomic(a, b, smem_d, H, rif, cg, rs, active, acc);
-      break;
+    for (int r = blockIdx.y * kRowLanes + rl; r < N; r += stride) {
+      const float4 v = ldg4(z + (int64_t)r * H + c);
+      const double x0 = v.x, x1 = v.y, x2 = v.z, x3 = v.w;
+      a[0] += x0; a[1] += x1; a[2] += x2; a[3] += x3;
+      b[0] = fma(x0, x0, b[0]); b[1] = fma(x1, x1, b[1]); b[2] = fma(x2, x2, b[2]); b[3] = fma(x3, x3, b[3]);
     }
   }
-  if (!last_block_ticket(counter, gridDim.x)) return;
-  const double n = (double)N;
-  for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    const double s1 = __ldcg(acc + c), s2 = __ldcg(acc + H + c);
-    acc[c] = 0.0;
-    acc[H + c] = 0.0;
-    if (N <= 0) continue;
-    const double mean = s1 / n;
-    double var = s2 / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float mean_f = (float)mean;
-    const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
-    mean_out[c] = mean_f;
-    invstd_out[c] = invstd;
-    const float sc = gamma[c] * invstd;
-    scale_out[c] = sc;
-    shift_out[c] = fmaf(-mean_f, sc, beta[c]);
-    if (running_mean) {
-      const float unbiased = (float)(N > 1 ? var * n / (n - 1.0) : var);
-      running_mean[c] = (1.f - kBnMomentum) * running_mean[c] + kBnMomentum * mean_f;
-      running_var[c] = (1.f - kBnMomentum) * running_var[c] + kBnMomentum * unbiased;
-    }
-  }
+  slab_reduce_atomic(a, b, H, c0, cl, rl, acc);
+  if (!last_block_ticket(counter, gridDim.x * gridDim.y)) return;
+  BnFuse f{acc, counter, gamma, beta, running_mean, running_var, mean_out, invstd_out, scale_out, shift_out, H};
+  bn_finalize(f, N);
 }
 
 int launch_bn_stats(const int* dims, const float* z, int H, const float* gamma, const float* beta, float* rmean,
                     float* rvar, float* mean, float* invstd, float* scale, float* shift, float* partials,
                     int max_nodes, cudaStream_t st) {
   if (H % 4 || H > 4096) return EIMS_ERR_ARG;
-  size_t smem = (size_t)bn_rif(H) * 2 * H * sizeof(double);
-  bn_stats_kernel<<<bn_blocks(H, max_nodes), 256, smem, st>>>(dims, z, H, gamma, beta, rmean, rvar, mean, invstd,
-                                                              scale, shift, partials);
+  launch_pdl(bn_stats_kernel, dim3(bn_grid(H, max_nodes)), dim3(256), 0, st, dims, z, H, gamma, beta, rmean, rvar, mean, invstd, scale,
+                                                         shift, partials);
   return 0;
 }
 
@@ -210,6 +177,7 @@ int launch_bn_stats(const int* dims, const float* z, int H, const float* gamma, 
 __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ rmean, const float* __restrict__ rvar, int H,
                                       float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_sync();
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < H; c += gridDim.x * blockDim.x) {
     float invstd = 1.f / sqrtf(rvar[c] + kBnEps);
     float sc = gamma[c] * invstd;
@@ -219,7 +187,7 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const flo
 }
 int launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* rmean, const float* rvar, int H,
                           float* scale, float* shift, cudaStream_t st) {
-  bn_eval_coeffs_kernel<<<(H + 255) / 256, 256, 0, st>>>(gamma, beta, rmean, rvar, H, scale, shift);
+  launch_pdl(bn_eval_coeffs_kernel, dim3((H + 255) / 256), dim3(256), 0, st, gamma, beta, rmean, rvar, H, scale, shift);
   return 0;
 }
 
@@ -258,106 +226,116 @@ __device__ __forceinline__ float4 load_dh(const DhSrc& s, int i, int c, int H) {
   return v;
 }
 
-// pass 1: column sums of dh and dh*xhat (fp64 accumulators + atomics, ticketed finalize)
-//         -> dgamma, dbeta (into grads) and the two column means.
-__global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const int* __restrict__ dims, DhSrc src,
+// pass 1: column sums of dh and dh*xhat (fp64) -> dgamma, dbeta (into grads) and the two column means.
+__global__ void __launch_bounds__(256, 4) bn_bwd_stats_kernel(const int* __restrict__ dims, DhSrc src,
                                                            const float* __restrict__ z, int H,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            float* __restrict__ means /*[2][H]*/, float* __restrict__ scratch) {
-  extern __shared__ double smem_d[];
+  pdl_sync();
   const int N = dims[DIM_N];
-  const int cols4 = H >> 2;
-  const bool wide = (int)blockDim.x < cols4;
-  const int rif = wide ? 1 : (int)blockDim.x / cols4;
   unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
   double* acc = reinterpret_cast<double*>(scratch + 16);
-  for (int cg0 = 0; cg0 < cols4; cg0 += blockDim.x) {
-    const int cg = wide ? cg0 + threadIdx.x : threadIdx.x % cols4;
-    const int rs = wide ? 0 : threadIdx.x / cols4;
-    const bool active = cg < cols4 && rs < rif;
-    double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
-    if (active) {
-      const float4 mu = ldg4(mean + 4 * cg), is = ldg4(invstd + 4 * cg);
-#pragma unroll 2
-      for (int r = blockIdx.x * rif + rs; r < N; r += gridDim.x * rif) {
-        const float4 d = load_dh(src, r, 4 * cg, H);
-        const float4 v = ldg4(z + (int64_t)r * H + 4 * cg);
-        a[0] += (double)d.x; a[1] += (double)d.y; a[2] += (double)d.z; a[3] += (double)d.w;
-        b[0] += (double)(d.x * ((v.x - mu.x) * is.x)); b[1] += (double)(d.y * ((v.y - mu.y) * is.y));
-        b[2] += (double)(d.z * ((v.z - mu.z) * is.z)); b[3] += (double)(d.w * ((v.w - mu.w) * is.w));
-      }
-    }
-    if (wide) {
-      if (active)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { atomicAdd(acc + 4 * cg + e, a[e]); atomicAdd(acc + H + 4 * cg + e, b[e]); }
-    } else {
-      bn_block_reduce_atomic(a, b, smem_d, H, rif, cg, rs, active, acc);
-      break;
+  const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int c0 = blockIdx.x * kSlab, c = c0 + cl * 4;
+  double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < H) {
+    const float4 mu = ldg4(mean + c), is = ldg4(invstd + c);
+    const int stride = gridDim.y * kRowLanes;
+#pragma unroll 4
+    for (int r = blockIdx.y * kRowLanes + rl; r < N; r += stride) {
+      const float4 d = load_dh(src, r, c, H);
+      const float4 v = ldg4(z + (int64_t)r * H + c);
+      a[0] += (double)d.x; a[1] += (double)d.y; a[2] += (double)d.z; a[3] += (double)d.w;
+      b[0] += (double)(d.x * ((v.x - mu.x) * is.x)); b[1] += (double)(d.y * ((v.y - mu.y) * is.y));
+      b[2] += (double)(d.z * ((v.z - mu.z) * is.z)); b[3] += (double)(d.w * ((v.w - mu.w) * is.w));
     }
   }
-  if (!last_block_ticket(counter, gridDim.x)) return;
-  for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    const double a = __ldcg(acc + c), b = __ldcg(acc + H + c);
-    acc[c] = 0.0;
-    acc[H + c] = 0.0;
-    dbeta[c] += (float)a;
-    dgamma[c] += (float)b;
-    means[c] = N > 0 ? (float)(a / N) : 0.f;
-    means[H + c] = N > 0 ? (float)(b / N) : 0.f;
+  slab_reduce_atomic(a, b, H, c0, cl, rl, acc);
+  if (!last_block_ticket(counter, gridDim.x * gridDim.y)) return;
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    const double sa = __ldcg(acc + k), sb = __ldcg(acc + H + k);
+    acc[k] = 0.0;
+    acc[H + k] = 0.0;
+    dbeta[k] += (float)sa;
+    dgamma[k] += (float)sb;
+    means[k] = N > 0 ? (float)(sa / N) : 0.f;
+    means[H + k] = N > 0 ? (float)(sb / N) : 0.f;
   }
 }
 
 // pass 2: q = gamma*invstd*(dh - mean(dh) - xhat*mean(dh*xhat)) * [z>0] * c_i ;  dbias += colsum(dr)
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const int* __restrict__ dims, DhSrc src,
-                                                           const float* __restrict__ z, int H,
-                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                           const float* __restrict__ gamma, const float* __restrict__ means,
-                                                           const float* __restrict__ norm, float* __restrict__ q,
-                                                           float* __restrict__ dbias) {
-  extern __shared__ float smem[];
+// LAYER0: the first GraphConv has no input gradient, so q is consumed on the spot by its weight
+// gradient dW0[f,k] += sum_i a0[i,f] * q[i,k] (F <= 8 rows) and never written.
+constexpr int kMaxF0d = 8;
+
+template <bool LAYER0>
+__global__ void __launch_bounds__(256, LAYER0 ? 2 : 4) bn_bwd_apply_kernel(
+    const int* __restrict__ dims, DhSrc src, const float* __restrict__ z, int H, const float* __restrict__ mean,
+    const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ means,
+    const float* __restrict__ norm, float* __restrict__ q, float* __restrict__ dbias, const float* __restrict__ a0,
+    int F, float* __restrict__ dW0) {
+  pdl_sync();
+  __shared__ float red[kRowLanes][kSlab];
   const int N = dims[DIM_N];
-  const int cols4 = H >> 2;
-  const bool wide = (int)blockDim.x < cols4;
-  const int rif = wide ? 1 : (int)blockDim.x / cols4;
-  for (int cg0 = 0; cg0 < cols4; cg0 += blockDim.x) {
-    const int cg = wide ? cg0 + threadIdx.x : threadIdx.x % cols4;
-    const int rs = wide ? 0 : threadIdx.x / cols4;
-    const bool active = cg < cols4 && rs < rif;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
-      const float4 mu = ldg4(mean + 4 * cg), is = ldg4(invstd + 4 * cg), ga = ldg4(gamma + 4 * cg);
-      const float4 m1 = ldg4(means + 4 * cg), m2 = ldg4(means + H + 4 * cg);
-#pragma unroll 2
-      for (int r = blockIdx.x * rif + rs; r < N; r += gridDim.x * rif) {
-        const float4 d = load_dh(src, r, 4 * cg, H);
-        const float4 v = ldg4(z + (int64_t)r * H + 4 * cg);
-        const float ci = __ldg(norm + r);
-        float4 o;
-        o.x = v.x > 0.f ? ga.x * is.x * (d.x - m1.x - (v.x - mu.x) * is.x * m2.x) : 0.f;
-        o.y = v.y > 0.f ? ga.y * is.y * (d.y - m1.y - (v.y - mu.y) * is.y * m2.y) : 0.f;
-        o.z = v.z > 0.f ? ga.z * is.z * (d.z - m1.z - (v.z - mu.z) * is.z * m2.z) : 0.f;
-        o.w = v.w > 0.f ? ga.w * is.w * (d.w - m1.w - (v.w - mu.w) * is.w * m2.w) : 0.f;
-        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-        o.x *= ci; o.y *= ci; o.z *= ci; o.w *= ci;
-        st4(q + (int64_t)r * H + 4 * cg, o);
+  const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int c0 = blockIdx.x * kSlab, c = c0 + cl * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 w[LAYER0 ? kMaxF0d : 1];
+#pragma unroll
+  for (int f = 0; f < (LAYER0 ? kMaxF0d : 1); ++f) w[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < H) {
+    const float4 mu = ldg4(mean + c), is = ldg4(invstd + c), ga = ldg4(gamma + c);
+    const float4 m1 = ldg4(means + c), m2 = ldg4(means + H + c);
+    const int stride = gridDim.y * kRowLanes;
+#pragma unroll 4
+    for (int r = blockIdx.y * kRowLanes + rl; r < N; r += stride) {
+      const float4 d = load_dh(src, r, c, H);
+      const float4 v = ldg4(z + (int64_t)r * H + c);
+      const float ci = __ldg(norm + r);
+      float4 o;
+      o.x = v.x > 0.f ? ga.x * is.x * (d.x - m1.x - (v.x - mu.x) * is.x * m2.x) : 0.f;
+      o.y = v.y > 0.f ? ga.y * is.y * (d.y - m1.y - (v.y - mu.y) * is.y * m2.y) : 0.f;
+      o.z = v.z > 0.f ? ga.z * is.z * (d.z - m1.z - (v.z - mu.z) * is.z * m2.z) : 0.f;
+      o.w = v.w > 0.f ? ga.w * is.w * (d.w - m1.w - (v.w - mu.w) * is.w * m2.w) : 0.f;
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+      o.x *= ci; o.y *= ci; o.z *= ci; o.w *= ci;
+      if (LAYER0) {
+#pragma unroll
+        for (int f = 0; f < kMaxF0d; ++f)
+          if (f < F) {
+            const float a = __ldg(a0 + (int64_t)r * F + f);
+            w[f].x = fmaf(a, o.x, w[f].x); w[f].y = fmaf(a, o.y, w[f].y);
+            w[f].z = fmaf(a, o.z, w[f].z); w[f].w = fmaf(a, o.w, w[f].w);
+          }
+      } else {
+        st4(q + (int64_t)r * H + c, o);
       }
     }
-    if (wide) {
-      if (active) {
-        atomicAdd(dbias + 4 * cg + 0, acc.x); atomicAdd(dbias + 4 * cg + 1, acc.y);
-        atomicAdd(dbias + 4 * cg + 2, acc.z); atomicAdd(dbias + 4 * cg + 3, acc.w);
-      }
-    } else {
-      if (active) st4(smem + rs * H + 4 * cg, acc);
+  }
+  red[rl][cl * 4 + 0] = acc.x; red[rl][cl * 4 + 1] = acc.y; red[rl][cl * 4 + 2] = acc.z; red[rl][cl * 4 + 3] = acc.w;
+  __syncthreads();
+  if (threadIdx.x < kSlab && c0 + threadIdx.x < H) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < kRowLanes; ++r) t += red[r][threadIdx.x];
+    atomicAdd(dbias + c0 + threadIdx.x, t);
+  }
+  if (LAYER0) {
+    for (int f = 0; f < F; ++f) {
       __syncthreads();
-      for (int c = threadIdx.x; c < H; c += blockDim.x) {
-        float a = 0.f;
-        for (int r = 0; r < rif; ++r) a += smem[r * H + c];
-        atomicAdd(dbias + c, a);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < kMaxF0d; ++k)
+        if (k == f) v = w[k];
+      red[rl][cl * 4 + 0] = v.x; red[rl][cl * 4 + 1] = v.y; red[rl][cl * 4 + 2] = v.z; red[rl][cl * 4 + 3] = v.w;
+      __syncthreads();
+      if (threadIdx.x < kSlab && c0 + threadIdx.x < H) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < kRowLanes; ++r) t += red[r][threadIdx.x];
+        atomicAdd(dW0 + (int64_t)f * H + c0 + threadIdx.x, t);
       }
-      break;
     }
   }
 }
@@ -365,15 +343,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const int* __restrict
 int launch_bn_bwd(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr, const int* argmax,
                   int pooling, const float* z, int H, const float* mean, const float* invstd, const float* gamma,
                   const float* norm, float* dgamma, float* dbeta, float* dbias, float* means, float* partials,
-                  float* q, int max_nodes, cudaStream_t st) {
-  if (H % 4 || H > 4096) return EIMS_ERR_ARG;
+                  float* q, int max_nodes, cudaStream_t st, const float* a0, int F, float* dW0) {
+  if (H % 4 || H > 4096 || (dW0 && (F < 1 || F > kMaxF0d))) return EIMS_ERR_ARG;
   DhSrc src{dh, dG, gid, gptr, argmax, pooling};
-  const int rif = bn_rif(H);
-  const int blocks = bn_blocks(H, max_nodes);
-  bn_bwd_stats_kernel<<<blocks, 256, (size_t)rif * 2 * H * sizeof(double), st>>>(dims, src, z, H, mean, invstd, dgamma,
-                                                                                 dbeta, means, partials);
-  bn_bwd_apply_kernel<<<blocks, 256, (size_t)rif * H * sizeof(float), st>>>(dims, src, z, H, mean, invstd, gamma, means,
-                                                                            norm, q, dbias);
+  const dim3 grid = bn_grid(H, max_nodes);
+  launch_pdl(bn_bwd_stats_kernel, dim3(grid), dim3(256), 0, st, dims, src, z, H, mean, invstd, dgamma, dbeta, means, partials);
+  if (dW0)
+    launch_pdl(bn_bwd_apply_kernel<true>, dim3(grid), dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, a0, F, dW0);
+  else
+    launch_pdl(bn_bwd_apply_kernel<false>, dim3(grid), dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, nullptr, 0, nullptr);
   return 0;
 }
 
@@ -384,6 +362,7 @@ __global__ void __launch_bounds__(256) ln_relu_drop_fwd_kernel(const int* __rest
                                                                int W, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, DropCfg drop,
                                                                float* __restrict__ y, float* __restrict__ stats) {
+  pdl_sync();
   const int B = dims[DIM_B];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -443,7 +422,7 @@ int launch_ln_fwd(const int* dims, const float* u, int W, const float* gamma, co
   int blocks = (max_graphs + 7) / 8;
   if (blocks < 1) blocks = 1;
   switch (ln_nv(W)) {
-#define EIMS_LN_F(NV) case NV: ln_relu_drop_fwd_kernel<NV><<<blocks, 256, 0, st>>>(dims, u, W, gamma, beta, drop, y, stats); break;
+#define EIMS_LN_F(NV) case NV: launch_pdl(ln_relu_drop_fwd_kernel<NV>, dim3(blocks), dim3(256), 0, st, dims, u, W, gamma, beta, drop, y, stats); break;
     EIMS_LN_F(1) EIMS_LN_F(2) EIMS_LN_F(4) EIMS_LN_F(8) EIMS_LN_F(16)
 #undef EIMS_LN_F
     default: return EIMS_ERR_ARG;
@@ -459,6 +438,7 @@ __global__ void __launch_bounds__(256) ln_relu_drop_bwd_kernel(const int* __rest
                                                                const float* __restrict__ stats, float drop_scale,
                                                                float* du, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta) {
+  pdl_sync();
   extern __shared__ float smem[];  // [8 warps][2][W] : per-warp column partials of dgamma / dbeta
   const int B = dims[DIM_B];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -533,7 +513,7 @@ int launch_ln_bwd(const int* dims, const float* u, const float* y, const float* 
   case NV:                                                                                                         \
     if (smem > 48 * 1024)                                                                                          \
       cudaFuncSetAttribute(ln_relu_drop_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    ln_relu_drop_bwd_kernel<NV><<<blocks, 256, smem, st>>>(dims, u, y, dy, W, gamma, stats, drop_scale, du, dgamma, dbeta); \
+    launch_pdl(ln_relu_drop_bwd_kernel<NV>, dim3(blocks), dim3(256), smem, st, dims, u, y, dy, W, gamma, stats, drop_scale, du, dgamma, dbeta); \
     break;
     EIMS_LN_B(1) EIMS_LN_B(2) EIMS_LN_B(4) EIMS_LN_B(8) EIMS_LN_B(16)
 #undef EIMS_LN_B
@@ -554,11 +534,34 @@ __device__ __forceinline__ float block_sum_128(float v, float* sh) {
   return sh[0] + sh[1] + sh[2] + sh[3];
 }
 
+// metrics += {mean loss, mean cos, 1}; [4],[5] = this step's values.  One block, fixed summation
+// order (deterministic).  This is the per-step `loss.item()` / `cos_sim.mean().item()` of
+// GCN:436-437 kept on the device.
+__device__ __forceinline__ void metrics_reduce(int B, const float* row_loss, const float* row_cos, int M, float* metrics) {
+  __shared__ double s1[256], s2[256];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) { a += (double)__ldcg(row_loss + i); b += (double)__ldcg(row_cos + i); }
+  if (threadIdx.x < 256) { s1[threadIdx.x] = a; s2[threadIdx.x] = b; }
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o && threadIdx.x + o < blockDim.x) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && B > 0) {
+    const float loss = (float)(s1[0] / ((double)B * (double)M));
+    const float cosm = (float)(s2[0] / (double)B);
+    metrics[0] += loss; metrics[1] += cosm; metrics[2] += 1.f;
+    metrics[4] = loss; metrics[5] = cosm;  // last step's values
+  }
+}
+
 __global__ void __launch_bounds__(128) loss_kernel(const int* __restrict__ dims, const float* __restrict__ logits,
                                                    const float* __restrict__ targets, const int* __restrict__ target_rows,
                                                    int M, int loss_kind, float* __restrict__ prob,
                                                    float* __restrict__ dlogits, float* __restrict__ row_loss,
-                                                   float* __restrict__ row_cos) {
+                                                   float* __restrict__ row_cos, float* __restrict__ metrics,
+                                                   unsigned int* __restrict__ ticket) {
+  pdl_sync();
   __shared__ float sh[4];
   const int B = dims[DIM_B];
   const int nv4 = M >> 2;
@@ -614,20 +617,24 @@ __global__ void __launch_bounds__(128) loss_kernel(const int* __restrict__ dims,
       }
     }
   }
+  // the last block to finish folds the row terms into the running metrics (no extra launch)
+  if (metrics && last_block_ticket(ticket, gridDim.x)) metrics_reduce(B, row_loss, row_cos, M, metrics);
 }
 
 int launch_loss(const int* dims, const float* logits, const float* targets, const int* target_rows, int M,
                 int loss_kind, float* prob, float* dlogits, float* row_loss, float* row_cos, int max_graphs,
-                cudaStream_t st) {
-  if (M % 4 || M > 4 * 128 * kLossMaxV4) return EIMS_ERR_ARG;
+                cudaStream_t st, float* metrics, unsigned int* ticket) {
+  if (M % 4 || M > 4 * 128 * kLossMaxV4 || (metrics && !ticket)) return EIMS_ERR_ARG;
   int blocks = max_graphs < 1 ? 1 : max_graphs;
-  loss_kernel<<<blocks, 128, 0, st>>>(dims, logits, targets, target_rows, M, loss_kind, prob, dlogits, row_loss, row_cos);
+  launch_pdl(loss_kernel, dim3(blocks), dim3(128), 0, st, dims, logits, targets, target_rows, M, loss_kind, prob, dlogits, row_loss, row_cos,
+                                      metrics, ticket);
   return 0;
 }
 
 // prob = sigmoid(logits) (inference) ; dlogits = dprob * p * (1-p) (autograd entry)
 __global__ void sigmoid_kernel(const int* __restrict__ dims, const float* __restrict__ logits, int M,
                                float* __restrict__ prob) {
+  pdl_sync();
   const int64_t n4 = (int64_t)dims[DIM_B] * M / 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 u = ldg4(logits + 4 * i), p;
@@ -638,6 +645,7 @@ __global__ void sigmoid_kernel(const int* __restrict__ dims, const float* __rest
 }
 __global__ void dprob_to_dlogits_kernel(const int* __restrict__ dims, const float* __restrict__ prob,
                                         const float* __restrict__ dprob, int M, float* __restrict__ dlogits) {
+  pdl_sync();
   const int64_t n4 = (int64_t)dims[DIM_B] * M / 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 p = ldg4(prob + 4 * i), d = ldg4(dprob + 4 * i);
@@ -651,38 +659,23 @@ static inline int ew_blocks(int64_t n4) {
   return b < 1 ? 1 : (int)b;
 }
 int launch_sigmoid(const int* dims, const float* logits, int M, float* prob, int max_graphs, cudaStream_t st) {
-  sigmoid_kernel<<<ew_blocks((int64_t)max_graphs * M / 4), 256, 0, st>>>(dims, logits, M, prob);
+  launch_pdl(sigmoid_kernel, dim3(ew_blocks((int64_t)max_graphs * M / 4)), dim3(256), 0, st, dims, logits, M, prob);
   return 0;
 }
 int launch_dprob_to_dlogits(const int* dims, const float* prob, const float* dprob, int M, float* dlogits,
                             int max_graphs, cudaStream_t st) {
-  dprob_to_dlogits_kernel<<<ew_blocks((int64_t)max_graphs * M / 4), 256, 0, st>>>(dims, prob, dprob, M, dlogits);
+  launch_pdl(dprob_to_dlogits_kernel, dim3(ew_blocks((int64_t)max_graphs * M / 4)), dim3(256), 0, st, dims, prob, dprob, M, dlogits);
   return 0;
 }
 
-// metrics += {mean loss, mean cos, 1}; one block, fixed summation order (deterministic).
 __global__ void __launch_bounds__(256) metrics_kernel(const int* __restrict__ dims, const float* __restrict__ row_loss,
                                                       const float* __restrict__ row_cos, int M,
                                                       float* __restrict__ metrics) {
-  __shared__ double s1[256], s2[256];
-  const int B = dims[DIM_B];
-  double a = 0.0, b = 0.0;
-  for (int i = threadIdx.x; i < B; i += 256) { a += (double)row_loss[i]; b += (double)row_cos[i]; }
-  s1[threadIdx.x] = a; s2[threadIdx.x] = b;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x + o]; s2[threadIdx.x] += s2[threadIdx.x + o]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0 && B > 0) {
-    const float loss = (float)(s1[0] / ((double)B * (double)M));
-    const float cosm = (float)(s2[0] / (double)B);
-    metrics[0] += loss; metrics[1] += cosm; metrics[2] += 1.f;
-    metrics[4] = loss; metrics[5] = cosm;  // last step's values
-  }
+  pdl_sync();
+  metrics_reduce(dims[DIM_B], row_loss, row_cos, M, metrics);
 }
 int launch_metrics(const int* dims, const float* row_loss, const float* row_cos, int M, float* metrics, cudaStream_t st) {
-  metrics_kernel<<<1, 256, 0, st>>>(dims, row_loss, row_cos, M, metrics);
+  launch_pdl(metrics_kernel, dim3(1), dim3(256), 0, st, dims, row_loss, row_cos, M, metrics);
   return 0;
 }
 
@@ -690,6 +683,7 @@ int launch_metrics(const int* dims, const float* row_loss, const float* row_cos,
 // out[c] += sum_r in[r,c]  for r < dims[dim_slot]
 __global__ void __launch_bounds__(256) colsum_kernel(const int* __restrict__ dims, int dim_slot,
                                                      const float* __restrict__ in, int C, int ld, float* __restrict__ out) {
+  pdl_sync();
   __shared__ float4 sh[4][64];
   const int R = dims[dim_slot];
   const int cg = blockIdx.x * 64 + (threadIdx.x & 63), rs = threadIdx.x >> 6;
@@ -715,7 +709,7 @@ int launch_colsum(const int* dims, int dim_slot, const float* in, int C, int ld,
   if (gy > 64) gy = 64;
   if (gy < 1) gy = 1;
   dim3 grid((C / 4 + 63) / 64, gy);
-  colsum_kernel<<<grid, 256, 0, st>>>(dims, dim_slot, in, C, ld, out);
+  launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, st, dims, dim_slot, in, C, ld, out);
   return 0;
 }
 
@@ -724,6 +718,7 @@ struct AdamK { float decay, one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_s
 
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, int64_t n, AdamK k) {
+  pdl_sync();
   const int64_t n4 = n >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = *reinterpret_cast<float4*>(p + 4 * i), gg = *reinterpret_cast<float4*>(g + 4 * i);
@@ -765,12 +760,13 @@ int launch_adamw(float* p, float* g, float* m, float* v, int64_t n, const eims_s
   k.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   k.eps = s->eps;
   k.grad_scale = s->grad_scale;
-  adamw_kernel<<<ew_blocks(n / 4), 256, 0, st>>>(p, g, m, v, n, k);
+  launch_pdl(adamw_kernel, dim3(ew_blocks(n / 4)), dim3(256), 0, st, p, g, m, v, n, k);
   return 0;
 }
 
 // =========================================================================== dropout mask (tests)
 __global__ void dropout_mask_kernel(DropCfg d, int64_t n4, float* __restrict__ out) {
+  pdl_sync();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 m = drop_mask4(d, (uint64_t)i * 4);
     m.x = m.x != 0.f; m.y = m.y != 0.f; m.z = m.z != 0.f; m.w = m.w != 0.f;
@@ -780,7 +776,7 @@ __global__ void dropout_mask_kernel(DropCfg d, int64_t n4, float* __restrict__ o
 int launch_dropout_mask(DropCfg d, int rows, int W, float* out, cudaStream_t st) {
   if (W % 4) return EIMS_ERR_ARG;
   int64_t n4 = (int64_t)rows * W / 4;
-  dropout_mask_kernel<<<ew_blocks(n4), 256, 0, st>>>(d, n4, out);
+  launch_pdl(dropout_mask_kernel, dim3(ew_blocks(n4)), dim3(256), 0, st, d, n4, out);
   return 0;
 }
 

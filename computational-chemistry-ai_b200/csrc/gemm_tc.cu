@@ -17,6 +17,8 @@
 //              or red.global.add.v4.f32 (split-K).
 // Sizes M and K may live in device memory (atoms in the current batch) so a captured step
 // can be replayed; tiles past the live range exit before touching barriers or TMEM.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launchers.h"
 
@@ -116,6 +118,7 @@ struct Args {
   const int* m_dev; const int* k_dev;
   const float* row_scale; const float* bias;
   int relu, accumulate, vec_a, vec_b;
+  BnFuse bn;  // bn.acc != null: column sums of the stored C (after bias / ReLU) -> BatchNorm statistics
 };
 
 // Load one 16-byte chunk (4 consecutive floats) with zero fill outside [0, lim) of the
@@ -258,18 +261,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
   __shared__ uint32_t tmem_base_slot;
 
-  const int M = g.m_dev ? *g.m_dev : g.M;
-  const int K = g.k_dev ? *g.k_dev : g.K;
-  const int N = g.N;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  if (m0 >= M || n0 >= N) return;
-  const int kblocks = (K + BK - 1) / BK;
-  const int per_split = (kblocks + gridDim.z - 1) / gridDim.z;
-  const int kb0 = blockIdx.z * per_split;
-  const int kb1 = min(kblocks, kb0 + per_split);
-  const int nkb = kb1 - kb0;
-  if (nkb <= 0) return;  // only possible for split-K slices past the live K (accumulate mode)
-
+  // Prologue that touches no global memory (barriers, TMEM) runs before the grid-dependency
+  // wait, i.e. while the preceding kernel of the step is still draining.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
   if (threadIdx.x == 0) {
@@ -283,7 +276,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   const uint32_t smem_base = smem_u32(smem);
+  pdl_sync();
 
+  const int M = g.m_dev ? *g.m_dev : g.M;
+  const int K = g.k_dev ? *g.k_dev : g.K;
+  const int N = g.N;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kblocks = (K + BK - 1) / BK;
+  const int per_split = (kblocks + gridDim.z - 1) / gridDim.z;
+  const int kb0 = blockIdx.z * per_split;
+  const int kb1 = min(kblocks, kb0 + per_split);
+  const int nkb = kb1 - kb0;
+  // dead tiles: past the live M (device-side size) or a split-K slice past the live K
+  const bool live = m0 < M && n0 < N && nkb > 0;
+
+  if (!live) {
+    // nothing to do, but TMEM must still be released below
+  } else
   if (warp < kProducerWarps) {
     // ---------------------------------------------------------------- producers
     const int group = warp >> 3, t = threadIdx.x & (kGroupThreads - 1);
@@ -338,6 +347,37 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
     }
     tc_fence_before();
     asm volatile("bar.sync 1, 512;" ::: "memory");  // the 16 epilogue warps only
+    if (g.bn.acc) {
+      // BatchNorm statistics of this tile: thread = (column, row slice), fp64 partial sums,
+      // combined over the row slices in shared memory, one fp64 atomic per column and statistic.
+      constexpr int PARTS = kProducerWarps * 32 / BN, RPP = BM / PARTS;
+      const int tt = threadIdx.x, colx = tt % BN, part = tt / BN;
+      double* red = reinterpret_cast<double*>(smem + BM * LDS * 4);
+      double s1 = 0.0, s2 = 0.0;
+      if (n0 + colx < N) {
+        const float bv = g.bias ? __ldg(g.bias + n0 + colx) : 0.f;
+        const int rend = min(RPP, M - m0 - part * RPP);
+        const float* src = stage + (part * RPP) * LDS + colx;
+#pragma unroll 4
+        for (int r = 0; r < rend; ++r) {
+          float v = src[r * LDS] + bv;
+          if (g.relu) v = fmaxf(v, 0.f);
+          const double d = (double)v;
+          s1 += d;
+          s2 = fma(d, d, s2);
+        }
+      }
+      red[(part * BN + colx) * 2] = s1;
+      red[(part * BN + colx) * 2 + 1] = s2;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (tt < 2 * BN) {
+        const int which = tt / BN, cc = tt % BN;
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < PARTS; ++q) t += red[(q * BN + cc) * 2 + which];
+        if (n0 + cc < N) atomicAdd(g.bn.acc + which * g.bn.H + n0 + cc, t);
+      }
+    }
     {
       const bool add_bias = g.bias && (!g.accumulate || blockIdx.z == 0);
       const bool vec_out = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
@@ -422,16 +462,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
   }
+  if (g.bn.acc && live) {  // gridDim.z == 1 here; tiles past the live M are not counted
+    const unsigned int live = (unsigned int)((M + BM - 1) / BM) * gridDim.x;
+    if (last_block_ticket(g.bn.ticket, live)) bn_finalize(g.bn, M);
+  }
 }
 
 }  // namespace tc
 
 int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
                    int N, int K, const int* m_dev, const int* k_dev, const float* row_scale, const float* bias,
-                   int relu, int accumulate, cudaStream_t st) {
+                   int relu, int accumulate, cudaStream_t st, const BnFuse* bn) {
   using namespace tc;
   if (M <= 0 || N <= 0 || K <= 0) return EIMS_ERR_ARG;
-  Args g{A, B, C, lda, ldb, ldc, a_mn, b_mn, M, N, K, m_dev, k_dev, row_scale, bias, relu, accumulate, 0, 0};
+  if (bn && (accumulate != 0 || bn->H != N)) return EIMS_ERR_ARG;
+  Args g{A, B, C, lda, ldb, ldc, a_mn, b_mn, M, N, K, m_dev, k_dev, row_scale, bias, relu, accumulate, 0, 0, BnFuse{}};
+  if (bn) g.bn = *bn;
   g.vec_a = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 4 == 0);
   g.vec_b = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 4 == 0);
   // 128 x 256 tiles (A read once per row block, 2 stages) when the problem is tall enough to
@@ -449,10 +495,16 @@ int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, i
   }
   const int mt = (M + BM - 1) / BM, nt = (N + BN - 1) / BN;
   const int kblocks = (K + BK - 1) / BK;
+  static int min_kb = 0;  // fewest k-blocks a split-K slice may get (tuning knob)
+  if (!min_kb) {
+    const char* e = getenv("EIMS_SPLITK_MIN_KB");
+    min_kb = e ? atoi(e) : 2;
+    if (min_kb < 1) min_kb = 1;
+  }
   int splits = 1;
   if (accumulate == 1) {  // split-K: weight gradients reduce over atoms / graphs
     splits = (148 + mt * nt - 1) / (mt * nt);
-    const int maxs = (kblocks + 3) / 4;  // at least 4 k-blocks per slice
+    const int maxs = (kblocks + min_kb - 1) / min_kb;  // at least min_kb k-blocks per slice
     if (splits > maxs) splits = maxs;
     if (splits < 1) splits = 1;
   } else if (accumulate == 2) {
@@ -461,7 +513,7 @@ int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, i
     g.accumulate = 0;
     if (!relu && !row_scale && mt * nt <= 37 && kblocks >= 8 && ldc == N) {
       splits = 148 / (mt * nt);
-      const int maxs = kblocks / 4;
+      const int maxs = kblocks / min_kb;
       if (splits > maxs) splits = maxs;
       if (splits > 1) {
         if (cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st) != cudaSuccess) return EIMS_ERR_CUDA;
@@ -472,8 +524,8 @@ int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, i
     }
   }
   dim3 grid(nt, mt, splits);
-  if (wide) gemm_3xtf32_kernel<256, 2><<<grid, kThreads, smem_bytes, st>>>(g);
-  else gemm_3xtf32_kernel<128, 3><<<grid, kThreads, smem_bytes, st>>>(g);
+  if (wide) launch_pdl(gemm_3xtf32_kernel<256, 2>, dim3(grid), dim3(kThreads), smem_bytes, st, g);
+  else launch_pdl(gemm_3xtf32_kernel<128, 3>, dim3(grid), dim3(kThreads), smem_bytes, st, g);
   return 0;
 }
 

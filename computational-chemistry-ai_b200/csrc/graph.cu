@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(1024) k1_scan_kernel(const int64_t* __restrict
                                                        const int32_t* __restrict__ ids, int B, int max_nodes,
                                                        int max_edges, int* __restrict__ gptr, int* __restrict__ eptr,
                                                        int* __restrict__ rowptr, int* __restrict__ dims) {
+  pdl_sync();
   __shared__ int wn[32], we[32];
   __shared__ int carry_n, carry_e;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(256) k1_build_kernel(const int64_t* __restrict
                                                        int* __restrict__ dst, int* __restrict__ rowptr,
                                                        int* __restrict__ col, float* __restrict__ norm,
                                                        float* __restrict__ x, int* __restrict__ dims) {
+  pdl_sync();
   if (dims[DIM_OVERFLOW]) return;
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -130,10 +132,10 @@ __global__ void __launch_bounds__(256) k1_build_kernel(const int64_t* __restrict
 int launch_csr_build(const eims_dataset* ds, const int32_t* ids, int B, int F, int max_nodes, int max_edges,
                      int* gptr, int* eptr, int* gid, int* src, int* dst, int* rowptr, int* col, float* norm,
                      float* x, int* dims, cudaStream_t st) {
-  k1_scan_kernel<<<1, 1024, 0, st>>>(ds->node_ptr, ds->bond_ptr, ids, B, max_nodes, max_edges, gptr, eptr, rowptr, dims);
+  launch_pdl(k1_scan_kernel, dim3(1), dim3(1024), 0, st, ds->node_ptr, ds->bond_ptr, ids, B, max_nodes, max_edges, gptr, eptr, rowptr, dims);
   if (B > 0) {
     int blocks = (B + 7) / 8;
-    k1_build_kernel<<<blocks, 256, 0, st>>>(ds->node_ptr, ds->bond_ptr, ds->feat, ds->bond_begin, ds->bond_end, ids, B,
+    launch_pdl(k1_build_kernel, dim3(blocks), dim3(256), 0, st, ds->node_ptr, ds->bond_ptr, ds->feat, ds->bond_begin, ds->bond_end, ids, B,
                                             F, gptr, eptr, gid, src, dst, rowptr, col, norm, x, dims);
   }
   return 0;
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(256) layer0_fwd_kernel(const int* __restrict__
                                                          const float* __restrict__ x, int F, const float* __restrict__ W,
                                                          const float* __restrict__ bias, int H, float* __restrict__ a0,
                                                          float* __restrict__ z) {
+  pdl_sync();
   const int N = dims[DIM_N];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -199,7 +202,7 @@ int launch_layer0_fwd(const int* dims, const int* rowptr, const int* col, const 
   int blocks = (max_nodes + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  layer0_fwd_kernel<<<blocks, 256, 0, st>>>(dims, rowptr, col, norm, x, F, W, bias, H, a0, z);
+  launch_pdl(layer0_fwd_kernel, dim3(blocks), dim3(256), 0, st, dims, rowptr, col, norm, x, F, W, bias, H, a0, z);
   return 0;
 }
 
@@ -208,6 +211,7 @@ int launch_layer0_fwd(const int* dims, const int* rowptr, const int* col, const 
 __global__ void __launch_bounds__(256) layer0_wgrad_kernel(const int* __restrict__ dims, const float* __restrict__ a0,
                                                            int F, const float* __restrict__ q, int H,
                                                            float* __restrict__ dW) {
+  pdl_sync();
   const int N = dims[DIM_N];
   __shared__ float sa[64 * kMaxF0];
   const int cols4 = H >> 2;
@@ -247,20 +251,25 @@ int launch_layer0_wgrad(const int* dims, const float* a0, int F, const float* q,
   int blocks = (max_nodes + 63) / 64;
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  layer0_wgrad_kernel<<<blocks, 256, 0, st>>>(dims, a0, F, q, H, dW);
+  launch_pdl(layer0_wgrad_kernel, dim3(blocks), dim3(256), 0, st, dims, a0, F, q, H, dW);
   return 0;
 }
 
 // ------------------------------------------------------------------------------------ K2
-// Warp per destination row, 128-bit gathers of the neighbour rows.
+// Warp per destination row; lane owns NV float4 column groups (columns (i*32+lane)*4), so a
+// whole row of H <= 128*NV floats is gathered by one warp-wide 128-bit load per neighbour and
+// all NV*UE loads of a trip are independent (UE neighbours per trip).  Neighbours are added in
+// ascending edge id, each with separate multiply and add roundings (torch's CPU index_add_).
 //   forward  (out_mode 0): out_i = sum_j fl( drop(bn(h_j)) * c_j )
 //   backward (out_mode 1): out_i = ( sum_j h_j ) * c_i * dropmask_i        (A symmetric)
+template <int NV, int UE>
 __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ dims, const int* __restrict__ rowptr,
                                                         const int* __restrict__ col, const float* __restrict__ norm,
                                                         const float* __restrict__ h, int H,
                                                         const float* __restrict__ bn_scale,
                                                         const float* __restrict__ bn_shift, DropCfg drop, int out_mode,
-                                                        float* __restrict__ out) {
+                                                        float* __restrict__ out, int parts) {
+  pdl_sync();
   const int N = dims[DIM_N];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -268,42 +277,77 @@ __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ 
   const bool has_bn = bn_scale != nullptr;
   const bool in_drop = drop.active() && out_mode == 0;
   const bool out_drop = drop.active() && out_mode == 1;
-  for (int i = warp; i < N; i += nwarps) {
+  // `parts` warps share a row when H > 128*NV (warp = row*parts + part; part fixed per warp
+  // because nwarps is a multiple of parts)
+  const int cbase = (warp % parts) * (128 * NV);
+  float4 sc[NV], sh[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = cbase + (v * 32 + lane) * 4;
+    sc[v] = make_float4(1.f, 1.f, 1.f, 1.f);
+    sh[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_bn && c < H) { sc[v] = ldg4(bn_scale + c); sh[v] = ldg4(bn_shift + c); }
+  }
+  for (int i = warp / parts; i < N; i += nwarps / parts) {
     const int e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
-    const float ci = __ldg(norm + i);
-    for (int c0 = 0; c0 < H; c0 += 128) {
-      const int c = c0 + 4 * lane;
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = e0; e < e1; e += UE) {
+      int j[UE];
+      float cj[UE];
+      float4 val[UE][NV];
+#pragma unroll
+      for (int u = 0; u < UE; ++u) j[u] = (e + u < e1) ? __ldg(col + e + u) : -1;
+#pragma unroll
+      for (int u = 0; u < UE; ++u) {
+        cj[u] = (out_mode == 0 && j[u] >= 0) ? __ldg(norm + j[u]) : 1.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = cbase + (v * 32 + lane) * 4;
+          val[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j[u] >= 0 && c < H) val[u][v] = ldg4(h + (int64_t)j[u] * H + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UE; ++u) {
+        if (j[u] < 0) continue;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = cbase + (v * 32 + lane) * 4;
+          if (c >= H) continue;
+          float4 x = val[u][v];
+          if (has_bn) {
+            x.x = fmaf(x.x, sc[v].x, sh[v].x); x.y = fmaf(x.y, sc[v].y, sh[v].y);
+            x.z = fmaf(x.z, sc[v].z, sh[v].z); x.w = fmaf(x.w, sc[v].w, sh[v].w);
+          }
+          if (in_drop) {
+            const float4 m = drop_mask4(drop, (uint64_t)j[u] * H + c);
+            x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+          }
+          if (out_mode == 0) {
+            x.x = __fmul_rn(x.x, cj[u]); x.y = __fmul_rn(x.y, cj[u]);
+            x.z = __fmul_rn(x.z, cj[u]); x.w = __fmul_rn(x.w, cj[u]);
+          }
+          acc[v].x = __fadd_rn(acc[v].x, x.x); acc[v].y = __fadd_rn(acc[v].y, x.y);
+          acc[v].z = __fadd_rn(acc[v].z, x.z); acc[v].w = __fadd_rn(acc[v].w, x.w);
+        }
+      }
+    }
+    const float ci = out_mode == 1 ? __ldg(norm + i) : 1.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = cbase + (v * 32 + lane) * 4;
       if (c >= H) continue;
-      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (has_bn) { sc = ldg4(bn_scale + c); sh = ldg4(bn_shift + c); }
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-      for (int e = e0; e < e1; ++e) {
-        const int j = __ldg(col + e);
-        float4 v = ldg4(h + (int64_t)j * H + c);
-        if (has_bn) {
-          v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-          v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-        }
-        if (in_drop) {
-          float4 m = drop_mask4(drop, (uint64_t)j * H + c);
-          v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
-        }
-        if (out_mode == 0) {
-          const float cj = __ldg(norm + j);
-          v.x = __fmul_rn(v.x, cj); v.y = __fmul_rn(v.y, cj); v.z = __fmul_rn(v.z, cj); v.w = __fmul_rn(v.w, cj);
-        }
-        acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
-        acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
-      }
+      float4 a = acc[v];
       if (out_mode == 1) {
-        acc.x *= ci; acc.y *= ci; acc.z *= ci; acc.w *= ci;
+        a.x *= ci; a.y *= ci; a.z *= ci; a.w *= ci;
         if (out_drop) {
-          float4 m = drop_mask4(drop, (uint64_t)i * H + c);
-          acc.x *= m.x; acc.y *= m.y; acc.z *= m.z; acc.w *= m.w;
+          const float4 m = drop_mask4(drop, (uint64_t)i * H + c);
+          a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w;
         }
       }
-      st4(out + (int64_t)i * H + c, acc);
+      st4(out + (int64_t)i * H + c, a);
     }
   }
 }
@@ -312,72 +356,95 @@ int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const f
                      const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
                      int max_nodes, cudaStream_t st) {
   if (H % 4) return EIMS_ERR_ARG;
-  int blocks = (max_nodes + 7) / 8;
+  const int parts = H <= 512 ? 1 : (H + 511) / 512;
+  if (parts > 8 || (8 % parts)) return EIMS_ERR_ARG;  // 8 warps per block must split evenly over a row
+  int blocks = (max_nodes * parts + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  spmm_norm_kernel<<<blocks, 256, 0, st>>>(dims, rowptr, col, norm, h, H, bn_scale, bn_shift, drop, out_mode, out);
+#define EIMS_SPMM(NV, UE) \
+  launch_pdl(spmm_norm_kernel<NV, UE>, dim3(blocks), dim3(256), 0, st, dims, rowptr, col, norm, h, H, bn_scale, bn_shift, drop, out_mode, out, parts)
+  if (H <= 128) EIMS_SPMM(1, 4);
+  else if (H <= 256) EIMS_SPMM(2, 2);
+  else EIMS_SPMM(4, 1);
+#undef EIMS_SPMM
   return 0;
 }
 
 // ------------------------------------------------------------------------------------ K5
-// Warp per (graph, 128-column chunk): BN apply + segment sum / mean / max / sum||max with the
-// first arg-max (strict '>' while scanning in node order = DGL's CPU SegmentCmp).
+// Block per graph: BN apply + segment sum / mean / max / sum||max with the first arg-max
+// (DGL's CPU SegmentCmp keeps the first maximum in node order).  256 threads = H/4 float4
+// column lanes x (1024/H) row lanes; row lane k takes nodes r0+k, r0+k+RL, ... and the row
+// lanes are combined in shared memory (ties between lanes go to the smaller node id).
 __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ dims, const int* __restrict__ gptr,
                                                       const float* __restrict__ z, int H,
                                                       const float* __restrict__ bn_scale,
                                                       const float* __restrict__ bn_shift, int pooling,
                                                       float* __restrict__ out, int* __restrict__ argmax) {
+  pdl_sync();
+  __shared__ float4 ssum[256], smax[256];
+  __shared__ int4 sarg[256];
   const int B = dims[DIM_B];
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int chunks = (H + 127) / 128;
+  const int g = blockIdx.x;
+  if (g >= B) return;
+  const int cpl = H >> 2;                       // float4 columns per row
+  const int CL = cpl < 256 ? cpl : 256;         // column lanes
+  const int RL = 256 / CL;                      // row lanes
+  const int cl = threadIdx.x % CL, rl = threadIdx.x / CL;
   const int pool_dim = pooling == EIMS_POOL_COMBINED ? 2 * H : H;
   const bool has_bn = bn_scale != nullptr;
-  for (int item = warp; item < B * chunks; item += nwarps) {
-    const int g = item / chunks, c = (item % chunks) * 128 + 4 * lane;
-    if (c >= H) continue;
-    const int r0 = __ldg(gptr + g), r1 = __ldg(gptr + g + 1);
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_bn) { sc = ldg4(bn_scale + c); sh = ldg4(bn_shift + c); }
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float ninf = -__int_as_float(0x7f800000);
-    float4 mx = make_float4(ninf, ninf, ninf, ninf);
+  const int r0 = __ldg(gptr + g), r1 = __ldg(gptr + g + 1);
+  const float ninf = -__int_as_float(0x7f800000);
+  for (int cb = 0; cb < cpl; cb += CL) {
+    const int c = (cb + cl) * 4;
+    const bool on = rl < RL && cb + cl < cpl;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), mx = make_float4(ninf, ninf, ninf, ninf);
     int4 am = make_int4(r0, r0, r0, r0);
+    if (on) {
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_bn) { sc = ldg4(bn_scale + c); sh = ldg4(bn_shift + c); }
 #pragma unroll 4
-    for (int i = r0; i < r1; ++i) {
-      float4 v = ldg4(z + (int64_t)i * H + c);
-      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-      v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      if (v.x > mx.x) { mx.x = v.x; am.x = i; }
-      if (v.y > mx.y) { mx.y = v.y; am.y = i; }
-      if (v.z > mx.z) { mx.z = v.z; am.z = i; }
-      if (v.w > mx.w) { mx.w = v.w; am.w = i; }
+      for (int i = r0 + rl; i < r1; i += RL) {
+        float4 v = ldg4(z + (int64_t)i * H + c);
+        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        if (v.x > mx.x) { mx.x = v.x; am.x = i; }
+        if (v.y > mx.y) { mx.y = v.y; am.y = i; }
+        if (v.z > mx.z) { mx.z = v.z; am.z = i; }
+        if (v.w > mx.w) { mx.w = v.w; am.w = i; }
+      }
     }
-    float* o = out + (int64_t)g * pool_dim;
-    if (pooling == EIMS_POOL_MEAN) {
-      const float inv = 1.f / (float)(r1 - r0);  // torch: S / n
-      s.x = s.x / (float)(r1 - r0); s.y = s.y / (float)(r1 - r0);
-      s.z = s.z / (float)(r1 - r0); s.w = s.w / (float)(r1 - r0);
-      (void)inv;
+    __syncthreads();
+    ssum[threadIdx.x] = s; smax[threadIdx.x] = mx; sarg[threadIdx.x] = am;
+    __syncthreads();
+    if (rl == 0 && on) {
+      for (int k = 1; k < RL; ++k) {
+        const float4 s2 = ssum[k * CL + cl], m2 = smax[k * CL + cl];
+        const int4 a2 = sarg[k * CL + cl];
+        s.x += s2.x; s.y += s2.y; s.z += s2.z; s.w += s2.w;
+        if (m2.x > mx.x || (m2.x == mx.x && a2.x < am.x)) { mx.x = m2.x; am.x = a2.x; }
+        if (m2.y > mx.y || (m2.y == mx.y && a2.y < am.y)) { mx.y = m2.y; am.y = a2.y; }
+        if (m2.z > mx.z || (m2.z == mx.z && a2.z < am.z)) { mx.z = m2.z; am.z = a2.z; }
+        if (m2.w > mx.w || (m2.w == mx.w && a2.w < am.w)) { mx.w = m2.w; am.w = a2.w; }
+      }
+      float* o = out + (int64_t)g * pool_dim;
+      if (pooling == EIMS_POOL_MEAN) {
+        const float n = (float)(r1 - r0);  // torch: S / n
+        s.x = s.x / n; s.y = s.y / n; s.z = s.z / n; s.w = s.w / n;
+      }
+      if (pooling == EIMS_POOL_SUM || pooling == EIMS_POOL_MEAN || pooling == EIMS_POOL_COMBINED) st4(o + c, s);
+      if (pooling == EIMS_POOL_MAX) st4(o + c, mx);
+      if (pooling == EIMS_POOL_COMBINED) st4(o + H + c, mx);
+      if (argmax && (pooling == EIMS_POOL_MAX || pooling == EIMS_POOL_COMBINED))
+        *reinterpret_cast<int4*>(argmax + (int64_t)g * H + c) = am;
     }
-    if (pooling == EIMS_POOL_SUM || pooling == EIMS_POOL_MEAN || pooling == EIMS_POOL_COMBINED) st4(o + c, s);
-    if (pooling == EIMS_POOL_MAX) st4(o + c, mx);
-    if (pooling == EIMS_POOL_COMBINED) st4(o + H + c, mx);
-    if (argmax && (pooling == EIMS_POOL_MAX || pooling == EIMS_POOL_COMBINED))
-      *reinterpret_cast<int4*>(argmax + (int64_t)g * H + c) = am;
   }
 }
 
 int launch_readout(const int* dims, const int* gptr, const float* z, int H, const float* bn_scale,
                    const float* bn_shift, int pooling, float* out, int* argmax, int max_graphs, cudaStream_t st) {
-  if (H % 4) return EIMS_ERR_ARG;
-  int items = max_graphs * ((H + 127) / 128);
-  int blocks = (items + 7) / 8;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  readout_kernel<<<blocks, 256, 0, st>>>(dims, gptr, z, H, bn_scale, bn_shift, pooling, out, argmax);
+  if (H % 4 || H < 4) return EIMS_ERR_ARG;
+  launch_pdl(readout_kernel, dim3(max_graphs < 1 ? 1 : max_graphs), dim3(256), 0, st, dims, gptr, z, H, bn_scale, bn_shift, pooling, out, argmax);
   return 0;
 }
 

@@ -36,7 +36,7 @@ int launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* rm
 int launch_bn_bwd(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr, const int* argmax,
                   int pooling, const float* z, int H, const float* mean, const float* invstd, const float* gamma,
                   const float* norm, float* dgamma, float* dbeta, float* dbias, float* means, float* partials,
-                  float* q, int max_nodes, cudaStream_t st);
+                  float* q, int max_nodes, cudaStream_t st, const float* a0 = nullptr, int F = 0, float* dW0 = nullptr);
 int launch_ln_fwd(const int* dims, const float* u, int W, const float* gamma, const float* beta, DropCfg drop, float* y,
                   float* stats, int max_graphs, cudaStream_t st);
 int launch_ln_bwd(const int* dims, const float* u, const float* y, const float* dy, int W, const float* gamma,
@@ -44,7 +44,7 @@ int launch_ln_bwd(const int* dims, const float* u, const float* y, const float* 
                   cudaStream_t st);
 int launch_loss(const int* dims, const float* logits, const float* targets, const int* target_rows, int M,
                 int loss_kind, float* prob, float* dlogits, float* row_loss, float* row_cos, int max_graphs,
-                cudaStream_t st);
+                cudaStream_t st, float* metrics = nullptr, unsigned int* ticket = nullptr);
 int launch_sigmoid(const int* dims, const float* logits, int M, float* prob, int max_graphs, cudaStream_t st);
 int launch_dprob_to_dlogits(const int* dims, const float* prob, const float* dprob, int M, float* dlogits,
                             int max_graphs, cudaStream_t st);
@@ -56,6 +56,6 @@ int launch_dropout_mask(DropCfg d, int rows, int W, float* out, cudaStream_t st)
 // gemm_tc.cu  (tcgen05 / TMEM, 3xTF32)
 int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
                    int N, int K, const int* m_dev, const int* k_dev, const float* row_scale, const float* bias,
-                   int relu, int accumulate, cudaStream_t st);
+                   int relu, int accumulate, cudaStream_t st, const BnFuse* bn = nullptr);
 
 }  // namespace eims

@@ -103,10 +103,10 @@ namespace {
 
 int gemm(eims_plan* p, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
          int N, int K, const int* m_dev, const int* k_dev, const float* rs, const float* bias, int relu, int acc,
-         cudaStream_t st) {
+         cudaStream_t st, const BnFuse* bn = nullptr) {
   if (p->gemm_backend == EIMS_GEMM_FP32_SIMT)
     return launch_gemm_simt(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, m_dev, k_dev, rs, bias, relu, acc, st);
-  return launch_gemm_tc(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, m_dev, k_dev, rs, bias, relu, acc, st);
+  return launch_gemm_tc(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, m_dev, k_dev, rs, bias, relu, acc, st, bn);
 }
 
 enum Stage {
@@ -375,22 +375,36 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
     STAGE(ST_SPMM_FWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f(L_("z", l - 1)), H,
                               p->f(L_("bn_scale", l - 1)), p->f(L_("bn_shift", l - 1)),
                               make_drop(drop_p, seed, step, l - 1), 0, p->f(L_("a", l)), p->Nc, st));
+    // training on the tensor-core path: the BatchNorm statistics of z_l come out of the GEMM epilogue
+    const bool fuse_bn = training && p->gemm_backend == EIMS_GEMM_TCGEN05;
+    BnFuse bf{};
+    if (fuse_bn) {
+      float* rm = bn_running + (int64_t)l * 2 * H;
+      float* scratch = p->f("bn_partials");
+      bf = BnFuse{reinterpret_cast<double*>(scratch + 16), reinterpret_cast<unsigned int*>(scratch),
+                  params + p->off_bn_g(l), params + p->off_bn_b(l), rm, rm + H, p->f(L_("bn_mean", l)),
+                  p->f(L_("bn_invstd", l)), p->f(L_("bn_scale", l)), p->f(L_("bn_shift", l)), H};
+    }
     STAGE(ST_GEMM_GCN_FWD, 1, gemm(p, p->f(L_("a", l)), H, 0, params + p->off_gcn_w(l), H, 1, p->f(L_("z", l)), H, p->Nc, H, H,
-                  dims + DIM_N, nullptr, p->f("norm"), params + p->off_gcn_b(l), 1, 0, st));
-    STAGE(ST_BN_STATS, 1, bn(l));
+                  dims + DIM_N, nullptr, p->f("norm"), params + p->off_gcn_b(l), 1, 0, st, fuse_bn ? &bf : nullptr));
+    if (!fuse_bn) STAGE(ST_BN_STATS, 1, bn(l));
   }
+  // The 512-row head GEMMs cannot fill 148 SMs with output tiles, so in training they split K and
+  // accumulate with float atomics (summation order varies in the last bit run to run); eval-mode
+  // forwards keep plain stores and are bit-reproducible.
+  const int head_acc = training ? 2 : 0;
   STAGE(ST_READOUT, 1, launch_readout(dims, p->i("gptr"), p->f(L_("z", L - 1)), H, p->f(L_("bn_scale", L - 1)),
                           p->f(L_("bn_shift", L - 1)), d.pooling, p->f("readout"), p->i("argmax"), p->Bc, st));
   STAGE(ST_GEMM_HEAD_FWD, 1, gemm(p, p->f("readout"), P, 0, params + p->off_head(0), P, 0, p->f("u1"), 2 * H, p->Bc, 2 * H, P,
-                dims + DIM_B, nullptr, nullptr, params + p->off_head(1), 0, 0, st));
+                dims + DIM_B, nullptr, nullptr, params + p->off_head(1), 0, head_acc, st));
   STAGE(ST_LN_FWD, 1, launch_ln_fwd(dims, p->f("u1"), 2 * H, params + p->off_head(2), params + p->off_head(3),
                          make_drop(drop_p, seed, step, L), p->f("y1"), p->f("ln1"), p->Bc, st));
   STAGE(ST_GEMM_HEAD_FWD, 1, gemm(p, p->f("y1"), 2 * H, 0, params + p->off_head(4), 2 * H, 0, p->f("u2"), H, p->Bc, H, 2 * H,
-                dims + DIM_B, nullptr, nullptr, params + p->off_head(5), 0, 0, st));
+                dims + DIM_B, nullptr, nullptr, params + p->off_head(5), 0, head_acc, st));
   STAGE(ST_LN_FWD, 1, launch_ln_fwd(dims, p->f("u2"), H, params + p->off_head(6), params + p->off_head(7),
                          make_drop(drop_p, seed, step, L + 1), p->f("y2"), p->f("ln2"), p->Bc, st));
   STAGE(ST_GEMM_HEAD_FWD, 1, gemm(p, p->f("y2"), H, 0, params + p->off_head(8), H, 0, p->f("logits"), M, p->Bc, M, H, dims + DIM_B,
-                nullptr, nullptr, params + p->off_head(9), 0, 0, st));
+                nullptr, nullptr, params + p->off_head(9), 0, head_acc, st));
   p->state = training ? 2 : 1;
   p->last_training = training;
   return check_launch("eims_forward");
@@ -403,16 +417,23 @@ int eims_sigmoid(eims_plan* p, eims_stream_t stream) {
   return check_launch("eims_sigmoid");
 }
 
-int eims_loss(eims_plan* p, const float* targets, const int32_t* target_rows, int32_t loss_kind, int32_t want_grad,
-              eims_stream_t stream) {
+static int loss_impl(eims_plan* p, const float* targets, const int32_t* target_rows, int32_t loss_kind, int32_t want_grad,
+                     float* metrics, eims_stream_t stream) {
   if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
   if (!targets) return fail(EIMS_ERR_ARG, "targets is NULL");
   cudaStream_t st = (cudaStream_t)stream;
+  // metrics != NULL: the last block of the loss kernel also folds the row terms into the running
+  // metrics (flags[0] is its ticket), which saves the separate one-block launch
   STAGE(ST_LOSS, 1, launch_loss(p->i("dims"), p->f("logits"), targets, target_rows, p->d.max_mz, loss_kind, p->f("prob"),
                        want_grad ? p->f("dlogits") : nullptr, p->f("row_loss"), p->f("row_cos"), p->Bc,
-                       (cudaStream_t)stream));
+                       (cudaStream_t)stream, metrics, reinterpret_cast<unsigned int*>(p->i("flags"))));
   if (want_grad && p->state == 2) p->state = 3;
   return check_launch("eims_loss");
+}
+
+int eims_loss(eims_plan* p, const float* targets, const int32_t* target_rows, int32_t loss_kind, int32_t want_grad,
+              eims_stream_t stream) {
+  return loss_impl(p, targets, target_rows, loss_kind, want_grad, nullptr, stream);
 }
 
 int eims_backward_part(eims_plan* p, const float* params, const float* dprob, float* grads, int32_t part,
@@ -468,7 +489,7 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
                            p->i("argmax"), d.pooling, p->f(L_("z", l)), H, p->f(L_("bn_mean", l)),
                            p->f(L_("bn_invstd", l)), params + p->off_bn_g(l), p->f("norm"), grads + p->off_bn_g(l),
                            grads + p->off_bn_b(l), grads + p->off_gcn_b(l), p->f("bn_means2"), p->f("bn_partials"),
-                           p->f("q"), p->Nc, st));
+                           p->f("q"), p->Nc, st, l == 0 ? p->f("a0") : nullptr, F, l == 0 ? grads + p->off_gcn_w(0) : nullptr));
     if (l > 0) {
       STAGE(ST_GEMM_GCN_WGRAD, 1, gemm(p, p->f(L_("a", l)), H, 1, p->f("q"), H, 1, grads + p->off_gcn_w(l), H, H, H, p->Nc, nullptr,
                     dims + DIM_N, nullptr, nullptr, 0, 1, st));
@@ -476,9 +497,7 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
                     nullptr, nullptr, nullptr, 0, 0, st));
       STAGE(ST_SPMM_BWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("da"), H, nullptr, nullptr,
                                 make_drop(drop_p, seed, step, l - 1), 1, p->f("dh"), p->Nc, st));
-    } else {
-      STAGE(ST_LAYER0_WGRAD, 1, launch_layer0_wgrad(dims, p->f("a0"), F, p->f("q"), H, grads + p->off_gcn_w(0), p->Nc, st));
-    }
+    }  // l == 0: dW0 came out of the BatchNorm-backward apply pass above (q_0 is never materialised)
   }
   p->state = 1;
   return check_launch("eims_backward_part");
@@ -502,8 +521,7 @@ int eims_train_step(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids
   if (!ds || !ds->targets) return fail(EIMS_ERR_ARG, "training needs dataset targets");
   EIMS_TRY(eims_batch_build(p, ds, mol_ids, num_graphs, stream));
   EIMS_TRY(eims_forward(p, params, bn_running, 1, s, stream));
-  EIMS_TRY(eims_loss(p, ds->targets, mol_ids, loss_kind, 1, stream));
-  if (metrics) EIMS_TRY(eims_metrics_accumulate(p, metrics, stream));
+  EIMS_TRY(loss_impl(p, ds->targets, mol_ids, loss_kind, 1, metrics, stream));
   EIMS_TRY(eims_backward(p, params, nullptr, grads, stream));
   if (adam_m && adam_v) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -256,7 +256,13 @@ def test_full_size_properties():
     assert rel_err(preds["tcgen05"], preds["simt"]) < REL
     plan.set_gemm_backend("tcgen05")
     prob2, _, _, _ = gpu_fwd_bwd(plan, ds, fp, ids, make_step())
-    assert np.array_equal(prob2, preds["tcgen05"])  # forward is deterministic (no float atomics on that path)
+    # training forward: BatchNorm sums (fp64 atomics) and the split-K head GEMMs (fp32 atomics) fix
+    # the result only up to the summation order - a replay agrees to the last bits, not bit for bit
+    assert rel_err(prob2, preds["tcgen05"]) < 1e-6
+    # eval forward has no atomics: a replay is bit-identical
+    e1 = plan.infer_batch(ds, ids, fp).clone().cpu().numpy()
+    e2 = plan.infer_batch(ds, ids, fp).clone().cpu().numpy()
+    assert np.array_equal(e1, e2)
     os.makedirs(os.path.join(os.path.dirname(golden_path()), "..", "gpurun_out"), exist_ok=True)
     with open(os.path.join(os.path.dirname(golden_path()), "..", "gpurun_out", "fullsize_grad_errors.json"), "w") as fh:
         json.dump(report, fh, indent=1)
