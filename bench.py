@@ -404,7 +404,25 @@ def init_weights(fp, d):
                 t.zero_()
 
 
+def _claim_stdout():
+    """Route everything libraries print on fd 1 (NCCL's version banner, ...) to stderr and keep
+    the real stdout for the ONE JSON line the driver parses."""
+    global print
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    import builtins
+
+    def _print(*args, **kw):
+        kw.setdefault("file", real)
+        kw["flush"] = True
+        builtins.print(*args, **kw)
+
+    print = _print
+
+
 if __name__ == "__main__":
+    _claim_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)

@@ -29,6 +29,18 @@ def _digest():
     return h.hexdigest()
 
 
+def build_variant(name: str, extra_flags) -> str:
+    """Diagnostic variant of the library (e.g. -DEIMS_GEMM_TRACE for tools/gemm_trace.py), written
+    next to the product library as libeims_b200_<name>.so; never loaded by the host layer."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out = OUT.replace(".so", f"_{name}.so")
+    cmd = [nvcc] + FLAGS + list(extra_flags) + ["-shared", "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{r.stdout}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     stamp = OUT + ".sha256"
     dig = _digest()

@@ -430,24 +430,26 @@ int launch_ln_fwd(const int* dims, const float* u, int W, const float* gamma, co
   return 0;
 }
 
-// backward: dy (grad w.r.t. the post-dropout output y) -> du (may alias dy); dgamma/dbeta += .
+// backward: dy (grad w.r.t. the post-dropout output y) -> du (may alias dy); dgamma/dbeta += ;
+// dbias (may be null) += column sums of du = bias gradient of the Linear that produced u.
 template <int NV>
 __global__ void __launch_bounds__(256) ln_relu_drop_bwd_kernel(const int* __restrict__ dims, const float* __restrict__ u,
                                                                const float* __restrict__ y, const float* dy, int W,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ stats, float drop_scale,
                                                                float* du, float* __restrict__ dgamma,
-                                                               float* __restrict__ dbeta) {
+                                                               float* __restrict__ dbeta, float* __restrict__ dbias) {
   pdl_sync();
-  extern __shared__ float smem[];  // [8 warps][2][W] : per-warp column partials of dgamma / dbeta
+  extern __shared__ float smem[];  // [8 warps][3][W] : per-warp column partials of dgamma / dbeta / dbias
   const int B = dims[DIM_B];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nv4 = W >> 2;
-  float* sg = smem + (wib * 2 + 0) * W;
-  float* sb = smem + (wib * 2 + 1) * W;
-  for (int c = lane; c < W; c += 32) { sg[c] = 0.f; sb[c] = 0.f; }
+  float* sg = smem + (wib * 3 + 0) * W;
+  float* sb = smem + (wib * 3 + 1) * W;
+  float* sd = smem + (wib * 3 + 2) * W;
+  for (int c = lane; c < W; c += 32) { sg[c] = 0.f; sb[c] = 0.f; sd[c] = 0.f; }
   __syncwarp();
   for (int r = warp; r < B; r += nwarps) {
     const float mean = stats[2 * r], rstd = stats[2 * r + 1];
@@ -487,33 +489,37 @@ __global__ void __launch_bounds__(256) ln_relu_drop_bwd_kernel(const int* __rest
         o.x = rstd * (g[i].x - m1 - xh[i].x * m2); o.y = rstd * (g[i].y - m1 - xh[i].y * m2);
         o.z = rstd * (g[i].z - m1 - xh[i].z * m2); o.w = rstd * (g[i].w - m1 - xh[i].w * m2);
         st4(du + (int64_t)r * W + 4 * c4, o);
+        float4 d4 = *reinterpret_cast<float4*>(sd + 4 * c4);
+        d4.x += o.x; d4.y += o.y; d4.z += o.z; d4.w += o.w;
+        *reinterpret_cast<float4*>(sd + 4 * c4) = d4;
       }
     }
   }
   __syncthreads();
   const int nw = blockDim.x >> 5;
   for (int c = threadIdx.x; c < W; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int w = 0; w < nw; ++w) { a += smem[(w * 2) * W + c]; b += smem[(w * 2 + 1) * W + c]; }
+    float a = 0.f, b = 0.f, d = 0.f;
+    for (int w = 0; w < nw; ++w) { a += smem[(w * 3) * W + c]; b += smem[(w * 3 + 1) * W + c]; d += smem[(w * 3 + 2) * W + c]; }
     atomicAdd(dgamma + c, a);
     atomicAdd(dbeta + c, b);
+    if (dbias) atomicAdd(dbias + c, d);
   }
 }
 
 int launch_ln_bwd(const int* dims, const float* u, const float* y, const float* dy, int W, const float* gamma,
-                  const float* stats, float drop_scale, float* du, float* dgamma, float* dbeta, int max_graphs,
-                  cudaStream_t st) {
+                  const float* stats, float drop_scale, float* du, float* dgamma, float* dbeta, float* dbias,
+                  int max_graphs, cudaStream_t st) {
   if (W % 4 || W > 2048 || W < 4) return EIMS_ERR_ARG;
-  int blocks = (max_graphs + 31) / 32;  // ~4 rows per warp
+  int blocks = (max_graphs + 15) / 16;  // ~2 rows per warp
   if (blocks < 1) blocks = 1;
   if (blocks > 148) blocks = 148;
-  size_t smem = (size_t)8 * 2 * W * sizeof(float);
+  size_t smem = (size_t)8 * 3 * W * sizeof(float);
   switch (ln_nv(W)) {
 #define EIMS_LN_B(NV)                                                                                              \
   case NV:                                                                                                         \
     if (smem > 48 * 1024)                                                                                          \
       cudaFuncSetAttribute(ln_relu_drop_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    launch_pdl(ln_relu_drop_bwd_kernel<NV>, dim3(blocks), dim3(256), smem, st, dims, u, y, dy, W, gamma, stats, drop_scale, du, dgamma, dbeta); \
+    launch_pdl(ln_relu_drop_bwd_kernel<NV>, dim3(blocks), dim3(256), smem, st, dims, u, y, dy, W, gamma, stats, drop_scale, du, dgamma, dbeta, dbias); \
     break;
     EIMS_LN_B(1) EIMS_LN_B(2) EIMS_LN_B(4) EIMS_LN_B(8) EIMS_LN_B(16)
 #undef EIMS_LN_B

@@ -26,6 +26,20 @@ namespace eims {
 
 namespace tc {
 
+// Optional pipeline trace (-DEIMS_GEMM_TRACE, tools/gemm_trace.py): SM-clock stamps of the phases
+// of a few CTAs, to see where a tile's time goes.  Compiled out of the product library.
+#ifdef EIMS_GEMM_TRACE
+constexpr int kTraceCtas = 8, kTraceSlots = 128;
+__device__ unsigned long long g_trace[kTraceCtas * kTraceSlots];
+#define TRACE(slot)                                                                                   \
+  do {                                                                                                \
+    const int _c = blockIdx.y * gridDim.x + blockIdx.x;                                               \
+    if (_c < kTraceCtas && blockIdx.z == 0 && (threadIdx.x & 31) == 0) g_trace[_c * kTraceSlots + (slot)] = clock64(); \
+  } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 constexpr int BM = 128, BK = 32;
 constexpr int kProducerWarps = 16, kGroupThreads = 256, kThreads = (kProducerWarps + 1) * 32;
 
@@ -264,6 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
   // Prologue that touches no global memory (barriers, TMEM) runs before the grid-dependency
   // wait, i.e. while the preceding kernel of the step is still draining.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) TRACE(0);
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, kGroupThreads / 32); mbar_init(empty0 + 8 * s, 1); }
@@ -276,7 +291,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   const uint32_t smem_base = smem_u32(smem);
+  if (warp == 0) TRACE(1);
   pdl_sync();
+  if (warp == 0) TRACE(2);
 
   const int M = g.m_dev ? *g.m_dev : g.M;
   const int K = g.k_dev ? *g.k_dev : g.K;
@@ -311,12 +328,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
       const int s = i % STAGES;
       const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
       mbar_wait(empty0 + 8 * s, ph ^ 1u);
+      if ((warp & 7) == 0 && i < 12) TRACE(8 + i * 4);
       const uint32_t st = smem_base + s * STAGE_BYTES;
       oa.store(ra, st, st + A_TILE);
       ob.store(rb, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full0 + 8 * s);
+      if ((warp & 7) == 0 && i < 12) TRACE(8 + i * 4 + 1);
       if (i + 2 < nkb) {  // prefetch this group's next k-block while the tensor core works
         const int k0 = (kb0 + i + 2) * BK;
         oa.load(ra, k0, K, t);
@@ -328,6 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
     // the accumulator barrier has fired) -> bias / ReLU -> coalesced 512-byte row stores.
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    if (warp == 0) TRACE(3);
     constexpr int LDS = BN + 4;  // padded row stride (floats): conflict-free float4 row writes
     float* stage = reinterpret_cast<float*>(smem);
     {
@@ -347,6 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
     }
     tc_fence_before();
     asm volatile("bar.sync 1, 512;" ::: "memory");  // the 16 epilogue warps only
+    if (warp == 0) TRACE(4);
     if (g.bn.acc) {
       // BatchNorm statistics of this tile: thread = (column, row slice), fp64 partial sums,
       // combined over the row slices in shared memory, one fp64 atomic per column and statistic.
@@ -378,6 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
         if (n0 + cc < N) atomicAdd(g.bn.acc + which * g.bn.H + n0 + cc, t);
       }
     }
+    if (warp == 0) TRACE(5);
     {
       const bool add_bias = g.bias && (!g.accumulate || blockIdx.z == 0);
       const bool vec_out = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
@@ -437,6 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
       const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
       mbar_wait(full0 + 8 * s, ph);
       tc_fence_after();
+      if (i < 12) TRACE(8 + i * 4 + 2);
       if (lane == 0) {
         const uint32_t sa = smem_base + s * STAGE_BYTES;
         const uint32_t a_hi = sa, a_lo = sa + A_TILE, b_hi = sa + 2 * A_TILE, b_lo = b_hi + B_TILE;
@@ -457,6 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
     }
     tc_fence_before();
   }
+  if (warp == 0) TRACE(6);
   __syncthreads();
   if (warp == kProducerWarps) {
     tc_fence_after();
@@ -466,9 +490,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
     const unsigned int live = (unsigned int)((M + BM - 1) / BM) * gridDim.x;
     if (last_block_ticket(g.bn.ticket, live)) bn_finalize(g.bn, M);
   }
+  if (warp == 0) TRACE(7);
 }
 
 }  // namespace tc
+
+#ifdef EIMS_GEMM_TRACE
+extern "C" __attribute__((visibility("default"))) int eims_debug_trace_read(unsigned long long* out, int n) {
+  if (n > tc::kTraceCtas * tc::kTraceSlots) n = tc::kTraceCtas * tc::kTraceSlots;
+  return cudaMemcpyFromSymbol(out, tc::g_trace, (size_t)n * sizeof(unsigned long long)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
                    int N, int K, const int* m_dev, const int* k_dev, const float* row_scale, const float* bias,

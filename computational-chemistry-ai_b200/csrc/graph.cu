@@ -7,251 +7,262 @@
 
 namespace eims {
 
-// ------------------------------------------------------------------------------------ K1a
-// One CTA: exclusive scan of atoms / directed edges per molecule -> gptr, eptr, dims.
-__global__ void __launch_bounds__(1024) k1_scan_kernel(const int64_t* __restrict__ node_ptr,
-                                                       const int64_t* __restrict__ bond_ptr,
-                                                       const int32_t* __restrict__ ids, int B, int max_nodes,
-                                                       int max_edges, int* __restrict__ gptr, int* __restrict__ eptr,
-                                                       int* __restrict__ rowptr, int* __restrict__ dims) {
-  pdl_sync();
-  __shared__ int wn[32], we[32];
-  __shared__ int carry_n, carry_e;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  if (tid == 0) { carry_n = 0; carry_e = 0; }
-  __syncthreads();
-  for (int base = 0; base < B; base += 1024) {
-    int g = base + tid, n = 0, e = 0;
-    if (g < B) {
-      int64_t id = ids ? (int64_t)ids[g] : (int64_t)g;
-      n = (int)(node_ptr[id + 1] - node_ptr[id]);
-      e = 2 * (int)(bond_ptr[id + 1] - bond_ptr[id]);
-    }
-    int in = n, ie = e;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int tn = __shfl_up_sync(0xffffffffu, in, o), te = __shfl_up_sync(0xffffffffu, ie, o);
-      if (lane >= o) { in += tn; ie += te; }
-    }
-    if (lane == 31) { wn[w] = in; we[w] = ie; }
-    __syncthreads();
-    if (w == 0) {
-      int a = wn[lane], b = we[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
-        if (lane >= o) { a += ta; b += tb; }
-      }
-      wn[lane] = a; we[lane] = b;  // inclusive over warps
-    }
-    __syncthreads();
-    int off_n = carry_n + (w ? wn[w - 1] : 0) + in - n;
-    int off_e = carry_e + (w ? we[w - 1] : 0) + ie - e;
-    if (g < B) { gptr[g] = off_n; eptr[g] = off_e; }
-    __syncthreads();
-    if (tid == 0) { carry_n += wn[31]; carry_e += we[31]; }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    int N = carry_n, E = carry_e;
-    bool over = N > max_nodes || E > max_edges || N < 0 || E < 0;
-    gptr[B] = N; eptr[B] = E;
-    dims[DIM_B] = over ? 0 : B;
-    dims[DIM_N] = over ? 0 : N;
-    dims[DIM_E] = over ? 0 : E;
-    dims[DIM_ZERO_DEG] = 0;
-    dims[DIM_OVERFLOW] = over ? 1 : 0;
-    dims[5] = dims[6] = dims[7] = 0;
-    rowptr[over ? 0 : N] = over ? 0 : E;
-  }
-}
+// ------------------------------------------------------------------------------------ K1
+// One launch, one warp per molecule (4 per block).  Every block first reduces the atom / edge
+// counts of the whole batch (B is a few hundred to a few thousand, the tables sit in L2): the
+// totals give the capacity check, the counts of the molecules before the block's own give its
+// node / edge offsets - so there is no separate scan launch.  Then each warp writes its
+// molecule: features, COO edge list in reference order, CSR by destination (ascending edge id
+// inside a row), per-atom graph id, degree normalisation, and (a0 != null) the 6-wide layer-0
+// aggregate a0 = A (x * c) of GraphConv (GCN:359, i = 0), which only needs the molecule itself.
+// dims[DIM_ZERO_DEG] holds the sequence number of the last batch that had an isolated atom and
+// dims[5] the current sequence number (no reset race between blocks).
+constexpr int kK1Warps = 4;
+constexpr int kMaxF0 = 8;
 
-// ------------------------------------------------------------------------------------ K1b
-// One warp per molecule: features, COO edge list in reference order, CSR by destination
-// (ascending edge id inside a row), per-atom graph id and degree normalisation.
-__global__ void __launch_bounds__(256) k1_build_kernel(const int64_t* __restrict__ node_ptr,
-                                                       const int64_t* __restrict__ bond_ptr,
-                                                       const float* __restrict__ feat,
-                                                       const int32_t* __restrict__ bond_begin,
-                                                       const int32_t* __restrict__ bond_end,
-                                                       const int32_t* __restrict__ ids, int B, int F,
-                                                       const int* __restrict__ gptr, const int* __restrict__ eptr,
-                                                       int* __restrict__ gid, int* __restrict__ src,
-                                                       int* __restrict__ dst, int* __restrict__ rowptr,
-                                                       int* __restrict__ col, float* __restrict__ norm,
-                                                       float* __restrict__ x, int* __restrict__ dims) {
+constexpr int kK1MaxN = 128, kK1MaxB = 192;  // molecule size staged in shared memory (bigger ones use global scratch)
+
+struct K1Stage {  // per-warp staging
+  int sb[kK1MaxB], se[kK1MaxB];   // bond ends (molecule-local)
+  int scol[2 * kK1MaxB];          // CSR columns (molecule-local source atom)
+  int srow[kK1MaxN + 1];          // row starts (molecule-local edge offset)
+  float snorm[kK1MaxN];
+  float sx[kK1MaxN * kMaxF0];
+};
+
+__global__ void __launch_bounds__(kK1Warps * 32) k1_build_kernel(
+    const int64_t* __restrict__ node_ptr, const int64_t* __restrict__ bond_ptr, const float* __restrict__ feat,
+    const int32_t* __restrict__ bond_begin, const int32_t* __restrict__ bond_end, const int32_t* __restrict__ ids, int B,
+    int F, int max_nodes, int max_edges, int seq, int* __restrict__ gptr, int* __restrict__ eptr, int* __restrict__ gid,
+    int* __restrict__ src, int* __restrict__ dst, int* __restrict__ rowptr, int* __restrict__ col,
+    float* __restrict__ norm, float* __restrict__ x, float* __restrict__ a0, int* __restrict__ dims) {
   pdl_sync();
-  if (dims[DIM_OVERFLOW]) return;
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int g = warp; g < B; g += nwarps) {
-    const int64_t id = ids ? (int64_t)ids[g] : (int64_t)g;
-    const int64_t a0 = node_ptr[id], b0 = bond_ptr[id];
-    const int n = (int)(node_ptr[id + 1] - a0), nb = (int)(bond_ptr[id + 1] - b0);
-    const int o = gptr[g], eo = eptr[g];
-    for (int t = lane; t < n * F; t += 32) x[(int64_t)o * F + t] = __ldg(feat + a0 * F + t);
-    const int32_t* bb = bond_begin + b0;
-    const int32_t* be = bond_end + b0;
-    for (int k = lane; k < nb; k += 32) {
-      int b = __ldg(bb + k), e = __ldg(be + k);
-      src[eo + 2 * k] = o + b; dst[eo + 2 * k] = o + e;          // GCN:142-143: [b->e, e->b]
-      src[eo + 2 * k + 1] = o + e; dst[eo + 2 * k + 1] = o + b;
-    }
-    int run = 0;
-    for (int base = 0; base < n; base += 32) {
-      const int i = base + lane;
-      int deg = 0;
-      if (i < n)
-        for (int k = 0; k < nb; ++k) deg += (__ldg(be + k) == i) + (__ldg(bb + k) == i);
-      int inc = deg;
+  __shared__ long long red[kK1Warps][4];
+  __shared__ int cnt_n[kK1Warps], cnt_e[kK1Warps];
+  __shared__ K1Stage stage[kK1Warps];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g0 = blockIdx.x * kK1Warps;
+  // ---- phase A: batch totals and this block's prefix (loads batched 4 deep: the molecule
+  // table is a random gather from HBM, so the two dependent latencies are paid once per batch)
+  long long tn = 0, te = 0, pn = 0, pe = 0;
+  for (int gb = threadIdx.x; gb < B; gb += 4 * blockDim.x) {
+    int64_t id[4];
+    long long n[4], e[4];
 #pragma unroll
-      for (int s = 1; s < 32; s <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, inc, s);
-        if (lane >= s) inc += t;
-      }
-      const int total = __shfl_sync(0xffffffffu, inc, 31);
-      if (i < n) {
-        int wpos = eo + run + inc - deg;
-        rowptr[o + i] = wpos;
-        gid[o + i] = g;
-        // torch.pow(deg.float().clamp(min=1), -0.5) on the CPU == fl(1/fl(sqrt(d)))
-        norm[o + i] = __fdiv_rn(1.0f, __fsqrt_rn((float)max(deg, 1)));
-        if (deg == 0) atomicOr(dims + DIM_ZERO_DEG, 1);
-        for (int k = 0; k < nb; ++k) {
-          int b = __ldg(bb + k), e = __ldg(be + k);
-          if (e == i) col[wpos++] = o + b;  // edge 2k   : b -> e
-          if (b == i) col[wpos++] = o + e;  // edge 2k+1 : e -> b
-        }
-      }
-      run += total;
+    for (int u = 0; u < 4; ++u) {
+      const int g = gb + u * blockDim.x;
+      id[u] = g < B ? (ids ? (int64_t)__ldg(ids + g) : (int64_t)g) : -1;
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      n[u] = e[u] = 0;
+      if (id[u] >= 0) {
+        n[u] = __ldg(node_ptr + id[u] + 1) - __ldg(node_ptr + id[u]);
+        e[u] = 2 * (__ldg(bond_ptr + id[u] + 1) - __ldg(bond_ptr + id[u]));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int g = gb + u * blockDim.x;
+      tn += n[u]; te += e[u];
+      if (g < g0) { pn += n[u]; pe += e[u]; }
+      if (g >= g0 && g < g0 + kK1Warps && g < B) { cnt_n[g - g0] = (int)n[u]; cnt_e[g - g0] = (int)e[u]; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tn += __shfl_xor_sync(0xffffffffu, tn, o); te += __shfl_xor_sync(0xffffffffu, te, o);
+    pn += __shfl_xor_sync(0xffffffffu, pn, o); pe += __shfl_xor_sync(0xffffffffu, pe, o);
+  }
+  if (lane == 0) { red[w][0] = tn; red[w][1] = te; red[w][2] = pn; red[w][3] = pe; }
+  __syncthreads();
+  tn = te = pn = pe = 0;
+#pragma unroll
+  for (int k = 0; k < kK1Warps; ++k) { tn += red[k][0]; te += red[k][1]; pn += red[k][2]; pe += red[k][3]; }
+  const bool over = tn > max_nodes || te > max_edges;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int N = over ? 0 : (int)tn, E = over ? 0 : (int)te;
+    dims[DIM_B] = over ? 0 : B;
+    dims[DIM_N] = N;
+    dims[DIM_E] = E;
+    dims[DIM_OVERFLOW] = over ? 1 : 0;
+    dims[5] = seq;
+    dims[6] = dims[7] = 0;
+    if (!over) { gptr[B] = N; eptr[B] = E; }
+    rowptr[N] = E;
+  }
+  if (over) return;
+  const int g = g0 + w;
+  if (g >= B) return;
+  int o = (int)pn, eo = (int)pe;
+  for (int k = 0; k < w; ++k) { o += cnt_n[k]; eo += cnt_e[k]; }
+  // ---- phase B: this warp's molecule; every loop below is lane-parallel (atoms or edges
+  // across lanes), the phases are separated by __syncwarp()
+  const int64_t id = ids ? (int64_t)ids[g] : (int64_t)g;
+  const int64_t a_0 = node_ptr[id], b_0 = bond_ptr[id];
+  const int n = cnt_n[w], nb = cnt_e[w] >> 1, ne = 2 * nb;
+  K1Stage& S = stage[w];
+  const bool staged = n <= kK1MaxN && nb <= kK1MaxB;
+  // molecule-local views: shared staging, or (oversized molecule) the global outputs themselves
+  const int* pb = staged ? S.sb : bond_begin + b_0;
+  const int* pe_ = staged ? S.se : bond_end + b_0;
+  int* prow = staged ? S.srow : rowptr + o;
+  int* pcol = staged ? S.scol : col + eo;
+  float* pnorm = staged ? S.snorm : norm + o;
+  const float* px = staged ? S.sx : x + (int64_t)o * F;
+  const int rowbase = staged ? 0 : eo, colbase = staged ? 0 : o;
+  if (lane == 0) { gptr[g] = o; eptr[g] = eo; }
+  for (int t = lane; t < n * F; t += 32) {
+    const float v = __ldg(feat + a_0 * F + t);
+    x[(int64_t)o * F + t] = v;
+    if (staged) S.sx[t] = v;
+  }
+  for (int k = lane; k < nb; k += 32) {
+    const int bgn = __ldg(bond_begin + b_0 + k), end = __ldg(bond_end + b_0 + k);
+    if (staged) { S.sb[k] = bgn; S.se[k] = end; }
+    src[eo + 2 * k] = o + bgn; dst[eo + 2 * k] = o + end;          // GCN:142-143: [b->e, e->b]
+    src[eo + 2 * k + 1] = o + end; dst[eo + 2 * k + 1] = o + bgn;
+  }
+  __syncwarp();
+  // degrees (lane per atom) -> row starts, degree normalisation
+  int run = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    int deg = 0;
+    if (i < n)
+      for (int k = 0; k < nb; ++k) deg += (pe_[k] == i) + (pb[k] == i);
+    int inc = deg;
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, sft);
+      if (lane >= sft) inc += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    if (i < n) {
+      const int wpos = run + inc - deg;  // molecule-local
+      // torch.pow(deg.float().clamp(min=1), -0.5) on the CPU == fl(1/fl(sqrt(d)))
+      const float c = __fdiv_rn(1.0f, __fsqrt_rn((float)max(deg, 1)));
+      rowptr[o + i] = eo + wpos;
+      gid[o + i] = g;
+      norm[o + i] = c;
+      if (staged) { S.srow[i] = wpos; S.snorm[i] = c; }
+      if (deg == 0) atomicMax(dims + DIM_ZERO_DEG, seq);
+    }
+    run += total;
+  }
+  if (staged && lane == 0) S.srow[n] = ne;
+  __syncwarp();
+  if (!staged) __threadfence_block();
+  // CSR columns (lane per directed edge): edge e = 2k (b->e) or 2k+1 (e->b) lands in row dst(e) at
+  // the rank it has among the edges with the same destination, i.e. in ascending edge id
+  for (int e = lane; e < ne; e += 32) {
+    const int k = e >> 1;
+    const int d = (e & 1) ? pb[k] : pe_[k], sv = (e & 1) ? pe_[k] : pb[k];
+    int rank = 0;
+    for (int k2 = 0; k2 < k; ++k2) rank += (pe_[k2] == d) + (pb[k2] == d);
+    if (e & 1) rank += (pe_[k] == d);  // edge 2k precedes edge 2k+1 (only matters for a self-bond)
+    const int pos = prow[d] - rowbase + rank;  // molecule-local edge offset
+    col[eo + pos] = o + sv;
+    if (staged) S.scol[pos] = sv;
+  }
+  if (!a0) return;
+  __syncwarp();
+  if (!staged) __threadfence_block();
+  // layer-0 aggregate (lane per atom): a0_i = sum_{j in row i} fl(x_j * c_j), ascending edge id,
+  // separate multiply and add roundings (torch's CPU index_add_ order)
+  for (int i = lane; i < n; i += 32) {
+    float acc[kMaxF0];
+#pragma unroll
+    for (int f = 0; f < kMaxF0; ++f) acc[f] = 0.f;
+    const int e0 = prow[i] - rowbase;
+    const int e1 = (staged || i + 1 < n) ? prow[i + 1] - rowbase : ne;
+    for (int e = e0; e < e1; ++e) {
+      const int j = pcol[e] - colbase;
+      const float cj = pnorm[j];
+#pragma unroll
+      for (int f = 0; f < kMaxF0; ++f)
+        if (f < F) acc[f] = __fadd_rn(acc[f], __fmul_rn(px[j * F + f], cj));
+    }
+#pragma unroll
+    for (int f = 0; f < kMaxF0; ++f)
+      if (f < F) a0[(int64_t)(o + i) * F + f] = acc[f];
   }
 }
 
 int launch_csr_build(const eims_dataset* ds, const int32_t* ids, int B, int F, int max_nodes, int max_edges,
                      int* gptr, int* eptr, int* gid, int* src, int* dst, int* rowptr, int* col, float* norm,
-                     float* x, int* dims, cudaStream_t st) {
-  launch_pdl(k1_scan_kernel, dim3(1), dim3(1024), 0, st, ds->node_ptr, ds->bond_ptr, ids, B, max_nodes, max_edges, gptr, eptr, rowptr, dims);
-  if (B > 0) {
-    int blocks = (B + 7) / 8;
-    launch_pdl(k1_build_kernel, dim3(blocks), dim3(256), 0, st, ds->node_ptr, ds->bond_ptr, ds->feat, ds->bond_begin, ds->bond_end, ids, B,
-                                            F, gptr, eptr, gid, src, dst, rowptr, col, norm, x, dims);
-  }
+                     float* x, int* dims, cudaStream_t st, float* a0, int seq) {
+  if (F > kMaxF0) return EIMS_ERR_ARG;
+  const int blocks = B > 0 ? (B + kK1Warps - 1) / kK1Warps : 1;
+  launch_pdl(k1_build_kernel, dim3(blocks), dim3(kK1Warps * 32), 0, st, ds->node_ptr, ds->bond_ptr, ds->feat, ds->bond_begin,
+             ds->bond_end, ids, B, F, max_nodes, max_edges, seq, gptr, eptr, gid, src, dst, rowptr, col, norm, x, a0, dims);
   return 0;
 }
 
 // --------------------------------------------------------------------------- layer 0 forward
-// GraphConv(6 -> H) + ReLU in one pass (GCN:359-360 for i = 0): a0 = A (x*c) is 6 wide, so the
-// transform is done in registers.  Warp per atom; writes a0 (saved for dW0) and z0 = relu(r).
-constexpr int kMaxF0 = 8;
-
-__global__ void __launch_bounds__(256) layer0_fwd_kernel(const int* __restrict__ dims, const int* __restrict__ rowptr,
-                                                         const int* __restrict__ col, const float* __restrict__ norm,
-                                                         const float* __restrict__ x, int F, const float* __restrict__ W,
-                                                         const float* __restrict__ bias, int H, float* __restrict__ a0,
-                                                         float* __restrict__ z) {
+// GraphConv(6 -> H) + ReLU (GCN:359-360 for i = 0) from the 6-wide aggregate a0 that K1 left:
+// z0 = relu((a0 W0) * c + b0), the transform done in registers, with the BatchNorm statistics
+// of z0 fused in (training).  Column-slab decomposition: grid = (H/64, row groups), thread =
+// (4 columns, 1 of 16 row lanes).
+__global__ void __launch_bounds__(256) layer0_fwd_kernel(const int* __restrict__ dims, const float* __restrict__ norm,
+                                                         const float* __restrict__ a0, int F, const float* __restrict__ W,
+                                                         const float* __restrict__ bias, int H, float* __restrict__ z,
+                                                         BnFuse bn) {
   pdl_sync();
   const int N = dims[DIM_N];
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int i = warp; i < N; i += nwarps) {
-    float a[kMaxF0];
+  const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int c0 = blockIdx.x * 64, c = c0 + cl * 4;
+  double sa[4] = {0.0, 0.0, 0.0, 0.0}, sb[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < H) {
+    float4 w[kMaxF0];
 #pragma unroll
-    for (int f = 0; f < kMaxF0; ++f) a[f] = 0.f;
-    const int e0 = rowptr[i], e1 = rowptr[i + 1];
-    for (int e = e0; e < e1; ++e) {
-      const int j = __ldg(col + e);
-      const float cj = __ldg(norm + j);
-#pragma unroll
-      for (int f = 0; f < kMaxF0; ++f)
-        if (f < F) a[f] = __fadd_rn(a[f], __fmul_rn(__ldg(x + (int64_t)j * F + f), cj));
-    }
-    if (lane < F) {
-      float v = 0.f;
-#pragma unroll
-      for (int f = 0; f < kMaxF0; ++f)
-        if (f == lane) v = a[f];
-      a0[(int64_t)i * F + lane] = v;
-    }
-    const float ci = __ldg(norm + i);
-    for (int c0 = 0; c0 < H; c0 += 128) {
-      const int c = c0 + 4 * lane;
-      if (c < H) {
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int f = 0; f < kMaxF0; ++f)
-          if (f < F) {
-            float4 w = ldg4(W + (int64_t)f * H + c);
-            r.x = fmaf(a[f], w.x, r.x); r.y = fmaf(a[f], w.y, r.y);
-            r.z = fmaf(a[f], w.z, r.z); r.w = fmaf(a[f], w.w, r.w);
-          }
-        float4 b = ldg4(bias + c);
-        r.x = fmaxf(fmaf(r.x, ci, b.x), 0.f); r.y = fmaxf(fmaf(r.y, ci, b.y), 0.f);
-        r.z = fmaxf(fmaf(r.z, ci, b.z), 0.f); r.w = fmaxf(fmaf(r.w, ci, b.w), 0.f);
-        st4(z + (int64_t)i * H + c, r);
-      }
-    }
-  }
-}
-
-int launch_layer0_fwd(const int* dims, const int* rowptr, const int* col, const float* norm, const float* x, int F,
-                      const float* W, const float* bias, int H, float* a0, float* z, int max_nodes, cudaStream_t st) {
-  if (F > kMaxF0) return EIMS_ERR_ARG;
-  int blocks = (max_nodes + 7) / 8;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  launch_pdl(layer0_fwd_kernel, dim3(blocks), dim3(256), 0, st, dims, rowptr, col, norm, x, F, W, bias, H, a0, z);
-  return 0;
-}
-
-// --------------------------------------------------------------------------- layer 0 weight grad
-// dW0[f,k] += sum_i a0[i,f] * q[i,k]   (F <= 8 rows): block = 64 atoms, thread = 4 columns.
-__global__ void __launch_bounds__(256) layer0_wgrad_kernel(const int* __restrict__ dims, const float* __restrict__ a0,
-                                                           int F, const float* __restrict__ q, int H,
-                                                           float* __restrict__ dW) {
-  pdl_sync();
-  const int N = dims[DIM_N];
-  __shared__ float sa[64 * kMaxF0];
-  const int cols4 = H >> 2;
-  for (int r0 = blockIdx.x * 64; r0 < N; r0 += gridDim.x * 64) {
-    const int rows = min(64, N - r0);
-    __syncthreads();
-    for (int t = threadIdx.x; t < rows * F; t += blockDim.x) sa[t] = a0[(int64_t)r0 * F + t];
-    __syncthreads();
-    for (int cg = threadIdx.x; cg < cols4; cg += blockDim.x) {
-      float4 acc[kMaxF0];
-#pragma unroll
-      for (int f = 0; f < kMaxF0; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < rows; ++r) {
-        float4 v = ldg4(q + (int64_t)(r0 + r) * H + 4 * cg);
-#pragma unroll
-        for (int f = 0; f < kMaxF0; ++f)
-          if (f < F) {
-            float a = sa[r * F + f];
-            acc[f].x = fmaf(a, v.x, acc[f].x); acc[f].y = fmaf(a, v.y, acc[f].y);
-            acc[f].z = fmaf(a, v.z, acc[f].z); acc[f].w = fmaf(a, v.w, acc[f].w);
-          }
-      }
+    for (int f = 0; f < kMaxF0; ++f) w[f] = f < F ? ldg4(W + (int64_t)f * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b = ldg4(bias + c);
+    const int stride = gridDim.y * 16;
+#pragma unroll 4
+    for (int r = blockIdx.y * 16 + rl; r < N; r += stride) {
+      const float ci = __ldg(norm + r);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int f = 0; f < kMaxF0; ++f)
         if (f < F) {
-          float* d = dW + (int64_t)f * H + 4 * cg;
-          atomicAdd(d + 0, acc[f].x); atomicAdd(d + 1, acc[f].y);
-          atomicAdd(d + 2, acc[f].z); atomicAdd(d + 3, acc[f].w);
+          const float a = __ldg(a0 + (int64_t)r * F + f);
+          v.x = fmaf(a, w[f].x, v.x); v.y = fmaf(a, w[f].y, v.y); v.z = fmaf(a, w[f].z, v.z); v.w = fmaf(a, w[f].w, v.w);
         }
+      v.x = fmaxf(fmaf(v.x, ci, b.x), 0.f); v.y = fmaxf(fmaf(v.y, ci, b.y), 0.f);
+      v.z = fmaxf(fmaf(v.z, ci, b.z), 0.f); v.w = fmaxf(fmaf(v.w, ci, b.w), 0.f);
+      st4(z + (int64_t)r * H + c, v);
+      if (bn.acc) {
+        const double x0 = v.x, x1 = v.y, x2 = v.z, x3 = v.w;
+        sa[0] += x0; sa[1] += x1; sa[2] += x2; sa[3] += x3;
+        sb[0] = fma(x0, x0, sb[0]); sb[1] = fma(x1, x1, sb[1]); sb[2] = fma(x2, x2, sb[2]); sb[3] = fma(x3, x3, sb[3]);
+      }
     }
   }
+  if (!bn.acc) return;
+  __shared__ double red[16][2][64];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { red[rl][0][cl * 4 + e] = sa[e]; red[rl][1][cl * 4 + e] = sb[e]; }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int which = threadIdx.x / 64, cc = threadIdx.x % 64;
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t += red[r][which][cc];
+    if (c0 + cc < H) atomicAdd(bn.acc + which * H + c0 + cc, t);
+  }
+  if (last_block_ticket(bn.ticket, gridDim.x * gridDim.y)) bn_finalize(bn, N);
 }
 
-int launch_layer0_wgrad(const int* dims, const float* a0, int F, const float* q, int H, float* dW, int max_nodes,
-                        cudaStream_t st) {
-  if (F > kMaxF0) return EIMS_ERR_ARG;
-  int blocks = (max_nodes + 63) / 64;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  if (blocks < 1) blocks = 1;
-  launch_pdl(layer0_wgrad_kernel, dim3(blocks), dim3(256), 0, st, dims, a0, F, q, H, dW);
+int launch_layer0_fwd(const int* dims, const float* norm, const float* a0, int F, const float* W, const float* bias,
+                      int H, float* z, int max_nodes, cudaStream_t st, const BnFuse* bn) {
+  if (F > kMaxF0 || H % 4) return EIMS_ERR_ARG;
+  const int slabs = (H + 63) / 64;
+  int rg = (148 * 4 + slabs - 1) / slabs;
+  const int need = (max_nodes + 63) / 64;
+  if (rg > need) rg = need;
+  if (rg < 1) rg = 1;
+  launch_pdl(layer0_fwd_kernel, dim3(slabs, rg), dim3(256), 0, st, dims, norm, a0, F, W, bias, H, z, bn ? *bn : BnFuse{});
   return 0;
 }
 

@@ -12,11 +12,9 @@ namespace eims {
 // graph.cu
 int launch_csr_build(const eims_dataset* ds, const int32_t* ids, int B, int F, int max_nodes, int max_edges,
                      int* gptr, int* eptr, int* gid, int* src, int* dst, int* rowptr, int* col, float* norm,
-                     float* x, int* dims, cudaStream_t st);
-int launch_layer0_fwd(const int* dims, const int* rowptr, const int* col, const float* norm, const float* x, int F,
-                      const float* W, const float* bias, int H, float* a0, float* z, int max_nodes, cudaStream_t st);
-int launch_layer0_wgrad(const int* dims, const float* a0, int F, const float* q, int H, float* dW, int max_nodes,
-                        cudaStream_t st);
+                     float* x, int* dims, cudaStream_t st, float* a0 = nullptr, int seq = 1);
+int launch_layer0_fwd(const int* dims, const float* norm, const float* a0, int F, const float* W, const float* bias,
+                      int H, float* z, int max_nodes, cudaStream_t st, const BnFuse* bn = nullptr);
 int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const float* norm, const float* h, int H,
                      const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
                      int max_nodes, cudaStream_t st);
@@ -40,8 +38,8 @@ int launch_bn_bwd(const int* dims, const float* dh, const float* dG, const int* 
 int launch_ln_fwd(const int* dims, const float* u, int W, const float* gamma, const float* beta, DropCfg drop, float* y,
                   float* stats, int max_graphs, cudaStream_t st);
 int launch_ln_bwd(const int* dims, const float* u, const float* y, const float* dy, int W, const float* gamma,
-                  const float* stats, float drop_scale, float* du, float* dgamma, float* dbeta, int max_graphs,
-                  cudaStream_t st);
+                  const float* stats, float drop_scale, float* du, float* dgamma, float* dbeta, float* dbias,
+                  int max_graphs, cudaStream_t st);
 int launch_loss(const int* dims, const float* logits, const float* targets, const int* target_rows, int M,
                 int loss_kind, float* prob, float* dlogits, float* row_loss, float* row_cos, int max_graphs,
                 cudaStream_t st, float* metrics = nullptr, unsigned int* ticket = nullptr);

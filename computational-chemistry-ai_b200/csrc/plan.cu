@@ -81,6 +81,7 @@ struct eims_plan {
   int state;  // 0 none, 1 batch built, 2 forward(train) done, 3 loss grad ready, 4 head backward done
   int last_training;
   // per-stage CUDA-event profiling (bench.py's roofline pass) and launch accounting
+  int batch_seq = 0;  // K1 sequence number (tags the zero-degree flag, see k1_build_kernel)
   bool prof = false;
   struct ProfRec { int stage; cudaEvent_t a, b; };
   std::vector<ProfRec> prof_recs;
@@ -190,6 +191,8 @@ int eims_csr_build(const eims_dataset* ds, const int32_t* mol_ids, int32_t num_g
                    int32_t* dst, int32_t* rowptr, int32_t* col, float* norm, float* x, int32_t* dims,
                    eims_stream_t stream) {
   if (!ds || num_graphs < 0) return fail(EIMS_ERR_ARG, "bad dataset / num_graphs");
+  if (cudaMemsetAsync(dims + DIM_ZERO_DEG, 0, sizeof(int32_t), (cudaStream_t)stream) != cudaSuccess)
+    return fail(EIMS_ERR_CUDA, "cudaMemsetAsync failed");
   EIMS_TRY(launch_csr_build(ds, mol_ids, num_graphs, node_feat_dim, max_nodes, max_edges, gptr, eptr, gid, src, dst,
                             rowptr, col, norm, x, dims, (cudaStream_t)stream));
   return check_launch("eims_csr_build");
@@ -337,9 +340,14 @@ int eims_batch_build(eims_plan* p, const eims_dataset* ds, const int32_t* mol_id
   if (!ds || num_graphs < 0) return fail(EIMS_ERR_ARG, "bad dataset / num_graphs");
   if (num_graphs > p->Bc) return fail(EIMS_ERR_CAPACITY, "num_graphs %d exceeds plan max_graphs %d", num_graphs, p->Bc);
   cudaStream_t st = (cudaStream_t)stream;
-  STAGE(ST_K1, num_graphs > 0 ? 2 : 1, launch_csr_build(ds, mol_ids, num_graphs, p->d.node_feat_dim, p->Nc, p->Ec, p->i("gptr"), p->i("eptr"),
+  if (p->batch_seq >= 0x7ffffff0) {  // sequence wrap: forget the old zero-degree tag
+    if (cudaMemsetAsync(p->i("dims") + DIM_ZERO_DEG, 0, sizeof(int), st) != cudaSuccess) return fail(EIMS_ERR_CUDA, "cudaMemsetAsync failed");
+    p->batch_seq = 0;
+  }
+  ++p->batch_seq;
+  STAGE(ST_K1, 1, launch_csr_build(ds, mol_ids, num_graphs, p->d.node_feat_dim, p->Nc, p->Ec, p->i("gptr"), p->i("eptr"),
                             p->i("gid"), p->i("src"), p->i("dst"), p->i("rowptr"), p->i("col"), p->f("norm"),
-                            p->f("x"), p->i("dims"), st));
+                            p->f("x"), p->i("dims"), st, p->f("a0"), p->batch_seq));
   p->state = 1;
   return check_launch("eims_batch_build");
 }
@@ -368,9 +376,20 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
     return launch_bn_eval_coeffs(params + p->off_bn_g(l), params + p->off_bn_b(l), rm, rv, H, p->f(L_("bn_scale", l)),
                                  p->f(L_("bn_shift", l)), st);
   };
-  STAGE(ST_LAYER0_FWD, 1, launch_layer0_fwd(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("x"), F, params + p->off_gcn_w(0),
-                             params + p->off_gcn_b(0), H, p->f("a0"), p->f("z0"), p->Nc, st));
-  STAGE(ST_BN_STATS, 1, bn(0));
+  auto fuse = [&](int l) {
+    float* rm = bn_running + (int64_t)l * 2 * H;
+    float* scratch = p->f("bn_partials");
+    return BnFuse{reinterpret_cast<double*>(scratch + 16), reinterpret_cast<unsigned int*>(scratch),
+                  params + p->off_bn_g(l), params + p->off_bn_b(l), rm, rm + H, p->f(L_("bn_mean", l)),
+                  p->f(L_("bn_invstd", l)), p->f(L_("bn_scale", l)), p->f(L_("bn_shift", l)), H};
+  };
+  {  // layer 0: dense transform of K1's 6-wide aggregate, BatchNorm statistics fused when training
+    BnFuse bf{};
+    if (training) bf = fuse(0);
+    STAGE(ST_LAYER0_FWD, 1, launch_layer0_fwd(dims, p->f("norm"), p->f("a0"), F, params + p->off_gcn_w(0), params + p->off_gcn_b(0),
+                               H, p->f("z0"), p->Nc, st, training ? &bf : nullptr));
+    if (!training) STAGE(ST_BN_STATS, 1, bn(0));
+  }
   for (int l = 1; l < L; ++l) {
     STAGE(ST_SPMM_FWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f(L_("z", l - 1)), H,
                               p->f(L_("bn_scale", l - 1)), p->f(L_("bn_shift", l - 1)),
@@ -378,13 +397,7 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
     // training on the tensor-core path: the BatchNorm statistics of z_l come out of the GEMM epilogue
     const bool fuse_bn = training && p->gemm_backend == EIMS_GEMM_TCGEN05;
     BnFuse bf{};
-    if (fuse_bn) {
-      float* rm = bn_running + (int64_t)l * 2 * H;
-      float* scratch = p->f("bn_partials");
-      bf = BnFuse{reinterpret_cast<double*>(scratch + 16), reinterpret_cast<unsigned int*>(scratch),
-                  params + p->off_bn_g(l), params + p->off_bn_b(l), rm, rm + H, p->f(L_("bn_mean", l)),
-                  p->f(L_("bn_invstd", l)), p->f(L_("bn_scale", l)), p->f(L_("bn_shift", l)), H};
-    }
+    if (fuse_bn) bf = fuse(l);
     STAGE(ST_GEMM_GCN_FWD, 1, gemm(p, p->f(L_("a", l)), H, 0, params + p->off_gcn_w(l), H, 1, p->f(L_("z", l)), H, p->Nc, H, H,
                   dims + DIM_N, nullptr, p->f("norm"), params + p->off_gcn_b(l), 1, 0, st, fuse_bn ? &bf : nullptr));
     if (!fuse_bn) STAGE(ST_BN_STATS, 1, bn(l));
@@ -465,18 +478,17 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
   STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, dl, M, M, grads + p->off_head(9), p->Bc, st));
   STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, dl, M, 0, params + p->off_head(8), H, 1, p->f("dy2"), H, p->Bc, H, M, dims + DIM_B, nullptr, nullptr,
                 nullptr, 0, 2, st));
+  // LayerNorm backward also leaves the bias gradient of the Linear in front of it (column sums of du)
   STAGE(ST_LN_BWD, 1, launch_ln_bwd(dims, p->f("u2"), p->f("y2"), p->f("dy2"), H, params + p->off_head(6), p->f("ln2"), drop_scale,
-                         p->f("dy2"), grads + p->off_head(6), grads + p->off_head(7), p->Bc, st));
+                         p->f("dy2"), grads + p->off_head(6), grads + p->off_head(7), grads + p->off_head(5), p->Bc, st));
   STAGE(ST_GEMM_HEAD_WGRAD, 1, gemm(p, p->f("dy2"), H, 1, p->f("y1"), 2 * H, 1, grads + p->off_head(4), 2 * H, H, 2 * H, p->Bc, nullptr,
                 dims + DIM_B, nullptr, nullptr, 0, 1, st));
-  STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, p->f("dy2"), H, H, grads + p->off_head(5), p->Bc, st));
   STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, p->f("dy2"), H, 0, params + p->off_head(4), 2 * H, 1, p->f("dy1"), 2 * H, p->Bc, 2 * H, H,
                 dims + DIM_B, nullptr, nullptr, nullptr, 0, 2, st));
   STAGE(ST_LN_BWD, 1, launch_ln_bwd(dims, p->f("u1"), p->f("y1"), p->f("dy1"), 2 * H, params + p->off_head(2), p->f("ln1"),
-                         drop_scale, p->f("dy1"), grads + p->off_head(2), grads + p->off_head(3), p->Bc, st));
+                         drop_scale, p->f("dy1"), grads + p->off_head(2), grads + p->off_head(3), grads + p->off_head(1), p->Bc, st));
   STAGE(ST_GEMM_HEAD_WGRAD, 1, gemm(p, p->f("dy1"), 2 * H, 1, p->f("readout"), P, 1, grads + p->off_head(0), P, 2 * H, P, p->Bc, nullptr,
                 dims + DIM_B, nullptr, nullptr, 0, 1, st));
-  STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, p->f("dy1"), 2 * H, 2 * H, grads + p->off_head(1), p->Bc, st));
   STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, p->f("dy1"), 2 * H, 0, params + p->off_head(0), P, 1, p->f("dG"), P, p->Bc, P, 2 * H, dims + DIM_B,
                 nullptr, nullptr, nullptr, 0, 2, st));
   p->state = 4;  // head gradients final (the data-parallel reducer may start on that bucket)
@@ -577,7 +589,7 @@ int eims_plan_check(eims_plan* p, int32_t* num_nodes, int32_t* num_edges, eims_s
   if (num_nodes) *num_nodes = h[DIM_N];
   if (num_edges) *num_edges = h[DIM_E];
   if (h[DIM_OVERFLOW]) return fail(EIMS_ERR_CAPACITY, "batch exceeds plan capacity (max_nodes %d, max_edges %d)", p->Nc, p->Ec);
-  if (h[DIM_ZERO_DEG]) return fail(EIMS_ERR_ZERO_DEGREE, "There are 0-in-degree nodes in the graph (DGL GraphConv would raise)");
+  if (h[DIM_ZERO_DEG] != 0 && h[DIM_ZERO_DEG] == h[5]) return fail(EIMS_ERR_ZERO_DEGREE, "There are 0-in-degree nodes in the graph (DGL GraphConv would raise)");
   return 0;
 }
 
