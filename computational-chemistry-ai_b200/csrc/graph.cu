@@ -204,34 +204,44 @@ int launch_csr_build(const eims_dataset* ds, const int32_t* ids, int B, int F, i
 // z0 = relu((a0 W0) * c + b0), the transform done in registers, with the BatchNorm statistics
 // of z0 fused in (training).  Column-slab decomposition: grid = (H/64, row groups), thread =
 // (4 columns, 1 of 16 row lanes).
+constexpr int kL0Rows = 256;  // rows of a0 / norm a block stages in shared memory
+
 __global__ void __launch_bounds__(256) layer0_fwd_kernel(const int* __restrict__ dims, const float* __restrict__ norm,
                                                          const float* __restrict__ a0, int F, const float* __restrict__ W,
                                                          const float* __restrict__ bias, int H, float* __restrict__ z,
                                                          BnFuse bn) {
   pdl_sync();
+  __shared__ float sa0[kL0Rows * kMaxF0];
+  __shared__ float sc[kL0Rows];
   const int N = dims[DIM_N];
   const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
   const int c0 = blockIdx.x * 64, c = c0 + cl * 4;
+  // this block's contiguous row range (<= kL0Rows by construction of the grid)
+  const int rpb = (N + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rpb, r1 = min(N, r0 + rpb);
+  const int nr = max(0, r1 - r0);
+  for (int t = threadIdx.x; t < nr * F; t += blockDim.x) sa0[t] = __ldg(a0 + (int64_t)r0 * F + t);
+  for (int t = threadIdx.x; t < nr; t += blockDim.x) sc[t] = __ldg(norm + r0 + t);
+  __syncthreads();
   double sa[4] = {0.0, 0.0, 0.0, 0.0}, sb[4] = {0.0, 0.0, 0.0, 0.0};
   if (c < H) {
     float4 w[kMaxF0];
 #pragma unroll
     for (int f = 0; f < kMaxF0; ++f) w[f] = f < F ? ldg4(W + (int64_t)f * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 b = ldg4(bias + c);
-    const int stride = gridDim.y * 16;
 #pragma unroll 4
-    for (int r = blockIdx.y * 16 + rl; r < N; r += stride) {
-      const float ci = __ldg(norm + r);
+    for (int r = rl; r < nr; r += 16) {
+      const float ci = sc[r];
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int f = 0; f < kMaxF0; ++f)
         if (f < F) {
-          const float a = __ldg(a0 + (int64_t)r * F + f);
+          const float a = sa0[r * F + f];
           v.x = fmaf(a, w[f].x, v.x); v.y = fmaf(a, w[f].y, v.y); v.z = fmaf(a, w[f].z, v.z); v.w = fmaf(a, w[f].w, v.w);
         }
       v.x = fmaxf(fmaf(v.x, ci, b.x), 0.f); v.y = fmaxf(fmaf(v.y, ci, b.y), 0.f);
       v.z = fmaxf(fmaf(v.z, ci, b.z), 0.f); v.w = fmaxf(fmaf(v.w, ci, b.w), 0.f);
-      st4(z + (int64_t)r * H + c, v);
+      st4(z + (int64_t)(r0 + r) * H + c, v);
       if (bn.acc) {
         const double x0 = v.x, x1 = v.y, x2 = v.z, x3 = v.w;
         sa[0] += x0; sa[1] += x1; sa[2] += x2; sa[3] += x3;
@@ -259,8 +269,8 @@ int launch_layer0_fwd(const int* dims, const float* norm, const float* a0, int F
   if (F > kMaxF0 || H % 4) return EIMS_ERR_ARG;
   const int slabs = (H + 63) / 64;
   int rg = (148 * 4 + slabs - 1) / slabs;
-  const int need = (max_nodes + 63) / 64;
-  if (rg > need) rg = need;
+  const int need = (max_nodes + kL0Rows - 1) / kL0Rows;  // a block stages at most kL0Rows rows
+  if (rg < need) rg = need;
   if (rg < 1) rg = 1;
   launch_pdl(layer0_fwd_kernel, dim3(slabs, rg), dim3(256), 0, st, dims, norm, a0, F, W, bias, H, z, bn ? *bn : BnFuse{});
   return 0;

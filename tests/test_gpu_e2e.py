@@ -223,6 +223,31 @@ def test_batched_inference_equals_single(backend):
     assert rel_err(batched, ref.numpy()) < REL
 
 
+def test_wide_deep_variant_vs_oracle():
+    """BASELINE configs[4] shapes: 6 GCN layers, hidden 1024, molecules up to 128 heavy atoms
+    (a small batch so that the CPU oracle finishes in seconds).  Exercises the 8-float4-per-lane
+    SpMM split, the 16-slab BatchNorm grids, LayerNorm at width 2048 and the 1024-wide GEMM
+    tiles.  Deep nets amplify the discontinuities of SURVEY 7.3-2 (ReLU flips, dead BN columns),
+    so gradients are held to max(1e-4, 8 x the fp32 oracle's own distance from fp64) - the head
+    tensors, which sit behind no such discontinuity, land at ~1e-6."""
+    d = ModelDims(hidden_dim=1024, num_gcn_layers=6, max_mz=1000, dropout=0.0)
+    table, targets, plan, ds, fp, sd = setup(d, 24, 128, 77, "tcgen05", wseed=5)
+    graph, feat = O.Graph.from_mols([table.mol(i) for i in range(24)])
+    # batched inference at this width (before the training-mode forward moves the running statistics)
+    out = plan.infer_batch(ds, None, fp).clone().cpu().numpy()
+    ref, _ = O.forward({k: v.cpu() for k, v in sd.items()}, graph, feat, odims(d), False)
+    assert rel_err(out, ref.numpy()) < REL
+    prob, loss, cos, grads = gpu_fwd_bwd(plan, ds, fp, None, make_step())
+    tt = torch.from_numpy(targets)
+    p64, l64, g64, _ = O.loss_and_grads(sd, graph, feat, tt, odims(d), dtype=torch.float64)
+    p32, l32, g32, _ = O.loss_and_grads(sd, graph, feat, tt, odims(d))
+    assert rel_err(prob, p64.numpy()) < REL
+    assert abs(loss - float(l64)) < REL * float(l64)
+    for n in grads:
+        own = rel_err(g32[n].numpy(), g64[n].numpy())
+        assert rel_err(grads[n], g64[n].numpy()) < max(REL, 8 * own), (n, rel_err(grads[n], g64[n].numpy()), own)
+
+
 def test_full_size_properties():
     """BASELINE cfg-2 shapes (batch 512, H 256, M 1000, N ~ 17k atoms).
 
