@@ -1,0 +1,169 @@
+// Data-parallel optimiser step in ONE kernel: gradient all-reduce + AdamW + parameter broadcast
+// over NVLink / NVSwitch peer memory (new functionality - the reference is single-GPU, GCN:63;
+// semantics = PyTorch DDP mean of per-rank gradients followed by GCN:429 `optimizer.step()`).
+//
+//   every rank r owns the slice [r*per, (r+1)*per) of the flat parameter vector
+//   phase 0  cross-GPU barrier "gradients of this step are complete everywhere"
+//   phase 1  g   = sum over ranks of grads[slice]       multimem.ld_reduce (the NVSwitch adds, one
+//                                                       reduced stream comes back) or peer loads
+//            AdamW on the slice (m, v exist for the own slice only - ZeRO-1 style)
+//            p  -> every rank's parameter buffer        multimem.st (switch multicast) or peer stores
+//            the gradient buffer of the PREVIOUS step (double-buffered) is zeroed for reuse
+//   phase 2  cross-GPU barrier "all slices of the new parameters have landed here"
+// Per rank and step the links carry ~P*4 bytes in and out (3.15 MB at BASELINE cfg 2-4) instead
+// of an NCCL all-reduce followed by a separate AdamW launch; every rank ends with bit-identical
+// parameters because each element is updated by exactly one rank.
+//
+// Barriers are monotonically increasing sequence numbers in each rank's signal pad
+// (st.release.sys / ld.acquire.sys); ranks are different GPUs, so spinning is safe.
+#include "common.cuh"
+#include "launchers.h"
+
+namespace eims {
+
+constexpr int kMaxRanks = 16;
+
+struct DpPeers {
+  float* grads[kMaxRanks];       // this step's gradient buffer of every rank (peer-mapped)
+  float* params[kMaxRanks];      // parameter buffer of every rank (peer-mapped)
+  uint32_t* signals[kMaxRanks];  // signal pad of every rank: [2][kMaxRanks] words used
+  float* grads_mc;               // multicast (NVLS) address of the gradient buffers, or null
+  float* params_mc;              // multicast address of the parameter buffers, or null
+};
+
+struct AdamKd { float decay, one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps, grad_scale; };
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+// wait until every rank has written `seq` (or later) into this rank's pad row `phase`
+__device__ __forceinline__ void wait_all(const uint32_t* my_pad, int phase, int world, uint32_t seq) {
+  if ((int)threadIdx.x < world) {
+    const uint32_t* p = my_pad + phase * kMaxRanks + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(p) - seq) < 0) {
+      if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a lost rank must not hang the GPU for ever
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) dp_adamw_kernel(DpPeers pr, int rank, int world, float* __restrict__ m,
+                                                       float* __restrict__ v, float* __restrict__ zero_buf,
+                                                       int64_t n4, int64_t per, uint32_t seq, unsigned int* ticket,
+                                                       AdamKd k) {
+  pdl_sync();
+  uint32_t* my_pad = pr.signals[rank];
+  // ---- phase 0: my gradients are complete (stream order) -> tell everyone, wait for everyone
+  if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(pr.signals[threadIdx.x] + 0 * kMaxRanks + rank, seq);
+  }
+  wait_all(my_pad, 0, world, seq);
+  // ---- phase 1: reduce + AdamW + broadcast of the own slice
+  const int64_t s0 = (int64_t)rank * per, s1 = min(n4, s0 + per);
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = s0 + tid; i < s1; i += nth) {
+    float4 g;
+    if (pr.grads_mc) {
+      g = multimem_ld_reduce_add(pr.grads_mc + 4 * i);
+    } else {
+      g = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < world; ++r) {  // fixed order: every rank would get the same bits
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(pr.grads[r] + 4 * i));  // L2 (coherence point), not L1
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+    }
+    float4 pp = *reinterpret_cast<float4*>(pr.params[rank] + 4 * i);
+    const int64_t j = i - s0;
+    float4 mm = *reinterpret_cast<float4*>(m + 4 * j), vv = *reinterpret_cast<float4*>(v + 4 * j);
+#define EIMS_ADAM1(P, G, Mm, V)                  \
+  {                                              \
+    float gr = G * k.grad_scale;                 \
+    P *= k.decay;                                \
+    Mm = Mm + (gr - Mm) * k.one_minus_b1;        \
+    V = V * k.b2 + k.one_minus_b2 * gr * gr;     \
+    float den = sqrtf(V) * k.inv_bc2_sqrt + k.eps; \
+    P = P - k.step_size * (Mm / den);            \
+  }
+    EIMS_ADAM1(pp.x, g.x, mm.x, vv.x) EIMS_ADAM1(pp.y, g.y, mm.y, vv.y)
+    EIMS_ADAM1(pp.z, g.z, mm.z, vv.z) EIMS_ADAM1(pp.w, g.w, mm.w, vv.w)
+#undef EIMS_ADAM1
+    *reinterpret_cast<float4*>(m + 4 * j) = mm;
+    *reinterpret_cast<float4*>(v + 4 * j) = vv;
+    if (pr.params_mc) {
+      multimem_st(pr.params_mc + 4 * i, pp);
+    } else {
+      for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(pr.params[r] + 4 * i) = pp;
+    }
+  }
+  // the other gradient buffer (read by the peers during the previous step, which every rank has
+  // left - they all passed phase 0 of this step) is zeroed for the step after this one
+  if (zero_buf)
+    for (int64_t i = tid; i < n4; i += nth) *reinterpret_cast<float4*>(zero_buf + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  // ---- phase 2: when the whole grid has stored its slice, signal; the last block leaves only
+  // after every rank's slice has landed in this rank's parameters
+  __threadfence_system();
+  if (!last_block_ticket(ticket, gridDim.x)) return;
+  if ((int)threadIdx.x < world) st_release_sys(pr.signals[threadIdx.x] + 1 * kMaxRanks + rank, seq);
+  wait_all(my_pad, 1, world, seq);
+}
+
+}  // namespace eims
+
+using namespace eims;
+
+#pragma GCC visibility push(default)
+extern "C" int eims_dp_adamw_fused(int32_t rank, int32_t world, const uint64_t* grad_ptrs, const uint64_t* param_ptrs,
+                                   const uint64_t* signal_ptrs, uint64_t grads_multicast, uint64_t params_multicast,
+                                   float* m_slice, float* v_slice, float* zero_buf, int64_t n_padded,
+                                   const eims_step* s, uint32_t seq, uint32_t* ticket, eims_stream_t stream) {
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !grad_ptrs || !param_ptrs || !signal_ptrs || !s ||
+      s->step < 1 || n_padded % (4 * (int64_t)world) || !ticket)
+    return EIMS_ERR_ARG;
+  DpPeers pr{};
+  for (int r = 0; r < world; ++r) {
+    pr.grads[r] = reinterpret_cast<float*>(grad_ptrs[r]);
+    pr.params[r] = reinterpret_cast<float*>(param_ptrs[r]);
+    pr.signals[r] = reinterpret_cast<uint32_t*>(signal_ptrs[r]);
+  }
+  pr.grads_mc = reinterpret_cast<float*>(grads_multicast);
+  pr.params_mc = reinterpret_cast<float*>(params_multicast);
+  const double b1 = s->beta1, b2 = s->beta2;
+  const double bc1 = 1.0 - pow(b1, (double)s->step), bc2 = 1.0 - pow(b2, (double)s->step);
+  AdamKd k;
+  k.decay = (float)(1.0 - (double)s->lr * (double)s->weight_decay);
+  k.one_minus_b1 = (float)(1.0 - b1);
+  k.b2 = (float)b2;
+  k.one_minus_b2 = (float)(1.0 - b2);
+  k.step_size = (float)((double)s->lr / bc1);
+  k.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  k.eps = s->eps;
+  k.grad_scale = s->grad_scale;
+  const int64_t n4 = n_padded / 4, per = n4 / world;
+  int64_t blocks = (n4 + 255) / 256;   // the zeroing pass covers the whole buffer
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  launch_pdl(dp_adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, pr, rank, world, m_slice, v_slice,
+             zero_buf, n4, per, seq, ticket, k);
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : EIMS_ERR_CUDA;
+}
+#pragma GCC visibility pop

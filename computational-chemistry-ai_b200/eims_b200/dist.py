@@ -96,6 +96,85 @@ class GradReducer:
         return grads
 
 
+class FusedP2PAdamW:
+    """Gradient all-reduce + AdamW + parameter broadcast as ONE kernel over NVLink / NVSwitch peer
+    memory (`eims_dp_adamw_fused`, csrc/dp_fused.cu) instead of NCCL all-reduce + AdamW.
+
+    The flat parameter buffer and two gradient buffers (double-buffered: peers read this step's
+    gradients while the next step's accumulate elsewhere) live in torch symmetric memory, so
+    every rank holds peer-mapped addresses of every other rank's buffers and, on an NVSwitch
+    box, a multicast address for in-switch reduction (`multimem.ld_reduce`) and multicast stores
+    (`multimem.st`).  Rank r owns 1/world of the parameter vector: it keeps Adam state for that
+    slice only and is the single writer of those parameters on every rank, so all ranks hold
+    bit-identical weights.  Host-side torch is plumbing (allocation, rendezvous); the exchange
+    itself is inside the kernel."""
+
+    SIGNAL_OFFSET = 8192  # bytes into torch's signal pad (its own barriers use the front)
+
+    def __init__(self, fp, group=None):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.C, self.lib = C, _lib.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.fp, dev, n = fp, fp.params.device, fp.numel
+        q = 4 * self.world
+        self.n_pad = (n + q - 1) // q * q
+        self.sym_params = symm.empty(self.n_pad, dtype=torch.float32, device=dev)
+        self.sym_params.zero_()
+        self.sym_params[:n].copy_(fp.params)
+        self.sym_grads = [symm.empty(self.n_pad, dtype=torch.float32, device=dev) for _ in range(2)]
+        for g in self.sym_grads:
+            g.zero_()
+        self.h_params = symm.rendezvous(self.sym_params, self.group)
+        self.h_grads = [symm.rendezvous(g, self.group) for g in self.sym_grads]
+        if self.h_params.signal_pad_size < self.SIGNAL_OFFSET + 128:
+            raise RuntimeError("symmetric-memory signal pad too small")
+        pad = self.h_params.get_signal_pad(self.rank, (self.h_params.signal_pad_size // 4,), torch.int32)
+        pad[self.SIGNAL_OFFSET // 4: self.SIGNAL_OFFSET // 4 + 32].zero_()
+        torch.cuda.synchronize(dev)
+        self.h_params.barrier()
+        arr = lambda ptrs, off=0: (C.c_uint64 * self.world)(*[int(p) + off for p in ptrs])
+        self.param_ptrs = arr(self.h_params.buffer_ptrs)
+        self.grad_ptrs = [arr(h.buffer_ptrs) for h in self.h_grads]
+        self.signal_ptrs = arr(self.h_params.signal_pad_ptrs, self.SIGNAL_OFFSET)
+        mc = lambda h: int(getattr(h, "multicast_ptr", 0) or 0)
+        self.params_mc, self.grads_mc = mc(self.h_params), [mc(h) for h in self.h_grads]
+        self.multicast = bool(self.params_mc and all(self.grads_mc))
+        self.m = torch.zeros(self.n_pad // self.world, dtype=torch.float32, device=dev)
+        self.v = torch.zeros_like(self.m)
+        self.ticket = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.seq = 0
+        # the plan and the checkpoint code see ordinary views of the symmetric buffers
+        fp.params = self.sym_params[:n]
+        fp.grads = self.sym_grads[0][:n]
+
+    def begin_step(self):
+        """Select the gradient buffer of the coming step (call before backward)."""
+        self.fp.grads = self.sym_grads[self.seq % 2][: self.fp.numel]
+
+    def step(self, step, stream):
+        """The fused kernel for the step whose gradients sit in the current buffer."""
+        from ._lib import check, ptr
+        C = self.C
+        cur = self.seq % 2
+        self.seq += 1
+        check(self.lib.eims_dp_adamw_fused(self.rank, self.world, self.grad_ptrs[cur], self.param_ptrs, self.signal_ptrs,
+                                           C.c_uint64(self.grads_mc[cur] if self.multicast else 0),
+                                           C.c_uint64(self.params_mc if self.multicast else 0), ptr(self.m), ptr(self.v),
+                                           ptr(self.sym_grads[1 - cur]), self.n_pad, C.byref(step), C.c_uint32(self.seq),
+                                           ptr(self.ticket), stream))
+
+
+def train_step_fused(plan, ds, ids, fp, step, fused: "FusedP2PAdamW", metrics=None, loss_kind="mse"):
+    """One data-parallel step with the fused exchange: K1 .. backward on this rank's batch (one C
+    call), then the all-reduce + AdamW + broadcast kernel."""
+    fused.begin_step()
+    plan.train_step(ds, ids, fp, step, metrics, loss_kind, optimizer=False)
+    fused.step(step, plan.stream)
+
+
 def broadcast_params(fp, src: int = 0, group=None):
     """Identical initial weights and BatchNorm buffers on every rank (DDP's constructor)."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -209,6 +209,22 @@ int eims_train_step(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids
 /* predict_spectrum (GCN:494-511) for a batch: batch build + eval forward + sigmoid. */
 int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
                      const float* params, const float* bn_running, float* prob_out, eims_stream_t stream);
+/* Data-parallel optimiser step in one kernel (new functionality; the reference is single-GPU,
+ * GCN:63): all-reduce of the flat gradient buffers + AdamW (GCN:429) + parameter broadcast over
+ * NVLink / NVSwitch peer memory.  Rank r updates the slice [r*n/world, (r+1)*n/world) from the sum
+ * of every rank's gradients (multimem.ld_reduce through the switch when `grads_multicast` != 0,
+ * else peer loads) and stores it into every rank's parameter buffer (multimem.st / peer stores).
+ * grad_ptrs / param_ptrs / signal_ptrs: `world` peer-mapped device addresses (host arrays) of
+ * this step's gradient buffer, the parameter buffer and the signal pad (>= 128 bytes, zeroed
+ * once) of every rank; m_slice / v_slice: Adam state of the own slice (n/world floats);
+ * zero_buf: this rank's OTHER gradient buffer (gradients are double-buffered because peers read
+ * them), zeroed here; n_padded: buffer length, a multiple of 4*world; seq: 1, 2, 3, ... the same
+ * on every rank; ticket: one zeroed device word.  s->grad_scale = 1/world. */
+int eims_dp_adamw_fused(int32_t rank, int32_t world, const uint64_t* grad_ptrs, const uint64_t* param_ptrs,
+                        const uint64_t* signal_ptrs, uint64_t grads_multicast, uint64_t params_multicast,
+                        float* m_slice, float* v_slice, float* zero_buf, int64_t n_padded, const eims_step* s,
+                        uint32_t seq, uint32_t* ticket, eims_stream_t stream);
+
 /* Per-stage device timing for the roofline report (bench.py): when enabled every kernel
  * launch of the plan is bracketed by CUDA events on the launching stream.  _read
  * synchronises, sums the elapsed ms and the bracket count per stage (eims_plan_num_stages()
