@@ -104,14 +104,14 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------
 # algorithmic bytes / flops per stage and step (fp32 values, int32 indices)
 # ------------------------------------------------------------------------------------------
-def stage_work(N, E, B, P):
+def stage_work(N, E, B, P, H=H, L=L):
     pd = 2 * H
     nb = E // 2
     gemm_head = 2 * B * (pd * 2 * H + 2 * H * H + H * M)
     return {
         # name: (bound, work per STEP in bytes or flops)
-        "k1_batch_build": ("hbm", 2 * N * F0 * 4 + nb * 8 + B * 16 + 3 * E * 4 + 3 * N * 4 + 2 * B * 4),
-        "layer0_fwd": ("hbm", 2 * N * F0 * 4 + 4 * E + 8 * N + 4 * N * H),
+        "k1_batch_build": ("hbm", 3 * N * F0 * 4 + nb * 8 + B * 16 + 3 * E * 4 + 3 * N * 4 + 2 * B * 4),
+        "layer0_fwd": ("hbm", N * F0 * 4 + 4 * N + 4 * N * H),
         "bn_stats": ("hbm", L * 4 * N * H),
         "spmm_fwd": ("hbm", (L - 1) * (8 * N * H + 4 * E + 8 * N)),
         "gemm_gcn_fwd": ("tensor", (L - 1) * 2 * N * H * H),
@@ -121,10 +121,11 @@ def stage_work(N, E, B, P):
         "loss": ("hbm", 16 * B * M),
         "metrics": ("hbm", 8 * B),
         "gemm_head_wgrad": ("tensor", gemm_head),
-        "colsum": ("hbm", 4 * B * (M + H + 2 * H)),
+        "colsum": ("hbm", 4 * B * M),
         "gemm_head_dgrad": ("tensor", gemm_head),
         "ln_bwd": ("hbm", 16 * B * (2 * H + H)),
-        "bn_bwd": ("hbm", L * 20 * N * H - 8 * N * H),
+        "bn_bwd_stats": ("hbm", L * 8 * N * H - 4 * N * H),      # dh + z per layer (last layer: z only)
+        "bn_bwd_apply": ("hbm", L * 12 * N * H - 8 * N * H),     # dh + z read, q written (layer 0 writes no q)
         "gemm_gcn_wgrad": ("tensor", (L - 1) * 2 * N * H * H),
         "gemm_gcn_dgrad": ("tensor", (L - 1) * 2 * N * H * H),
         "spmm_bwd": ("hbm", (L - 1) * (8 * N * H + 4 * E + 8 * N)),
@@ -132,6 +133,23 @@ def stage_work(N, E, B, P):
         "adamw": ("hbm", 28 * P),
         "elementwise": ("hbm", 0),
     }
+
+
+def stage_report(prof, work, n_steps, pk_):
+    """Per-stage timing (CUDA events around every launch) -> achieved GB/s or TFLOP/s."""
+    tot_ms = sum(v[0] for v in prof.values())
+    out = {}
+    for name, (tms, cnt) in prof.items():
+        if cnt == 0 or name not in work:
+            continue
+        bound, w = work[name]
+        per_step_ms = tms / n_steps
+        ach = w / (per_step_ms * 1e-3) / (1e9 if bound == "hbm" else 1e12) if per_step_ms > 0 else 0.0
+        peak = pk_["hbm_gbs"] if bound == "hbm" else pk_["bf16_tflops"]
+        out[name] = {"ms_per_step": round(per_step_ms, 5), "share": round(tms / tot_ms, 4), "launches_per_step": cnt / n_steps,
+                     "bound": bound, "achieved": round(ach, 3), "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                     "frac": round(ach / peak, 4)}
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -313,18 +331,7 @@ def run_ours(args):
         prof, _ = plan.profile_read()
         plan.profile(False)
         work = stage_work(float(np.mean(Ns)), float(np.mean(Es)), BATCH, fp.numel)
-        tot_ms = sum(v[0] for v in prof.values())
-        stages_out = {}
-        for name, (tms, cnt) in prof.items():
-            if cnt == 0:
-                continue
-            bound, w = work[name]
-            per_step_ms = tms / args.profile_steps
-            ach = w / (per_step_ms * 1e-3) / (1e9 if bound == "hbm" else 1e12) if per_step_ms > 0 else 0.0
-            peak = pk_["hbm_gbs"] if bound == "hbm" else pk_["bf16_tflops"]
-            stages_out[name] = {"ms_per_step": round(per_step_ms, 5), "share": round(tms / tot_ms, 4), "launches_per_step": cnt / args.profile_steps,
-                                "bound": bound, "achieved": round(ach, 3), "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
-                                "frac": round(ach / peak, 4)}
+        stages_out = stage_report(prof, work, args.profile_steps, pk_)
         dom = max(stages_out, key=lambda n: stages_out[n]["ms_per_step"])
         s = stages_out[dom]
         traffic = None
@@ -485,13 +492,27 @@ def run_extra(args):
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
+    stages_out = None
+    if args.profile_steps > 0:
+        plan.profile(True)
+        n_prof = min(args.profile_steps, 10)
+        Ns, Es = [], []
+        perm_h = perm.cpu().numpy()
+        for j in range(n_prof):
+            n_, e_ = ds.batch_counts(perm_h[j * batch:(j + 1) * batch])
+            Ns.append(n_)
+            Es.append(e_)
+            step(j)
+        prof, _ = plan.profile_read()
+        plan.profile(False)
+        stages_out = stage_report(prof, stage_work(float(np.mean(Ns)), float(np.mean(Es)), batch, fp.numel, hid, layers), n_prof, peaks())
     wl = ("BASELINE configs[2]: inference-only spectrum prediction, synthetic molecules (<=64 heavy atoms), batch 4096, single B200"
           if infer else "BASELINE configs[4] shapes on one B200: 6 GCN layers, hidden 1024, molecules up to 128 heavy atoms, batch 512, training")
     print(json.dumps({"metric": "gcn_eims_infer_molecules_per_sec" if infer else METRIC, "value": args.steps * batch / (ms * 1e-3),
                       "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                       "higher_is_better": True, "dtype": "f32", "data": "synthetic", "clocks": clocks,
                       "config": {"workload": wl, "batch_per_gpu": batch, "hidden_dim": hid, "num_gcn_layers": layers, "max_mz": M,
-                                 "resident_molecules": n_mols}}))
+                                 "resident_molecules": n_mols}, "stages": stages_out}))
 
 
 if __name__ == "__main__":

@@ -340,18 +340,26 @@ __global__ void __launch_bounds__(256, LAYER0 ? 2 : 4) bn_bwd_apply_kernel(
   }
 }
 
-int launch_bn_bwd(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr, const int* argmax,
-                  int pooling, const float* z, int H, const float* mean, const float* invstd, const float* gamma,
-                  const float* norm, float* dgamma, float* dbeta, float* dbias, float* means, float* partials,
-                  float* q, int max_nodes, cudaStream_t st, const float* a0, int F, float* dW0) {
+int launch_bn_bwd_stats(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr,
+                        const int* argmax, int pooling, const float* z, int H, const float* mean, const float* invstd,
+                        float* dgamma, float* dbeta, float* means, float* partials, int max_nodes, cudaStream_t st) {
+  if (H % 4 || H > 4096) return EIMS_ERR_ARG;
+  DhSrc src{dh, dG, gid, gptr, argmax, pooling};
+  launch_pdl(bn_bwd_stats_kernel, bn_grid(H, max_nodes), dim3(256), 0, st, dims, src, z, H, mean, invstd, dgamma, dbeta, means, partials);
+  return 0;
+}
+
+int launch_bn_bwd_apply(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr,
+                        const int* argmax, int pooling, const float* z, int H, const float* mean, const float* invstd,
+                        const float* gamma, const float* norm, float* dbias, const float* means, float* q, int max_nodes,
+                        cudaStream_t st, const float* a0, int F, float* dW0) {
   if (H % 4 || H > 4096 || (dW0 && (F < 1 || F > kMaxF0d))) return EIMS_ERR_ARG;
   DhSrc src{dh, dG, gid, gptr, argmax, pooling};
   const dim3 grid = bn_grid(H, max_nodes);
-  launch_pdl(bn_bwd_stats_kernel, dim3(grid), dim3(256), 0, st, dims, src, z, H, mean, invstd, dgamma, dbeta, means, partials);
   if (dW0)
-    launch_pdl(bn_bwd_apply_kernel<true>, dim3(grid), dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, a0, F, dW0);
+    launch_pdl(bn_bwd_apply_kernel<true>, grid, dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, a0, F, dW0);
   else
-    launch_pdl(bn_bwd_apply_kernel<false>, dim3(grid), dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, nullptr, 0, nullptr);
+    launch_pdl(bn_bwd_apply_kernel<false>, grid, dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, nullptr, 0, nullptr);
   return 0;
 }
 

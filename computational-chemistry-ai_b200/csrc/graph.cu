@@ -20,6 +20,67 @@ namespace eims {
 constexpr int kK1Warps = 4;
 constexpr int kMaxF0 = 8;
 
+// Large batches (inference, thousands of molecules): the per-block batch reduction of the fused
+// kernel below would cost O(B) per block, so one 1024-thread block scans the counts first
+// (exclusive scan of atoms / directed edges per molecule -> gptr, eptr, dims) and the build
+// kernel reads its offsets from there.
+__global__ void __launch_bounds__(1024) k1_scan_kernel(const int64_t* __restrict__ node_ptr,
+                                                       const int64_t* __restrict__ bond_ptr,
+                                                       const int32_t* __restrict__ ids, int B, int max_nodes,
+                                                       int max_edges, int* __restrict__ gptr, int* __restrict__ eptr,
+                                                       int* __restrict__ rowptr, int* __restrict__ dims, int seq) {
+  pdl_sync();
+  __shared__ int wn[32], we[32];
+  __shared__ int carry_n, carry_e;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) { carry_n = 0; carry_e = 0; }
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    int g = base + tid, n = 0, e = 0;
+    if (g < B) {
+      int64_t id = ids ? (int64_t)ids[g] : (int64_t)g;
+      n = (int)(node_ptr[id + 1] - node_ptr[id]);
+      e = 2 * (int)(bond_ptr[id + 1] - bond_ptr[id]);
+    }
+    int in = n, ie = e;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int tn = __shfl_up_sync(0xffffffffu, in, o), te = __shfl_up_sync(0xffffffffu, ie, o);
+      if (lane >= o) { in += tn; ie += te; }
+    }
+    if (lane == 31) { wn[w] = in; we[w] = ie; }
+    __syncthreads();
+    if (w == 0) {
+      int a = wn[lane], b = we[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
+        if (lane >= o) { a += ta; b += tb; }
+      }
+      wn[lane] = a; we[lane] = b;  // inclusive over warps
+    }
+    __syncthreads();
+    int off_n = carry_n + (w ? wn[w - 1] : 0) + in - n;
+    int off_e = carry_e + (w ? we[w - 1] : 0) + ie - e;
+    if (g < B) { gptr[g] = off_n; eptr[g] = off_e; }
+    __syncthreads();
+    if (tid == 0) { carry_n += wn[31]; carry_e += we[31]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int N = carry_n, E = carry_e;
+    bool over = N > max_nodes || E > max_edges || N < 0 || E < 0;
+    gptr[B] = N; eptr[B] = E;
+    dims[DIM_B] = over ? 0 : B;
+    dims[DIM_N] = over ? 0 : N;
+    dims[DIM_E] = over ? 0 : E;
+    dims[DIM_OVERFLOW] = over ? 1 : 0;
+    dims[5] = seq;
+    dims[6] = dims[7] = 0;
+    rowptr[over ? 0 : N] = over ? 0 : E;
+  }
+}
+
 constexpr int kK1MaxN = 128, kK1MaxB = 192;  // molecule size staged in shared memory (bigger ones use global scratch)
 
 struct K1Stage {  // per-warp staging
@@ -35,13 +96,22 @@ __global__ void __launch_bounds__(kK1Warps * 32) k1_build_kernel(
     const int32_t* __restrict__ bond_begin, const int32_t* __restrict__ bond_end, const int32_t* __restrict__ ids, int B,
     int F, int max_nodes, int max_edges, int seq, int* __restrict__ gptr, int* __restrict__ eptr, int* __restrict__ gid,
     int* __restrict__ src, int* __restrict__ dst, int* __restrict__ rowptr, int* __restrict__ col,
-    float* __restrict__ norm, float* __restrict__ x, float* __restrict__ a0, int* __restrict__ dims) {
+    float* __restrict__ norm, float* __restrict__ x, float* __restrict__ a0, int* __restrict__ dims, int prescanned) {
   pdl_sync();
   __shared__ long long red[kK1Warps][4];
   __shared__ int cnt_n[kK1Warps], cnt_e[kK1Warps];
   __shared__ K1Stage stage[kK1Warps];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int g0 = blockIdx.x * kK1Warps;
+  int o, eo;
+  if (prescanned) {  // offsets and dims[] come from k1_scan_kernel
+    if (dims[DIM_OVERFLOW]) return;
+    const int g = g0 + w;
+    if (g >= B) return;
+    o = gptr[g]; eo = eptr[g];
+    if (lane == 0) { cnt_n[w] = gptr[g + 1] - o; cnt_e[w] = eptr[g + 1] - eo; }
+    __syncwarp();
+  } else {
   // ---- phase A: batch totals and this block's prefix (loads batched 4 deep: the molecule
   // table is a random gather from HBM, so the two dependent latencies are paid once per batch)
   long long tn = 0, te = 0, pn = 0, pe = 0;
@@ -92,10 +162,11 @@ __global__ void __launch_bounds__(kK1Warps * 32) k1_build_kernel(
     rowptr[N] = E;
   }
   if (over) return;
-  const int g = g0 + w;
-  if (g >= B) return;
-  int o = (int)pn, eo = (int)pe;
+  if (g0 + w >= B) return;
+  o = (int)pn; eo = (int)pe;
   for (int k = 0; k < w; ++k) { o += cnt_n[k]; eo += cnt_e[k]; }
+  }
+  const int g = g0 + w;
   // ---- phase B: this warp's molecule; every loop below is lane-parallel (atoms or edges
   // across lanes), the phases are separated by __syncwarp()
   const int64_t id = ids ? (int64_t)ids[g] : (int64_t)g;
@@ -111,7 +182,7 @@ __global__ void __launch_bounds__(kK1Warps * 32) k1_build_kernel(
   float* pnorm = staged ? S.snorm : norm + o;
   const float* px = staged ? S.sx : x + (int64_t)o * F;
   const int rowbase = staged ? 0 : eo, colbase = staged ? 0 : o;
-  if (lane == 0) { gptr[g] = o; eptr[g] = eo; }
+  if (lane == 0 && !prescanned) { gptr[g] = o; eptr[g] = eo; }
   for (int t = lane; t < n * F; t += 32) {
     const float v = __ldg(feat + a_0 * F + t);
     x[(int64_t)o * F + t] = v;
@@ -194,8 +265,13 @@ int launch_csr_build(const eims_dataset* ds, const int32_t* ids, int B, int F, i
                      float* x, int* dims, cudaStream_t st, float* a0, int seq) {
   if (F > kMaxF0) return EIMS_ERR_ARG;
   const int blocks = B > 0 ? (B + kK1Warps - 1) / kK1Warps : 1;
+  const int prescanned = B > 1024;
+  if (prescanned)
+    launch_pdl(k1_scan_kernel, dim3(1), dim3(1024), 0, st, ds->node_ptr, ds->bond_ptr, ids, B, max_nodes, max_edges, gptr, eptr,
+               rowptr, dims, seq);
   launch_pdl(k1_build_kernel, dim3(blocks), dim3(kK1Warps * 32), 0, st, ds->node_ptr, ds->bond_ptr, ds->feat, ds->bond_begin,
-             ds->bond_end, ids, B, F, max_nodes, max_edges, seq, gptr, eptr, gid, src, dst, rowptr, col, norm, x, a0, dims);
+             ds->bond_end, ids, B, F, max_nodes, max_edges, seq, gptr, eptr, gid, src, dst, rowptr, col, norm, x, a0, dims,
+             prescanned);
   return 0;
 }
 

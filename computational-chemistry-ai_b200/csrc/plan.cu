@@ -112,12 +112,12 @@ int gemm(eims_plan* p, const float* A, int lda, int a_mn, const float* B, int ld
 
 enum Stage {
   ST_K1 = 0, ST_LAYER0_FWD, ST_BN_STATS, ST_SPMM_FWD, ST_GEMM_GCN_FWD, ST_READOUT, ST_GEMM_HEAD_FWD, ST_LN_FWD, ST_LOSS,
-  ST_METRICS, ST_GEMM_HEAD_WGRAD, ST_COLSUM, ST_GEMM_HEAD_DGRAD, ST_LN_BWD, ST_BN_BWD, ST_GEMM_GCN_WGRAD,
+  ST_METRICS, ST_GEMM_HEAD_WGRAD, ST_COLSUM, ST_GEMM_HEAD_DGRAD, ST_LN_BWD, ST_BN_BWD_STATS, ST_BN_BWD_APPLY, ST_GEMM_GCN_WGRAD,
   ST_GEMM_GCN_DGRAD, ST_SPMM_BWD, ST_LAYER0_WGRAD, ST_ADAMW, ST_ELEMENTWISE, ST_COUNT
 };
 const char* kStageNames[ST_COUNT] = {
   "k1_batch_build", "layer0_fwd", "bn_stats", "spmm_fwd", "gemm_gcn_fwd", "readout", "gemm_head_fwd", "ln_fwd", "loss",
-  "metrics", "gemm_head_wgrad", "colsum", "gemm_head_dgrad", "ln_bwd", "bn_bwd", "gemm_gcn_wgrad",
+  "metrics", "gemm_head_wgrad", "colsum", "gemm_head_dgrad", "ln_bwd", "bn_bwd_stats", "bn_bwd_apply", "gemm_gcn_wgrad",
   "gemm_gcn_dgrad", "spmm_bwd", "layer0_wgrad", "adamw", "elementwise"};
 
 void prof_begin(eims_plan* p, int stage, int nkernels, cudaStream_t st) {
@@ -345,7 +345,7 @@ int eims_batch_build(eims_plan* p, const eims_dataset* ds, const int32_t* mol_id
     p->batch_seq = 0;
   }
   ++p->batch_seq;
-  STAGE(ST_K1, 1, launch_csr_build(ds, mol_ids, num_graphs, p->d.node_feat_dim, p->Nc, p->Ec, p->i("gptr"), p->i("eptr"),
+  STAGE(ST_K1, num_graphs > 1024 ? 2 : 1, launch_csr_build(ds, mol_ids, num_graphs, p->d.node_feat_dim, p->Nc, p->Ec, p->i("gptr"), p->i("eptr"),
                             p->i("gid"), p->i("src"), p->i("dst"), p->i("rowptr"), p->i("col"), p->f("norm"),
                             p->f("x"), p->i("dims"), st, p->f("a0"), p->batch_seq));
   p->state = 1;
@@ -497,11 +497,14 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
   // ---- GCN layers, last to first (GCN:358-363 backwards)
   for (int l = L - 1; l >= 0; --l) {
     const bool from_readout = (l == L - 1);
-    STAGE(ST_BN_BWD, 2, launch_bn_bwd(dims, from_readout ? nullptr : p->f("dh"), p->f("dG"), p->i("gid"), p->i("gptr"),
-                           p->i("argmax"), d.pooling, p->f(L_("z", l)), H, p->f(L_("bn_mean", l)),
-                           p->f(L_("bn_invstd", l)), params + p->off_bn_g(l), p->f("norm"), grads + p->off_bn_g(l),
-                           grads + p->off_bn_b(l), grads + p->off_gcn_b(l), p->f("bn_means2"), p->f("bn_partials"),
-                           p->f("q"), p->Nc, st, l == 0 ? p->f("a0") : nullptr, F, l == 0 ? grads + p->off_gcn_w(0) : nullptr));
+    const float* dh_in = from_readout ? nullptr : p->f("dh");
+    STAGE(ST_BN_BWD_STATS, 1, launch_bn_bwd_stats(dims, dh_in, p->f("dG"), p->i("gid"), p->i("gptr"), p->i("argmax"), d.pooling,
+                                 p->f(L_("z", l)), H, p->f(L_("bn_mean", l)), p->f(L_("bn_invstd", l)), grads + p->off_bn_g(l),
+                                 grads + p->off_bn_b(l), p->f("bn_means2"), p->f("bn_partials"), p->Nc, st));
+    STAGE(ST_BN_BWD_APPLY, 1, launch_bn_bwd_apply(dims, dh_in, p->f("dG"), p->i("gid"), p->i("gptr"), p->i("argmax"), d.pooling,
+                                 p->f(L_("z", l)), H, p->f(L_("bn_mean", l)), p->f(L_("bn_invstd", l)), params + p->off_bn_g(l),
+                                 p->f("norm"), grads + p->off_gcn_b(l), p->f("bn_means2"), p->f("q"), p->Nc, st,
+                                 l == 0 ? p->f("a0") : nullptr, F, l == 0 ? grads + p->off_gcn_w(0) : nullptr));
     if (l > 0) {
       STAGE(ST_GEMM_GCN_WGRAD, 1, gemm(p, p->f(L_("a", l)), H, 1, p->f("q"), H, 1, grads + p->off_gcn_w(l), H, H, H, p->Nc, nullptr,
                     dims + DIM_N, nullptr, nullptr, 0, 1, st));

@@ -42,7 +42,7 @@ def graph_arrays(table, ids):
 
 
 # ------------------------------------------------------------------------------- K1
-@pytest.mark.parametrize("n_mols,max_atoms,shuffle", [(1, 9, False), (64, 64, True), (700, 40, True), (33, 128, True)])
+@pytest.mark.parametrize("n_mols,max_atoms,shuffle", [(1, 9, False), (64, 64, True), (700, 40, True), (33, 128, True), (1500, 24, True)])
 def test_csr_build_bit_exact(n_mols, max_atoms, shuffle):
     table = synth_molecules(max(n_mols, 8) * 2, max_atoms=max_atoms, seed=5)
     rng = np.random.default_rng(0)
