@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="N=1: build each batch inside its own step instead of one step ahead")
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"], help="N>1: gradient exchange implementation")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one-shot all-reduce after backward instead of two overlapped buckets")
     ap.add_argument("--profile-steps", type=int, default=20)
@@ -275,8 +276,12 @@ def run_ours(args):
     def step_fn(i, k):
         ids = perm[i * BATCH:(i + 1) * BATCH]
         st = make_step(lr=sched[k][0], beta1=sched[k][1], grad_scale=gscale, step=k + 1, seed=2024 + rank)
-        if fused is not None:
-            train_step_fused(plan, ds, ids, fp, st, fused, metrics)
+        if world == 1 and not args.no_prefetch:
+            # K1 of the next batch is built on a side stream while this step runs
+            plan.train_step_prefetch(ds, ids, perm[(i + 1) * BATCH:(i + 2) * BATCH], fp, st, metrics)
+        elif fused is not None:
+            train_step_fused(plan, ds, ids, fp, st, fused, metrics,
+                             next_ids=None if args.no_prefetch else perm[(i + 1) * BATCH:(i + 2) * BATCH])
         else:
             train_step_dp(plan, ds, ids, fp, st, reducer, metrics)
 

@@ -89,7 +89,17 @@ struct eims_plan {
   int64_t launches = 0;
   eims_step last_step;
   int pool_dim() const { return d.pooling == EIMS_POOL_COMBINED ? 2 * d.hidden_dim : d.hidden_dim; }
-  template <class T> T* get(const std::string& n) { return reinterpret_cast<T*>(buf[n].ptr); }
+  // The batch tables K1 writes exist twice ("name#0" / "name#1"): eims_batch_build always fills the
+  // set the kernels enqueued so far do NOT use and makes it current for what is enqueued next, so
+  // the next batch can be built on a side stream while the current step is still running.
+  int cur = 0;
+  static bool pingpong(const std::string& n) {
+    static const char* k[] = {"dims", "gptr", "eptr", "gid", "src", "dst", "rowptr", "col", "norm", "x", "a0"};
+    for (const char* s : k) if (n == s) return true;
+    return false;
+  }
+  std::string key(const std::string& n) const { return pingpong(n) ? n + (cur ? "#1" : "#0") : n; }
+  template <class T> T* get(const std::string& n) { return reinterpret_cast<T*>(buf[key(n)].ptr); }
   float* f(const std::string& n) { return get<float>(n); }
   int* i(const std::string& n) { return get<int>(n); }
   // parameter accessors (flat buffer)
@@ -147,6 +157,13 @@ void prof_end(eims_plan* p, cudaStream_t st) {
 
 void add(eims_plan* p, const std::string& name, int64_t bytes) {
   bytes = (bytes + 255) & ~(int64_t)255;
+  if (eims_plan::pingpong(name)) {
+    for (const char* sfx : {"#0", "#1"}) {
+      p->order.emplace_back(name + sfx, bytes);
+      p->ws_bytes += bytes;
+    }
+    return;
+  }
   p->order.emplace_back(name, bytes);
   p->ws_bytes += bytes;
 }
@@ -310,7 +327,8 @@ int eims_plan_bind(eims_plan* p, void* workspace, int64_t bytes) {
   char* c = reinterpret_cast<char*>(workspace);
   for (auto& kv : p->order) { p->buf[kv.first] = Buf{c, kv.second}; c += kv.second; }
   // counters / flags / dims start at zero (the ticket counter in bn_partials must be 0)
-  if (cudaMemset(p->buf["dims"].ptr, 0, p->buf["dims"].bytes) != cudaSuccess ||
+  if (cudaMemset(p->buf["dims#0"].ptr, 0, p->buf["dims#0"].bytes) != cudaSuccess ||
+      cudaMemset(p->buf["dims#1"].ptr, 0, p->buf["dims#1"].bytes) != cudaSuccess ||
       cudaMemset(p->buf["flags"].ptr, 0, p->buf["flags"].bytes) != cudaSuccess ||
       cudaMemset(p->buf["bn_partials"].ptr, 0, p->buf["bn_partials"].bytes) != cudaSuccess)
     return fail(EIMS_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -327,7 +345,7 @@ int eims_plan_set_gemm_backend(eims_plan* p, int32_t backend) {
 
 int eims_plan_buffer(eims_plan* p, const char* name, void** ptr, int64_t* bytes) {
   if (!p || !p->bound || !name) return fail(EIMS_ERR_STATE, "plan not bound");
-  auto it = p->buf.find(name);
+  auto it = p->buf.find(p->key(name));
   if (it == p->buf.end()) return fail(EIMS_ERR_ARG, "no workspace buffer named '%s'", name);
   if (ptr) *ptr = it->second.ptr;
   if (bytes) *bytes = it->second.bytes;
@@ -340,8 +358,11 @@ int eims_batch_build(eims_plan* p, const eims_dataset* ds, const int32_t* mol_id
   if (!ds || num_graphs < 0) return fail(EIMS_ERR_ARG, "bad dataset / num_graphs");
   if (num_graphs > p->Bc) return fail(EIMS_ERR_CAPACITY, "num_graphs %d exceeds plan max_graphs %d", num_graphs, p->Bc);
   cudaStream_t st = (cudaStream_t)stream;
+  p->cur ^= 1;  // build into the other set of batch tables; later calls use it
   if (p->batch_seq >= 0x7ffffff0) {  // sequence wrap: forget the old zero-degree tag
-    if (cudaMemsetAsync(p->i("dims") + DIM_ZERO_DEG, 0, sizeof(int), st) != cudaSuccess) return fail(EIMS_ERR_CUDA, "cudaMemsetAsync failed");
+    for (const char* nm : {"dims#0", "dims#1"})
+      if (cudaMemsetAsync(reinterpret_cast<int*>(p->buf[nm].ptr) + DIM_ZERO_DEG, 0, sizeof(int), st) != cudaSuccess)
+        return fail(EIMS_ERR_CUDA, "cudaMemsetAsync failed");
     p->batch_seq = 0;
   }
   ++p->batch_seq;
@@ -537,6 +558,21 @@ int eims_train_step(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids
   EIMS_TRY(eims_batch_build(p, ds, mol_ids, num_graphs, stream));
   EIMS_TRY(eims_forward(p, params, bn_running, 1, s, stream));
   EIMS_TRY(loss_impl(p, ds->targets, mol_ids, loss_kind, 1, metrics, stream));
+  EIMS_TRY(eims_backward(p, params, nullptr, grads, stream));
+  if (adam_m && adam_v) {
+    cudaStream_t st = (cudaStream_t)stream;
+    STAGE(ST_ADAMW, 1, launch_adamw(params, grads, adam_m, adam_v, p->poff.back(), s, st));
+  }
+  return 0;
+}
+
+int eims_train_step_built(eims_plan* p, const float* targets, const int32_t* target_rows, float* params, float* grads,
+                          float* adam_m, float* adam_v, float* bn_running, int32_t loss_kind, const eims_step* s,
+                          float* metrics, eims_stream_t stream) {
+  if (!s) return fail(EIMS_ERR_ARG, "step scalars are NULL");
+  if (!targets) return fail(EIMS_ERR_ARG, "training needs target spectra");
+  EIMS_TRY(eims_forward(p, params, bn_running, 1, s, stream));
+  EIMS_TRY(loss_impl(p, targets, target_rows, loss_kind, 1, metrics, stream));
   EIMS_TRY(eims_backward(p, params, nullptr, grads, stream));
   if (adam_m && adam_v) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -76,6 +76,7 @@ _SIGS = {
     "eims_backward_part": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp]),
     "eims_metrics_accumulate": (C.c_int, [_vp, _vp, _vp]),
     "eims_train_step": (C.c_int, [_vp, C.POINTER(Dataset), _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(Step), _vp, _vp]),
+    "eims_train_step_built": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(Step), _vp, _vp]),
     "eims_infer_batch": (C.c_int, [_vp, C.POINTER(Dataset), _vp, _i32, _vp, _vp, _vp, _vp]),
     "eims_dp_adamw_fused": (C.c_int, [_i32, _i32, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _u64, _u64, _vp, _vp, _vp,
                                       _i64, C.POINTER(Step), C.c_uint32, _vp, _vp]),

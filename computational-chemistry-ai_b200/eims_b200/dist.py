@@ -167,11 +167,15 @@ class FusedP2PAdamW:
                                            ptr(self.ticket), stream))
 
 
-def train_step_fused(plan, ds, ids, fp, step, fused: "FusedP2PAdamW", metrics=None, loss_kind="mse"):
+def train_step_fused(plan, ds, ids, fp, step, fused: "FusedP2PAdamW", metrics=None, loss_kind="mse", next_ids=None):
     """One data-parallel step with the fused exchange: K1 .. backward on this rank's batch (one C
-    call), then the all-reduce + AdamW + broadcast kernel."""
+    call; with `next_ids` the next batch is built one step ahead on a side stream), then the
+    all-reduce + AdamW + broadcast kernel."""
     fused.begin_step()
-    plan.train_step(ds, ids, fp, step, metrics, loss_kind, optimizer=False)
+    if next_ids is not None:
+        plan.train_step_prefetch(ds, ids, next_ids, fp, step, metrics, loss_kind, optimizer=False)
+    else:
+        plan.train_step(ds, ids, fp, step, metrics, loss_kind, optimizer=False)
     fused.step(step, plan.stream)
 
 

@@ -296,6 +296,44 @@ class Plan:
         for l in range(self.d.num_gcn_layers):
             fp.num_batches_tracked[l] += 1
 
+    def train_step_prefetch(self, ds: DeviceDataset, ids, next_ids, fp: FlatParams, step: Step, metrics=None, loss_kind="mse",
+                            optimizer=True):
+        """A training step whose batch tables were built ahead of time: K1 of the NEXT batch runs on
+        a side stream while this step computes (the plan double-buffers the tables), which takes
+        the batch build off the critical path.  Call with next_ids=None for the last step."""
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.device)
+            self._built = None       # (event, ids data_ptr) of the batch waiting in the current table set
+            self._step_end = [None, None]
+        n = len(ids)
+        if self._built is None or self._built[1] != ids.data_ptr():
+            self.batch_build(ds, ids, n)             # cold start: build on the compute stream
+        else:
+            cur.wait_event(self._built[0])
+        if optimizer:
+            fp.ensure_adam()
+        check(self.lib.eims_train_step_built(self.h, ptr(ds.targets), ptr(ids), ptr(fp.params), ptr(fp.grads),
+                                             ptr(fp.adam_m) if optimizer else None, ptr(fp.adam_v) if optimizer else None,
+                                             ptr(fp.bn_running), _lib.LOSS[loss_kind], C.byref(step), ptr(metrics), self.stream))
+        self.num_graphs = n
+        for l in range(self.d.num_gcn_layers):
+            fp.num_batches_tracked[l] += 1
+        end = torch.cuda.Event()
+        end.record(cur)
+        prev_end, self._step_end = self._step_end[1], [self._step_end[1], end]
+        self._built = None
+        if next_ids is not None:
+            # the table set the next build overwrites was last read by the PREVIOUS step
+            if prev_end is not None:
+                self._side.wait_event(prev_end)
+            with torch.cuda.stream(self._side):
+                self.batch_build(ds, next_ids, len(next_ids))
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+            self._built = (ev, next_ids.data_ptr())
+            self._keep_ids = next_ids
+
     def train_step_split(self, ds: DeviceDataset, ids, fp: FlatParams, step: Step, metrics=None, loss_kind="mse",
                          on_head_grads=None, num_graphs=None):
         """K1 + forward + loss + backward without the optimiser, with a host callback between the

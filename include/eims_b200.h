@@ -206,6 +206,14 @@ int eims_metrics_accumulate(eims_plan* p, float* metrics, eims_stream_t stream);
 int eims_train_step(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
                     float* params, float* grads, float* adam_m, float* adam_v, float* bn_running,
                     int32_t loss_kind, const eims_step* s, float* metrics, eims_stream_t stream);
+/* The same step on the batch eims_batch_build built last (forward + loss + backward [+ AdamW]).
+ * The plan keeps two sets of batch tables and eims_batch_build always fills the set that the
+ * work enqueued so far does not use, so the caller may build batch t+1 on a side stream while
+ * step t runs (order the streams with events: the build of batch t+1 must wait for the end of
+ * step t-1, step t+1 for the build).  targets / target_rows as in eims_loss. */
+int eims_train_step_built(eims_plan* p, const float* targets, const int32_t* target_rows, float* params, float* grads,
+                          float* adam_m, float* adam_v, float* bn_running, int32_t loss_kind, const eims_step* s,
+                          float* metrics, eims_stream_t stream);
 /* predict_spectrum (GCN:494-511) for a batch: batch build + eval forward + sigmoid. */
 int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
                      const float* params, const float* bn_running, float* prob_out, eims_stream_t stream);
