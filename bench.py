@@ -361,15 +361,16 @@ def run_ours(args):
         def e2e_step(j, slot_next):
             st = make_step(lr=sched[k + j][0], beta1=sched[k + j][1], grad_scale=gscale, step=k + j + 1, seed=2024 + rank)
             slot = slot_next
-            nxt = runner.upload(hbs[j + 1]) if j + 1 < len(hbs) else None
             if world == 1:
                 runner.train_step(slot, hbs[j], st)
             else:
                 raise NotImplementedError
-            return nxt
+            # enqueue the next batch's H2D copy (+ its K1) after this step: it runs on the copy stream
+            # as soon as the step that last used that slot has finished, i.e. concurrently with this one
+            return runner.upload(hbs[j + 1], build=not args.no_prefetch) if j + 1 < len(hbs) else None
 
         if world == 1:
-            slot = runner.upload(hbs[0])
+            slot = runner.upload(hbs[0], build=not args.no_prefetch)
             for j in range(3):
                 slot = e2e_step(j, slot)
             torch.cuda.synchronize()

@@ -4,7 +4,8 @@ backward + AdamW -> loss / cosine read back to the host.
 
 This is what `collate_fn` + `.to(device)` + one `train_model` iteration do in the reference
 (GCN:292-297, 411-439); bench.py times it as `e2e`.  Two device slots are used so the
-upload of batch i+1 (copy stream) overlaps the compute of batch i.
+upload of batch i+1 and its K1 batch build (both on the copy stream; the plan double-buffers
+the batch tables) overlap the compute of batch i.
 """
 from __future__ import annotations
 
@@ -58,6 +59,7 @@ class HostBatchRunner:
         self.copy_stream = torch.cuda.Stream(dev)
         self.copied = [torch.cuda.Event() for _ in range(n_slots)]
         self.consumed = [None] * n_slots
+        self.built = [False] * n_slots
         self.metrics = torch.zeros(8, dtype=torch.float32, device=dev)
         self.host_metrics = torch.zeros(8, dtype=torch.float32, pin_memory=True)
         self.h2d_bytes = 0
@@ -70,16 +72,26 @@ class HostBatchRunner:
         return Dataset(base + o["node_ptr"], base + o["bond_ptr"], base + o["feat"], base + o["bond_begin"],
                        base + o["bond_end"], (base + o["targets"]) if hb.has_targets else None, hb.num_graphs)
 
-    def upload(self, hb: PackedHostBatch):
-        """Enqueue the H2D copy of `hb` on the copy stream; returns the slot index."""
+    def upload(self, hb: PackedHostBatch, build: bool = False):
+        """Enqueue the H2D copy of `hb` (and, with build=True, its K1 batch build) on the copy
+        stream; returns the slot index.  With build=True uploads and steps must alternate."""
         slot = self._i % len(self.slots)
         self._i += 1
         if hb.nbytes > self.slots[slot].numel():
             raise _lib.EimsError(_lib.ERR_CAPACITY, "host batch larger than the staging slot")
+        if len(self.slots) != 2 and build:
+            raise ValueError("building ahead needs exactly two slots (the plan has two sets of batch tables)")
         with torch.cuda.stream(self.copy_stream):
             if self.consumed[slot] is not None:
                 self.copy_stream.wait_event(self.consumed[slot])  # the step that read this slot is done
             self.slots[slot][:hb.nbytes].copy_(self.buf_of(hb), non_blocking=True)
+            if build:
+                # K1 on the copy stream: the table set it overwrites was last read by the step that
+                # consumed this slot, which the wait above already covers
+                ds = self._dataset(slot, hb)
+                check(self.plan.lib.eims_batch_build(self.plan.h, C.byref(ds), None, hb.num_graphs,
+                                                     C.c_void_p(self.copy_stream.cuda_stream)))
+            self.built[slot] = build
             self.copied[slot].record(self.copy_stream)
         self.h2d_bytes += hb.nbytes
         return slot
@@ -96,11 +108,18 @@ class HostBatchRunner:
         ds = self._dataset(slot, hb)
         self.fp.ensure_adam()
         fp = self.fp
-        check(self.plan.lib.eims_train_step(self.plan.h, C.byref(ds), None, hb.num_graphs, _lib.ptr(fp.params),
-                                            _lib.ptr(fp.grads), _lib.ptr(fp.adam_m) if optimizer else None,
-                                            _lib.ptr(fp.adam_v) if optimizer else None,
-                                            _lib.ptr(fp.bn_running), _lib.LOSS[loss_kind], C.byref(step),
-                                            _lib.ptr(self.metrics), self.plan.stream))
+        if self.built[slot]:
+            check(self.plan.lib.eims_train_step_built(self.plan.h, C.c_void_p(ds.targets), None, _lib.ptr(fp.params),
+                                                      _lib.ptr(fp.grads), _lib.ptr(fp.adam_m) if optimizer else None,
+                                                      _lib.ptr(fp.adam_v) if optimizer else None, _lib.ptr(fp.bn_running),
+                                                      _lib.LOSS[loss_kind], C.byref(step), _lib.ptr(self.metrics),
+                                                      self.plan.stream))
+        else:
+            check(self.plan.lib.eims_train_step(self.plan.h, C.byref(ds), None, hb.num_graphs, _lib.ptr(fp.params),
+                                                _lib.ptr(fp.grads), _lib.ptr(fp.adam_m) if optimizer else None,
+                                                _lib.ptr(fp.adam_v) if optimizer else None,
+                                                _lib.ptr(fp.bn_running), _lib.LOSS[loss_kind], C.byref(step),
+                                                _lib.ptr(self.metrics), self.plan.stream))
         ev = torch.cuda.Event()
         ev.record(cur)
         self.consumed[slot] = ev
