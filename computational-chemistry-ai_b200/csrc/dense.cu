@@ -201,10 +201,33 @@ struct DhSrc {
   const int* gptr;       // [B+1]
   const int* argmax;     // [B,H]
   int pooling;
+  // third source: the GraphConv input gradient computed on the fly from the layer above,
+  //   dh_i = (sum_{j in row i} da_j) * c_i * dropmask_i      (K2 backward form, A symmetric)
+  // which saves materialising dh (one launch, one [N,H] write and two reads per layer)
+  const float* da;       // [N,H] or null
+  const int* rowptr;
+  const int* col;
+  const float* norm;
+  DropCfg drop;
 };
 
 __device__ __forceinline__ float4 load_dh(const DhSrc& s, int i, int c, int H) {
   if (s.dh) return ldg4(s.dh + (int64_t)i * H + c);
+  if (s.da) {
+    const int e0 = __ldg(s.rowptr + i), e1 = __ldg(s.rowptr + i + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = e0; e < e1; ++e) {
+      const float4 v = ldg4(s.da + (int64_t)__ldg(s.col + e) * H + c);
+      acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+    }
+    const float ci = __ldg(s.norm + i);
+    acc.x *= ci; acc.y *= ci; acc.z *= ci; acc.w *= ci;
+    if (s.drop.active()) {
+      const float4 m = drop_mask4(s.drop, (uint64_t)i * H + c);
+      acc.x *= m.x; acc.y *= m.y; acc.z *= m.z; acc.w *= m.w;
+    }
+    return acc;
+  }
   const int g = __ldg(s.gid + i);
   const int pd = s.pooling == EIMS_POOL_COMBINED ? 2 * H : H;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -342,9 +365,11 @@ __global__ void __launch_bounds__(256, LAYER0 ? 2 : 4) bn_bwd_apply_kernel(
 
 int launch_bn_bwd_stats(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr,
                         const int* argmax, int pooling, const float* z, int H, const float* mean, const float* invstd,
-                        float* dgamma, float* dbeta, float* means, float* partials, int max_nodes, cudaStream_t st) {
+                        float* dgamma, float* dbeta, float* means, float* partials, int max_nodes, cudaStream_t st,
+                        const GatherSrc* gs) {
   if (H % 4 || H > 4096) return EIMS_ERR_ARG;
-  DhSrc src{dh, dG, gid, gptr, argmax, pooling};
+  DhSrc src{dh, dG, gid, gptr, argmax, pooling, nullptr, nullptr, nullptr, nullptr, DropCfg{}};
+  if (gs) { src.da = gs->da; src.rowptr = gs->rowptr; src.col = gs->col; src.norm = gs->norm; src.drop = gs->drop; }
   launch_pdl(bn_bwd_stats_kernel, bn_grid(H, max_nodes), dim3(256), 0, st, dims, src, z, H, mean, invstd, dgamma, dbeta, means, partials);
   return 0;
 }
@@ -352,9 +377,10 @@ int launch_bn_bwd_stats(const int* dims, const float* dh, const float* dG, const
 int launch_bn_bwd_apply(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr,
                         const int* argmax, int pooling, const float* z, int H, const float* mean, const float* invstd,
                         const float* gamma, const float* norm, float* dbias, const float* means, float* q, int max_nodes,
-                        cudaStream_t st, const float* a0, int F, float* dW0) {
+                        cudaStream_t st, const float* a0, int F, float* dW0, const GatherSrc* gs) {
   if (H % 4 || H > 4096 || (dW0 && (F < 1 || F > kMaxF0d))) return EIMS_ERR_ARG;
-  DhSrc src{dh, dG, gid, gptr, argmax, pooling};
+  DhSrc src{dh, dG, gid, gptr, argmax, pooling, nullptr, nullptr, nullptr, nullptr, DropCfg{}};
+  if (gs) { src.da = gs->da; src.rowptr = gs->rowptr; src.col = gs->col; src.norm = gs->norm; src.drop = gs->drop; }
   const dim3 grid = bn_grid(H, max_nodes);
   if (dW0)
     launch_pdl(bn_bwd_apply_kernel<true>, grid, dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, a0, F, dW0);

@@ -31,13 +31,17 @@ int launch_bn_stats(const int* dims, const float* z, int H, const float* gamma, 
                     int max_nodes, cudaStream_t st);
 int launch_bn_eval_coeffs(const float* gamma, const float* beta, const float* rmean, const float* rvar, int H,
                           float* scale, float* shift, cudaStream_t st);
+// dh computed on the fly from the layer above (see DhSrc in dense.cu)
+struct GatherSrc { const float* da; const int* rowptr; const int* col; const float* norm; DropCfg drop; };
 int launch_bn_bwd_stats(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr,
                         const int* argmax, int pooling, const float* z, int H, const float* mean, const float* invstd,
-                        float* dgamma, float* dbeta, float* means, float* partials, int max_nodes, cudaStream_t st);
+                        float* dgamma, float* dbeta, float* means, float* partials, int max_nodes, cudaStream_t st,
+                        const GatherSrc* gs = nullptr);
 int launch_bn_bwd_apply(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr,
                         const int* argmax, int pooling, const float* z, int H, const float* mean, const float* invstd,
                         const float* gamma, const float* norm, float* dbias, const float* means, float* q, int max_nodes,
-                        cudaStream_t st, const float* a0 = nullptr, int F = 0, float* dW0 = nullptr);
+                        cudaStream_t st, const float* a0 = nullptr, int F = 0, float* dW0 = nullptr,
+                        const GatherSrc* gs = nullptr);
 int launch_ln_fwd(const int* dims, const float* u, int W, const float* gamma, const float* beta, DropCfg drop, float* y,
                   float* stats, int max_graphs, cudaStream_t st);
 int launch_ln_bwd(const int* dims, const float* u, const float* y, const float* dy, int W, const float* gamma,

@@ -81,6 +81,7 @@ struct eims_plan {
   int state;  // 0 none, 1 batch built, 2 forward(train) done, 3 loss grad ready, 4 head backward done
   int last_training;
   // per-stage CUDA-event profiling (bench.py's roofline pass) and launch accounting
+  bool fuse_spmm_bwd = false;  // measured slower at cfg 2 (0.405 vs 0.386 ms/step): the slab-layout gather costs more than K2 saves
   int batch_seq = 0;  // K1 sequence number (tags the zero-degree flag, see k1_build_kernel)
   bool prof = false;
   struct ProfRec { int stage; cudaEvent_t a, b; };
@@ -281,6 +282,7 @@ int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, 
   p->d = *d;
   p->Bc = max_graphs; p->Nc = max_nodes; p->Ec = max_edges > 0 ? max_edges : 1;
   p->gemm_backend = EIMS_GEMM_TCGEN05;
+  if (const char* e = getenv("EIMS_FUSE_SPMM_BWD")) p->fuse_spmm_bwd = e[0] != '0';
   p->ws_bytes = 0; p->bound = false; p->state = 0; p->last_training = 0;
   memset(&p->last_step, 0, sizeof(p->last_step));
   auto s = param_sizes(d);
@@ -518,21 +520,27 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
   // ---- GCN layers, last to first (GCN:358-363 backwards)
   for (int l = L - 1; l >= 0; --l) {
     const bool from_readout = (l == L - 1);
-    const float* dh_in = from_readout ? nullptr : p->f("dh");
+    // layers below the last get their dh = (A da) * c * dropmask from the layer above, gathered on
+    // the fly inside both BatchNorm-backward passes when EIMS_FUSE_SPMM_BWD=1; by default K2 materialises it
+    const bool gather = !from_readout && p->fuse_spmm_bwd;
+    const float* dh_in = (from_readout || gather) ? nullptr : p->f("dh");
+    GatherSrc gsrc{p->f("da"), p->i("rowptr"), p->i("col"), p->f("norm"), make_drop(drop_p, seed, step, l)};
+    const GatherSrc* gs = gather ? &gsrc : nullptr;
     STAGE(ST_BN_BWD_STATS, 1, launch_bn_bwd_stats(dims, dh_in, p->f("dG"), p->i("gid"), p->i("gptr"), p->i("argmax"), d.pooling,
                                  p->f(L_("z", l)), H, p->f(L_("bn_mean", l)), p->f(L_("bn_invstd", l)), grads + p->off_bn_g(l),
-                                 grads + p->off_bn_b(l), p->f("bn_means2"), p->f("bn_partials"), p->Nc, st));
+                                 grads + p->off_bn_b(l), p->f("bn_means2"), p->f("bn_partials"), p->Nc, st, gs));
     STAGE(ST_BN_BWD_APPLY, 1, launch_bn_bwd_apply(dims, dh_in, p->f("dG"), p->i("gid"), p->i("gptr"), p->i("argmax"), d.pooling,
                                  p->f(L_("z", l)), H, p->f(L_("bn_mean", l)), p->f(L_("bn_invstd", l)), params + p->off_bn_g(l),
                                  p->f("norm"), grads + p->off_gcn_b(l), p->f("bn_means2"), p->f("q"), p->Nc, st,
-                                 l == 0 ? p->f("a0") : nullptr, F, l == 0 ? grads + p->off_gcn_w(0) : nullptr));
+                                 l == 0 ? p->f("a0") : nullptr, F, l == 0 ? grads + p->off_gcn_w(0) : nullptr, gs));
     if (l > 0) {
       STAGE(ST_GEMM_GCN_WGRAD, 1, gemm(p, p->f(L_("a", l)), H, 1, p->f("q"), H, 1, grads + p->off_gcn_w(l), H, H, H, p->Nc, nullptr,
                     dims + DIM_N, nullptr, nullptr, 0, 1, st));
       STAGE(ST_GEMM_GCN_DGRAD, 1, gemm(p, p->f("q"), H, 0, params + p->off_gcn_w(l), H, 0, p->f("da"), H, p->Nc, H, H, dims + DIM_N,
                     nullptr, nullptr, nullptr, 0, 0, st));
-      STAGE(ST_SPMM_BWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("da"), H, nullptr, nullptr,
-                                make_drop(drop_p, seed, step, l - 1), 1, p->f("dh"), p->Nc, st));
+      if (!p->fuse_spmm_bwd)
+        STAGE(ST_SPMM_BWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("da"), H, nullptr, nullptr,
+                                  make_drop(drop_p, seed, step, l - 1), 1, p->f("dh"), p->Nc, st));
     }  // l == 0: dW0 came out of the BatchNorm-backward apply pass above (q_0 is never materialised)
   }
   p->state = 1;
