@@ -342,7 +342,7 @@ def run_ours(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(dom)
+            traffic = json.load(open(tp)).get(dom)  # bytes per launch, ncu dram__bytes_read + dram__bytes_write
         roofline = {"kernel": dom, "bound": s["bound"], "achieved": s["achieved"], "peak": peaks()["hbm_gbs"] if s["bound"] == "hbm" else peaks()["bf16_tflops"],
                     "unit": s["unit"], "frac": s["frac"], "traffic": traffic,
                     "peak_source": f"{pk_['source']} ({'copy bandwidth' if s['bound'] == 'hbm' else 'cuBLAS bf16 burst; tf32 is half of it and the kernel runs 3 tf32 passes, so 1/6 is the ceiling'})",
