@@ -82,7 +82,7 @@ int launch_gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb,
                      int N, int K, const int* m_dev, const int* k_dev, const float* row_scale, const float* bias,
                      int relu, int accumulate, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return EIMS_ERR_ARG;
-  if (accumulate == 2) accumulate = 0;  // split-K-allowed store: plain store on this path
+  if (accumulate == 2 || accumulate == 3) accumulate = 0;  // split-K-allowed store: plain store on this path
   GemmArgs g{A, B, C, lda, ldb, ldc, a_mn, b_mn, M, N, K, m_dev, k_dev, row_scale, bias, relu, accumulate};
   int splits = 1;
   if (accumulate) {  // split-K for the weight gradients (K = atoms or graphs)
@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_stats_kernel(const int* __restr
   double* acc = reinterpret_cast<double*>(scratch + 16);
   const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
   const int c0 = blockIdx.x * kSlab, c = c0 + cl * 4;
-  double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+  // per-thread partial sums in fp32 (a few rows each, no cancellation involved), fp64 from there on
+  float af[4] = {0.f, 0.f, 0.f, 0.f}, bf[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < H) {
     const float4 mu = ldg4(mean + c), is = ldg4(invstd + c);
     const int stride = gridDim.y * kRowLanes;
@@ -269,11 +270,14 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_stats_kernel(const int* __restr
     for (int r = blockIdx.y * kRowLanes + rl; r < N; r += stride) {
       const float4 d = load_dh(src, r, c, H);
       const float4 v = ldg4(z + (int64_t)r * H + c);
-      a[0] += (double)d.x; a[1] += (double)d.y; a[2] += (double)d.z; a[3] += (double)d.w;
-      b[0] += (double)(d.x * ((v.x - mu.x) * is.x)); b[1] += (double)(d.y * ((v.y - mu.y) * is.y));
-      b[2] += (double)(d.z * ((v.z - mu.z) * is.z)); b[3] += (double)(d.w * ((v.w - mu.w) * is.w));
+      af[0] += d.x; af[1] += d.y; af[2] += d.z; af[3] += d.w;
+      bf[0] = fmaf(d.x, (v.x - mu.x) * is.x, bf[0]); bf[1] = fmaf(d.y, (v.y - mu.y) * is.y, bf[1]);
+      bf[2] = fmaf(d.z, (v.z - mu.z) * is.z, bf[2]); bf[3] = fmaf(d.w, (v.w - mu.w) * is.w, bf[3]);
     }
   }
+  double a[4], b[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { a[e] = (double)af[e]; b[e] = (double)bf[e]; }
   slab_reduce_atomic(a, b, H, c0, cl, rl, acc);
   if (!last_block_ticket(counter, gridDim.x * gridDim.y)) return;
   for (int k = threadIdx.x; k < H; k += blockDim.x) {

@@ -561,7 +561,7 @@ int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, i
     const int maxs = (kblocks + min_kb - 1) / min_kb;  // at least min_kb k-blocks per slice
     if (splits > maxs) splits = maxs;
     if (splits < 1) splits = 1;
-  } else if (accumulate == 2) {
+  } else if (accumulate == 2 || accumulate == 3) {
     // store semantics, but the caller tolerates atomic accumulation order (backward dgrads of the
     // 512-row head): when the tile grid cannot fill the chip, split K and add into a zeroed C.
     g.accumulate = 0;
@@ -570,7 +570,8 @@ int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, i
       const int maxs = kblocks / min_kb;
       if (splits > maxs) splits = maxs;
       if (splits > 1) {
-        if (cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st) != cudaSuccess) return EIMS_ERR_CUDA;
+        // accumulate == 3: the caller has zeroed C already
+        if (accumulate == 2 && cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st) != cudaSuccess) return EIMS_ERR_CUDA;
         g.accumulate = 1;
       } else {
         splits = 1;

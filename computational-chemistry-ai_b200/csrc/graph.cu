@@ -285,8 +285,14 @@ constexpr int kL0Rows = 256;  // rows of a0 / norm a block stages in shared memo
 __global__ void __launch_bounds__(256) layer0_fwd_kernel(const int* __restrict__ dims, const float* __restrict__ norm,
                                                          const float* __restrict__ a0, int F, const float* __restrict__ W,
                                                          const float* __restrict__ bias, int H, float* __restrict__ z,
-                                                         BnFuse bn) {
+                                                         BnFuse bn, float4* __restrict__ zero, int64_t zero_n4) {
   pdl_sync();
+  // side job (training): zero the outputs of the split-K head GEMMs of this step
+  if (zero) {
+    const int64_t nth = (int64_t)gridDim.x * gridDim.y * blockDim.x;
+    for (int64_t i = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < zero_n4; i += nth)
+      zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   __shared__ float sa0[kL0Rows * kMaxF0];
   __shared__ float sc[kL0Rows];
   const int N = dims[DIM_N];
@@ -341,14 +347,15 @@ __global__ void __launch_bounds__(256) layer0_fwd_kernel(const int* __restrict__
 }
 
 int launch_layer0_fwd(const int* dims, const float* norm, const float* a0, int F, const float* W, const float* bias,
-                      int H, float* z, int max_nodes, cudaStream_t st, const BnFuse* bn) {
+                      int H, float* z, int max_nodes, cudaStream_t st, const BnFuse* bn, float* zero, int64_t zero_n4) {
   if (F > kMaxF0 || H % 4) return EIMS_ERR_ARG;
   const int slabs = (H + 63) / 64;
   int rg = (148 * 4 + slabs - 1) / slabs;
   const int need = (max_nodes + kL0Rows - 1) / kL0Rows;  // a block stages at most kL0Rows rows
   if (rg < need) rg = need;
   if (rg < 1) rg = 1;
-  launch_pdl(layer0_fwd_kernel, dim3(slabs, rg), dim3(256), 0, st, dims, norm, a0, F, W, bias, H, z, bn ? *bn : BnFuse{});
+  launch_pdl(layer0_fwd_kernel, dim3(slabs, rg), dim3(256), 0, st, dims, norm, a0, F, W, bias, H, z, bn ? *bn : BnFuse{},
+             reinterpret_cast<float4*>(zero), zero_n4);
   return 0;
 }
 

@@ -14,7 +14,8 @@ int launch_csr_build(const eims_dataset* ds, const int32_t* ids, int B, int F, i
                      int* gptr, int* eptr, int* gid, int* src, int* dst, int* rowptr, int* col, float* norm,
                      float* x, int* dims, cudaStream_t st, float* a0 = nullptr, int seq = 1);
 int launch_layer0_fwd(const int* dims, const float* norm, const float* a0, int F, const float* W, const float* bias,
-                      int H, float* z, int max_nodes, cudaStream_t st, const BnFuse* bn = nullptr);
+                      int H, float* z, int max_nodes, cudaStream_t st, const BnFuse* bn = nullptr, float* zero = nullptr,
+                      int64_t zero_n4 = 0);
 int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const float* norm, const float* h, int H,
                      const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
                      int max_nodes, cudaStream_t st);

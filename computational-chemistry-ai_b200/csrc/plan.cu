@@ -305,11 +305,15 @@ int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, 
   add(p, "bn_means2", 2 * H * 4);
   add(p, "bn_partials", bn_scratch_floats(d->hidden_dim, p->Nc) * 4);
   add(p, "readout", B * P * 4);
-  add(p, "u1", B * 2 * H * 4); add(p, "y1", B * 2 * H * 4); add(p, "ln1", B * 2 * 4);
-  add(p, "u2", B * H * 4); add(p, "y2", B * H * 4); add(p, "ln2", B * 2 * 4);
-  add(p, "logits", B * M * 4); add(p, "prob", B * M * 4); add(p, "dlogits", B * M * 4);
-  add(p, "row_loss", B * 4); add(p, "row_cos", B * 4);
+  // outputs of the split-K head GEMMs, contiguous: a training forward zeroes the whole range once
+  // (inside the layer-0 kernel) instead of one memset per GEMM, which would also break the
+  // programmatic-dependent-launch chain six times per step
+  add(p, "u1", B * 2 * H * 4); add(p, "u2", B * H * 4); add(p, "logits", B * M * 4);
   add(p, "dy2", B * H * 4); add(p, "dy1", B * 2 * H * 4); add(p, "dG", B * P * 4);
+  add(p, "y1", B * 2 * H * 4); add(p, "ln1", B * 2 * 4);
+  add(p, "y2", B * H * 4); add(p, "ln2", B * 2 * 4);
+  add(p, "prob", B * M * 4); add(p, "dlogits", B * M * 4);
+  add(p, "row_loss", B * 4); add(p, "row_cos", B * 4);
   add(p, "dh", N * H * 4); add(p, "q", N * H * 4); add(p, "da", N * H * 4);
   *out = p;
   return 0;
@@ -409,8 +413,10 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
   {  // layer 0: dense transform of K1's 6-wide aggregate, BatchNorm statistics fused when training
     BnFuse bf{};
     if (training) bf = fuse(0);
+    float* zero = training ? p->f("u1") : nullptr;
+    const int64_t zero_bytes = reinterpret_cast<char*>(p->buf["dG"].ptr) + p->buf["dG"].bytes - reinterpret_cast<char*>(p->buf["u1"].ptr);
     STAGE(ST_LAYER0_FWD, 1, launch_layer0_fwd(dims, p->f("norm"), p->f("a0"), F, params + p->off_gcn_w(0), params + p->off_gcn_b(0),
-                               H, p->f("z0"), p->Nc, st, training ? &bf : nullptr));
+                               H, p->f("z0"), p->Nc, st, training ? &bf : nullptr, zero, zero_bytes / 16));
     if (!training) STAGE(ST_BN_STATS, 1, bn(0));
   }
   for (int l = 1; l < L; ++l) {
@@ -428,7 +434,7 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
   // The 512-row head GEMMs cannot fill 148 SMs with output tiles, so in training they split K and
   // accumulate with float atomics (summation order varies in the last bit run to run); eval-mode
   // forwards keep plain stores and are bit-reproducible.
-  const int head_acc = training ? 2 : 0;
+  const int head_acc = training ? 3 : 0;  // 3 = split-K allowed, C already zeroed (by the layer-0 kernel)
   STAGE(ST_READOUT, 1, launch_readout(dims, p->i("gptr"), p->f(L_("z", L - 1)), H, p->f(L_("bn_scale", L - 1)),
                           p->f(L_("bn_shift", L - 1)), d.pooling, p->f("readout"), p->i("argmax"), p->Bc, st));
   STAGE(ST_GEMM_HEAD_FWD, 1, gemm(p, p->f("readout"), P, 0, params + p->off_head(0), P, 0, p->f("u1"), 2 * H, p->Bc, 2 * H, P,
@@ -500,20 +506,20 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
                 nullptr, 0, 1, st));
   STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, dl, M, M, grads + p->off_head(9), p->Bc, st));
   STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, dl, M, 0, params + p->off_head(8), H, 1, p->f("dy2"), H, p->Bc, H, M, dims + DIM_B, nullptr, nullptr,
-                nullptr, 0, 2, st));
+                nullptr, 0, 3, st));
   // LayerNorm backward also leaves the bias gradient of the Linear in front of it (column sums of du)
   STAGE(ST_LN_BWD, 1, launch_ln_bwd(dims, p->f("u2"), p->f("y2"), p->f("dy2"), H, params + p->off_head(6), p->f("ln2"), drop_scale,
                          p->f("dy2"), grads + p->off_head(6), grads + p->off_head(7), grads + p->off_head(5), p->Bc, st));
   STAGE(ST_GEMM_HEAD_WGRAD, 1, gemm(p, p->f("dy2"), H, 1, p->f("y1"), 2 * H, 1, grads + p->off_head(4), 2 * H, H, 2 * H, p->Bc, nullptr,
                 dims + DIM_B, nullptr, nullptr, 0, 1, st));
   STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, p->f("dy2"), H, 0, params + p->off_head(4), 2 * H, 1, p->f("dy1"), 2 * H, p->Bc, 2 * H, H,
-                dims + DIM_B, nullptr, nullptr, nullptr, 0, 2, st));
+                dims + DIM_B, nullptr, nullptr, nullptr, 0, 3, st));
   STAGE(ST_LN_BWD, 1, launch_ln_bwd(dims, p->f("u1"), p->f("y1"), p->f("dy1"), 2 * H, params + p->off_head(2), p->f("ln1"),
                          drop_scale, p->f("dy1"), grads + p->off_head(2), grads + p->off_head(3), grads + p->off_head(1), p->Bc, st));
   STAGE(ST_GEMM_HEAD_WGRAD, 1, gemm(p, p->f("dy1"), 2 * H, 1, p->f("readout"), P, 1, grads + p->off_head(0), P, 2 * H, P, p->Bc, nullptr,
                 dims + DIM_B, nullptr, nullptr, 0, 1, st));
   STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, p->f("dy1"), 2 * H, 0, params + p->off_head(0), P, 1, p->f("dG"), P, p->Bc, P, 2 * H, dims + DIM_B,
-                nullptr, nullptr, nullptr, 0, 2, st));
+                nullptr, nullptr, nullptr, 0, 3, st));
   p->state = 4;  // head gradients final (the data-parallel reducer may start on that bucket)
   }
   if (part == EIMS_BWD_HEAD) return check_launch("eims_backward_part");

@@ -119,7 +119,7 @@ int eims_spmm_norm(const int32_t* dims, const int32_t* rowptr, const int32_t* co
  * row-major (GraphConv weight).  Epilogue: C = act(acc * row_scale[m] + bias[n]);
  * row_scale / bias may be NULL; relu != 0 applies max(.,0); accumulate = 1 adds into C
  * atomically (split-K weight gradients), accumulate = 2 stores but lets a small grid split K
- * (C is zeroed first; summation order then varies run to run).  m_dev / k_dev (may be NULL) override M / K with
+ * (C is zeroed first; summation order then varies run to run), accumulate = 3 the same with C already zeroed by the caller.  m_dev / k_dev (may be NULL) override M / K with
  * a device-side int (the number of atoms of the current batch).
  * backend: EIMS_GEMM_TCGEN05 or EIMS_GEMM_FP32_SIMT. */
 int eims_gemm(int32_t backend, const float* A, int32_t lda, int32_t a_mn_major,
