@@ -82,15 +82,18 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 // kernel can be relaunched / replayed from a CUDA graph.
 __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigned int nblocks) {
   __shared__ bool is_last;
-  __threadfence();
+  // Release: the barrier orders every thread's earlier global writes / atomics before thread 0's
+  // fence, and the fence is cumulative, so one fence per block (not one per thread) makes them
+  // visible before the ticket is taken - the pattern cooperative-groups' grid sync uses.
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     unsigned int t = atomicAdd(counter, 1u);
     is_last = (t == nblocks - 1);
     if (is_last) *counter = 0u;
   }
   __syncthreads();
-  if (is_last) __threadfence();
+  if (is_last) __threadfence();  // acquire side, last block only
   return is_last;
 }
 
