@@ -40,8 +40,12 @@ def parse():
     ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stratify", action="store_true", help="N>1: plain random batches instead of equal-work (size-stratified) ones")
     ap.add_argument("--no-prefetch", action="store_true", help="N=1: build each batch inside its own step instead of one step ahead")
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"], help="N>1: gradient exchange implementation")
+    ap.add_argument("--dp-overlap", action="store_true",
+                    help="fused path: exchange the head bucket early on a side stream (measured slower at N=2: the step then "
+                         "needs four C calls instead of one)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one-shot all-reduce after backward instead of two overlapped buckets")
     ap.add_argument("--profile-steps", type=int, default=20)
     ap.add_argument("--workload", default="train", choices=["train", "infer", "wide"],
@@ -225,7 +229,7 @@ def workload_config(n_gpus):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from eims_b200.dist import FusedP2PAdamW, GradReducer, broadcast_params, train_step_dp, train_step_fused
+    from eims_b200.dist import FusedP2PAdamW, GradReducer, broadcast_params, stratified_epoch, train_step_dp, train_step_fused
     from eims_b200.engine import DeviceDataset, FlatParams, ModelDims, Plan, make_step, onecycle_schedule
     from eims_b200.hostpath import HostBatchRunner, PackedHostBatch
     from eims_b200.synth import dense_spectra, synth_molecules, synth_peaks
@@ -250,7 +254,13 @@ def run_ours(args):
     ds = DeviceDataset(table, targets, dev)
     d = ModelDims(F0, H, L, M, "combined", DROPOUT)
     rng = np.random.default_rng(99 + rank)
-    perm_host = np.concatenate([rng.permutation(n_mols) for _ in range((steps_total * BATCH) // n_mols + 2)]).astype(np.int32)
+    n_epochs = (steps_total * BATCH) // n_mols + 2
+    if world > 1 and not args.no_stratify:
+        # equal-work batches on every rank (see dist.stratified_epoch): no straggler tax
+        sizes = np.diff(table.node_ptr)
+        perm_host = np.concatenate([stratified_epoch(sizes, BATCH, ep, seed=99 + rank).reshape(-1) for ep in range(n_epochs)]).astype(np.int32)
+    else:
+        perm_host = np.concatenate([rng.permutation(n_mols) for _ in range(n_epochs)]).astype(np.int32)
     cap_nodes = BATCH * MAX_ATOMS
     cap_edges = 2 * (cap_nodes + 3 * BATCH)
     plan = Plan(d, BATCH, cap_nodes, cap_edges, dev, gemm_backend=args.gemm)
@@ -263,7 +273,7 @@ def run_ours(args):
         dp_note = "NCCL all-reduce (two buckets) + AdamW kernel"
         if args.dp == "fused":
             try:
-                fused = FusedP2PAdamW(fp)
+                fused = FusedP2PAdamW(fp, L, overlap=args.dp_overlap)
                 dp_note = ("one fused kernel: all-reduce + AdamW + parameter broadcast over NVLink peer memory ("
                            + ("NVSwitch multimem" if fused.multicast else "peer loads/stores") + ")")
             except Exception as exc:  # symmetric memory unavailable: say so, use the NCCL path
@@ -280,8 +290,7 @@ def run_ours(args):
             # K1 of the next batch is built on a side stream while this step runs
             plan.train_step_prefetch(ds, ids, perm[(i + 1) * BATCH:(i + 2) * BATCH], fp, st, metrics)
         elif fused is not None:
-            train_step_fused(plan, ds, ids, fp, st, fused, metrics,
-                             next_ids=None if args.no_prefetch else perm[(i + 1) * BATCH:(i + 2) * BATCH])
+            train_step_fused(plan, ds, ids, fp, st, fused, metrics, next_ids=perm[(i + 1) * BATCH:(i + 2) * BATCH])
         else:
             train_step_dp(plan, ds, ids, fp, st, reducer, metrics)
 

@@ -56,9 +56,9 @@ __device__ __forceinline__ void multimem_st(float* mc, float4 v) {
 }
 
 // wait until every rank has written `seq` (or later) into this rank's pad row `phase`
-__device__ __forceinline__ void wait_all(const uint32_t* my_pad, int phase, int world, uint32_t seq) {
+__device__ __forceinline__ void wait_all(const uint32_t* my_pad, int row, int world, uint32_t seq) {
   if ((int)threadIdx.x < world) {
-    const uint32_t* p = my_pad + phase * kMaxRanks + threadIdx.x;
+    const uint32_t* p = my_pad + row * kMaxRanks + threadIdx.x;
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(p) - seq) < 0) {
       if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a lost rank must not hang the GPU for ever
@@ -67,20 +67,24 @@ __device__ __forceinline__ void wait_all(const uint32_t* my_pad, int phase, int 
   __syncthreads();
 }
 
+// The kernel works on the range [base4, base4 + n4) (in float4 units) of the flat buffers, so a step
+// can exchange the head bucket early (on a side stream, while the GCN layers are still being
+// differentiated) and the GCN / BatchNorm bucket at the end; `row` selects the bucket's pair of
+// signal rows.
 __global__ void __launch_bounds__(256) dp_adamw_kernel(DpPeers pr, int rank, int world, float* __restrict__ m,
                                                        float* __restrict__ v, float* __restrict__ zero_buf,
-                                                       int64_t n4, int64_t per, uint32_t seq, unsigned int* ticket,
-                                                       AdamKd k) {
+                                                       int64_t base4, int64_t n4, int64_t per, uint32_t seq, int row,
+                                                       unsigned int* ticket, AdamKd k) {
   pdl_sync();
   uint32_t* my_pad = pr.signals[rank];
   // ---- phase 0: my gradients are complete (stream order) -> tell everyone, wait for everyone
   if (blockIdx.x == 0 && (int)threadIdx.x < world) {
     __threadfence_system();
-    st_release_sys(pr.signals[threadIdx.x] + 0 * kMaxRanks + rank, seq);
+    st_release_sys(pr.signals[threadIdx.x] + (2 * row) * kMaxRanks + rank, seq);
   }
-  wait_all(my_pad, 0, world, seq);
+  wait_all(my_pad, 2 * row, world, seq);
   // ---- phase 1: reduce + AdamW + broadcast of the own slice
-  const int64_t s0 = (int64_t)rank * per, s1 = min(n4, s0 + per);
+  const int64_t s0 = base4 + (int64_t)rank * per, s1 = min(base4 + n4, s0 + per);
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = s0 + tid; i < s1; i += nth) {
     float4 g;
@@ -119,13 +123,14 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(DpPeers pr, int rank, int
   // the other gradient buffer (read by the peers during the previous step, which every rank has
   // left - they all passed phase 0 of this step) is zeroed for the step after this one
   if (zero_buf)
-    for (int64_t i = tid; i < n4; i += nth) *reinterpret_cast<float4*>(zero_buf + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = base4 + tid; i < base4 + n4; i += nth)
+      *reinterpret_cast<float4*>(zero_buf + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
   // ---- phase 2: when the whole grid has stored its slice, signal; the last block leaves only
   // after every rank's slice has landed in this rank's parameters
   __threadfence_system();
   if (!last_block_ticket(ticket, gridDim.x)) return;
-  if ((int)threadIdx.x < world) st_release_sys(pr.signals[threadIdx.x] + 1 * kMaxRanks + rank, seq);
-  wait_all(my_pad, 1, world, seq);
+  if ((int)threadIdx.x < world) st_release_sys(pr.signals[threadIdx.x] + (2 * row + 1) * kMaxRanks + rank, seq);
+  wait_all(my_pad, 2 * row + 1, world, seq);
 }
 
 }  // namespace eims
@@ -135,10 +140,12 @@ using namespace eims;
 #pragma GCC visibility push(default)
 extern "C" int eims_dp_adamw_fused(int32_t rank, int32_t world, const uint64_t* grad_ptrs, const uint64_t* param_ptrs,
                                    const uint64_t* signal_ptrs, uint64_t grads_multicast, uint64_t params_multicast,
-                                   float* m_slice, float* v_slice, float* zero_buf, int64_t n_padded,
-                                   const eims_step* s, uint32_t seq, uint32_t* ticket, eims_stream_t stream) {
+                                   float* m_slice, float* v_slice, float* zero_buf, int64_t range_off,
+                                   int64_t range_len, const eims_step* s, uint32_t seq, int32_t bucket,
+                                   uint32_t* ticket, eims_stream_t stream) {
   if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !grad_ptrs || !param_ptrs || !signal_ptrs || !s ||
-      s->step < 1 || n_padded % (4 * (int64_t)world) || !ticket)
+      s->step < 1 || range_off < 0 || range_off % 4 || range_len <= 0 || range_len % (4 * (int64_t)world) || bucket < 0 ||
+      bucket > 3 || !ticket)
     return EIMS_ERR_ARG;
   DpPeers pr{};
   for (int r = 0; r < world; ++r) {
@@ -159,11 +166,11 @@ extern "C" int eims_dp_adamw_fused(int32_t rank, int32_t world, const uint64_t* 
   k.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   k.eps = s->eps;
   k.grad_scale = s->grad_scale;
-  const int64_t n4 = n_padded / 4, per = n4 / world;
-  int64_t blocks = (n4 + 255) / 256;   // the zeroing pass covers the whole buffer
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  const int64_t n4 = range_len / 4, per = n4 / world;
+  int64_t blocks = (n4 + 255) / 256;   // the zeroing pass covers the whole range
+  if (blocks > 148) blocks = 148;  // one block per SM: the early bucket shares the GPU with the backward pass
   launch_pdl(dp_adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, pr, rank, world, m_slice, v_slice,
-             zero_buf, n4, per, seq, ticket, k);
+             zero_buf, range_off / 4, n4, per, seq, (int)bucket, ticket, k);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : EIMS_ERR_CUDA;
 }
 #pragma GCC visibility pop

@@ -79,7 +79,7 @@ _SIGS = {
     "eims_train_step_built": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, C.POINTER(Step), _vp, _vp]),
     "eims_infer_batch": (C.c_int, [_vp, C.POINTER(Dataset), _vp, _i32, _vp, _vp, _vp, _vp]),
     "eims_dp_adamw_fused": (C.c_int, [_i32, _i32, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _u64, _u64, _vp, _vp, _vp,
-                                      _i64, C.POINTER(Step), C.c_uint32, _vp, _vp]),
+                                      _i64, _i64, C.POINTER(Step), C.c_uint32, _i32, _vp, _vp]),
     "eims_plan_profile": (C.c_int, [_vp, _i32]),
     "eims_plan_profile_read": (C.c_int, [_vp, C.POINTER(_f32), C.POINTER(_i32), _i32, C.POINTER(_i64)]),
     "eims_plan_num_stages": (C.c_int, []),

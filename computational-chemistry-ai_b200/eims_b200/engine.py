@@ -297,7 +297,7 @@ class Plan:
             fp.num_batches_tracked[l] += 1
 
     def train_step_prefetch(self, ds: DeviceDataset, ids, next_ids, fp: FlatParams, step: Step, metrics=None, loss_kind="mse",
-                            optimizer=True):
+                            optimizer=True, on_head_grads=None):
         """A training step whose batch tables were built ahead of time: K1 of the NEXT batch runs on
         a side stream while this step computes (the plan double-buffers the tables), which takes
         the batch build off the critical path.  Call with next_ids=None for the last step."""
@@ -313,9 +313,21 @@ class Plan:
             cur.wait_event(self._built[0])
         if optimizer:
             fp.ensure_adam()
-        check(self.lib.eims_train_step_built(self.h, ptr(ds.targets), ptr(ids), ptr(fp.params), ptr(fp.grads),
-                                             ptr(fp.adam_m) if optimizer else None, ptr(fp.adam_v) if optimizer else None,
-                                             ptr(fp.bn_running), _lib.LOSS[loss_kind], C.byref(step), ptr(metrics), self.stream))
+        if on_head_grads is None:
+            check(self.lib.eims_train_step_built(self.h, ptr(ds.targets), ptr(ids), ptr(fp.params), ptr(fp.grads),
+                                                 ptr(fp.adam_m) if optimizer else None, ptr(fp.adam_v) if optimizer else None,
+                                                 ptr(fp.bn_running), _lib.LOSS[loss_kind], C.byref(step), ptr(metrics), self.stream))
+        else:
+            # backward in two parts with a host callback in between (data-parallel bucket overlap)
+            if optimizer:
+                raise ValueError("on_head_grads is for the data-parallel path, which runs its own optimiser kernel")
+            self.forward(fp, True, step)
+            self.loss(ds.targets, ids, loss_kind, True)
+            if metrics is not None:
+                self.metrics_accumulate(metrics)
+            check(self.lib.eims_backward_part(self.h, ptr(fp.params), None, ptr(fp.grads), _lib.BWD_HEAD, self.stream))
+            on_head_grads()
+            check(self.lib.eims_backward_part(self.h, ptr(fp.params), None, ptr(fp.grads), _lib.BWD_GCN, self.stream))
         self.num_graphs = n
         for l in range(self.d.num_gcn_layers):
             fp.num_batches_tracked[l] += 1

@@ -223,15 +223,18 @@ int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_id
  * of every rank's gradients (multimem.ld_reduce through the switch when `grads_multicast` != 0,
  * else peer loads) and stores it into every rank's parameter buffer (multimem.st / peer stores).
  * grad_ptrs / param_ptrs / signal_ptrs: `world` peer-mapped device addresses (host arrays) of
- * this step's gradient buffer, the parameter buffer and the signal pad (>= 128 bytes, zeroed
- * once) of every rank; m_slice / v_slice: Adam state of the own slice (n/world floats);
+ * this step's gradient buffer, the parameter buffer and the signal pad (>= 512 bytes, zeroed
+ * once) of every rank.  The call covers the float range [range_off, range_off + range_len) of the
+ * flat buffers (range_off % 4 == 0, range_len a multiple of 4*world) so that a step can exchange
+ * the head bucket early and the rest at the end; `bucket` (0..3) selects that range's signal rows
+ * and m_slice / v_slice / ticket belong to the bucket (range_len/world floats; one zeroed word).
  * zero_buf: this rank's OTHER gradient buffer (gradients are double-buffered because peers read
- * them), zeroed here; n_padded: buffer length, a multiple of 4*world; seq: 1, 2, 3, ... the same
- * on every rank; ticket: one zeroed device word.  s->grad_scale = 1/world. */
+ * them); its range is zeroed here.  seq: 1, 2, 3, ... the same on every rank.
+ * s->grad_scale = 1/world. */
 int eims_dp_adamw_fused(int32_t rank, int32_t world, const uint64_t* grad_ptrs, const uint64_t* param_ptrs,
                         const uint64_t* signal_ptrs, uint64_t grads_multicast, uint64_t params_multicast,
-                        float* m_slice, float* v_slice, float* zero_buf, int64_t n_padded, const eims_step* s,
-                        uint32_t seq, uint32_t* ticket, eims_stream_t stream);
+                        float* m_slice, float* v_slice, float* zero_buf, int64_t range_off, int64_t range_len,
+                        const eims_step* s, uint32_t seq, int32_t bucket, uint32_t* ticket, eims_stream_t stream);
 
 /* Per-stage device timing for the roofline report (bench.py): when enabled every kernel
  * launch of the plan is bracketed by CUDA events on the launching stream.  _read

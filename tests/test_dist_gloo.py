@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "computational-chemistry-ai_b200"))
 
-from eims_b200.dist import GradReducer, broadcast_params, head_split, shard_epoch  # noqa: E402
+from eims_b200.dist import GradReducer, broadcast_params, head_split, shard_epoch, stratified_epoch  # noqa: E402
 from eims_b200.engine import FlatParams, ModelDims, param_offsets, param_spec  # noqa: E402
 from eims_b200.synth import dense_spectra, synth_molecules, synth_peaks  # noqa: E402
 from oracle import gcn_oracle as O  # noqa: E402
@@ -95,6 +95,21 @@ def test_shard_epoch_partitions_the_permutation():
         shard_epoch(100, 4, 0, 32, epoch=0)
     with pytest.raises(ValueError):
         shard_epoch(1000, 4, 4, 32, epoch=0)
+
+
+def test_stratified_epoch_equalises_batch_work():
+    table = synth_molecules(4096 + 37, max_atoms=64, seed=8)
+    sizes = np.diff(table.node_ptr)
+    ids = stratified_epoch(sizes, 128, epoch=1, seed=3)
+    assert ids.shape == (4133 // 128, 128) and ids.dtype == np.int32
+    flat = ids.reshape(-1)
+    assert len(np.unique(flat)) == len(flat) and flat.min() >= 0 and flat.max() < len(sizes)   # each molecule at most once
+    work = sizes[ids].sum(axis=1)
+    rnd = sizes[np.random.default_rng(0).permutation(len(sizes))[: ids.size]].reshape(ids.shape).sum(axis=1)
+    assert work.std() < 0.2 * rnd.std()          # far tighter than uniform shuffling
+    assert abs(work.mean() - rnd.mean()) < 0.01 * rnd.mean()
+    assert not np.array_equal(ids, stratified_epoch(sizes, 128, epoch=2, seed=3))
+    assert np.array_equal(ids, stratified_epoch(sizes, 128, epoch=1, seed=3))
 
 
 def test_head_bucket_is_the_tail_of_the_flat_buffer():

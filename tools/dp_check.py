@@ -38,12 +38,12 @@ def main():
         init_weights(fp, d)
         broadcast_params(fp)
         metrics = torch.zeros(8, device=dev)
-        fused = FusedP2PAdamW(fp) if path == "fused" else None
+        fused = FusedP2PAdamW(fp, d.num_gcn_layers) if path == "fused" else None
         reducer = GradReducer(fp.offsets, d.num_gcn_layers)
         for k in range(steps):
             st = make_step(lr=sched[k][0], beta1=sched[k][1], grad_scale=1.0 / world, step=k + 1, seed=5)
             if fused is not None:
-                train_step_fused(plan, ds, ids[k], fp, st, fused, metrics)
+                train_step_fused(plan, ds, ids[k], fp, st, fused, metrics, next_ids=ids[k + 1] if k + 1 < steps else None)
             else:
                 train_step_dp(plan, ds, ids[k], fp, st, reducer, metrics)
         torch.cuda.synchronize()
