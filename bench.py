@@ -137,6 +137,9 @@ def stage_work(N, E, B, P, H=H, L=L):
         "layer0_wgrad": ("hbm", 4 * N * H + 4 * N * F0),
         "adamw": ("hbm", 28 * P),
         "elementwise": ("hbm", 0),
+        # weight gradient + data gradient of a layer in one launch (the default)
+        "gemm_head_bwd": ("tensor", 2 * gemm_head),
+        "gemm_gcn_bwd": ("tensor", 2 * (L - 1) * 2 * N * H * H),
     }
 
 

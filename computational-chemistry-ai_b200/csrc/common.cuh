@@ -104,8 +104,26 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigne
 // writes are visible (nothing - not even the device-side sizes in dims[] - is read before it),
 // then `griddepcontrol.launch_dependents` lets the next kernel's blocks be scheduled as soon as
 // this grid leaves room.  EIMS_PDL=0 in the environment turns the attribute off.
+// -DEIMS_TIMELINE (tools/step_timeline.py, built with -rdc=true; never in the product library):
+// block 0 of every kernel stamps the global timer right after its grid-dependency wait, i.e. when
+// the preceding kernel of the chain has completed, so consecutive stamps give the in-situ
+// duration of every launch of a step with programmatic dependent launch left on.
+#ifdef EIMS_TIMELINE
+constexpr int kTimelineSlots = 8192;
+extern __device__ unsigned long long g_timeline[kTimelineSlots];
+extern __device__ unsigned int g_timeline_n;
+#endif
+
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef EIMS_TIMELINE
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned int i = atomicAdd(&g_timeline_n, 1u);
+    if (i < kTimelineSlots) g_timeline[i] = t;
+  }
+#endif
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
@@ -137,8 +155,27 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // producer adds per-column sums of z and z^2 (fp64) into `acc`, and the last block to finish
 // (ticket) turns them into mean / invstd / scale / shift, updates the running buffers
 // (momentum 0.1, unbiased variance) and re-zeroes `acc` so the launch can be replayed.
+// The fp64 column accumulators exist kBnReplicas times (block b adds into replica b % R, the
+// finalizer sums them): hundreds of blocks finishing together would otherwise serialise their
+// atomics on the handful of L2 slices that hold one 2*H*8-byte array.
+constexpr int kBnReplicas = 8;
+__device__ __forceinline__ double* bn_acc_slot(double* acc, int H, unsigned int block, int which, int col) {
+  return acc + ((size_t)(block % kBnReplicas) * 2 + which) * H + col;
+}
+// sum of the replicas of one (statistic, column); re-zeroes them so the launch can be replayed
+__device__ __forceinline__ double bn_acc_take(double* acc, int H, int which, int col) {
+  double t = 0.0;
+#pragma unroll
+  for (int r = 0; r < kBnReplicas; ++r) {
+    double* p = acc + ((size_t)r * 2 + which) * H + col;
+    t += __ldcg(p);
+    *p = 0.0;
+  }
+  return t;
+}
+
 struct BnFuse {
-  double* acc;            // [2][H]; null = no fusion
+  double* acc;            // [kBnReplicas][2][H]; null = no fusion
   unsigned int* ticket;
   const float* gamma; const float* beta;
   float* running_mean; float* running_var;   // may be null
@@ -150,9 +187,7 @@ struct BnFuse {
 __device__ __forceinline__ void bn_finalize(const BnFuse& f, int n_rows) {
   const double n = (double)n_rows;
   for (int c = threadIdx.x; c < f.H; c += blockDim.x) {
-    const double s1 = __ldcg(f.acc + c), s2 = __ldcg(f.acc + f.H + c);
-    f.acc[c] = 0.0;
-    f.acc[f.H + c] = 0.0;
+    const double s1 = bn_acc_take(f.acc, f.H, 0, c), s2 = bn_acc_take(f.acc, f.H, 1, c);
     if (n_rows <= 0) continue;
     const double mean = s1 / n;
     double var = s2 / n - mean * mean;

@@ -116,8 +116,8 @@ static inline dim3 bn_grid(int H, int max_nodes) {
   return dim3(slabs, rg);
 }
 
-// scratch: [16 floats: ticket counter] [2H doubles: accumulators]
-int64_t bn_scratch_floats(int H, int max_nodes) { (void)max_nodes; return 16 + 4 * (int64_t)H + 16; }
+// scratch: [16 floats: ticket counter] [kBnReplicas x 2H doubles: accumulators]
+int64_t bn_scratch_floats(int H, int max_nodes) { (void)max_nodes; return 16 + 4 * (int64_t)H * kBnReplicas + 16; }
 
 // combine the 16 row lanes of a block and add into acc[which*H + col] (fp64)
 __device__ __forceinline__ void slab_reduce_atomic(const double (&a)[4], const double (&b)[4], int H, int c0, int cl,
@@ -131,7 +131,7 @@ __device__ __forceinline__ void slab_reduce_atomic(const double (&a)[4], const d
     double t = 0.0;
 #pragma unroll
     for (int r = 0; r < kRowLanes; ++r) t += red[r][which][c];
-    if (c0 + c < H) atomicAdd(acc + which * H + c0 + c, t);
+    if (c0 + c < H) atomicAdd(bn_acc_slot(acc, H, blockIdx.y, which, c0 + c), t);
   }
 }
 
@@ -281,9 +281,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_stats_kernel(const int* __restr
   slab_reduce_atomic(a, b, H, c0, cl, rl, acc);
   if (!last_block_ticket(counter, gridDim.x * gridDim.y)) return;
   for (int k = threadIdx.x; k < H; k += blockDim.x) {
-    const double sa = __ldcg(acc + k), sb = __ldcg(acc + H + k);
-    acc[k] = 0.0;
-    acc[H + k] = 0.0;
+    const double sa = bn_acc_take(acc, H, 0, k), sb = bn_acc_take(acc, H, 1, k);
     dbeta[k] += (float)sa;
     dgamma[k] += (float)sb;
     means[k] = N > 0 ? (float)(sa / N) : 0.f;

@@ -33,8 +33,8 @@ constexpr int kTraceCtas = 8, kTraceSlots = 128;
 __device__ unsigned long long g_trace[kTraceCtas * kTraceSlots];
 #define TRACE(slot)                                                                                   \
   do {                                                                                                \
-    const int _c = blockIdx.y * gridDim.x + blockIdx.x;                                               \
-    if (_c < kTraceCtas && blockIdx.z == 0 && (threadIdx.x & 31) == 0) g_trace[_c * kTraceSlots + (slot)] = clock64(); \
+    const int _c = blockIdx.x;                                                                        \
+    if (_c < kTraceCtas && (threadIdx.x & 31) == 0) g_trace[_c * kTraceSlots + (slot)] = clock64();   \
   } while (0)
 #else
 #define TRACE(slot) do { } while (0)
@@ -132,7 +132,15 @@ struct Args {
   const int* m_dev; const int* k_dev;
   const float* row_scale; const float* bias;
   int relu, accumulate, vec_a, vec_b;
+  int nt, mt, splits;  // tile grid of this problem: CTA `local` -> (local % nt, local / nt % mt, local / (nt * mt))
   BnFuse bn;  // bn.acc != null: column sums of the stored C (after bias / ReLU) -> BatchNorm statistics
+};
+
+// One launch runs up to two independent problems (a weight gradient and the data gradient that
+// consume the same dy): CTAs [0, ctas0) work on g[0], the rest on g[1].
+struct Group {
+  Args g[2];
+  int ctas0;
 };
 
 // Load one 16-byte chunk (4 consecutive floats) with zero fill outside [0, lim) of the
@@ -267,7 +275,11 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(const __grid_constant__ Group grp) {
+  const int which = (int)blockIdx.x >= grp.ctas0 ? 1 : 0;
+  const Args& g = grp.g[which];
+  const int local = (int)blockIdx.x - (which ? grp.ctas0 : 0);
+  const int bx = local % g.nt, by = (local / g.nt) % g.mt, bz = local / (g.nt * g.mt);
   constexpr int A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;
   constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
   // Two fp32 accumulators in TMEM: columns [0,BN) take the A_hi*B_hi products, columns [BN,2BN)
@@ -309,10 +321,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
   const int M = g.m_dev ? *g.m_dev : g.M;
   const int K = g.k_dev ? *g.k_dev : g.K;
   const int N = g.N;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = by * BM, n0 = bx * BN;
   const int kblocks = (K + BK - 1) / BK;
-  const int per_split = (kblocks + gridDim.z - 1) / gridDim.z;
-  const int kb0 = blockIdx.z * per_split;
+  const int per_split = (kblocks + g.splits - 1) / g.splits;
+  const int kb0 = bz * per_split;
   const int kb1 = min(kblocks, kb0 + per_split);
   const int nkb = kb1 - kb0;
   // dead tiles: past the live M (device-side size) or a split-K slice past the live K
@@ -417,12 +429,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
         double t = 0.0;
 #pragma unroll
         for (int q = 0; q < PARTS; ++q) t += red[(q * BN + cc) * 2 + which];
-        if (n0 + cc < N) atomicAdd(g.bn.acc + which * g.bn.H + n0 + cc, t);
+        if (n0 + cc < N) atomicAdd(bn_acc_slot(g.bn.acc, g.bn.H, blockIdx.x, which, n0 + cc), t);
       }
     }
     if (warp == 0) TRACE(5);
     {
-      const bool add_bias = g.bias && (!g.accumulate || blockIdx.z == 0);
+      const bool add_bias = g.bias && (!g.accumulate || bz == 0);
       const bool vec_out = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
       for (int c = 4 * lane; c < BN; c += 128) {
         const int n = n0 + c;
@@ -508,8 +520,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(Args g) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
-  if (g.bn.acc && live) {  // gridDim.z == 1 here; tiles past the live M are not counted
-    const unsigned int live = (unsigned int)((M + BM - 1) / BM) * gridDim.x;
+  if (g.bn.acc && live) {  // splits == 1 here; tiles past the live M are not counted
+    const unsigned int live = (unsigned int)((M + BM - 1) / BM) * (unsigned int)g.nt;
     if (last_block_ticket(g.bn.ticket, live)) bn_finalize(g.bn, M);
   }
   if (warp == 0) TRACE(7);
@@ -524,31 +536,22 @@ extern "C" __attribute__((visibility("default"))) int eims_debug_trace_read(unsi
 }
 #endif
 
-int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
-                   int N, int K, const int* m_dev, const int* k_dev, const float* row_scale, const float* bias,
-                   int relu, int accumulate, cudaStream_t st, const BnFuse* bn) {
+namespace {
+
+// Tile shape and split-K factor of one problem.  `budget` = CTAs this problem should aim for
+// (148 alone, 74 when it shares the launch with a second problem).
+int configure(tc::Args& g, int accumulate, int budget, bool* wide_out, bool* need_memset) {
   using namespace tc;
-  if (M <= 0 || N <= 0 || K <= 0) return EIMS_ERR_ARG;
-  if (bn && (accumulate != 0 || bn->H != N)) return EIMS_ERR_ARG;
-  Args g{A, B, C, lda, ldb, ldc, a_mn, b_mn, M, N, K, m_dev, k_dev, row_scale, bias, relu, accumulate, 0, 0, BnFuse{}};
-  if (bn) g.bn = *bn;
-  g.vec_a = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && (lda % 4 == 0);
-  g.vec_b = ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (ldb % 4 == 0);
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return EIMS_ERR_ARG;
+  if (g.bn.acc && (accumulate != 0 || g.bn.H != g.N)) return EIMS_ERR_ARG;
+  g.vec_a = ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) && (g.lda % 4 == 0);
+  g.vec_b = ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0) && (g.ldb % 4 == 0);
   // 128 x 256 tiles (A read once per row block, 2 stages) when the problem is tall enough to
   // fill the chip with them; 128 x 128 tiles (3 stages) otherwise.
-  const bool wide = (N % 256 == 0) && ((int64_t)((M + BM - 1) / BM) * (N / 256) >= 64 || (accumulate == 1 && K >= 4096));
+  const bool wide = (g.N % 256 == 0) && ((int64_t)((g.M + BM - 1) / BM) * (g.N / 256) >= 64 || (accumulate == 1 && g.K >= 4096));
   const int BN = wide ? 256 : 128;
-  const int stages = wide ? 2 : 3;
-  const int smem_bytes = stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e1 = cudaFuncSetAttribute(gemm_3xtf32_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * BM * BK * 4 + 2 * 128 * BK * 4) + 1024);
-    cudaError_t e2 = cudaFuncSetAttribute(gemm_3xtf32_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * BM * BK * 4 + 2 * 256 * BK * 4) + 1024);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) return EIMS_ERR_CUDA;
-    attr_done = true;
-  }
-  const int mt = (M + BM - 1) / BM, nt = (N + BN - 1) / BN;
-  const int kblocks = (K + BK - 1) / BK;
+  const int mt = (g.M + BM - 1) / BM, nt = (g.N + BN - 1) / BN;
+  const int kblocks = (g.K + BK - 1) / BK;
   static int min_kb = 0;  // fewest k-blocks a split-K slice may get (tuning knob)
   if (!min_kb) {
     const char* e = getenv("EIMS_SPLITK_MIN_KB");
@@ -556,8 +559,10 @@ int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, i
     if (min_kb < 1) min_kb = 1;
   }
   int splits = 1;
+  g.accumulate = accumulate;
+  *need_memset = false;
   if (accumulate == 1) {  // split-K: weight gradients reduce over atoms / graphs
-    splits = (148 + mt * nt - 1) / (mt * nt);
+    splits = (budget + mt * nt - 1) / (mt * nt);
     const int maxs = (kblocks + min_kb - 1) / min_kb;  // at least min_kb k-blocks per slice
     if (splits > maxs) splits = maxs;
     if (splits < 1) splits = 1;
@@ -565,23 +570,95 @@ int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, i
     // store semantics, but the caller tolerates atomic accumulation order (backward dgrads of the
     // 512-row head): when the tile grid cannot fill the chip, split K and add into a zeroed C.
     g.accumulate = 0;
-    if (!relu && !row_scale && mt * nt <= 37 && kblocks >= 8 && ldc == N) {
-      splits = 148 / (mt * nt);
+    if (!g.relu && !g.row_scale && mt * nt <= budget / 4 && kblocks >= 8 && g.ldc == g.N) {
+      splits = budget / (mt * nt);
       const int maxs = kblocks / min_kb;
       if (splits > maxs) splits = maxs;
       if (splits > 1) {
-        // accumulate == 3: the caller has zeroed C already
-        if (accumulate == 2 && cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st) != cudaSuccess) return EIMS_ERR_CUDA;
+        *need_memset = accumulate == 2;  // accumulate == 3: the caller has zeroed C already
         g.accumulate = 1;
       } else {
         splits = 1;
       }
     }
   }
-  dim3 grid(nt, mt, splits);
-  if (wide) launch_pdl(gemm_3xtf32_kernel<256, 2>, dim3(grid), dim3(kThreads), smem_bytes, st, g);
-  else launch_pdl(gemm_3xtf32_kernel<128, 3>, dim3(grid), dim3(kThreads), smem_bytes, st, g);
+  g.nt = nt; g.mt = mt; g.splits = splits;
+  *wide_out = wide;
   return 0;
+}
+
+int set_attrs() {
+  using namespace tc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e1 = cudaFuncSetAttribute(gemm_3xtf32_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * BM * BK * 4 + 2 * 128 * BK * 4) + 1024);
+    cudaError_t e2 = cudaFuncSetAttribute(gemm_3xtf32_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * BM * BK * 4 + 2 * 256 * BK * 4) + 1024);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) return EIMS_ERR_CUDA;
+    attr_done = true;
+  }
+  return 0;
+}
+
+int launch_group(const tc::Group& grp, int ctas, bool wide, cudaStream_t st) {
+  using namespace tc;
+  const int BN = wide ? 256 : 128, stages = wide ? 2 : 3;
+  const int smem_bytes = stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
+  cudaError_t e = wide ? launch_pdl(gemm_3xtf32_kernel<256, 2>, dim3(ctas), dim3(kThreads), smem_bytes, st, grp)
+                       : launch_pdl(gemm_3xtf32_kernel<128, 3>, dim3(ctas), dim3(kThreads), smem_bytes, st, grp);
+  return e == cudaSuccess ? 0 : EIMS_ERR_CUDA;
+}
+
+tc::Args make_args(const GemmProblem& q) {
+  tc::Args g{q.A, q.B, q.C, q.lda, q.ldb, q.ldc, q.a_mn, q.b_mn, q.M, q.N, q.K, q.m_dev, q.k_dev, q.row_scale, q.bias,
+             q.relu, q.accumulate, 0, 0, 1, 1, 1, BnFuse{}};
+  if (q.bn) g.bn = *q.bn;
+  return g;
+}
+
+}  // namespace
+
+int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
+                   int N, int K, const int* m_dev, const int* k_dev, const float* row_scale, const float* bias,
+                   int relu, int accumulate, cudaStream_t st, const BnFuse* bn) {
+  GemmProblem q{A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, m_dev, k_dev, row_scale, bias, relu, accumulate, bn};
+  tc::Group grp{};
+  grp.g[0] = make_args(q);
+  bool wide = false, zero = false;
+  if (int rc = configure(grp.g[0], accumulate, 148, &wide, &zero)) return rc;
+  if (int rc = set_attrs()) return rc;
+  if (zero && cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st) != cudaSuccess) return EIMS_ERR_CUDA;
+  grp.g[1] = grp.g[0];
+  grp.ctas0 = grp.g[0].nt * grp.g[0].mt * grp.g[0].splits;
+  return launch_group(grp, grp.ctas0, wide, st);
+}
+
+// Two independent problems in one launch (the weight gradient and the data gradient of a layer):
+// one launch latency and one pipeline fill / drain instead of two, and the second problem's CTAs
+// fill the SMs the first leaves idle.  Falls back to two launches when the tile shapes differ.
+int launch_gemm_tc_pair(const GemmProblem& p0, const GemmProblem& p1, cudaStream_t st) {
+  tc::Group grp{};
+  grp.g[0] = make_args(p0);
+  grp.g[1] = make_args(p1);
+  bool w0 = false, w1 = false, z0 = false, z1 = false;
+  if (int rc = configure(grp.g[0], p0.accumulate, 148, &w0, &z0)) return rc;
+  if (int rc = configure(grp.g[1], p1.accumulate, 148, &w1, &z1)) return rc;
+  if (w0 != w1 || z0 || z1 || p0.bn || p1.bn) {
+    if (int rc = launch_gemm_tc(p0.A, p0.lda, p0.a_mn, p0.B, p0.ldb, p0.b_mn, p0.C, p0.ldc, p0.M, p0.N, p0.K, p0.m_dev, p0.k_dev,
+                                p0.row_scale, p0.bias, p0.relu, p0.accumulate, st, p0.bn)) return rc;
+    return launch_gemm_tc(p1.A, p1.lda, p1.a_mn, p1.B, p1.ldb, p1.b_mn, p1.C, p1.ldc, p1.M, p1.N, p1.K, p1.m_dev, p1.k_dev,
+                          p1.row_scale, p1.bias, p1.relu, p1.accumulate, st, p1.bn);
+  }
+  // small problems share one wave: aim each at half the chip
+  const int c0 = grp.g[0].nt * grp.g[0].mt * grp.g[0].splits, c1 = grp.g[1].nt * grp.g[1].mt * grp.g[1].splits;
+  if (c0 + c1 > 148 && c0 <= 148 && c1 <= 148 && grp.g[0].nt * grp.g[0].mt <= 37 && grp.g[1].nt * grp.g[1].mt <= 37) {
+    if (int rc = configure(grp.g[0], p0.accumulate, 74, &w0, &z0)) return rc;
+    if (int rc = configure(grp.g[1], p1.accumulate, 74, &w1, &z1)) return rc;
+    if (z0 || z1) return EIMS_ERR_ARG;
+  }
+  if (int rc = set_attrs()) return rc;
+  grp.ctas0 = grp.g[0].nt * grp.g[0].mt * grp.g[0].splits;
+  const int ctas = grp.ctas0 + grp.g[1].nt * grp.g[1].mt * grp.g[1].splits;
+  return launch_group(grp, ctas, w0, st);
 }
 
 }  // namespace eims

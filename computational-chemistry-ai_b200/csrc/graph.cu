@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(256) layer0_fwd_kernel(const int* __restrict__
     double t = 0.0;
 #pragma unroll
     for (int r = 0; r < 16; ++r) t += red[r][which][cc];
-    if (c0 + cc < H) atomicAdd(bn.acc + which * H + c0 + cc, t);
+    if (c0 + cc < H) atomicAdd(bn_acc_slot(bn.acc, H, blockIdx.y, which, c0 + cc), t);
   }
   if (last_block_ticket(bn.ticket, gridDim.x * gridDim.y)) bn_finalize(bn, N);
 }
@@ -366,13 +366,18 @@ int launch_layer0_fwd(const int* dims, const float* norm, const float* a0, int F
 // ascending edge id, each with separate multiply and add roundings (torch's CPU index_add_).
 //   forward  (out_mode 0): out_i = sum_j fl( drop(bn(h_j)) * c_j )
 //   backward (out_mode 1): out_i = ( sum_j h_j ) * c_i * dropmask_i        (A symmetric)
-template <int NV, int UE>
+// STATS (backward form only): the rows written are the dh of the BatchNorm below, so the kernel also
+// produces that BatchNorm's backward statistics - column sums of dh and dh*xhat (fp32 over a warp's
+// few rows, combined per block in shared memory, fp64 from there on) -> dgamma, dbeta and the two
+// column means - which saves the separate statistics pass over dh and z.
+template <int NV, int UE, bool STATS>
 __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ dims, const int* __restrict__ rowptr,
                                                         const int* __restrict__ col, const float* __restrict__ norm,
                                                         const float* __restrict__ h, int H,
                                                         const float* __restrict__ bn_scale,
                                                         const float* __restrict__ bn_shift, DropCfg drop, int out_mode,
-                                                        float* __restrict__ out, int parts) {
+                                                        float* __restrict__ out, int parts, BnBwdFuse bf) {
+  extern __shared__ float s_stats[];  // STATS: [warps per block][2][128 * NV]
   pdl_sync();
   const int N = dims[DIM_N];
   const int lane = threadIdx.x & 31;
@@ -392,8 +397,25 @@ __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ 
     sh[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has_bn && c < H) { sc[v] = ldg4(bn_scale + c); sh[v] = ldg4(bn_shift + c); }
   }
+  float4 mu[STATS ? NV : 1], is[STATS ? NV : 1], s1[STATS ? NV : 1], s2[STATS ? NV : 1];
+  if (STATS) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = cbase + (v * 32 + lane) * 4;
+      mu[v] = is[v] = s1[v] = s2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < H) { mu[v] = ldg4(bf.mean + c); is[v] = ldg4(bf.invstd + c); }
+    }
+  }
   for (int i = warp / parts; i < N; i += nwarps / parts) {
     const int e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
+    float4 zrow[STATS ? NV : 1];
+    if (STATS) {  // issued before the gather so that it is in flight with it
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = cbase + (v * 32 + lane) * 4;
+        zrow[v] = c < H ? ldg4(bf.z + (int64_t)i * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
     float4 acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -452,21 +474,74 @@ __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ 
         }
       }
       st4(out + (int64_t)i * H + c, a);
+      if (STATS) {
+        s1[v].x += a.x; s1[v].y += a.y; s1[v].z += a.z; s1[v].w += a.w;
+        s2[v].x = fmaf(a.x, (zrow[v].x - mu[v].x) * is[v].x, s2[v].x); s2[v].y = fmaf(a.y, (zrow[v].y - mu[v].y) * is[v].y, s2[v].y);
+        s2[v].z = fmaf(a.z, (zrow[v].z - mu[v].z) * is[v].z, s2[v].z); s2[v].w = fmaf(a.w, (zrow[v].w - mu[v].w) * is[v].w, s2[v].w);
+      }
+    }
+  }
+  if (STATS) {
+    constexpr int CW = 128 * NV;  // columns per warp
+    float* mine = s_stats + (threadIdx.x >> 5) * 2 * CW;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      st4(mine + (v * 32 + lane) * 4, s1[v]);
+      st4(mine + CW + (v * 32 + lane) * 4, s2[v]);
+    }
+    __syncthreads();
+    const int wpb = blockDim.x >> 5;
+    // fp32 atomics (these are plain sums - no cancellation as in a variance - and the L2 executes
+    // fp32 reductions an order of magnitude faster than fp64 ones); the replicas are summed in fp64
+    float* facc = reinterpret_cast<float*>(bf.acc);
+    for (int k = threadIdx.x; k < 2 * H; k += blockDim.x) {
+      const int which = k / H, cc = k % H, part = cc / CW, j = cc % CW;
+      float t = 0.f;
+      for (int w = part; w < wpb; w += parts) t += s_stats[(w * 2 + which) * CW + j];
+      atomicAdd(facc + (size_t)(blockIdx.x % kBnReplicas) * 2 * H + k, t);
+    }
+    if (!last_block_ticket(bf.ticket, gridDim.x)) return;
+    for (int k = threadIdx.x; k < H; k += blockDim.x) {
+      double sa = 0.0, sb = 0.0;
+#pragma unroll
+      for (int r = 0; r < kBnReplicas; ++r) {
+        float* q = facc + (size_t)r * 2 * H;
+        sa += (double)__ldcg(q + k);
+        sb += (double)__ldcg(q + H + k);
+        q[k] = 0.f;
+        q[H + k] = 0.f;
+      }
+      bf.dbeta[k] += (float)sa;
+      bf.dgamma[k] += (float)sb;
+      bf.means[k] = N > 0 ? (float)(sa / N) : 0.f;
+      bf.means[H + k] = N > 0 ? (float)(sb / N) : 0.f;
     }
   }
 }
 
 int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const float* norm, const float* h, int H,
                      const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
-                     int max_nodes, cudaStream_t st) {
+                     int max_nodes, cudaStream_t st, const BnBwdFuse* bf) {
   if (H % 4) return EIMS_ERR_ARG;
+  if (bf && out_mode != 1) return EIMS_ERR_ARG;
   const int parts = H <= 512 ? 1 : (H + 511) / 512;
   if (parts > 8 || (8 % parts)) return EIMS_ERR_ARG;  // 8 warps per block must split evenly over a row
   int blocks = (max_nodes * parts + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-#define EIMS_SPMM(NV, UE) \
-  launch_pdl(spmm_norm_kernel<NV, UE>, dim3(blocks), dim3(256), 0, st, dims, rowptr, col, norm, h, H, bn_scale, bn_shift, drop, out_mode, out, parts)
+  const BnBwdFuse none{};
+  // STATS: every block ends with one atomic per column and statistic, and their number is what the
+  // tail of the kernel costs (measured at cfg 2: 23 us with 296 blocks, 26 with 592, 31 with 1184)
+  static int sblocks = 0;
+  if (!sblocks) { const char* e = getenv("EIMS_SPMM_STATS_BLOCKS"); sblocks = e ? atoi(e) : 148 * 2; if (sblocks < 1) sblocks = 1; }
+  const int blocks_s = blocks < sblocks ? blocks : sblocks;
+#define EIMS_SPMM(NV, UE)                                                                                              \
+  do {                                                                                                                 \
+    if (bf) launch_pdl(spmm_norm_kernel<NV, UE, true>, dim3(blocks_s), dim3(256), (size_t)8 * 2 * 128 * NV * sizeof(float), st, dims, rowptr, col, norm, \
+                       h, H, bn_scale, bn_shift, drop, out_mode, out, parts, *bf);                                      \
+    else launch_pdl(spmm_norm_kernel<NV, UE, false>, dim3(blocks), dim3(256), 0, st, dims, rowptr, col, norm, h, H, bn_scale,   \
+                    bn_shift, drop, out_mode, out, parts, none);                                                        \
+  } while (0)
   if (H <= 128) EIMS_SPMM(1, 4);
   else if (H <= 256) EIMS_SPMM(2, 2);
   else EIMS_SPMM(4, 1);

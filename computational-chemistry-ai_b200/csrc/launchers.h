@@ -16,9 +16,15 @@ int launch_csr_build(const eims_dataset* ds, const int32_t* ids, int B, int F, i
 int launch_layer0_fwd(const int* dims, const float* norm, const float* a0, int F, const float* W, const float* bias,
                       int H, float* z, int max_nodes, cudaStream_t st, const BnFuse* bn = nullptr, float* zero = nullptr,
                       int64_t zero_n4 = 0);
+// backward statistics of the BatchNorm whose output gradient the backward-form SpMM writes (see graph.cu)
+struct BnBwdFuse {
+  const float* z; const float* mean; const float* invstd;  // of that BatchNorm: its input and forward statistics
+  double* acc; unsigned int* ticket;                       // bn_partials scratch
+  float* dgamma; float* dbeta; float* means;               // outputs: gradients (+=) and the two column means [2][H]
+};
 int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const float* norm, const float* h, int H,
                      const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
-                     int max_nodes, cudaStream_t st);
+                     int max_nodes, cudaStream_t st, const BnBwdFuse* bf = nullptr);
 int launch_readout(const int* dims, const int* gptr, const float* z, int H, const float* bn_scale,
                    const float* bn_shift, int pooling, float* out, int* argmax, int max_graphs, cudaStream_t st);
 
@@ -63,5 +69,10 @@ int launch_dropout_mask(DropCfg d, int rows, int W, float* out, cudaStream_t st)
 int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
                    int N, int K, const int* m_dev, const int* k_dev, const float* row_scale, const float* bias,
                    int relu, int accumulate, cudaStream_t st, const BnFuse* bn = nullptr);
+struct GemmProblem {
+  const float* A; int lda, a_mn; const float* B; int ldb, b_mn; float* C; int ldc, M, N, K;
+  const int* m_dev; const int* k_dev; const float* row_scale; const float* bias; int relu, accumulate; const BnFuse* bn;
+};
+int launch_gemm_tc_pair(const GemmProblem& p0, const GemmProblem& p1, cudaStream_t st);
 
 }  // namespace eims

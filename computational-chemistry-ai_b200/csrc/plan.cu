@@ -13,6 +13,13 @@
 
 using namespace eims;
 
+#ifdef EIMS_TIMELINE
+namespace eims {
+__device__ unsigned long long g_timeline[kTimelineSlots];
+__device__ unsigned int g_timeline_n = 0;
+}  // namespace eims
+#endif
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -81,6 +88,8 @@ struct eims_plan {
   int state;  // 0 none, 1 batch built, 2 forward(train) done, 3 loss grad ready, 4 head backward done
   int last_training;
   // per-stage CUDA-event profiling (bench.py's roofline pass) and launch accounting
+  bool pair_gemms = true;     // wgrad + dgrad of a layer share one launch (EIMS_PAIR_GEMMS=0: two launches)
+  bool fuse_bn_bwd_stats = true;  // BatchNorm-backward statistics come out of the SpMM that writes dh (EIMS_FUSE_BN_BWD_STATS=0: own pass)
   bool fuse_spmm_bwd = false;  // measured slower at cfg 2 (0.405 vs 0.386 ms/step): the slab-layout gather costs more than K2 saves
   int batch_seq = 0;  // K1 sequence number (tags the zero-degree flag, see k1_build_kernel)
   bool prof = false;
@@ -121,15 +130,26 @@ int gemm(eims_plan* p, const float* A, int lda, int a_mn, const float* B, int ld
   return launch_gemm_tc(A, lda, a_mn, B, ldb, b_mn, C, ldc, M, N, K, m_dev, k_dev, rs, bias, relu, acc, st, bn);
 }
 
+// weight gradient + data gradient of one layer (both consume the same dy) in one launch
+int gemm_pair(eims_plan* p, const GemmProblem& a, const GemmProblem& b, cudaStream_t st) {
+  if (p->gemm_backend == EIMS_GEMM_FP32_SIMT || !p->pair_gemms) {
+    for (const GemmProblem* q : {&a, &b})
+      if (int rc = gemm(p, q->A, q->lda, q->a_mn, q->B, q->ldb, q->b_mn, q->C, q->ldc, q->M, q->N, q->K, q->m_dev, q->k_dev,
+                        q->row_scale, q->bias, q->relu, q->accumulate, st, q->bn)) return rc;
+    return 0;
+  }
+  return launch_gemm_tc_pair(a, b, st);
+}
+
 enum Stage {
   ST_K1 = 0, ST_LAYER0_FWD, ST_BN_STATS, ST_SPMM_FWD, ST_GEMM_GCN_FWD, ST_READOUT, ST_GEMM_HEAD_FWD, ST_LN_FWD, ST_LOSS,
   ST_METRICS, ST_GEMM_HEAD_WGRAD, ST_COLSUM, ST_GEMM_HEAD_DGRAD, ST_LN_BWD, ST_BN_BWD_STATS, ST_BN_BWD_APPLY, ST_GEMM_GCN_WGRAD,
-  ST_GEMM_GCN_DGRAD, ST_SPMM_BWD, ST_LAYER0_WGRAD, ST_ADAMW, ST_ELEMENTWISE, ST_COUNT
+  ST_GEMM_GCN_DGRAD, ST_SPMM_BWD, ST_LAYER0_WGRAD, ST_ADAMW, ST_ELEMENTWISE, ST_GEMM_HEAD_BWD, ST_GEMM_GCN_BWD, ST_COUNT
 };
 const char* kStageNames[ST_COUNT] = {
   "k1_batch_build", "layer0_fwd", "bn_stats", "spmm_fwd", "gemm_gcn_fwd", "readout", "gemm_head_fwd", "ln_fwd", "loss",
   "metrics", "gemm_head_wgrad", "colsum", "gemm_head_dgrad", "ln_bwd", "bn_bwd_stats", "bn_bwd_apply", "gemm_gcn_wgrad",
-  "gemm_gcn_dgrad", "spmm_bwd", "layer0_wgrad", "adamw", "elementwise"};
+  "gemm_gcn_dgrad", "spmm_bwd", "layer0_wgrad", "adamw", "elementwise", "gemm_head_bwd", "gemm_gcn_bwd"};
 
 void prof_begin(eims_plan* p, int stage, int nkernels, cudaStream_t st) {
   p->launches += nkernels;
@@ -283,6 +303,8 @@ int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, 
   p->Bc = max_graphs; p->Nc = max_nodes; p->Ec = max_edges > 0 ? max_edges : 1;
   p->gemm_backend = EIMS_GEMM_TCGEN05;
   if (const char* e = getenv("EIMS_FUSE_SPMM_BWD")) p->fuse_spmm_bwd = e[0] != '0';
+  if (const char* e = getenv("EIMS_PAIR_GEMMS")) p->pair_gemms = e[0] != '0';
+  if (const char* e = getenv("EIMS_FUSE_BN_BWD_STATS")) p->fuse_bn_bwd_stats = e[0] != '0';
   p->ws_bytes = 0; p->bound = false; p->state = 0; p->last_training = 0;
   memset(&p->last_step, 0, sizeof(p->last_step));
   auto s = param_sizes(d);
@@ -502,24 +524,22 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
   if (dprob) STAGE(ST_ELEMENTWISE, 1, launch_dprob_to_dlogits(dims, p->f("prob"), dprob, M, p->f("dlogits"), p->Bc, st));
   float* dl = p->f("dlogits");
   // ---- head (GCN:341-352 backwards)
-  STAGE(ST_GEMM_HEAD_WGRAD, 1, gemm(p, dl, M, 1, p->f("y2"), H, 1, grads + p->off_head(8), H, M, H, p->Bc, nullptr, dims + DIM_B, nullptr,
-                nullptr, 0, 1, st));
+  const int* dB = dims + DIM_B;
   STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, dl, M, M, grads + p->off_head(9), p->Bc, st));
-  STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, dl, M, 0, params + p->off_head(8), H, 1, p->f("dy2"), H, p->Bc, H, M, dims + DIM_B, nullptr, nullptr,
-                nullptr, 0, 3, st));
+  STAGE(ST_GEMM_HEAD_BWD, (p->pair_gemms && p->gemm_backend == EIMS_GEMM_TCGEN05) ? 1 : 2, gemm_pair(p,
+        GemmProblem{dl, M, 1, p->f("y2"), H, 1, grads + p->off_head(8), H, M, H, p->Bc, nullptr, dB, nullptr, nullptr, 0, 1, nullptr},
+        GemmProblem{dl, M, 0, params + p->off_head(8), H, 1, p->f("dy2"), H, p->Bc, H, M, dB, nullptr, nullptr, nullptr, 0, 3, nullptr}, st));
   // LayerNorm backward also leaves the bias gradient of the Linear in front of it (column sums of du)
   STAGE(ST_LN_BWD, 1, launch_ln_bwd(dims, p->f("u2"), p->f("y2"), p->f("dy2"), H, params + p->off_head(6), p->f("ln2"), drop_scale,
                          p->f("dy2"), grads + p->off_head(6), grads + p->off_head(7), grads + p->off_head(5), p->Bc, st));
-  STAGE(ST_GEMM_HEAD_WGRAD, 1, gemm(p, p->f("dy2"), H, 1, p->f("y1"), 2 * H, 1, grads + p->off_head(4), 2 * H, H, 2 * H, p->Bc, nullptr,
-                dims + DIM_B, nullptr, nullptr, 0, 1, st));
-  STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, p->f("dy2"), H, 0, params + p->off_head(4), 2 * H, 1, p->f("dy1"), 2 * H, p->Bc, 2 * H, H,
-                dims + DIM_B, nullptr, nullptr, nullptr, 0, 3, st));
+  STAGE(ST_GEMM_HEAD_BWD, (p->pair_gemms && p->gemm_backend == EIMS_GEMM_TCGEN05) ? 1 : 2, gemm_pair(p,
+        GemmProblem{p->f("dy2"), H, 1, p->f("y1"), 2 * H, 1, grads + p->off_head(4), 2 * H, H, 2 * H, p->Bc, nullptr, dB, nullptr, nullptr, 0, 1, nullptr},
+        GemmProblem{p->f("dy2"), H, 0, params + p->off_head(4), 2 * H, 1, p->f("dy1"), 2 * H, p->Bc, 2 * H, H, dB, nullptr, nullptr, nullptr, 0, 3, nullptr}, st));
   STAGE(ST_LN_BWD, 1, launch_ln_bwd(dims, p->f("u1"), p->f("y1"), p->f("dy1"), 2 * H, params + p->off_head(2), p->f("ln1"),
                          drop_scale, p->f("dy1"), grads + p->off_head(2), grads + p->off_head(3), grads + p->off_head(1), p->Bc, st));
-  STAGE(ST_GEMM_HEAD_WGRAD, 1, gemm(p, p->f("dy1"), 2 * H, 1, p->f("readout"), P, 1, grads + p->off_head(0), P, 2 * H, P, p->Bc, nullptr,
-                dims + DIM_B, nullptr, nullptr, 0, 1, st));
-  STAGE(ST_GEMM_HEAD_DGRAD, 1, gemm(p, p->f("dy1"), 2 * H, 0, params + p->off_head(0), P, 1, p->f("dG"), P, p->Bc, P, 2 * H, dims + DIM_B,
-                nullptr, nullptr, nullptr, 0, 3, st));
+  STAGE(ST_GEMM_HEAD_BWD, (p->pair_gemms && p->gemm_backend == EIMS_GEMM_TCGEN05) ? 1 : 2, gemm_pair(p,
+        GemmProblem{p->f("dy1"), 2 * H, 1, p->f("readout"), P, 1, grads + p->off_head(0), P, 2 * H, P, p->Bc, nullptr, dB, nullptr, nullptr, 0, 1, nullptr},
+        GemmProblem{p->f("dy1"), 2 * H, 0, params + p->off_head(0), P, 1, p->f("dG"), P, p->Bc, P, 2 * H, dB, nullptr, nullptr, nullptr, 0, 3, nullptr}, st));
   p->state = 4;  // head gradients final (the data-parallel reducer may start on that bucket)
   }
   if (part == EIMS_BWD_HEAD) return check_launch("eims_backward_part");
@@ -532,6 +552,8 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
     const float* dh_in = (from_readout || gather) ? nullptr : p->f("dh");
     GatherSrc gsrc{p->f("da"), p->i("rowptr"), p->i("col"), p->f("norm"), make_drop(drop_p, seed, step, l)};
     const GatherSrc* gs = gather ? &gsrc : nullptr;
+    // the statistics pass of layer l < L-1 rides on the SpMM that wrote its dh (see below)
+    if (from_readout || gather || !p->fuse_bn_bwd_stats)
     STAGE(ST_BN_BWD_STATS, 1, launch_bn_bwd_stats(dims, dh_in, p->f("dG"), p->i("gid"), p->i("gptr"), p->i("argmax"), d.pooling,
                                  p->f(L_("z", l)), H, p->f(L_("bn_mean", l)), p->f(L_("bn_invstd", l)), grads + p->off_bn_g(l),
                                  grads + p->off_bn_b(l), p->f("bn_means2"), p->f("bn_partials"), p->Nc, st, gs));
@@ -540,13 +562,18 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
                                  p->f("norm"), grads + p->off_gcn_b(l), p->f("bn_means2"), p->f("q"), p->Nc, st,
                                  l == 0 ? p->f("a0") : nullptr, F, l == 0 ? grads + p->off_gcn_w(0) : nullptr, gs));
     if (l > 0) {
-      STAGE(ST_GEMM_GCN_WGRAD, 1, gemm(p, p->f(L_("a", l)), H, 1, p->f("q"), H, 1, grads + p->off_gcn_w(l), H, H, H, p->Nc, nullptr,
-                    dims + DIM_N, nullptr, nullptr, 0, 1, st));
-      STAGE(ST_GEMM_GCN_DGRAD, 1, gemm(p, p->f("q"), H, 0, params + p->off_gcn_w(l), H, 0, p->f("da"), H, p->Nc, H, H, dims + DIM_N,
-                    nullptr, nullptr, nullptr, 0, 0, st));
-      if (!p->fuse_spmm_bwd)
+      STAGE(ST_GEMM_GCN_BWD, (p->pair_gemms && p->gemm_backend == EIMS_GEMM_TCGEN05) ? 1 : 2, gemm_pair(p,
+            GemmProblem{p->f(L_("a", l)), H, 1, p->f("q"), H, 1, grads + p->off_gcn_w(l), H, H, H, p->Nc, nullptr, dims + DIM_N, nullptr, nullptr, 0, 1, nullptr},
+            GemmProblem{p->f("q"), H, 0, params + p->off_gcn_w(l), H, 0, p->f("da"), H, p->Nc, H, H, dims + DIM_N, nullptr, nullptr, nullptr, 0, 0, nullptr}, st));
+      if (!p->fuse_spmm_bwd) {
+        float* scratch = p->f("bn_partials");
+        BnBwdFuse bf{p->f(L_("z", l - 1)), p->f(L_("bn_mean", l - 1)), p->f(L_("bn_invstd", l - 1)),
+                     reinterpret_cast<double*>(scratch + 16), reinterpret_cast<unsigned int*>(scratch),
+                     grads + p->off_bn_g(l - 1), grads + p->off_bn_b(l - 1), p->f("bn_means2")};
         STAGE(ST_SPMM_BWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("da"), H, nullptr, nullptr,
-                                  make_drop(drop_p, seed, step, l - 1), 1, p->f("dh"), p->Nc, st));
+                                  make_drop(drop_p, seed, step, l - 1), 1, p->f("dh"), p->Nc, st,
+                                  p->fuse_bn_bwd_stats ? &bf : nullptr));
+      }
     }  // l == 0: dW0 came out of the BatchNorm-backward apply pass above (q_0 is never materialised)
   }
   p->state = 1;
@@ -645,6 +672,19 @@ int eims_plan_check(eims_plan* p, int32_t* num_nodes, int32_t* num_edges, eims_s
   if (h[DIM_ZERO_DEG] != 0 && h[DIM_ZERO_DEG] == h[5]) return fail(EIMS_ERR_ZERO_DEGREE, "There are 0-in-degree nodes in the graph (DGL GraphConv would raise)");
   return 0;
 }
+
+#ifdef EIMS_TIMELINE
+// diagnostic build only: read (and reset) the per-launch time stamps, see common.cuh
+int eims_debug_timeline_read(unsigned long long* out, int32_t n) {
+  unsigned int used = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(&used, eims::g_timeline_n, sizeof(used)) != cudaSuccess) return -2;
+  if ((int)used > n) used = (unsigned int)n;
+  if (used && cudaMemcpyFromSymbol(out, eims::g_timeline, (size_t)used * sizeof(unsigned long long)) != cudaSuccess) return -2;
+  const unsigned int zero = 0;
+  if (cudaMemcpyToSymbol(eims::g_timeline_n, &zero, sizeof(zero)) != cudaSuccess) return -2;
+  return (int)used;
+}
+#endif
 
 }  // extern "C"
 #pragma GCC visibility pop
