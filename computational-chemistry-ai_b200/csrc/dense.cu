@@ -597,19 +597,73 @@ __device__ __forceinline__ void metrics_reduce(int B, const float* row_loss, con
   }
 }
 
+// ---- peak list -> spectrum (CuPySpectrumProcessor.peaks_to_spectrum_batch, GCN:166-205)
+// One block (128 threads) bins one spectrum into `bins` (shared, M floats): zero, scatter-max,
+// row maximum.  Non-negative floats order like their bit patterns, so the max-merge is an integer
+// atomicMax in shared memory; intensities <= 0 / NaN never replace the initial 0 (the reference's
+// max(spectra[i, k], intensity) keeps its first argument unless the second is greater).
+// Returns the divisor: the row maximum, or 1 for an all-zero row (GCN:200-201).
+struct PeakSrc { const int64_t* ptr; const void* mz; const float* inten; int is_f64; };
+
+__device__ __forceinline__ float bin_peaks_row(const PeakSrc& pk, int64_t row, int M, float* bins, float* sh) {
+  for (int c = threadIdx.x; c < M; c += 128) bins[c] = 0.f;
+  __syncthreads();
+  const int64_t k0 = pk.ptr[row], k1 = pk.ptr[row + 1];
+  for (int64_t k = k0 + threadIdx.x; k < k1; k += 128) {
+    // np.round / cp.round: to nearest, ties to even, in the precision the m/z is stored in
+    const double r = pk.is_f64 ? rint(reinterpret_cast<const double*>(pk.mz)[k])
+                               : (double)rintf(reinterpret_cast<const float*>(pk.mz)[k]);
+    const float v = pk.inten[k];
+    if (r >= 0.0 && r < (double)M && v > 0.f) atomicMax(reinterpret_cast<int*>(bins) + (int)r, __float_as_int(v));
+  }
+  __syncthreads();
+  float mx = 0.f;
+  for (int c = threadIdx.x; c < M; c += 128) mx = fmaxf(mx, bins[c]);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(sh[0], sh[1]), fmaxf(sh[2], sh[3]));
+  __syncthreads();
+  return mx > 0.f ? mx : 1.f;
+}
+
+__global__ void __launch_bounds__(128) peaks_to_spectrum_kernel(PeakSrc pk, const int* __restrict__ rows, int num_rows,
+                                                                int M, float* __restrict__ out) {
+  pdl_sync();
+  __shared__ float bins[4 * 128 * 8];
+  __shared__ float sh[4];
+  for (int b = blockIdx.x; b < num_rows; b += gridDim.x) {
+    const float mx = bin_peaks_row(pk, rows ? (int64_t)rows[b] : (int64_t)b, M, bins, sh);
+    for (int c = threadIdx.x; c < M; c += 128) out[(int64_t)b * M + c] = __fdiv_rn(bins[c], mx);
+    __syncthreads();
+  }
+}
+
+int launch_peaks_to_spectrum(const eims_peaks* pk, const int* rows, int num_rows, int M, float* out, cudaStream_t st) {
+  if (!pk || !pk->peak_ptr || !pk->mz || !pk->intensity || !out || M < 1 || M > 4096 || num_rows < 0) return EIMS_ERR_ARG;
+  if (num_rows == 0) return 0;
+  PeakSrc src{pk->peak_ptr, pk->mz, pk->intensity, pk->mz_is_f64};
+  const int blocks = num_rows < 148 * 16 ? num_rows : 148 * 16;
+  launch_pdl(peaks_to_spectrum_kernel, dim3(blocks), dim3(128), 0, st, src, rows, num_rows, M, out);
+  return 0;
+}
+
 __global__ void __launch_bounds__(128) loss_kernel(const int* __restrict__ dims, const float* __restrict__ logits,
                                                    const float* __restrict__ targets, const int* __restrict__ target_rows,
                                                    int M, int loss_kind, float* __restrict__ prob,
                                                    float* __restrict__ dlogits, float* __restrict__ row_loss,
                                                    float* __restrict__ row_cos, float* __restrict__ metrics,
-                                                   unsigned int* __restrict__ ticket) {
+                                                   unsigned int* __restrict__ ticket, PeakSrc pk) {
   pdl_sync();
   __shared__ float sh[4];
+  __shared__ __align__(16) float bins[4 * 128 * kLossMaxV4];  // the target row when it is binned here (pk.ptr != null)
   const int B = dims[DIM_B];
   const int nv4 = M >> 2;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const int64_t trow = target_rows ? (int64_t)target_rows[b] : (int64_t)b;
     const float* t = targets + trow * M;
+    float tmax = 1.f;
+    if (pk.ptr) tmax = bin_peaks_row(pk, trow, M, bins, sh);
     float4 p[kLossMaxV4], tt[kLossMaxV4];
     float se = 0.f, pp = 0.f, tq = 0.f, pt = 0.f;
 #pragma unroll
@@ -617,7 +671,12 @@ __global__ void __launch_bounds__(128) loss_kernel(const int* __restrict__ dims,
       const int c4 = i * 128 + threadIdx.x;
       if (c4 < nv4) {
         float4 u = ldg4(logits + (int64_t)b * M + 4 * c4);
-        tt[i] = ldg4(t + 4 * c4);
+        if (pk.ptr) {
+          const float4 raw = *reinterpret_cast<const float4*>(bins + 4 * c4);
+          tt[i] = make_float4(__fdiv_rn(raw.x, tmax), __fdiv_rn(raw.y, tmax), __fdiv_rn(raw.z, tmax), __fdiv_rn(raw.w, tmax));
+        } else {
+          tt[i] = ldg4(t + 4 * c4);
+        }
         p[i].x = 1.f / (1.f + expf(-u.x)); p[i].y = 1.f / (1.f + expf(-u.y));
         p[i].z = 1.f / (1.f + expf(-u.z)); p[i].w = 1.f / (1.f + expf(-u.w));
         float dx = p[i].x - tt[i].x, dy = p[i].y - tt[i].y, dz = p[i].z - tt[i].z, dw = p[i].w - tt[i].w;
@@ -665,11 +724,14 @@ __global__ void __launch_bounds__(128) loss_kernel(const int* __restrict__ dims,
 
 int launch_loss(const int* dims, const float* logits, const float* targets, const int* target_rows, int M,
                 int loss_kind, float* prob, float* dlogits, float* row_loss, float* row_cos, int max_graphs,
-                cudaStream_t st, float* metrics, unsigned int* ticket) {
+                cudaStream_t st, float* metrics, unsigned int* ticket, const eims_peaks* peaks) {
   if (M % 4 || M > 4 * 128 * kLossMaxV4 || (metrics && !ticket)) return EIMS_ERR_ARG;
+  if (!targets && !(peaks && peaks->peak_ptr && peaks->mz && peaks->intensity)) return EIMS_ERR_ARG;
+  PeakSrc src{nullptr, nullptr, nullptr, 0};
+  if (!targets) src = PeakSrc{peaks->peak_ptr, peaks->mz, peaks->intensity, peaks->mz_is_f64};
   int blocks = max_graphs < 1 ? 1 : max_graphs;
   launch_pdl(loss_kernel, dim3(blocks), dim3(128), 0, st, dims, logits, targets, target_rows, M, loss_kind, prob, dlogits, row_loss, row_cos,
-                                      metrics, ticket);
+                                      metrics, ticket, src);
   return 0;
 }
 

@@ -56,7 +56,9 @@ int launch_ln_bwd(const int* dims, const float* u, const float* y, const float* 
                   int max_graphs, cudaStream_t st);
 int launch_loss(const int* dims, const float* logits, const float* targets, const int* target_rows, int M,
                 int loss_kind, float* prob, float* dlogits, float* row_loss, float* row_cos, int max_graphs,
-                cudaStream_t st, float* metrics = nullptr, unsigned int* ticket = nullptr);
+                cudaStream_t st, float* metrics = nullptr, unsigned int* ticket = nullptr,
+                const eims_peaks* peaks = nullptr);
+int launch_peaks_to_spectrum(const eims_peaks* pk, const int* rows, int num_rows, int M, float* out, cudaStream_t st);
 int launch_sigmoid(const int* dims, const float* logits, int M, float* prob, int max_graphs, cudaStream_t st);
 int launch_dprob_to_dlogits(const int* dims, const float* prob, const float* dprob, int M, float* dlogits,
                             int max_graphs, cudaStream_t st);

@@ -88,6 +88,7 @@ struct eims_plan {
   int state;  // 0 none, 1 batch built, 2 forward(train) done, 3 loss grad ready, 4 head backward done
   int last_training;
   // per-stage CUDA-event profiling (bench.py's roofline pass) and launch accounting
+  eims_peaks peak_targets{};  // targets as peak lists (eims_plan_set_peak_targets); peak_ptr == NULL: unset
   bool pair_gemms = true;     // wgrad + dgrad of a layer share one launch (EIMS_PAIR_GEMMS=0: two launches)
   bool fuse_bn_bwd_stats = true;  // BatchNorm-backward statistics come out of the SpMM that writes dh (EIMS_FUSE_BN_BWD_STATS=0: own pass)
   bool fuse_spmm_bwd = false;  // measured slower at cfg 2 (0.405 vs 0.386 ms/step): the slab-layout gather costs more than K2 saves
@@ -281,6 +282,14 @@ int eims_loss_mse_cos(const int32_t* dims, const float* logits, const float* tar
   EIMS_TRY(launch_loss(dims, logits, targets, target_rows, max_mz, loss_kind, prob, dlogits, row_loss, row_cos,
                        max_graphs, (cudaStream_t)stream));
   return check_launch("eims_loss_mse_cos");
+}
+
+int eims_peaks_to_spectrum(const eims_peaks* pk, const int32_t* rows, int32_t num_rows, int32_t max_mz, float* out,
+                           eims_stream_t stream) {
+  if (!pk) return fail(EIMS_ERR_ARG, "peaks is NULL");
+  if (max_mz < 1 || max_mz > 4096) return fail(EIMS_ERR_ARG, "max_mz must be in [1,4096]");
+  EIMS_TRY(launch_peaks_to_spectrum(pk, rows, num_rows, max_mz, out, (cudaStream_t)stream));
+  return check_launch("eims_peaks_to_spectrum");
 }
 
 int eims_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const eims_step* s, eims_stream_t stream) {
@@ -481,16 +490,24 @@ int eims_sigmoid(eims_plan* p, eims_stream_t stream) {
   return check_launch("eims_sigmoid");
 }
 
+int eims_plan_set_peak_targets(eims_plan* p, const eims_peaks* pk) {
+  if (!p) return fail(EIMS_ERR_ARG, "plan is NULL");
+  if (pk && !(pk->peak_ptr && pk->mz && pk->intensity)) return fail(EIMS_ERR_ARG, "peak_ptr / mz / intensity is NULL");
+  p->peak_targets = pk ? *pk : eims_peaks{};
+  return 0;
+}
+
 static int loss_impl(eims_plan* p, const float* targets, const int32_t* target_rows, int32_t loss_kind, int32_t want_grad,
-                     float* metrics, eims_stream_t stream) {
+                     float* metrics, eims_stream_t stream, const eims_peaks* peaks = nullptr) {
   if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
-  if (!targets) return fail(EIMS_ERR_ARG, "targets is NULL");
+  if (!targets && !peaks && p->peak_targets.peak_ptr) peaks = &p->peak_targets;
+  if (!targets && !peaks) return fail(EIMS_ERR_ARG, "targets is NULL (and no peak-list targets are set)");
   cudaStream_t st = (cudaStream_t)stream;
   // metrics != NULL: the last block of the loss kernel also folds the row terms into the running
   // metrics (flags[0] is its ticket), which saves the separate one-block launch
   STAGE(ST_LOSS, 1, launch_loss(p->i("dims"), p->f("logits"), targets, target_rows, p->d.max_mz, loss_kind, p->f("prob"),
                        want_grad ? p->f("dlogits") : nullptr, p->f("row_loss"), p->f("row_cos"), p->Bc,
-                       (cudaStream_t)stream, metrics, reinterpret_cast<unsigned int*>(p->i("flags"))));
+                       (cudaStream_t)stream, metrics, reinterpret_cast<unsigned int*>(p->i("flags")), peaks));
   if (want_grad && p->state == 2) p->state = 3;
   return check_launch("eims_loss");
 }
@@ -595,10 +612,10 @@ int eims_train_step(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids
                     float* grads, float* adam_m, float* adam_v, float* bn_running, int32_t loss_kind,
                     const eims_step* s, float* metrics, eims_stream_t stream) {
   if (!s) return fail(EIMS_ERR_ARG, "step scalars are NULL");
-  if (!ds || !ds->targets) return fail(EIMS_ERR_ARG, "training needs dataset targets");
+  if (!ds || (!ds->targets && !ds->peaks)) return fail(EIMS_ERR_ARG, "training needs dataset targets (dense rows or peak lists)");
   EIMS_TRY(eims_batch_build(p, ds, mol_ids, num_graphs, stream));
   EIMS_TRY(eims_forward(p, params, bn_running, 1, s, stream));
-  EIMS_TRY(loss_impl(p, ds->targets, mol_ids, loss_kind, 1, metrics, stream));
+  EIMS_TRY(loss_impl(p, ds->targets, mol_ids, loss_kind, 1, metrics, stream, ds->targets ? nullptr : ds->peaks));
   EIMS_TRY(eims_backward(p, params, nullptr, grads, stream));
   if (adam_m && adam_v) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -611,7 +628,7 @@ int eims_train_step_built(eims_plan* p, const float* targets, const int32_t* tar
                           float* adam_m, float* adam_v, float* bn_running, int32_t loss_kind, const eims_step* s,
                           float* metrics, eims_stream_t stream) {
   if (!s) return fail(EIMS_ERR_ARG, "step scalars are NULL");
-  if (!targets) return fail(EIMS_ERR_ARG, "training needs target spectra");
+  if (!targets && !(p && p->peak_targets.peak_ptr)) return fail(EIMS_ERR_ARG, "training needs target spectra");
   EIMS_TRY(eims_forward(p, params, bn_running, 1, s, stream));
   EIMS_TRY(loss_impl(p, targets, target_rows, loss_kind, 1, metrics, stream));
   EIMS_TRY(eims_backward(p, params, nullptr, grads, stream));

@@ -34,10 +34,15 @@ class Dims(C.Structure):
                 ("max_mz", C.c_int32), ("pooling", C.c_int32), ("dropout", C.c_float)]
 
 
+class Peaks(C.Structure):
+    _fields_ = [("peak_ptr", C.c_void_p), ("mz", C.c_void_p), ("intensity", C.c_void_p),
+                ("mz_is_f64", C.c_int32), ("num_spectra", C.c_int64)]
+
+
 class Dataset(C.Structure):
     _fields_ = [("node_ptr", C.c_void_p), ("bond_ptr", C.c_void_p), ("feat", C.c_void_p),
                 ("bond_begin", C.c_void_p), ("bond_end", C.c_void_p), ("targets", C.c_void_p),
-                ("num_mols", C.c_int64)]
+                ("num_mols", C.c_int64), ("peaks", C.POINTER(Peaks))]
 
 
 class Step(C.Structure):
@@ -53,6 +58,8 @@ _SIGS = {
     "eims_param_count": (_i64, [C.POINTER(Dims)]),
     "eims_param_num_tensors": (C.c_int, [C.POINTER(Dims)]),
     "eims_param_layout": (C.c_int, [C.POINTER(Dims), C.POINTER(_i64), _i32]),
+    "eims_peaks_to_spectrum": (C.c_int, [C.POINTER(Peaks), _vp, _i32, _i32, _vp, _vp]),
+    "eims_plan_set_peak_targets": (C.c_int, [_vp, C.POINTER(Peaks)]),
     "eims_csr_build": (C.c_int, [C.POINTER(Dataset), _vp, _i32, _i32, _i32, _i32] + [_vp] * 10 + [_vp]),
     "eims_spmm_norm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp]),
     "eims_gemm": (C.c_int, [_i32, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),

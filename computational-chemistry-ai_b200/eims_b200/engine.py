@@ -146,11 +146,59 @@ class FlatParams:
                     self.num_batches_tracked[int(name.split(".")[1])] = int(t)
 
 
-class DeviceDataset:
-    """A MolTable (+ dense target spectra) resident in HBM: ~1 KB of graph data and
-    4*max_mz bytes of targets per molecule."""
+class DevicePeaks:
+    """Peak lists of a set of spectra resident in HBM (flat: peak_ptr int64[G+1], mz, intensity):
+    the `peaks_list` of CuPySpectrumProcessor.peaks_to_spectrum_batch (GCN:166).  m/z is kept in
+    float64 (the precision the reference's NumPy branch rounds in, GCN:193-196) unless the arrays
+    handed in are float32 (what its CuPy branch rounds, GCN:176-179)."""
 
-    def __init__(self, table: MolTable, targets=None, device="cuda", pinned_stage=False):
+    def __init__(self, peak_ptr, mz, intensity, device="cuda"):
+        self.device = torch.device(device)
+        peak_ptr = np.ascontiguousarray(peak_ptr, np.int64)
+        mz = np.ascontiguousarray(mz)
+        if mz.dtype != np.float32:
+            mz = mz.astype(np.float64)
+        self.num_spectra = len(peak_ptr) - 1
+        self.num_peaks = int(peak_ptr[-1]) if len(peak_ptr) else 0
+        pad = lambda a: a if a.size else np.zeros(1, a.dtype)
+        self.peak_ptr = torch.from_numpy(peak_ptr).to(self.device)
+        self.mz = torch.from_numpy(pad(mz)).to(self.device)
+        self.intensity = torch.from_numpy(pad(np.ascontiguousarray(intensity, np.float32))).to(self.device)
+        self._struct = _lib.Peaks(self.peak_ptr.data_ptr(), self.mz.data_ptr(), self.intensity.data_ptr(),
+                                  int(mz.dtype == np.float64), self.num_spectra)
+
+    @classmethod
+    def from_lists(cls, peaks_list, device="cuda"):
+        """From the reference's list-of-lists-of-(mz, intensity) form (GCN:166, 260-278)."""
+        lens = np.fromiter((len(p) for p in peaks_list), np.int64, len(peaks_list))
+        ptr_ = np.zeros(len(peaks_list) + 1, np.int64)
+        np.cumsum(lens, out=ptr_[1:])
+        flat = np.array([q for p in peaks_list for q in p], dtype=np.float64).reshape(-1, 2)
+        return cls(ptr_, flat[:, 0], flat[:, 1].astype(np.float32), device)
+
+    @property
+    def struct(self):
+        return self._struct
+
+    @property
+    def nbytes(self):
+        return self.peak_ptr.numel() * 8 + self.mz.numel() * self.mz.element_size() + self.intensity.numel() * 4
+
+    def to_spectrum(self, max_mz, rows=None, out=None):
+        """peaks_to_spectrum_batch on the device: [len(rows) or num_spectra, max_mz] float32."""
+        n = self.num_spectra if rows is None else len(rows)
+        if out is None:
+            out = torch.empty((n, max_mz), dtype=torch.float32, device=self.device)
+        check(_lib.load().eims_peaks_to_spectrum(C.byref(self._struct), ptr(rows), n, int(max_mz), ptr(out),
+                                                 C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out
+
+
+class DeviceDataset:
+    """A MolTable (+ target spectra, dense rows or peak lists) resident in HBM: ~1 KB of graph data
+    and 4*max_mz bytes of dense targets - or ~12 bytes per peak - per molecule."""
+
+    def __init__(self, table: MolTable, targets=None, device="cuda", pinned_stage=False, peaks: "DevicePeaks" = None):
         self.device = torch.device(device)
         self.num_mols = table.num_mols
         self.host_num_atoms = np.diff(table.node_ptr).astype(np.int64)
@@ -162,9 +210,11 @@ class DeviceDataset:
         self.bond_begin = up(table.bond_begin, torch.int32) if table.bond_begin.size else torch.zeros(1, dtype=torch.int32, device=self.device)
         self.bond_end = up(table.bond_end, torch.int32) if table.bond_end.size else torch.zeros(1, dtype=torch.int32, device=self.device)
         self.targets = None if targets is None else up(np.asarray(targets, np.float32), torch.float32)
+        self.peaks = peaks
         self._struct = Dataset(self.node_ptr.data_ptr(), self.bond_ptr.data_ptr(), self.feat.data_ptr(),
                                self.bond_begin.data_ptr(), self.bond_end.data_ptr(),
-                               0 if self.targets is None else self.targets.data_ptr(), self.num_mols)
+                               0 if self.targets is None else self.targets.data_ptr(), self.num_mols,
+                               C.pointer(peaks.struct) if peaks is not None else None)
 
     @property
     def struct(self) -> Dataset:
@@ -270,6 +320,17 @@ class Plan:
     def sigmoid(self):
         check(self.lib.eims_sigmoid(self.h, self.stream))
 
+    def set_peak_targets(self, peaks: "DevicePeaks"):
+        """Targets as peak lists, binned inside the loss kernel (eims_plan_set_peak_targets)."""
+        check(self.lib.eims_plan_set_peak_targets(self.h, C.byref(peaks.struct) if peaks is not None else None))
+        self._peak_targets = peaks  # keeps the arrays alive
+
+    def _targets(self, ds: "DeviceDataset"):
+        """Dense target pointer of a dataset, or None after pointing the plan at its peak lists."""
+        if ds.targets is None and ds.peaks is not None and getattr(self, "_peak_targets", None) is not ds.peaks:
+            self.set_peak_targets(ds.peaks)
+        return ds.targets
+
     def loss(self, targets, target_rows=None, loss_kind="mse", want_grad=True):
         check(self.lib.eims_loss(self.h, ptr(targets), ptr(target_rows), _lib.LOSS[loss_kind], int(want_grad), self.stream))
 
@@ -314,7 +375,7 @@ class Plan:
         if optimizer:
             fp.ensure_adam()
         if on_head_grads is None:
-            check(self.lib.eims_train_step_built(self.h, ptr(ds.targets), ptr(ids), ptr(fp.params), ptr(fp.grads),
+            check(self.lib.eims_train_step_built(self.h, ptr(self._targets(ds)), ptr(ids), ptr(fp.params), ptr(fp.grads),
                                                  ptr(fp.adam_m) if optimizer else None, ptr(fp.adam_v) if optimizer else None,
                                                  ptr(fp.bn_running), _lib.LOSS[loss_kind], C.byref(step), ptr(metrics), self.stream))
         else:
@@ -322,7 +383,7 @@ class Plan:
             if optimizer:
                 raise ValueError("on_head_grads is for the data-parallel path, which runs its own optimiser kernel")
             self.forward(fp, True, step)
-            self.loss(ds.targets, ids, loss_kind, True)
+            self.loss(self._targets(ds), ids, loss_kind, True)
             if metrics is not None:
                 self.metrics_accumulate(metrics)
             check(self.lib.eims_backward_part(self.h, ptr(fp.params), None, ptr(fp.grads), _lib.BWD_HEAD, self.stream))
@@ -353,7 +414,7 @@ class Plan:
         n = int(num_graphs if num_graphs is not None else (len(ids) if ids is not None else ds.num_mols))
         self.batch_build(ds, ids, n)
         self.forward(fp, True, step)
-        self.loss(ds.targets, ids, loss_kind, True)
+        self.loss(self._targets(ds), ids, loss_kind, True)
         if metrics is not None:
             self.metrics_accumulate(metrics)
         check(self.lib.eims_backward_part(self.h, ptr(fp.params), None, ptr(fp.grads), _lib.BWD_HEAD, self.stream))

@@ -65,7 +65,20 @@ typedef struct {
   const int32_t* bond_end;
   const float* targets;
   int64_t num_mols;
+  const struct eims_peaks* peaks; /* optional: the target spectra as peak lists; used when targets == NULL */
 } eims_dataset;
+
+/* Peak lists of a set of spectra - what OptimizedEIMSDataset.load_peaks (GCN:260-278) returns per
+ * molecule - stored flat: spectrum s owns peaks [peak_ptr[s], peak_ptr[s+1]).  m/z values are
+ * float32 (what the reference's CuPy branch rounds, GCN:176-179) or float64 (what its NumPy
+ * branch rounds, GCN:193-196); intensities are float32 in both (GCN:171,191). */
+typedef struct eims_peaks {
+  const int64_t* peak_ptr;
+  const void* mz;
+  const float* intensity;
+  int32_t mz_is_f64;
+  int64_t num_spectra;
+} eims_peaks;
 
 /* Per-step optimiser scalars, computed on the host exactly as torch's AdamW + OneCycleLR
  * do (GCN:385-391, 429-431): lr and beta1 follow the one-cycle schedule. */
@@ -89,6 +102,15 @@ int eims_param_layout(const eims_dims* d, int64_t* offsets, int32_t n_entries);
 
 /* ---------------------------------------------------------------- stand-alone kernels
  * (each is also a stage of eims_train_step; exposed for per-kernel parity tests) */
+
+/* CuPySpectrumProcessor.peaks_to_spectrum_batch (GCN:166-205) on the device: for output row b
+ * the spectrum rows[b] (b itself when rows == NULL) of `pk` is binned - bin = round-half-even(m/z),
+ * bins outside [0, max_mz) dropped, duplicates max-merged (intensities <= 0 and NaN leave the
+ * zero-initialised bin as it is, like the reference's max()), row divided by its maximum
+ * (by 1 when the row is all zero).  Bit-exact with the reference's loops.  out is [num_rows, max_mz]. */
+int eims_peaks_to_spectrum(const eims_peaks* pk, const int32_t* rows, int32_t num_rows, int32_t max_mz,
+                           float* out, eims_stream_t stream);
+
 
 /* K1  replaces collate_fn -> dgl.batch (GCN:292-297), the in-degree pass and the
  * degree normalisation of DGL GraphConv.  Outputs (all int32 / fp32, device):
@@ -185,6 +207,12 @@ int eims_batch_build(eims_plan* p, const eims_dataset* ds, const int32_t* mol_id
 int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t training,
                  const eims_step* s, eims_stream_t stream);
 int eims_sigmoid(eims_plan* p, eims_stream_t stream); /* prob = sigmoid(logits), inference */
+/* Targets as peak lists: after this call eims_loss / eims_train_step_built accept targets == NULL
+ * and bin row target_rows[b] of `pk` on the fly inside the loss kernel (same arithmetic as
+ * eims_peaks_to_spectrum), so a training set keeps ~1 KB of peaks per molecule in HBM instead
+ * of a 4*max_mz-byte dense row.  pk == NULL switches back.  The struct is copied; the arrays
+ * it points to must stay alive. */
+int eims_plan_set_peak_targets(eims_plan* p, const eims_peaks* pk);
 int eims_loss(eims_plan* p, const float* targets, const int32_t* target_rows, int32_t loss_kind,
               int32_t want_grad, eims_stream_t stream);
 /* dprob: optional [B,M] gradient w.r.t. the spectrum (autograd use); NULL = use the

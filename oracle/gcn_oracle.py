@@ -15,6 +15,7 @@ What it restates (GCN:n = /root/reference/templates/ms-pred-gcn-eims-cupy.py:n):
   * `mse_loss`             GCN:393,427
   * `cosine_similarity_batch`  GCN:207-221 (both the CuPy/NumPy and the torch branch)
   * `peaks_to_spectrum_batch`  GCN:193-205 (the NumPy branch, which `cp = np` aliases to, GCN:59)
+  * `peaks_to_spectrum_batch_f32`  GCN:170-191 (the CuPy branch: float32 rounding)
   * `make_optimizer`       GCN:385-391   AdamW + OneCycleLR (torch's own classes)
   * `train_step` / `train_epoch`   GCN:410-431
 
@@ -175,6 +176,25 @@ def peaks_to_spectrum_batch(peaks_list, max_mz: int) -> np.ndarray:
             mz_int = int(np.round(mz))
             if 0 <= mz_int < max_mz:
                 spectra[i, mz_int] = max(spectra[i, mz_int], intensity)
+    max_vals = np.max(spectra, axis=1, keepdims=True)
+    max_vals = np.where(max_vals > 0, max_vals, 1.0)
+    return spectra / max_vals
+
+
+def peaks_to_spectrum_batch_f32(peaks_list, max_mz: int) -> np.ndarray:
+    """Literal restatement of the CuPy branch GCN:170-191 with `cp` bound to NumPy (the alias
+    of GCN:59): m/z and intensities become float32 arrays first, so the rounding (half to even)
+    happens in float32 - which can pick a different bin than the NumPy branch for m/z within a
+    float32 ulp of a half-integer."""
+    spectra = np.zeros((len(peaks_list), max_mz), dtype=np.float32)
+    for i, peaks in enumerate(peaks_list):
+        if peaks:
+            mz_array = np.array([p[0] for p in peaks], dtype=np.float32)
+            intensity_array = np.array([p[1] for p in peaks], dtype=np.float32)
+            mz_indices = np.round(mz_array).astype(np.int32)
+            valid_mask = (mz_indices >= 0) & (mz_indices < max_mz)
+            for idx, intensity in zip(mz_indices[valid_mask], intensity_array[valid_mask]):
+                spectra[i, idx] = np.maximum(spectra[i, idx], intensity)
     max_vals = np.max(spectra, axis=1, keepdims=True)
     max_vals = np.where(max_vals > 0, max_vals, 1.0)
     return spectra / max_vals

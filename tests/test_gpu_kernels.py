@@ -9,8 +9,8 @@ import torch
 
 from eims_b200 import _lib
 from eims_b200._lib import check, ptr
-from eims_b200.engine import DeviceDataset, FlatParams, ModelDims, Plan, make_step
-from eims_b200.synth import MolTable, dense_spectra, synth_molecules, synth_peaks
+from eims_b200.engine import DeviceDataset, DevicePeaks, FlatParams, ModelDims, Plan, make_step
+from eims_b200.synth import MolTable, dense_spectra, peaks_as_lists, synth_molecules, synth_peaks
 from oracle import gcn_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -329,3 +329,87 @@ def test_adamw_matches_torch():
         assert bool((gd == 0).all())  # zero_grad fused
     err = (p.cpu() - ref.detach()).abs().max().item()
     assert err < 2e-6, err
+
+
+# ------------------------------------------------------------------------------- peak binning (GCN:166-205)
+def _golden(name):
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)))
+
+
+def test_peaks_to_spectrum_golden():
+    """The device kernel reproduces the reference script's own outputs bit for bit: its NumPy
+    branch (float64 rounding) and its CuPy branch run with cp = numpy (float32 rounding)."""
+    g = _golden("binning_f32.npz")
+    for name in ("a", "b"):
+        ptr_, mz, inten, M = g[f"{name}_ptr"], g[f"{name}_mz"], g[f"{name}_inten"], int(g[f"{name}_max_mz"])
+        out64 = DevicePeaks(ptr_, mz, inten.astype(np.float32), DEV).to_spectrum(M).cpu().numpy()
+        assert np.array_equal(out64, g[f"{name}_spec_f64"])
+        out32 = DevicePeaks(ptr_, mz.astype(np.float32), inten.astype(np.float32), DEV).to_spectrum(M).cpu().numpy()
+        assert np.array_equal(out32, g[f"{name}_spec_f32"])
+    b = _golden("binning.npz")
+    flat, lens = b["peaks_flat"].reshape(-1, 2), b["peaks_len"]
+    peaks, o = [], 0
+    for n in lens:
+        peaks.append([tuple(r) for r in flat[o:o + n]])
+        o += n
+    assert np.array_equal(DevicePeaks.from_lists(peaks, DEV).to_spectrum(100).cpu().numpy(), b["spec"])
+    pk = synth_peaks(8, 100, seed=5)
+    assert np.array_equal(DevicePeaks(*pk, DEV).to_spectrum(100).cpu().numpy(), b["spec2"])
+
+
+@pytest.mark.parametrize("n,M,f64", [(1, 4, True), (300, 1000, True), (300, 1000, False), (5000, 500, True), (64, 4096, False)])
+def test_peaks_to_spectrum_oracle(n, M, f64):
+    """Random peak lists (ties, duplicates, out-of-range and negative m/z, non-positive and NaN
+    intensities, empty spectra) and a row gather against the oracle; bit-exact."""
+    rng = np.random.default_rng(n + M)
+    k = rng.integers(0, 200, size=n)
+    k[rng.random(n) < 0.05] = 0
+    ptr_ = np.zeros(n + 1, np.int64)
+    np.cumsum(k, out=ptr_[1:])
+    tot = int(ptr_[-1])
+    mz = rng.uniform(-2.0, M + 2.0, size=tot)
+    half = rng.random(tot) < 0.3
+    mz[half] = np.floor(mz[half]) + 0.5
+    inten = rng.uniform(-10.0, 999.0, size=tot).astype(np.float32)
+    inten[rng.random(tot) < 0.02] = 0.0
+    mz = mz.astype(np.float64 if f64 else np.float32)
+    rows = rng.permutation(n)[: max(1, n // 2)].astype(np.int32)
+    dp = DevicePeaks(ptr_, mz, inten, DEV)
+    got = dp.to_spectrum(M, rows=dev(rows, torch.int32)).cpu().numpy()
+    lists = peaks_as_lists(ptr_, mz, inten)
+    ref_fn = O.peaks_to_spectrum_batch if f64 else O.peaks_to_spectrum_batch_f32
+    ref = ref_fn([lists[r] for r in rows], M).astype(np.float32)
+    assert np.array_equal(got, ref)
+    # NaN intensities never replace a bin (Python's max keeps its first argument)
+    if tot:
+        inten2 = inten.copy()
+        inten2[:: 7] = np.nan
+        got2 = DevicePeaks(ptr_, mz, inten2, DEV).to_spectrum(M).cpu().numpy()
+        keep = ~np.isnan(inten2)
+        ptr2 = np.zeros(n + 1, np.int64)
+        np.cumsum([int(keep[ptr_[i]:ptr_[i + 1]].sum()) for i in range(n)], out=ptr2[1:])
+        ref2 = ref_fn(peaks_as_lists(ptr2, mz[keep], inten2[keep]), M).astype(np.float32)
+        assert np.array_equal(got2, ref2)
+
+
+def test_loss_with_peak_targets_matches_dense():
+    """The loss kernel binning its targets from peak lists == the same kernel reading the dense rows."""
+    B, M = 37, 1000
+    d = ModelDims(hidden_dim=64, max_mz=M)
+    table = synth_molecules(B, max_atoms=12, seed=3)
+    pk = synth_peaks(B, M, seed=4)
+    dense = dense_spectra(*pk, M)
+    plan = Plan(d, B, int(table.node_ptr[-1]), int(2 * table.bond_ptr[-1]), DEV)
+    fp = FlatParams(d, DEV)
+    fp.load_state_dict(O.init_params(O.Dims(6, 64, 3, M, "combined", 0.0), 0))
+    ids = dev(np.random.default_rng(0).permutation(B), torch.int32)
+    res = []
+    for ds in (DeviceDataset(table, dense, DEV), DeviceDataset(table, None, DEV, peaks=DevicePeaks(*pk, DEV))):
+        plan.batch_build(ds, ids, B)
+        plan.forward(fp, True, make_step())
+        plan.loss(plan._targets(ds), ids, "mse", True)
+        res.append((plan.buffer("dlogits", torch.float32, (B, M)).clone(), plan.buffer("row_loss", torch.float32, (B,)).clone(),
+                    plan.buffer("row_cos", torch.float32, (B,)).clone()))
+        plan.set_peak_targets(None)
+    for a, b in zip(*res):
+        assert torch.equal(a, b)

@@ -139,3 +139,15 @@ def test_features(golden_dir):
     t = synth_molecules(3, max_atoms=8, seed=9)
     for i in range(3):
         assert np.array_equal(t.mol(i)[0], g[f"f{i}"])
+
+
+def test_binning_float32_branch(golden_dir):
+    """oracle restatement of the CuPy branch (GCN:170-191) == the reference run with cp = numpy."""
+    g = load(golden_dir, "binning_f32.npz")
+    for name in ("a", "b"):
+        peaks = peaks_as_lists(g[f"{name}_ptr"], g[f"{name}_mz"], g[f"{name}_inten"])
+        M = int(g[f"{name}_max_mz"])
+        assert np.array_equal(O.peaks_to_spectrum_batch_f32(peaks, M), g[f"{name}_spec_f32"])
+        assert np.array_equal(O.peaks_to_spectrum_batch(peaks, M).astype(np.float32), g[f"{name}_spec_f64"])
+    pk = synth_peaks(8, 100, seed=5)
+    assert np.array_equal(O.peaks_to_spectrum_batch_f32(peaks_as_lists(*pk), 100), g["c_spec_f32"])
