@@ -1,5 +1,5 @@
 """The reference-facing call with HOST buffers: a batch of molecules (packed MolTable slice +
-dense target spectra) in pinned host memory -> one H2D copy -> K1 + forward + loss +
+target spectra, as dense rows or as the peak lists they are binned from) in pinned host memory -> one H2D copy -> K1 + forward + loss +
 backward + AdamW -> loss / cosine read back to the host.
 
 This is what `collate_fn` + `.to(device)` + one `train_model` iteration do in the reference
@@ -25,16 +25,29 @@ def _align(n, a=256):
 
 class PackedHostBatch:
     """One batch packed into a single pinned byte buffer:
-    [node_ptr i64 | bond_ptr i64 | bond_begin i32 | bond_end i32 | feat f32 | targets f32]."""
+    [node_ptr i64 | bond_ptr i64 | bond_begin i32 | bond_end i32 | feat f32 | targets f32]
+    or, with peaks=(peak_ptr, mz, intensity) of the batch instead of dense targets,
+    [... | feat f32 | peak_ptr i64 | peak_mz f32/f64 | peak_inten f32]  (binned on the device inside
+    the loss kernel: ~1 KB instead of 4*max_mz bytes per molecule over PCIe)."""
 
-    def __init__(self, table: MolTable, targets: np.ndarray | None, pin=True):
+    def __init__(self, table: MolTable, targets: np.ndarray | None, pin=True, peaks=None):
         B, N, nb = table.num_mols, int(table.node_ptr[-1]), int(table.bond_ptr[-1])
         F = table.feat.shape[1] if table.feat.ndim == 2 else 6
         parts = [("node_ptr", table.node_ptr.astype(np.int64)), ("bond_ptr", table.bond_ptr.astype(np.int64)),
                  ("bond_begin", table.bond_begin.astype(np.int32)), ("bond_end", table.bond_end.astype(np.int32)),
                  ("feat", np.ascontiguousarray(table.feat, np.float32).reshape(-1))]
+        self.mz_is_f64 = 0
         if targets is not None:
             parts.append(("targets", np.ascontiguousarray(targets, np.float32).reshape(-1)))
+        elif peaks is not None:
+            pptr, mz, inten = peaks
+            mz = np.ascontiguousarray(mz)
+            if mz.dtype != np.float32:
+                mz = mz.astype(np.float64)
+            self.mz_is_f64 = int(mz.dtype == np.float64)
+            pad = lambda a: a if a.size else np.zeros(1, a.dtype)
+            parts += [("peak_ptr", np.ascontiguousarray(pptr, np.int64)), ("peak_mz", pad(mz)),
+                      ("peak_inten", pad(np.ascontiguousarray(inten, np.float32)))]
         self.offsets, off = {}, 0
         for name, a in parts:
             self.offsets[name] = off
@@ -47,6 +60,7 @@ class PackedHostBatch:
             view[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
         self.num_graphs, self.num_nodes, self.num_edges, self.feat_dim = B, N, 2 * nb, F
         self.has_targets = targets is not None
+        self.has_peaks = targets is None and peaks is not None
 
 
 class HostBatchRunner:
@@ -69,8 +83,14 @@ class HostBatchRunner:
     def _dataset(self, slot, hb: PackedHostBatch) -> Dataset:
         base = self.slots[slot].data_ptr()
         o = hb.offsets
-        return Dataset(base + o["node_ptr"], base + o["bond_ptr"], base + o["feat"], base + o["bond_begin"],
-                       base + o["bond_end"], (base + o["targets"]) if hb.has_targets else None, hb.num_graphs)
+        pk = None
+        if hb.has_peaks:
+            pk = _lib.Peaks(base + o["peak_ptr"], base + o["peak_mz"], base + o["peak_inten"], hb.mz_is_f64, hb.num_graphs)
+        ds = Dataset(base + o["node_ptr"], base + o["bond_ptr"], base + o["feat"], base + o["bond_begin"],
+                     base + o["bond_end"], (base + o["targets"]) if hb.has_targets else None, hb.num_graphs,
+                     C.pointer(pk) if pk is not None else None)
+        ds._peaks_keepalive = pk
+        return ds
 
     def upload(self, hb: PackedHostBatch, build: bool = False):
         """Enqueue the H2D copy of `hb` (and, with build=True, its K1 batch build) on the copy
@@ -109,6 +129,9 @@ class HostBatchRunner:
         self.fp.ensure_adam()
         fp = self.fp
         if self.built[slot]:
+            # targets as peak lists: point the plan at this slot's arrays (the struct is copied)
+            check(self.plan.lib.eims_plan_set_peak_targets(self.plan.h, ds.peaks if hb.has_peaks else None))
+            self.plan._peak_targets = None
             check(self.plan.lib.eims_train_step_built(self.plan.h, C.c_void_p(ds.targets), None, _lib.ptr(fp.params),
                                                       _lib.ptr(fp.grads), _lib.ptr(fp.adam_m) if optimizer else None,
                                                       _lib.ptr(fp.adam_v) if optimizer else None, _lib.ptr(fp.bn_running),

@@ -205,8 +205,18 @@ class CuPySpectrumProcessor:
 
     def peaks_to_spectrum_batch(self, peaks_list):
         """Round half-to-even, max-merge duplicates, drop bins outside [0, max_mz), divide by
-        the row maximum (GCN:193-205); vectorised, bit-identical to the reference's NumPy branch."""
+        the row maximum.  use_cupy (the reference's default on a GPU machine): the device kernel
+        eims_peaks_to_spectrum on float32 m/z - the reference's CuPy branch (GCN:170-191);
+        otherwise its NumPy branch (GCN:193-205) on the host, vectorised.  Both bit-identical to
+        the reference (tests/test_gpu_kernels.py, tests/test_host_logic.py)."""
         n = len(peaks_list)
+        if self.use_cupy and n and torch.cuda.is_available():
+            from .engine import DevicePeaks
+            lens = np.fromiter((len(p) for p in peaks_list), np.int64, n)
+            ptr_ = np.zeros(n + 1, np.int64)
+            np.cumsum(lens, out=ptr_[1:])
+            flat = np.array([q for p in peaks_list for q in p], dtype=np.float32).reshape(-1, 2)
+            return DevicePeaks(ptr_, flat[:, 0], flat[:, 1], device).to_spectrum(self.max_mz).cpu().numpy()
         spectra = np.zeros((n, self.max_mz), dtype=np.float32)
         lens = np.fromiter((len(p) for p in peaks_list), np.int64, n)
         if lens.sum():

@@ -91,3 +91,15 @@ def test_train_model_matches_reference_history(golden_dir):
     for n in ("spectrum_predictor.8.weight", "spectrum_predictor.4.weight", "gcn_layers.2.weight", "batch_norms.2.running_var"):
         assert rel_err(sd[n].cpu().numpy(), g[f"sd:{n}"]) < 2e-3, n
     assert int(sd["batch_norms.0.num_batches_tracked"]) == int(g["sd:batch_norms.0.num_batches_tracked"])
+
+
+def test_processor_device_branch_matches_reference_cupy_branch(golden_dir):
+    """CuPySpectrumProcessor(use_cupy=True) runs the device kernel and equals the reference's CuPy
+    branch (recorded with cp = numpy); use_cupy=False equals its NumPy branch."""
+    from eims_b200.synth import peaks_as_lists
+    g = dict(np.load(os.path.join(golden_dir, "binning_f32.npz")))
+    for name in ("a", "b"):
+        peaks = peaks_as_lists(g[f"{name}_ptr"], g[f"{name}_mz"], g[f"{name}_inten"])
+        M = int(g[f"{name}_max_mz"])
+        assert np.array_equal(S.CuPySpectrumProcessor(M, True).peaks_to_spectrum_batch(peaks), g[f"{name}_spec_f32"])
+        assert np.array_equal(S.CuPySpectrumProcessor(M, False).peaks_to_spectrum_batch(peaks).astype(np.float32), g[f"{name}_spec_f64"])

@@ -60,7 +60,7 @@ def test_spectrum_processor_matches_reference(golden_dir):
     for n in lens:
         peaks.append([tuple(r) for r in flat[o:o + n]])
         o += n
-    proc = S.CuPySpectrumProcessor(100, True)
+    proc = S.CuPySpectrumProcessor(100, False)  # the NumPy branch (GCN:193-205); use_cupy=True is the device kernel
     assert np.array_equal(proc.peaks_to_spectrum_batch(peaks), g["spec"])
     pk = synth_peaks(8, 100, seed=5)
     assert np.array_equal(proc.peaks_to_spectrum_batch(peaks_as_lists(*pk)), g["spec2"])
