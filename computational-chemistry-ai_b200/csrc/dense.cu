@@ -735,6 +735,66 @@ int launch_loss(const int* dims, const float* logits, const float* targets, cons
   return 0;
 }
 
+// ---- top-k peaks of predicted spectra (the report of `--mode predict`, GCN:610-613)
+// Block (128 threads) per spectrum, k selection rounds: every thread keeps its M/128 bins in
+// registers, a round is a block arg-max over the bins not taken yet.  Order: value descending,
+// ties to the HIGHER bin - what np.argsort(spectrum, kind="stable")[-k:][::-1] gives (the
+// reference's default-kind argsort leaves the order of exact ties unspecified).
+constexpr int kTopkMaxPerThread = 32;  // max_mz <= 4096
+
+__global__ void __launch_bounds__(128) topk_peaks_kernel(const float* __restrict__ spectra, int num_rows, int M, int k,
+                                                         int* __restrict__ idx_out, float* __restrict__ val_out) {
+  pdl_sync();
+  __shared__ float sv[4];
+  __shared__ int si[4];
+  const float ninf = -__int_as_float(0x7f800000);
+  for (int b = blockIdx.x; b < num_rows; b += gridDim.x) {
+    float v[kTopkMaxPerThread];
+    unsigned int taken = 0u;  // bit i: bin i*128+tid is out of the race (selected already, or past M)
+#pragma unroll
+    for (int i = 0; i < kTopkMaxPerThread; ++i) {
+      const int c = i * 128 + threadIdx.x;
+      v[i] = c < M ? __ldg(spectra + (int64_t)b * M + c) : ninf;
+      if (!(v[i] == v[i])) v[i] = ninf;  // NaN ranks last
+      if (c >= M) taken |= 1u << i;
+    }
+    for (int r = 0; r < k; ++r) {
+      float bv = ninf;
+      int bi = -1;
+#pragma unroll
+      for (int i = 0; i < kTopkMaxPerThread; ++i)
+        if (!((taken >> i) & 1u) && (bi < 0 || v[i] >= bv)) { bv = v[i]; bi = i * 128 + threadIdx.x; }  // higher bin wins ties
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi > bi))) { bv = ov; bi = oi; }
+      }
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+      __syncthreads();
+      bv = sv[0]; bi = si[0];
+#pragma unroll
+      for (int w = 1; w < 4; ++w)
+        if (si[w] >= 0 && (bi < 0 || sv[w] > bv || (sv[w] == bv && si[w] > bi))) { bv = sv[w]; bi = si[w]; }
+      if (threadIdx.x == 0) {
+        idx_out[(int64_t)b * k + r] = bi;
+        if (val_out) val_out[(int64_t)b * k + r] = bv;
+      }
+      if (bi >= 0 && (bi & 127) == (int)threadIdx.x) taken |= 1u << (bi >> 7);
+    }
+    __syncthreads();
+  }
+}
+
+int launch_topk_peaks(const float* spectra, int num_rows, int M, int k, int* idx_out, float* val_out, cudaStream_t st) {
+  if (!spectra || !idx_out || M < 1 || M > 128 * kTopkMaxPerThread || k < 1 || k > M || num_rows < 0) return EIMS_ERR_ARG;
+  if (num_rows == 0) return 0;
+  const int blocks = num_rows < 148 * 16 ? num_rows : 148 * 16;
+  launch_pdl(topk_peaks_kernel, dim3(blocks), dim3(128), 0, st, spectra, num_rows, M, k, idx_out, val_out);
+  return 0;
+}
+
 // prob = sigmoid(logits) (inference) ; dlogits = dprob * p * (1-p) (autograd entry)
 __global__ void sigmoid_kernel(const int* __restrict__ dims, const float* __restrict__ logits, int M,
                                float* __restrict__ prob) {

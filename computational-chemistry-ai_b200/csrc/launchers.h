@@ -59,6 +59,7 @@ int launch_loss(const int* dims, const float* logits, const float* targets, cons
                 cudaStream_t st, float* metrics = nullptr, unsigned int* ticket = nullptr,
                 const eims_peaks* peaks = nullptr);
 int launch_peaks_to_spectrum(const eims_peaks* pk, const int* rows, int num_rows, int M, float* out, cudaStream_t st);
+int launch_topk_peaks(const float* spectra, int num_rows, int M, int k, int* idx_out, float* val_out, cudaStream_t st);
 int launch_sigmoid(const int* dims, const float* logits, int M, float* prob, int max_graphs, cudaStream_t st);
 int launch_dprob_to_dlogits(const int* dims, const float* prob, const float* dprob, int M, float* dlogits,
                             int max_graphs, cudaStream_t st);

@@ -292,6 +292,14 @@ int eims_peaks_to_spectrum(const eims_peaks* pk, const int32_t* rows, int32_t nu
   return check_launch("eims_peaks_to_spectrum");
 }
 
+int eims_topk_peaks(const float* spectra, int32_t num_rows, int32_t max_mz, int32_t k, int32_t* idx_out, float* val_out,
+                    eims_stream_t stream) {
+  if (!spectra || !idx_out) return fail(EIMS_ERR_ARG, "spectra / idx_out is NULL");
+  if (max_mz < 1 || max_mz > 4096 || k < 1 || k > max_mz) return fail(EIMS_ERR_ARG, "need 1 <= k <= max_mz <= 4096");
+  EIMS_TRY(launch_topk_peaks(spectra, num_rows, max_mz, k, idx_out, val_out, (cudaStream_t)stream));
+  return check_launch("eims_topk_peaks");
+}
+
 int eims_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const eims_step* s, eims_stream_t stream) {
   EIMS_TRY(launch_adamw(p, g, m, v, n, s, (cudaStream_t)stream));
   return check_launch("eims_adamw_flat");

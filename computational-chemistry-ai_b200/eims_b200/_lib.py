@@ -59,6 +59,7 @@ _SIGS = {
     "eims_param_num_tensors": (C.c_int, [C.POINTER(Dims)]),
     "eims_param_layout": (C.c_int, [C.POINTER(Dims), C.POINTER(_i64), _i32]),
     "eims_peaks_to_spectrum": (C.c_int, [C.POINTER(Peaks), _vp, _i32, _i32, _vp, _vp]),
+    "eims_topk_peaks": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "eims_plan_set_peak_targets": (C.c_int, [_vp, C.POINTER(Peaks)]),
     "eims_csr_build": (C.c_int, [C.POINTER(Dataset), _vp, _i32, _i32, _i32, _i32] + [_vp] * 10 + [_vp]),
     "eims_spmm_norm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp]),

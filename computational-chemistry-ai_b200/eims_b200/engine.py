@@ -194,6 +194,18 @@ class DevicePeaks:
         return out
 
 
+def topk_peaks(spectra: torch.Tensor, k: int = 5):
+    """(bins int32 [n,k], intensities float32 [n,k]) of the k largest bins of every row of a
+    device tensor of spectra: the report of `--mode predict` (GCN:610-613) for a whole batch."""
+    spectra = spectra.contiguous()
+    n, m = spectra.shape
+    idx = torch.empty((n, k), dtype=torch.int32, device=spectra.device)
+    val = torch.empty((n, k), dtype=torch.float32, device=spectra.device)
+    check(_lib.load().eims_topk_peaks(ptr(spectra), n, m, int(k), ptr(idx), ptr(val),
+                                      C.c_void_p(torch.cuda.current_stream(spectra.device).cuda_stream)))
+    return idx, val
+
+
 class DeviceDataset:
     """A MolTable (+ target spectra, dense rows or peak lists) resident in HBM: ~1 KB of graph data
     and 4*max_mz bytes of dense targets - or ~12 bytes per peak - per molecule."""

@@ -519,15 +519,50 @@ def predict_spectrum(model, smiles, config):
     return predict_graphs(model, [graph])[0]
 
 
-def predict_graphs(model, graphs, batch_size=4096):
+def predict_spectrum_batch(model, smiles_list, config, batch_size=4096, top_k=0):
+    """predict_spectrum for a list of SMILES in batches of `batch_size` (BASELINE configs[2]):
+    a list aligned with the input, None where the reference would return None (GCN:497-502).
+    top_k > 0: also the top_k bins (value descending) and their intensities per molecule, found
+    on the device (GCN:610-613) -> (spectra, bins, intensities)."""
+    from rdkit import Chem
+    graphs, where = [], []
+    for i, smi in enumerate(smiles_list):
+        mol = Chem.MolFromSmiles(smi)
+        g = mol_to_dgl_graph(mol) if mol is not None else None
+        if g is not None:
+            graphs.append(g)
+            where.append(i)
+    res = predict_graphs(model, graphs, batch_size, top_k=top_k)
+    spectra = [None] * len(smiles_list)
+    if not top_k:
+        for j, i in enumerate(where):
+            spectra[i] = res[j]
+        return spectra
+    bins, vals = [None] * len(smiles_list), [None] * len(smiles_list)
+    for j, i in enumerate(where):
+        spectra[i], bins[i], vals[i] = res[0][j], res[1][j], res[2][j]
+    return spectra, bins, vals
+
+
+def predict_graphs(model, graphs, batch_size=4096, top_k=0):
     """Batched eval-mode prediction (BASELINE configs[2]); equals the looped single-molecule
     result because eval mode couples nothing across molecules."""
     model.eval()
-    out = []
+    out, bins, vals = [], [], []
     with torch.no_grad():
         for s in range(0, len(graphs), batch_size):
-            out.append(model._run_forward(batch(graphs[s:s + batch_size]).to(model.flat.device), training=False).cpu().numpy())
-    return np.concatenate(out) if out else np.zeros((0, model.dims.max_mz), np.float32)
+            prob = model._run_forward(batch(graphs[s:s + batch_size]).to(model.flat.device), training=False)
+            if top_k:
+                from .engine import topk_peaks
+                bi, va = topk_peaks(prob, top_k)
+                bins.append(bi.cpu().numpy())
+                vals.append(va.cpu().numpy())
+            out.append(prob.cpu().numpy())
+    spectra = np.concatenate(out) if out else np.zeros((0, model.dims.max_mz), np.float32)
+    if not top_k:
+        return spectra
+    return (spectra, np.concatenate(bins) if bins else np.zeros((0, top_k), np.int32),
+            np.concatenate(vals) if vals else np.zeros((0, top_k), np.float32))
 
 
 # ------------------------------------------------------------------------------ CLI (GCN:517-633)

@@ -111,6 +111,13 @@ int eims_param_layout(const eims_dims* d, int64_t* offsets, int32_t n_entries);
 int eims_peaks_to_spectrum(const eims_peaks* pk, const int32_t* rows, int32_t num_rows, int32_t max_mz,
                            float* out, eims_stream_t stream);
 
+/* The peak report of `--mode predict` (GCN:610-613: np.argmax and np.argsort(spectrum)[-5:][::-1])
+ * for a batch of predicted spectra [num_rows, max_mz]: the k largest bins of every row, value
+ * descending; exact ties go to the higher bin (= a stable argsort; the reference's default-kind
+ * argsort leaves tie order unspecified).  idx_out [num_rows, k] int32; val_out [num_rows, k] or NULL. */
+int eims_topk_peaks(const float* spectra, int32_t num_rows, int32_t max_mz, int32_t k,
+                    int32_t* idx_out, float* val_out, eims_stream_t stream);
+
 
 /* K1  replaces collate_fn -> dgl.batch (GCN:292-297), the in-degree pass and the
  * degree normalisation of DGL GraphConv.  Outputs (all int32 / fp32, device):

@@ -9,7 +9,7 @@ import torch
 
 from eims_b200 import _lib
 from eims_b200._lib import check, ptr
-from eims_b200.engine import DeviceDataset, DevicePeaks, FlatParams, ModelDims, Plan, make_step
+from eims_b200.engine import DeviceDataset, DevicePeaks, FlatParams, ModelDims, Plan, make_step, topk_peaks
 from eims_b200.synth import MolTable, dense_spectra, peaks_as_lists, synth_molecules, synth_peaks
 from oracle import gcn_oracle as O
 
@@ -413,3 +413,21 @@ def test_loss_with_peak_targets_matches_dense():
         plan.set_peak_targets(None)
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------- top-k peaks (GCN:610-613)
+@pytest.mark.parametrize("n,M,k", [(1, 4, 4), (700, 1000, 5), (64, 500, 1), (33, 4096, 32), (5, 100, 100)])
+def test_topk_peaks(n, M, k):
+    rng = np.random.default_rng(n * M + k)
+    x = rng.random((n, M)).astype(np.float32)
+    x[:, ::7] = np.round(x[:, ::7], 1)           # plenty of exact ties
+    if n > 2:
+        x[1] = 0.25                                # a constant row: ties everywhere
+    bins, vals = topk_peaks(dev(x), k)
+    bins, vals = bins.cpu().numpy(), vals.cpu().numpy()
+    for r in range(n):
+        ref = np.argsort(x[r], kind="stable")[-k:][::-1]          # GCN:613 with a stable sort
+        assert np.array_equal(bins[r], ref), r
+        assert np.array_equal(vals[r], x[r][ref])
+        # np.argmax (GCN:612) is the first maximum; the top-1 bin holds the same value
+        assert x[r][bins[r, 0]] == x[r][np.argmax(x[r])]

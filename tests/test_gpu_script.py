@@ -103,3 +103,27 @@ def test_processor_device_branch_matches_reference_cupy_branch(golden_dir):
         M = int(g[f"{name}_max_mz"])
         assert np.array_equal(S.CuPySpectrumProcessor(M, True).peaks_to_spectrum_batch(peaks), g[f"{name}_spec_f32"])
         assert np.array_equal(S.CuPySpectrumProcessor(M, False).peaks_to_spectrum_batch(peaks).astype(np.float32), g[f"{name}_spec_f64"])
+
+
+def test_predict_spectrum_batch(monkeypatch):
+    """Batched SMILES prediction == the reference-style one-call-per-molecule loop; invalid SMILES
+    give None as in GCN:497-502; the device top-k equals the printed report of GCN:610-613."""
+    import sys
+    dgl_shim.install()
+    table = synth_molecules(9, max_atoms=14, seed=21)
+    mols = {f"M{g}": dgl_shim.FakeMol(*table.mol(g)) for g in range(9)}
+    monkeypatch.setattr(sys.modules["rdkit.Chem"], "MolFromSmiles", lambda smi, *a, **k: mols.get(smi))
+    config = cfg()
+    model = S.GCNSpectrum(6, config).to(DEV)
+    model.load_state_dict(O.init_params(O.Dims(6, 64, 3, 100, "combined", 0.0), 3))
+    smiles = ["M0", "bad", "M3", "M8", "M1", "also bad", "M2"]
+    spectra, bins, vals = S.predict_spectrum_batch(model, smiles, config, batch_size=3, top_k=5)
+    for smi, sp, bi, va in zip(smiles, spectra, bins, vals):
+        one = S.predict_spectrum(model, smi, config)
+        if smi not in mols:
+            assert sp is None and one is None and bi is None
+            continue
+        assert rel_err(sp, one) < 1e-5
+        assert np.array_equal(bi, np.argsort(sp, kind="stable")[-5:][::-1])
+        assert np.array_equal(va, sp[bi])
+    assert S.predict_spectrum_batch(model, ["bad"], config) == [None]
