@@ -242,20 +242,43 @@ class CuPySpectrumProcessor:
 
 # ------------------------------------------------------------------------------ dataset (GCN:227-290)
 class OptimizedEIMSDataset(torch.utils.data.Dataset):
-    def __init__(self, mol_files, msp_files, config):
-        from rdkit import Chem  # RDKit stays on the host; imported lazily (absent offline)
+    """GCN:227-290.  Two additions, both off the reference's path unless asked for:
+    `cache_path` - a packed binary cache (dataio.save_packed) written after the first load and
+    read instead of the MOL / MSP files afterwards (no RDKit needed then); `robust_msp` - read peak
+    lines with several `mz intensity;` pairs (real NIST exports), which the reference's reader
+    drops (GCN:277-278)."""
+
+    def __init__(self, mol_files, msp_files, config, cache_path=None, robust_msp=False):
+        from . import dataio
         self.graphs, self.spectra, self.config = [], [], config
         self.processor = CuPySpectrumProcessor(config.max_mz, config.use_cupy)
         all_peaks = []
         print("Loading molecular data...")
-        for mol_file, msp_file in zip(mol_files, msp_files):
-            mol = Chem.MolFromMolFile(mol_file) if os.path.exists(mol_file) else None
-            peaks = self.load_peaks(msp_file) if os.path.exists(msp_file) else None
-            if mol is not None and peaks is not None:
-                graph = mol_to_dgl_graph(mol) if config.cache_graphs else mol
-                if graph is not None:
-                    self.graphs.append(graph)
-                    all_peaks.append(peaks)
+        if cache_path and os.path.exists(cache_path):
+            table, (pptr, pmz, pint), _ = dataio.load_packed(cache_path)
+            self.graphs = [MolGraph(*table.mol(g)) for g in range(table.num_mols)]
+            all_peaks = [list(zip(pmz[pptr[g]:pptr[g + 1]].tolist(), pint[pptr[g]:pptr[g + 1]].tolist())) for g in range(table.num_mols)]
+        else:
+            from rdkit import Chem  # RDKit stays on the host; imported lazily (absent offline)
+            names = []
+            for mol_file, msp_file in zip(mol_files, msp_files):
+                mol = Chem.MolFromMolFile(mol_file) if os.path.exists(mol_file) else None
+                peaks = self.load_peaks(msp_file) if os.path.exists(msp_file) else None
+                if peaks is None and robust_msp and os.path.exists(msp_file):
+                    recs = dataio.parse_msp(msp_file)
+                    peaks = recs[0]["peaks"] if recs and recs[0]["peaks"] else None
+                if mol is not None and peaks is not None:
+                    graph = mol_to_dgl_graph(mol) if config.cache_graphs else mol
+                    if graph is not None:
+                        self.graphs.append(graph)
+                        all_peaks.append(peaks)
+                        names.append(os.path.basename(mol_file))
+            if cache_path and self.graphs and config.cache_graphs:
+                lens = np.fromiter((len(p) for p in all_peaks), np.int64, len(all_peaks))
+                pptr = np.zeros(len(all_peaks) + 1, np.int64)
+                np.cumsum(lens, out=pptr[1:])
+                flat = np.array([q for p in all_peaks for q in p], np.float64).reshape(-1, 2)
+                dataio.save_packed(cache_path, dataio.pack_graphs(self.graphs), pptr, flat[:, 0], flat[:, 1], names)
         if all_peaks:
             print("Processing spectra...")
             self.spectra = self.processor.peaks_to_spectrum_batch(all_peaks)
@@ -265,20 +288,8 @@ class OptimizedEIMSDataset(torch.utils.data.Dataset):
     def load_peaks(msp_file):
         """One `mz intensity` pair per line after a `Num Peaks:` line; any parse error drops
         the molecule (GCN:260-278)."""
-        peaks = []
-        try:
-            with open(msp_file, "r") as f:
-                reading = False
-                for line in f.readlines():
-                    if reading:
-                        parts = line.strip().split()
-                        if len(parts) >= 2:
-                            peaks.append((float(parts[0]), float(parts[1])))
-                    elif "Num Peaks:" in line or "NUM PEAKS:" in line:
-                        reading = True
-            return peaks if peaks else None
-        except Exception:
-            return None
+        from .dataio import load_peaks_reference
+        return load_peaks_reference(msp_file)
 
     def __len__(self):
         return len(self.graphs)
@@ -617,6 +628,10 @@ def main(argv=None):
                 print("Failed to predict spectrum")
         else:
             print("Please provide SMILES with --smiles option")
+    elif args.mode == "preprocess" and args.msp_file and args.mol_dir:
+        # the mode the reference advertises (GCN:626-627) but leaves unimplemented (GCN:619-620)
+        from .dataio import preprocess
+        preprocess(args.msp_file, args.mol_dir, args.data_dir)
     else:
         print("Mode not implemented")
 
