@@ -648,6 +648,7 @@ int launch_peaks_to_spectrum(const eims_peaks* pk, const int* rows, int num_rows
   return 0;
 }
 
+template <bool PEAKS>
 __global__ void __launch_bounds__(128) loss_kernel(const int* __restrict__ dims, const float* __restrict__ logits,
                                                    const float* __restrict__ targets, const int* __restrict__ target_rows,
                                                    int M, int loss_kind, float* __restrict__ prob,
@@ -656,14 +657,14 @@ __global__ void __launch_bounds__(128) loss_kernel(const int* __restrict__ dims,
                                                    unsigned int* __restrict__ ticket, PeakSrc pk) {
   pdl_sync();
   __shared__ float sh[4];
-  __shared__ __align__(16) float bins[4 * 128 * kLossMaxV4];  // the target row when it is binned here (pk.ptr != null)
+  __shared__ __align__(16) float bins[PEAKS ? 4 * 128 * kLossMaxV4 : 4];  // PEAKS: the target row is binned here
   const int B = dims[DIM_B];
   const int nv4 = M >> 2;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const int64_t trow = target_rows ? (int64_t)target_rows[b] : (int64_t)b;
     const float* t = targets + trow * M;
     float tmax = 1.f;
-    if (pk.ptr) tmax = bin_peaks_row(pk, trow, M, bins, sh);
+    if (PEAKS) tmax = bin_peaks_row(pk, trow, M, bins, sh);
     float4 p[kLossMaxV4], tt[kLossMaxV4];
     float se = 0.f, pp = 0.f, tq = 0.f, pt = 0.f;
 #pragma unroll
@@ -671,7 +672,7 @@ __global__ void __launch_bounds__(128) loss_kernel(const int* __restrict__ dims,
       const int c4 = i * 128 + threadIdx.x;
       if (c4 < nv4) {
         float4 u = ldg4(logits + (int64_t)b * M + 4 * c4);
-        if (pk.ptr) {
+        if (PEAKS) {
           const float4 raw = *reinterpret_cast<const float4*>(bins + 4 * c4);
           tt[i] = make_float4(__fdiv_rn(raw.x, tmax), __fdiv_rn(raw.y, tmax), __fdiv_rn(raw.z, tmax), __fdiv_rn(raw.w, tmax));
         } else {
@@ -730,8 +731,12 @@ int launch_loss(const int* dims, const float* logits, const float* targets, cons
   PeakSrc src{nullptr, nullptr, nullptr, 0};
   if (!targets) src = PeakSrc{peaks->peak_ptr, peaks->mz, peaks->intensity, peaks->mz_is_f64};
   int blocks = max_graphs < 1 ? 1 : max_graphs;
-  launch_pdl(loss_kernel, dim3(blocks), dim3(128), 0, st, dims, logits, targets, target_rows, M, loss_kind, prob, dlogits, row_loss, row_cos,
-                                      metrics, ticket, src);
+  if (src.ptr)
+    launch_pdl(loss_kernel<true>, dim3(blocks), dim3(128), 0, st, dims, logits, targets, target_rows, M, loss_kind, prob, dlogits,
+               row_loss, row_cos, metrics, ticket, src);
+  else
+    launch_pdl(loss_kernel<false>, dim3(blocks), dim3(128), 0, st, dims, logits, targets, target_rows, M, loss_kind, prob, dlogits,
+               row_loss, row_cos, metrics, ticket, src);
   return 0;
 }
 

@@ -401,42 +401,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(const __grid_c
     tc_fence_before();
     asm volatile("bar.sync 1, 512;" ::: "memory");  // the 16 epilogue warps only
     if (warp == 0) TRACE(4);
-    if (g.bn.acc) {
-      // BatchNorm statistics of this tile: thread = (column, row slice), fp64 partial sums,
-      // combined over the row slices in shared memory, one fp64 atomic per column and statistic.
-      constexpr int PARTS = kProducerWarps * 32 / BN, RPP = BM / PARTS;
-      const int tt = threadIdx.x, colx = tt % BN, part = tt / BN;
-      double* red = reinterpret_cast<double*>(smem + BM * LDS * 4);
-      double s1 = 0.0, s2 = 0.0;
-      if (n0 + colx < N) {
-        const float bv = g.bias ? __ldg(g.bias + n0 + colx) : 0.f;
-        const int rend = min(RPP, M - m0 - part * RPP);
-        const float* src = stage + (part * RPP) * LDS + colx;
-#pragma unroll 4
-        for (int r = 0; r < rend; ++r) {
-          float v = src[r * LDS] + bv;
-          if (g.relu) v = fmaxf(v, 0.f);
-          const double d = (double)v;
-          s1 += d;
-          s2 = fma(d, d, s2);
-        }
-      }
-      red[(part * BN + colx) * 2] = s1;
-      red[(part * BN + colx) * 2 + 1] = s2;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (tt < 2 * BN) {
-        const int which = tt / BN, cc = tt % BN;
-        double t = 0.0;
-#pragma unroll
-        for (int q = 0; q < PARTS; ++q) t += red[(q * BN + cc) * 2 + which];
-        if (n0 + cc < N) atomicAdd(bn_acc_slot(g.bn.acc, g.bn.H, blockIdx.x, which, n0 + cc), t);
-      }
-    }
     if (warp == 0) TRACE(5);
     {
       const bool add_bias = g.bias && (!g.accumulate || bz == 0);
       const bool vec_out = (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
-      for (int c = 4 * lane; c < BN; c += 128) {
+      const bool stats = g.bn.acc != nullptr;
+      // BatchNorm statistics of this tile ride on the store loop: a thread owns BN/128 column quads
+      // and every 16th row, and keeps fp64 sums of what it stores (after bias / ReLU)
+      constexpr int QUADS = BN / 128;
+      double s1[QUADS][4], s2[QUADS][4];
+#pragma unroll
+      for (int qd = 0; qd < QUADS; ++qd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s1[qd][e] = s2[qd][e] = 0.0;
+#pragma unroll
+      for (int qd = 0; qd < QUADS; ++qd) {
+        const int c = 4 * lane + qd * 128;
         const int n = n0 + c;
         if (n >= N) break;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -454,6 +434,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(const __grid_c
           float4 v = *reinterpret_cast<const float4*>(stage + row * LDS + c);
           v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
           if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (stats) {
+            const double d0 = v.x, d1 = v.y, d2 = v.z, d3 = v.w;
+            s1[qd][0] += d0; s1[qd][1] += d1; s1[qd][2] += d2; s1[qd][3] += d3;
+            s2[qd][0] = fma(d0, d0, s2[qd][0]); s2[qd][1] = fma(d1, d1, s2[qd][1]);
+            s2[qd][2] = fma(d2, d2, s2[qd][2]); s2[qd][3] = fma(d3, d3, s2[qd][3]);
+          }
           float* dst = g.C + (int64_t)m * g.ldc + n;
           if (g.accumulate) {
             if (v4) {
@@ -472,6 +458,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(const __grid_c
             if (n + 2 < N) dst[2] = v.z;
             if (n + 3 < N) dst[3] = v.w;
           }
+        }
+      }
+      if (stats) {
+        // combine the 16 warps in shared memory (the staging tile is dead once every warp has read
+        // its rows), then one fp64 atomic per column and statistic
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        double* red = reinterpret_cast<double*>(smem);  // [16 warps][2][BN]
+#pragma unroll
+        for (int qd = 0; qd < QUADS; ++qd)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = 4 * lane + qd * 128 + e;
+            red[(warp * 2 + 0) * BN + c] = s1[qd][e];
+            red[(warp * 2 + 1) * BN + c] = s2[qd][e];
+          }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        for (int k = threadIdx.x; k < 2 * BN; k += kProducerWarps * 32) {
+          const int which = k / BN, cc = k % BN;
+          double tsum = 0.0;
+#pragma unroll
+          for (int w = 0; w < kProducerWarps; ++w) tsum += red[(w * 2 + which) * BN + cc];
+          if (n0 + cc < N) atomicAdd(bn_acc_slot(g.bn.acc, g.bn.H, blockIdx.x, which, n0 + cc), tsum);
         }
       }
     }

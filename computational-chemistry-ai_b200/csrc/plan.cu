@@ -459,13 +459,13 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
     if (!training) STAGE(ST_BN_STATS, 1, bn(0));
   }
   for (int l = 1; l < L; ++l) {
-    STAGE(ST_SPMM_FWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f(L_("z", l - 1)), H,
-                              p->f(L_("bn_scale", l - 1)), p->f(L_("bn_shift", l - 1)),
-                              make_drop(drop_p, seed, step, l - 1), 0, p->f(L_("a", l)), p->Nc, st));
     // training on the tensor-core path: the BatchNorm statistics of z_l come out of the GEMM epilogue
     const bool fuse_bn = training && p->gemm_backend == EIMS_GEMM_TCGEN05;
     BnFuse bf{};
     if (fuse_bn) bf = fuse(l);
+    STAGE(ST_SPMM_FWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f(L_("z", l - 1)), H,
+                              p->f(L_("bn_scale", l - 1)), p->f(L_("bn_shift", l - 1)),
+                              make_drop(drop_p, seed, step, l - 1), 0, p->f(L_("a", l)), p->Nc, st));
     STAGE(ST_GEMM_GCN_FWD, 1, gemm(p, p->f(L_("a", l)), H, 0, params + p->off_gcn_w(l), H, 1, p->f(L_("z", l)), H, p->Nc, H, H,
                   dims + DIM_N, nullptr, p->f("norm"), params + p->off_gcn_b(l), 1, 0, st, fuse_bn ? &bf : nullptr));
     if (!fuse_bn) STAGE(ST_BN_STATS, 1, bn(l));

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeims_b200.so")
+# EIMS_LIB: another build of the same library (A/B timing of kernel variants); never a different implementation
+LIB_PATH = os.environ.get("EIMS_LIB") or os.path.join(_HERE, "libeims_b200.so")
 
 POOLING = {"sum": 0, "mean": 1, "max": 2, "combined": 3}
 LOSS = {"mse": 0, "cosine": 1}
