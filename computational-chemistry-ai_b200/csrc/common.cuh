@@ -104,14 +104,27 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigne
 // writes are visible (nothing - not even the device-side sizes in dims[] - is read before it),
 // then `griddepcontrol.launch_dependents` lets the next kernel's blocks be scheduled as soon as
 // this grid leaves room.  EIMS_PDL=0 in the environment turns the attribute off.
-// -DEIMS_TIMELINE (tools/step_timeline.py, built with -rdc=true; never in the product library):
-// block 0 of every kernel stamps the global timer right after its grid-dependency wait, i.e. when
-// the preceding kernel of the chain has completed, so consecutive stamps give the in-situ
-// duration of every launch of a step with programmatic dependent launch left on.
+// -DEIMS_TIMELINE (tools/step_timeline.py; never in the product library): block 0 of every kernel
+// stamps the global timer right after its grid-dependency wait, i.e. when the preceding kernel of
+// the chain has completed, so consecutive stamps give the in-situ duration of every launch of a
+// step with programmatic dependent launch left on.  Every translation unit keeps its own log
+// (no relocatable device code needed) and exports a reader; the tool merges them by time.
 #ifdef EIMS_TIMELINE
 constexpr int kTimelineSlots = 8192;
-extern __device__ unsigned long long g_timeline[kTimelineSlots];
-extern __device__ unsigned int g_timeline_n;
+static __device__ unsigned long long g_timeline[kTimelineSlots];
+static __device__ unsigned int g_timeline_n;
+#define EIMS_TIMELINE_READER(tu)                                                                                   \
+  extern "C" __attribute__((visibility("default"))) int eims_debug_timeline_read_##tu(unsigned long long* out, int n) { \
+    unsigned int used = 0;                                                                                         \
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(&used, eims::g_timeline_n, sizeof(used)) != cudaSuccess) return -2; \
+    if ((int)used > n) used = (unsigned int)n;                                                                     \
+    if (used && cudaMemcpyFromSymbol(out, eims::g_timeline, (size_t)used * sizeof(unsigned long long)) != cudaSuccess) return -2; \
+    const unsigned int zero = 0;                                                                                   \
+    if (cudaMemcpyToSymbol(eims::g_timeline_n, &zero, sizeof(zero)) != cudaSuccess) return -2;                      \
+    return (int)used;                                                                                              \
+  }
+#else
+#define EIMS_TIMELINE_READER(tu)
 #endif
 
 __device__ __forceinline__ void pdl_sync() {

@@ -950,3 +950,5 @@ int launch_dropout_mask(DropCfg d, int rows, int W, float* out, cudaStream_t st)
 }
 
 }  // namespace eims
+
+EIMS_TIMELINE_READER(dense)

@@ -174,3 +174,5 @@ extern "C" int eims_dp_adamw_fused(int32_t rank, int32_t world, const uint64_t* 
   return cudaPeekAtLastError() == cudaSuccess ? 0 : EIMS_ERR_CUDA;
 }
 #pragma GCC visibility pop
+
+EIMS_TIMELINE_READER(dp_fused)

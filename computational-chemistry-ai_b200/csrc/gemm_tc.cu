@@ -670,3 +670,5 @@ int launch_gemm_tc_pair(const GemmProblem& p0, const GemmProblem& p1, cudaStream
 }
 
 }  // namespace eims
+
+EIMS_TIMELINE_READER(gemm_tc)

@@ -350,7 +350,9 @@ int launch_layer0_fwd(const int* dims, const float* norm, const float* a0, int F
                       int H, float* z, int max_nodes, cudaStream_t st, const BnFuse* bn, float* zero, int64_t zero_n4) {
   if (F > kMaxF0 || H % 4) return EIMS_ERR_ARG;
   const int slabs = (H + 63) / 64;
-  int rg = (148 * 4 + slabs - 1) / slabs;
+  static int per_sm = 0;  // blocks per SM in total (tuning knob)
+  if (!per_sm) { const char* e = getenv("EIMS_L0_BLOCKS_PER_SM"); per_sm = e ? atoi(e) : 4; if (per_sm < 1) per_sm = 1; }
+  int rg = (148 * per_sm + slabs - 1) / slabs;
   const int need = (max_nodes + kL0Rows - 1) / kL0Rows;  // a block stages at most kL0Rows rows
   if (rg < need) rg = need;
   if (rg < 1) rg = 1;
@@ -628,3 +630,5 @@ int launch_readout(const int* dims, const int* gptr, const float* z, int H, cons
 }
 
 }  // namespace eims
+
+EIMS_TIMELINE_READER(graph)

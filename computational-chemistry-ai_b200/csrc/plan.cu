@@ -13,12 +13,6 @@
 
 using namespace eims;
 
-#ifdef EIMS_TIMELINE
-namespace eims {
-__device__ unsigned long long g_timeline[kTimelineSlots];
-__device__ unsigned int g_timeline_n = 0;
-}  // namespace eims
-#endif
 
 namespace {
 
@@ -698,18 +692,8 @@ int eims_plan_check(eims_plan* p, int32_t* num_nodes, int32_t* num_edges, eims_s
   return 0;
 }
 
-#ifdef EIMS_TIMELINE
-// diagnostic build only: read (and reset) the per-launch time stamps, see common.cuh
-int eims_debug_timeline_read(unsigned long long* out, int32_t n) {
-  unsigned int used = 0;
-  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpyFromSymbol(&used, eims::g_timeline_n, sizeof(used)) != cudaSuccess) return -2;
-  if ((int)used > n) used = (unsigned int)n;
-  if (used && cudaMemcpyFromSymbol(out, eims::g_timeline, (size_t)used * sizeof(unsigned long long)) != cudaSuccess) return -2;
-  const unsigned int zero = 0;
-  if (cudaMemcpyToSymbol(eims::g_timeline_n, &zero, sizeof(zero)) != cudaSuccess) return -2;
-  return (int)used;
-}
-#endif
 
 }  // extern "C"
 #pragma GCC visibility pop
+
+EIMS_TIMELINE_READER(plan)

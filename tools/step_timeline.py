@@ -48,7 +48,7 @@ def main():
     ap.add_argument("--max-atoms", type=int, default=64)
     ap.add_argument("--no-build", action="store_true")
     a = ap.parse_args()
-    path = b.OUT.replace(".so", "_timeline.so") if a.no_build else b.build_variant("timeline", ["-DEIMS_TIMELINE", "-rdc=true"])
+    path = b.OUT.replace(".so", "_timeline.so") if a.no_build else b.build_variant("timeline", ["-DEIMS_TIMELINE"])
     from eims_b200 import _lib
     _lib.LIB_PATH = path
     import torch
@@ -57,8 +57,18 @@ def main():
     from eims_b200.synth import dense_spectra, synth_molecules, synth_peaks
 
     lib = _lib.load()
-    lib.eims_debug_timeline_read.restype = C.c_int
-    lib.eims_debug_timeline_read.argtypes = [C.c_void_p, C.c_int32]
+    readers = [getattr(lib, f"eims_debug_timeline_read_{tu}") for tu in ("graph", "dense", "gemm_tc", "dp_fused", "plan")]
+    for r in readers:
+        r.restype, r.argtypes = C.c_int, [C.c_void_p, C.c_int32]
+
+    def read_all():
+        out = []
+        buf = (C.c_ulonglong * 8192)()
+        for r in readers:
+            n = r(buf, 8192)
+            assert n >= 0
+            out.extend(buf[:n])
+        return np.sort(np.array(out, dtype=np.int64))
     dev = torch.device("cuda", 0)
     M, B = 1000, a.batch
     n_mols = 20000
@@ -81,12 +91,11 @@ def main():
     for k in range(20):
         step(k)
     torch.cuda.synchronize()
-    buf = (C.c_ulonglong * 8192)()
-    lib.eims_debug_timeline_read(buf, 8192)  # reset
+    read_all()  # reset
     for k in range(20, 20 + a.steps):
         step(k)
-    n = lib.eims_debug_timeline_read(buf, 8192)
-    t = np.array(buf[:n], dtype=np.int64)
+    t = read_all()
+    n = len(t)
     seq = sequence(a.layers)
     per = len(seq)
     assert n == per * a.steps, (n, per, a.steps)
