@@ -20,8 +20,8 @@ constexpr float kCosEps = 1e-8f;      // GCN:213-214
 
 // Dropout sites: GCN layer l -> site l (GCN:362-363); head dropouts -> L, L+1 (GCN:345,349).
 // torch's generator cannot be bit-matched, so the keep-mask is a counter-based stream of our
-// own: one SplitMix64 output (Steele et al. 2014) per 4 consecutive elements, keyed by
-// (seed, step, site), 16 random bits per element compared with p * 2^16.  It is a pure
+// own: two 32-bit hash words per 4 consecutive elements, keyed by a SplitMix64-derived 64-bit
+// key of (seed, step, site), 16 random bits per element compared with p * 2^16.  It is a pure
 // function of the element index, so the forward gather, the backward scatter and
 // eims_dropout_mask all see the same mask without storing it.
 struct DropCfg {
@@ -46,10 +46,23 @@ static inline DropCfg make_drop(float p, uint64_t seed, int step, int site) {
   return d;
 }
 
-// keep-mask (scaled) for the 4 consecutive elements starting at flat index `elem` (elem % 4 == 0)
+// 32-bit finaliser (two multiply / xor-shift rounds, the "lowbias32" constants of the hash-prospector
+// search): ~8 integer instructions, against ~25 for a 64-bit SplitMix round on this machine - the forward
+// SpMM hashes once per gathered float4 and is instruction-issue bound at BASELINE cfg 2 (ncu: IPC 2.1
+// of 4, 38 % SM busy, 22 % memory).
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x21f0aaadu;
+  h ^= h >> 15; h *= 0x735a2d97u;
+  h ^= h >> 15;
+  return h;
+}
+
+// keep-mask (scaled) for the 4 consecutive elements starting at flat index `elem` (elem % 4 == 0):
+// two 32-bit words from the counter (elem / 4) and the 64-bit key, 16 random bits per element
 __device__ __forceinline__ float4 drop_mask4(const DropCfg& d, uint64_t elem) {
-  const uint64_t r = mix64(d.key + (elem >> 2) * 0x9E3779B97F4A7C15ULL);
-  const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+  const uint32_t ctr = (uint32_t)(elem >> 2) ^ (uint32_t)(elem >> 34);
+  const uint32_t lo = mix32(ctr * 0x9E3779B1u + (uint32_t)d.key);
+  const uint32_t hi = mix32((lo ^ (uint32_t)(d.key >> 32)) * 0x85EBCA77u + ctr);
   float4 m;
   m.x = (lo & 0xffffu) >= d.threshold ? d.scale : 0.f;
   m.y = (lo >> 16) >= d.threshold ? d.scale : 0.f;
