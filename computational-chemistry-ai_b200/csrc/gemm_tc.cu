@@ -141,6 +141,7 @@ struct Args {
 struct Group {
   Args g[2];
   int ctas0;
+  int tiles;  // persistent kernel: tiles of both problems (ctas0 + tiles of g[1])
 };
 
 // Load one 16-byte chunk (4 consecutive floats) with zero fill outside [0, lim) of the
@@ -180,28 +181,29 @@ __device__ __forceinline__ void store_split(uint32_t hi_saddr, uint32_t lo_saddr
 // c = t%8.  MN-major: one warp = one 512-byte atom (lanes 0-7 -> k-row 0, 8-15 -> k-row 1, ..),
 // atom = it*8 + t/32.  In both layouts the shared offset is  soff(t) + it*4096  and the global
 // element offset is  goff(t) + it*gstride,  which is what the predicate-free path uses.
-template <int ROWS>
+// GT = threads that share one operand tile (a producer group of 8 warps)
+template <int ROWS, int GT = kGroupThreads>
 struct TileRegs {
-  static constexpr int PER = ROWS * BK / 4 / kGroupThreads;  // 16-byte chunks per producer thread
+  static constexpr int PER = ROWS * BK / 4 / GT;  // 16-byte chunks per producer thread
   float4 v[PER];
 };
 
 // (k, mn) element coordinates inside the tile of chunk `it` of thread t
-template <int ROWS>
+template <int ROWS, int GT = kGroupThreads>
 __device__ __forceinline__ void chunk_coords(int mn_major, int it, int t, int& mn, int& k) {
   if (!mn_major) {
-    const int idx = it * kGroupThreads + t;
+    const int idx = it * GT + t;
     mn = idx >> 3;
     k = (idx & 7) * 4;
   } else {
     constexpr int MNA = ROWS / 32;  // mn atoms per 4-k-row group
-    const int atom = it * 8 + (t >> 5);
+    const int atom = it * (GT / 32) + (t >> 5);
     k = (atom / MNA) * 4 + ((t >> 3) & 3);
     mn = ((atom % MNA) * 8 + (t & 7)) * 4;
   }
 }
 
-// shared-memory byte offset of chunk 0 of thread t (chunk `it` is 4096 bytes further)
+// shared-memory byte offset of chunk 0 of thread t (chunk `it` is GT * 16 bytes further)
 template <int ROWS>
 __device__ __forceinline__ uint32_t chunk_soff(int mn_major, int t) {
   if (!mn_major) {
@@ -213,38 +215,38 @@ __device__ __forceinline__ uint32_t chunk_soff(int mn_major, int t) {
 }
 
 // One operand as seen by one producer thread.
-template <int ROWS>
+template <int ROWS, int GT = kGroupThreads>
 struct Operand {
   const float* base;   // matrix origin
   const float* fast;   // pointer of chunk 0 of this thread in the group's current k-block
-  int64_t kadv;        // elements between successive k-blocks of this group (2*BK or 2*BK*ld)
+  int64_t kadv;        // elements between successive k-blocks of this thread's group (kb_stride k-blocks)
   int64_t gstride;     // elements between chunks it and it+1
   int ld, mn_major, vec, mn0, mn_lim, full;
   uint32_t soff;
 
   __device__ __forceinline__ void init(const float* b, int ld_, int mn_major_, int vec_, int mn0_, int mn_lim_, int kbeg,
-                                       int t) {
+                                       int t, int kb_stride = 2) {
     base = b; ld = ld_; mn_major = mn_major_; vec = vec_; mn0 = mn0_; mn_lim = mn_lim_;
     full = vec_ && (mn0_ + ROWS <= mn_lim_);
     int mn, k, mn1, k1;
-    chunk_coords<ROWS>(mn_major_, 0, t, mn, k);
-    chunk_coords<ROWS>(mn_major_, 1, t, mn1, k1);
+    chunk_coords<ROWS, GT>(mn_major_, 0, t, mn, k);
+    chunk_coords<ROWS, GT>(mn_major_, 1, t, mn1, k1);
     if (!mn_major_) {
       fast = b + (int64_t)(mn0_ + mn) * ld_ + kbeg + k;
       gstride = (int64_t)(mn1 - mn) * ld_;
-      kadv = 2 * BK;
+      kadv = kb_stride * BK;
     } else {
       fast = b + (int64_t)(kbeg + k) * ld_ + mn0_ + mn;
       gstride = (int64_t)(k1 - k) * ld_ + (mn1 - mn);
-      kadv = (int64_t)2 * BK * ld_;
+      kadv = (int64_t)kb_stride * BK * ld_;
     }
     soff = chunk_soff<ROWS>(mn_major_, t);
   }
 
   // global -> registers for the k-block starting at k0 (issued early: the loads of a group's
   // next k-block are in flight while it waits for the stage to be released)
-  __device__ __forceinline__ void load(TileRegs<ROWS>& r, int k0, int k_lim, int t) {
-    constexpr int PER = TileRegs<ROWS>::PER;
+  __device__ __forceinline__ void load(TileRegs<ROWS, GT>& r, int k0, int k_lim, int t) {
+    constexpr int PER = TileRegs<ROWS, GT>::PER;
     if (full && k0 + BK <= k_lim) {
 #pragma unroll
       for (int it = 0; it < PER; ++it) r.v[it] = ldg4(fast + it * gstride);
@@ -252,7 +254,7 @@ struct Operand {
 #pragma unroll
       for (int it = 0; it < PER; ++it) {
         int mn, k;
-        chunk_coords<ROWS>(mn_major, it, t, mn, k);
+        chunk_coords<ROWS, GT>(mn_major, it, t, mn, k);
         mn += mn0;
         k += k0;
         if (!mn_major) r.v[it] = load_chunk(base, (int64_t)mn * ld + k, k, k_lim, mn < mn_lim, vec);
@@ -263,10 +265,10 @@ struct Operand {
   }
 
   // registers -> hi/lo split -> canonical UMMA shared-memory layout
-  __device__ __forceinline__ void store(const TileRegs<ROWS>& r, uint32_t hi_tile, uint32_t lo_tile) const {
-    constexpr int PER = TileRegs<ROWS>::PER;
+  __device__ __forceinline__ void store(const TileRegs<ROWS, GT>& r, uint32_t hi_tile, uint32_t lo_tile) const {
+    constexpr int PER = TileRegs<ROWS, GT>::PER;
 #pragma unroll
-    for (int it = 0; it < PER; ++it) store_split(hi_tile + soff + it * 4096u, lo_tile + soff + it * 4096u, r.v[it]);
+    for (int it = 0; it < PER; ++it) store_split(hi_tile + soff + it * (GT * 16u), lo_tile + soff + it * (GT * 16u), r.v[it]);
   }
 };
 
@@ -535,6 +537,253 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(const __grid_c
   if (warp == 0) TRACE(7);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant for launches with several tiles per SM (inference forwards, the grouped
+// weight- + data-gradient launches).  A kernel that allocates tensor memory runs ONE CTA per SM on this
+// driver (cudaOccupancyMaxActiveBlocksPerMultiprocessor says 1 for any kernel containing tcgen05.alloc,
+// tools/ubench/occ_probe.cu), so a tile's fill (operands in flight, first stage stored) and epilogue
+// (accumulator drained, 128 KB written) cannot hide behind another CTA's main loop; with one CTA per
+// tile they were half of a tile's 26 k cycles.  Here one CTA per SM walks over its tiles
+// (tile = blockIdx.x + n * gridDim.x): the 16 producer warps and the MMA warp run straight
+// through the tile boundaries, the accumulator is double-buffered in TMEM (2 x 256 columns, all three
+// products of a k-step in one accumulator - K <= 512 per tile keeps the accumulate-truncation bias
+// at ~1e-6), and four epilogue warps drain accumulator b (TMEM -> registers -> row scale / bias /
+// ReLU -> global) while the tensor core is already filling accumulator b^1.
+constexpr int kPersistThreads = (kProducerWarps + 1 + 4) * 32;
+constexpr int kPersistPatchBytes = 4 * 32 * 36 * 4;  // one padded 32 x 32 staging patch per epilogue warp
+
+struct TileInfo {
+  int which, m0, n0, kb0, nkb, bz, M, K;
+  bool live;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const Group& grp, int tile, const int (&Mv)[2], const int (&Kv)[2]) {
+  TileInfo ti;
+  ti.which = tile >= grp.ctas0 ? 1 : 0;
+  const Args& g = grp.g[ti.which];
+  const int local = tile - (ti.which ? grp.ctas0 : 0);
+  const int bx = local % g.nt, by = (local / g.nt) % g.mt;
+  ti.bz = local / (g.nt * g.mt);
+  ti.M = Mv[ti.which];
+  ti.K = Kv[ti.which];
+  ti.m0 = by * BM;
+  ti.n0 = bx * 256;
+  const int kblocks = (ti.K + BK - 1) / BK;
+  const int per_split = (kblocks + g.splits - 1) / g.splits;
+  ti.kb0 = ti.bz * per_split;
+  ti.nkb = min(kblocks, ti.kb0 + per_split) - ti.kb0;
+  ti.live = ti.m0 < ti.M && ti.n0 < g.N && ti.nkb > 0;
+  return ti;
+}
+
+// Producers of the persistent kernel: warps 0-7 bring the A tile (IS_B = false, ROWS = BM), warps 8-15 the B
+// tile (ROWS = 256) of EVERY k-block of the CTA's flattened (tile, k-block) sequence: global -> registers
+// (prefetched one k-block ahead, across tile boundaries) -> hi/lo split -> stage n & 1.  One operand per
+// thread keeps the prefetched k-block at 16 / 32 registers (21 warps leave 80 registers per thread); all 16
+// warps on both operands (2 + 4 chunks each) measured slower, 124 against 110 us for the cfg-3 forward.
+// `op_off` = byte offset of the operand's hi tile inside a stage; its lo tile follows it.
+template <int ROWS, bool IS_B>
+__device__ __forceinline__ void persistent_producer(const Group& grp, const int (&Mv)[2], const int (&Kv)[2], int T, int G,
+                                                        uint32_t smem_base, uint32_t full0, uint32_t empty0, uint32_t stage_bytes,
+                                                        uint32_t op_off) {
+  const int t = threadIdx.x & (kGroupThreads - 1), lane = threadIdx.x & 31;
+  TileRegs<ROWS> regs;
+  Operand<ROWS> op;
+  int tile = blockIdx.x, i = 0;
+  TileInfo ti;
+  ti.nkb = 0;
+  bool valid = false;
+  auto enter_tile = [&]() -> bool {
+    while (tile < T) {
+      ti = decode_tile(grp, tile, Mv, Kv);
+      if (ti.live) return true;
+      tile += G;
+    }
+    return false;
+  };
+  auto seek = [&](bool moved) {
+    while (i >= ti.nkb) {
+      tile += G;
+      if (!enter_tile()) { valid = false; return; }
+      i = 0;
+      moved = true;
+    }
+    valid = true;
+    if (moved) {
+      const Args& g = grp.g[ti.which];
+      if (!IS_B) op.init(g.A, g.lda, g.a_mn, g.vec_a, ti.m0, ti.M, (ti.kb0 + i) * BK, t, 1);
+      else op.init(g.B, g.ldb, g.b_mn, g.vec_b, ti.n0, g.N, (ti.kb0 + i) * BK, t, 1);
+    }
+  };
+  if (enter_tile()) seek(true);
+  if (valid) op.load(regs, (ti.kb0 + i) * BK, ti.K, t);
+  uint32_t n = 0;
+  while (valid) {
+    const uint32_t sidx = n & 1u;
+    mbar_wait(empty0 + 8 * sidx, ((n >> 1) & 1u) ^ 1u);
+    const uint32_t hi = smem_base + sidx * stage_bytes + op_off;
+    op.store(regs, hi, hi + ROWS * BK * 4);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(full0 + 8 * sidx);
+    ++n;
+    ++i;
+    seek(false);
+    if (valid) op.load(regs, (ti.kb0 + i) * BK, ti.K, t);
+  }
+}
+
+__global__ void __launch_bounds__(kPersistThreads, 1) gemm_3xtf32_persistent_kernel(const __grid_constant__ Group grp) {
+  constexpr int BN = 256, STAGES = 2;
+  constexpr int A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;
+  constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bars[8];  // full[2], empty[2], acc_full[2], acc_empty[2]
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]), accf0 = smem_u32(&bars[4]), acce0 = smem_u32(&bars[6]);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full0 + 8 * s, kProducerWarps);
+      mbar_init(empty0 + 8 * s, 1);
+      mbar_init(accf0 + 8 * s, 1);
+      mbar_init(acce0 + 8 * s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kProducerWarps) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t smem_base = smem_u32(smem);
+  pdl_sync();
+  if (warp == 0) TRACE(0);
+
+  int Mv[2], Kv[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    Mv[k] = grp.g[k].m_dev ? *grp.g[k].m_dev : grp.g[k].M;
+    Kv[k] = grp.g[k].k_dev ? *grp.g[k].k_dev : grp.g[k].K;
+  }
+  const int T = grp.tiles, G = gridDim.x;
+
+  if (warp < kProducerWarps) {
+    // ---------------------------------------------------------------- producers
+    if (warp < 8) persistent_producer<BM, false>(grp, Mv, Kv, T, G, smem_base, full0, empty0, STAGE_BYTES, 0u);
+    else persistent_producer<BN, true>(grp, Mv, Kv, T, G, smem_base, full0, empty0, STAGE_BYTES, 2u * A_TILE);
+  } else if (warp == kProducerWarps) {
+    // ---------------------------------------------------------------- MMA issuer
+    uint32_t n = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < T; tile += G) {
+      const TileInfo ti = decode_tile(grp, tile, Mv, Kv);
+      if (!ti.live) continue;
+      const Args& g = grp.g[ti.which];
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_lbo = g.a_mn ? 512u : 16u, a_sbo = g.a_mn ? (uint32_t)(BM / 32 * 512) : 1024u;
+      const uint32_t b_lbo = g.b_mn ? 512u : 16u, b_sbo = g.b_mn ? (uint32_t)(BN / 32 * 512) : 1024u;
+      const uint32_t a_kstep = g.a_mn ? (uint32_t)(BM / 32 * 1024) : 32u;
+      const uint32_t b_kstep = g.b_mn ? (uint32_t)(BN / 32 * 1024) : 32u;
+      const uint32_t a_lt = g.a_mn ? 1u : 2u, b_lt = g.b_mn ? 1u : 2u;
+      const uint32_t b = tcount & 1u;
+      if (tcount < 8) TRACE(16 + tcount * 8 + 0);
+      mbar_wait(acce0 + 8 * b, ((tcount >> 1) & 1u) ^ 1u);  // accumulator b drained by the epilogue warps
+      tc_fence_after();
+      if (tcount < 8) TRACE(16 + tcount * 8 + 1);
+      const uint32_t acc = tmem_base + b * BN;
+      for (int i = 0; i < ti.nkb; ++i, ++n) {
+        const uint32_t s = n & 1u, ph = (n >> 1) & 1u;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        if (tcount < 8 && i == 0) TRACE(16 + tcount * 8 + 2);
+        if (tcount < 8 && i == ti.nkb - 1) TRACE(16 + tcount * 8 + 3);
+        if (lane == 0) {
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t a_hi = sa, a_lo = sa + A_TILE, b_hi = sa + 2 * A_TILE, b_lo = b_hi + B_TILE;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t dah = make_desc(a_hi + ks * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t dal = make_desc(a_lo + ks * a_kstep, a_lbo, a_sbo, a_lt);
+            const uint64_t dbh = make_desc(b_hi + ks * b_kstep, b_lbo, b_sbo, b_lt);
+            const uint64_t dbl = make_desc(b_lo + ks * b_kstep, b_lbo, b_sbo, b_lt);
+            umma_tf32(acc, dal, dbh, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+            umma_tf32(acc, dah, dbl, idesc, 1u);
+            umma_tf32(acc, dah, dbh, idesc, 1u);
+          }
+          umma_commit(empty0 + 8 * s);                        // frees the stage when these MMAs retire
+          if (i == ti.nkb - 1) umma_commit(accf0 + 8 * b);    // accumulator b complete
+        }
+        __syncwarp();
+      }
+      ++tcount;
+    }
+    tc_fence_before();
+  } else {
+    // ---------------------------------------------------------------- epilogue warps
+    const int q = warp & 3;  // the TMEM lane quarter this warp may read
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < T; tile += G) {
+      const TileInfo ti = decode_tile(grp, tile, Mv, Kv);
+      if (!ti.live) continue;
+      const Args& g = grp.g[ti.which];
+      const uint32_t b = tcount & 1u;
+      if (tcount < 8 && q == 0) TRACE(16 + tcount * 8 + 4);
+      mbar_wait(accf0 + 8 * b, (tcount >> 1) & 1u);
+      tc_fence_after();
+      if (tcount < 8 && q == 0) TRACE(16 + tcount * 8 + 5);
+      const int row = q * 32 + lane, m = ti.m0 + row;
+      const bool in = m < ti.M;
+      const float rs = (g.row_scale && in) ? __ldg(g.row_scale + m) : 1.f;
+      const bool add_bias = g.bias && (!g.accumulate || ti.bz == 0);
+      // 32 x 32 blocks go through a private, padded shared-memory patch so that every global store
+      // instruction writes four full 128-byte row segments.  (A thread owns a whole row of the accumulator:
+      // stored straight from registers every instruction touches 32 different lines, and the load/store
+      // pipe it shares with the producers became the bottleneck - measured 116 us against 110 us for the
+      // cfg-3 forward, with 16- or 32-byte stores alike.)
+      float* patch = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + (warp - kProducerWarps - 1) * (32 * 36);
+#pragma unroll 1
+      for (int col0 = 0; col0 < BN; col0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + b * BN + (uint32_t)col0, r);
+        __syncwarp();  // the previous block's reads of the patch are done
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          st4(patch + lane * 36 + j, make_float4(__uint_as_float(r[j]) * rs, __uint_as_float(r[j + 1]) * rs,
+                                                 __uint_as_float(r[j + 2]) * rs, __uint_as_float(r[j + 3]) * rs));
+        __syncwarp();
+        const int cc = (lane & 7) * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (add_bias) b4 = ldg4(g.bias + ti.n0 + col0 + cc);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          const int mm = ti.m0 + q * 32 + rr;
+          if (mm >= ti.M) continue;
+          float4 v = *reinterpret_cast<const float4*>(patch + rr * 36 + cc);
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          float* dst = g.C + (int64_t)mm * g.ldc + ti.n0 + col0 + cc;
+          if (g.accumulate) red_add_v4(dst, v);
+          else st4(dst, v);
+        }
+      }
+      if (tcount < 8 && q == 0) TRACE(16 + tcount * 8 + 6);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce0 + 8 * b);
+      ++tcount;
+    }
+  }
+  __syncthreads();
+  if (warp == kProducerWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace tc
 
 #ifdef EIMS_GEMM_TRACE
@@ -601,18 +850,47 @@ int set_attrs() {
   if (!attr_done) {
     cudaError_t e1 = cudaFuncSetAttribute(gemm_3xtf32_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * BM * BK * 4 + 2 * 128 * BK * 4) + 1024);
     cudaError_t e2 = cudaFuncSetAttribute(gemm_3xtf32_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * BM * BK * 4 + 2 * 256 * BK * 4) + 1024);
-    if (e1 != cudaSuccess || e2 != cudaSuccess) return EIMS_ERR_CUDA;
+    cudaError_t e3 = cudaFuncSetAttribute(gemm_3xtf32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * BM * BK * 4 + 2 * 256 * BK * 4) + 1024 + kPersistPatchBytes);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return EIMS_ERR_CUDA;
     attr_done = true;
   }
   return 0;
 }
 
-int launch_group(const tc::Group& grp, int ctas, bool wide, cudaStream_t st) {
+// The persistent kernel (one CTA per SM walking over its tiles, double-buffered accumulator) takes
+// the launches with several 128 x 256 tiles per SM whose epilogue it implements: no BatchNorm fusion,
+// vector stores, full column tiles, and K <= 512 per tile (single accumulator, see the kernel).
+bool use_persistent(const tc::Group& grp, int ctas, bool wide) {
+  using namespace tc;
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("EIMS_GEMM_PERSISTENT"); on = (e && e[0] == '0') ? 0 : 1; }
+  // measured: 13 % faster at ~7 tiles per SM (cfg-3 forward, 127 -> 110 us), no gain at ~2 tiles per SM (the
+  // grouped wgrad + dgrad launches of cfg 2): overlapping a tile's epilogue with the next tile's main loop buys
+  // less than the tile timeline suggests, because both queue in the same load/store / shared-memory pipe
+  if (!on || !wide || ctas < 4 * 148) return false;
+  for (int k = 0; k < 2; ++k) {
+    const Args& g = grp.g[k];
+    if (g.bn.acc || (g.N % 256) || (g.ldc & 3) || (reinterpret_cast<uintptr_t>(g.C) & 15)) return false;
+    if (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15)) return false;
+    const int kblocks = (g.K + BK - 1) / BK;  // upper bound when K lives on the device (capacity)
+    if ((kblocks + g.splits - 1) / g.splits > 16) return false;
+  }
+  return true;
+}
+
+int launch_group(const tc::Group& grp_in, int ctas, bool wide, cudaStream_t st) {
   using namespace tc;
   const int BN = wide ? 256 : 128, stages = wide ? 2 : 3;
   const int smem_bytes = stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
-  cudaError_t e = wide ? launch_pdl(gemm_3xtf32_kernel<256, 2>, dim3(ctas), dim3(kThreads), smem_bytes, st, grp)
-                       : launch_pdl(gemm_3xtf32_kernel<128, 3>, dim3(ctas), dim3(kThreads), smem_bytes, st, grp);
+  cudaError_t e;
+  if (use_persistent(grp_in, ctas, wide)) {
+    Group grp = grp_in;
+    grp.tiles = ctas;
+    e = launch_pdl(gemm_3xtf32_persistent_kernel, dim3(ctas < 148 ? ctas : 148), dim3(kPersistThreads), smem_bytes + kPersistPatchBytes, st, grp);
+  } else {
+    e = wide ? launch_pdl(gemm_3xtf32_kernel<256, 2>, dim3(ctas), dim3(kThreads), smem_bytes, st, grp_in)
+             : launch_pdl(gemm_3xtf32_kernel<128, 3>, dim3(ctas), dim3(kThreads), smem_bytes, st, grp_in);
+  }
   return e == cudaSuccess ? 0 : EIMS_ERR_CUDA;
 }
 
