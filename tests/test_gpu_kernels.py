@@ -160,6 +160,36 @@ def test_gemm_epilogue_dynamic_and_splitk(backend):
     assert (dW.double() - ref).abs().max().item() / ref.abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_persistent_kernel(a_mn, b_mn):
+    """Launches with >= 4 tiles of 128x256 per SM take the persistent kernel (one CTA per SM walking its
+    tiles, double-buffered TMEM accumulator): all four storage orders, a live size on the device that leaves
+    a ragged last tile and hundreds of dead tiles, row scale + bias + ReLU, a K that is not a multiple of 32,
+    and the split-K accumulate form."""
+    g = torch.Generator(device="cpu").manual_seed(5 + 2 * a_mn + b_mn)
+    Mcap, M, N, K = 80000, 40777, 512, 200           # 625 x 2 tiles of capacity, 319 x 2 live
+    A = torch.randn(Mcap, K, generator=g)
+    B = torch.randn(K, N, generator=g)
+    Ad = (A.t().contiguous() if a_mn else A.contiguous()).to(DEV)
+    Bd = (B.contiguous() if b_mn else B.t().contiguous()).to(DEV)
+    rs = torch.rand(Mcap, generator=g).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    m_dev = dev(np.array([M], np.int32))
+    out = torch.full((Mcap, N), 7.0, device=DEV)
+    check(_lib.load().eims_gemm(_lib.GEMM_TCGEN05, ptr(Ad), Ad.stride(0), a_mn, ptr(Bd), Bd.stride(0), b_mn, ptr(out), N,
+                                Mcap, N, K, ptr(m_dev), None, ptr(rs), ptr(bias), 1, 0, stream()))
+    ref = torch.relu((A[:M].double() @ B.double()) * rs[:M, None].cpu().double() + bias.cpu().double())
+    assert (out[:M].cpu().double() - ref).abs().max().item() / ref.abs().max().item() < 1e-5
+    assert bool((out[M:] == 7.0).all())               # dead tiles and the rows past M of the ragged tile are untouched
+    # accumulate into C (every CTA adds its tiles with red.global.add.v4.f32)
+    out2 = torch.ones(Mcap, N, device=DEV)
+    check(_lib.load().eims_gemm(_lib.GEMM_TCGEN05, ptr(Ad), Ad.stride(0), a_mn, ptr(Bd), Bd.stride(0), b_mn, ptr(out2), N,
+                                Mcap, N, K, ptr(m_dev), None, None, None, 0, 1, stream()))
+    ref2 = 1.0 + A[:M].double() @ B.double()
+    assert (out2[:M].cpu().double() - ref2).abs().max().item() / ref2.abs().max().item() < 1e-5
+    assert bool((out2[M:] == 1.0).all())
+
+
 # ------------------------------------------------------------------------------- K2
 @pytest.mark.parametrize("H", [64, 256, 1024])
 def test_spmm_forward_backward(H):
