@@ -542,7 +542,11 @@ def run_extra(args):
             step(j)
         prof, _ = plan.profile_read()
         plan.profile(False)
-        stages_out = stage_report(prof, stage_work(float(np.mean(Ns)), float(np.mean(Es)), batch, fp.numel, hid, layers), n_prof, peaks())
+        work = stage_work(float(np.mean(Ns)), float(np.mean(Es)), batch, fp.numel, hid, layers)
+        if infer:  # eval mode: "bn_stats" only turns the running buffers into scale / shift; "elementwise" is the sigmoid
+            work["bn_stats"] = ("hbm", layers * 6 * hid * 4)
+            work["elementwise"] = ("hbm", 8 * batch * M)
+        stages_out = stage_report(prof, work, n_prof, peaks())
     wl = ("BASELINE configs[2]: inference-only spectrum prediction, synthetic molecules (<=64 heavy atoms), batch 4096, single B200"
           if infer else "BASELINE configs[4] shapes on one B200: 6 GCN layers, hidden 1024, molecules up to 128 heavy atoms, batch 512, training")
     print(json.dumps({"metric": "gcn_eims_infer_molecules_per_sec" if infer else METRIC, "value": args.steps * batch / (ms * 1e-3),
