@@ -86,20 +86,33 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(DpPeers pr, int rank, int
   // ---- phase 1: reduce + AdamW + broadcast of the own slice
   const int64_t s0 = base4 + (int64_t)rank * per, s1 = min(base4 + n4, s0 + per);
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = s0 + tid; i < s1; i += nth) {
-    float4 g;
-    if (pr.grads_mc) {
-      g = multimem_ld_reduce_add(pr.grads_mc + 4 * i);
-    } else {
-      g = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < world; ++r) {  // fixed order: every rank would get the same bits
-        const float4 t = __ldcg(reinterpret_cast<const float4*>(pr.grads[r] + 4 * i));  // L2 (coherence point), not L1
-        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+  // kDpUnroll independent reductions in flight per thread: a multimem.ld_reduce is a round trip through the
+  // switch (microseconds), and at 2 GPUs a thread owns 2-3 elements of the slice
+  constexpr int kDpUnroll = 4;
+  for (int64_t i0 = s0 + tid; i0 < s1; i0 += kDpUnroll * nth) {
+    float4 gs[kDpUnroll];
+#pragma unroll
+    for (int u = 0; u < kDpUnroll; ++u) {
+      const int64_t i = i0 + u * nth;
+      gs[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i >= s1) continue;
+      if (pr.grads_mc) {
+        gs[u] = multimem_ld_reduce_add(pr.grads_mc + 4 * i);
+      } else {
+        for (int r = 0; r < world; ++r) {  // fixed order: every rank would get the same bits
+          const float4 t = __ldcg(reinterpret_cast<const float4*>(pr.grads[r] + 4 * i));  // L2 (coherence point), not L1
+          gs[u].x += t.x; gs[u].y += t.y; gs[u].z += t.z; gs[u].w += t.w;
+        }
       }
     }
-    float4 pp = *reinterpret_cast<float4*>(pr.params[rank] + 4 * i);
-    const int64_t j = i - s0;
-    float4 mm = *reinterpret_cast<float4*>(m + 4 * j), vv = *reinterpret_cast<float4*>(v + 4 * j);
+#pragma unroll
+    for (int u = 0; u < kDpUnroll; ++u) {
+      const int64_t i = i0 + u * nth;
+      if (i >= s1) continue;
+      const float4 g = gs[u];
+      float4 pp = *reinterpret_cast<float4*>(pr.params[rank] + 4 * i);
+      const int64_t j = i - s0;
+      float4 mm = *reinterpret_cast<float4*>(m + 4 * j), vv = *reinterpret_cast<float4*>(v + 4 * j);
 #define EIMS_ADAM1(P, G, Mm, V)                  \
   {                                              \
     float gr = G * k.grad_scale;                 \
@@ -109,15 +122,16 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(DpPeers pr, int rank, int
     float den = sqrtf(V) * k.inv_bc2_sqrt + k.eps; \
     P = P - k.step_size * (Mm / den);            \
   }
-    EIMS_ADAM1(pp.x, g.x, mm.x, vv.x) EIMS_ADAM1(pp.y, g.y, mm.y, vv.y)
-    EIMS_ADAM1(pp.z, g.z, mm.z, vv.z) EIMS_ADAM1(pp.w, g.w, mm.w, vv.w)
+      EIMS_ADAM1(pp.x, g.x, mm.x, vv.x) EIMS_ADAM1(pp.y, g.y, mm.y, vv.y)
+      EIMS_ADAM1(pp.z, g.z, mm.z, vv.z) EIMS_ADAM1(pp.w, g.w, mm.w, vv.w)
 #undef EIMS_ADAM1
-    *reinterpret_cast<float4*>(m + 4 * j) = mm;
-    *reinterpret_cast<float4*>(v + 4 * j) = vv;
-    if (pr.params_mc) {
-      multimem_st(pr.params_mc + 4 * i, pp);
-    } else {
-      for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(pr.params[r] + 4 * i) = pp;
+      *reinterpret_cast<float4*>(m + 4 * j) = mm;
+      *reinterpret_cast<float4*>(v + 4 * j) = vv;
+      if (pr.params_mc) {
+        multimem_st(pr.params_mc + 4 * i, pp);
+      } else {
+        for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(pr.params[r] + 4 * i) = pp;
+      }
     }
   }
   // the other gradient buffer (read by the peers during the previous step, which every rank has
