@@ -399,14 +399,12 @@ __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ 
     sh[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has_bn && c < H) { sc[v] = ldg4(bn_scale + c); sh[v] = ldg4(bn_shift + c); }
   }
-  float4 mu[STATS ? NV : 1], is[STATS ? NV : 1], s1[STATS ? NV : 1], s2[STATS ? NV : 1];
+  // (the BatchNorm's mean / invstd vectors are re-read per row - L1 hits - rather than held in 16 registers:
+  // the gather needs the occupancy more)
+  float4 s1[STATS ? NV : 1], s2[STATS ? NV : 1];
   if (STATS) {
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c = cbase + (v * 32 + lane) * 4;
-      mu[v] = is[v] = s1[v] = s2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < H) { mu[v] = ldg4(bf.mean + c); is[v] = ldg4(bf.invstd + c); }
-    }
+    for (int v = 0; v < NV; ++v) s1[v] = s2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int i = warp / parts; i < N; i += nwarps / parts) {
     const int e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
@@ -477,9 +475,10 @@ __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ 
       }
       st4(out + (int64_t)i * H + c, a);
       if (STATS) {
+        const float4 mu = ldg4(bf.mean + c), is = ldg4(bf.invstd + c);
         s1[v].x += a.x; s1[v].y += a.y; s1[v].z += a.z; s1[v].w += a.w;
-        s2[v].x = fmaf(a.x, (zrow[v].x - mu[v].x) * is[v].x, s2[v].x); s2[v].y = fmaf(a.y, (zrow[v].y - mu[v].y) * is[v].y, s2[v].y);
-        s2[v].z = fmaf(a.z, (zrow[v].z - mu[v].z) * is[v].z, s2[v].z); s2[v].w = fmaf(a.w, (zrow[v].w - mu[v].w) * is[v].w, s2[v].w);
+        s2[v].x = fmaf(a.x, (zrow[v].x - mu.x) * is.x, s2[v].x); s2[v].y = fmaf(a.y, (zrow[v].y - mu.y) * is.y, s2[v].y);
+        s2[v].z = fmaf(a.z, (zrow[v].z - mu.z) * is.z, s2[v].z); s2[v].w = fmaf(a.w, (zrow[v].w - mu.w) * is.w, s2[v].w);
       }
     }
   }
@@ -532,14 +531,14 @@ int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const f
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   const BnBwdFuse none{};
-  // STATS: every block ends with one atomic per column and statistic, and their number is what the
-  // tail of the kernel costs (measured at cfg 2: 23 us with 296 blocks, 26 with 592, 31 with 1184)
+  // STATS: one wave of three blocks per SM (77 registers with one neighbour in flight per trip; measured at cfg 2:
+  // 20 us with 444 blocks, 25 with 296 or 592)
   static int sblocks = 0;
-  if (!sblocks) { const char* e = getenv("EIMS_SPMM_STATS_BLOCKS"); sblocks = e ? atoi(e) : 148 * 2; if (sblocks < 1) sblocks = 1; }
+  if (!sblocks) { const char* e = getenv("EIMS_SPMM_STATS_BLOCKS"); sblocks = e ? atoi(e) : 148 * 3; if (sblocks < 1) sblocks = 1; }
   const int blocks_s = blocks < sblocks ? blocks : sblocks;
 #define EIMS_SPMM(NV, UE)                                                                                              \
   do {                                                                                                                 \
-    if (bf) launch_pdl(spmm_norm_kernel<NV, UE, true>, dim3(blocks_s), dim3(256), (size_t)8 * 2 * 128 * NV * sizeof(float), st, dims, rowptr, col, norm, \
+    if (bf) launch_pdl(spmm_norm_kernel<NV, 1, true>, dim3(blocks_s), dim3(256), (size_t)8 * 2 * 128 * NV * sizeof(float), st, dims, rowptr, col, norm, \
                        h, H, bn_scale, bn_shift, drop, out_mode, out, parts, *bf);                                      \
     else launch_pdl(spmm_norm_kernel<NV, UE, false>, dim3(blocks), dim3(256), 0, st, dims, rowptr, col, norm, h, H, bn_scale,   \
                     bn_shift, drop, out_mode, out, parts, none);                                                        \

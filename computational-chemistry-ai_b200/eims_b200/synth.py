@@ -190,7 +190,7 @@ def dense_spectra(ptr, mz, inten, max_mz: int) -> np.ndarray:
     """Vectorised equivalent of `peaks_to_spectrum_batch` (reference :193-205): round
     half-to-even, drop bins outside [0,max_mz), max-merge duplicates, divide each row
     by its max (1.0 when the row is all zero).  Bit-identical to the reference's NumPy
-    branch (checked in tests/test_oracle_spectrum.py)."""
+    branch (checked in tests/test_oracle_golden.py)."""
     G = len(ptr) - 1
     out = np.zeros((G, max_mz), np.float32)
     row = np.repeat(np.arange(G), np.diff(ptr))
