@@ -527,8 +527,10 @@ int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const f
   if (bf && out_mode != 1) return EIMS_ERR_ARG;
   const int parts = H <= 512 ? 1 : (H + 511) / 512;
   if (parts > 8 || (8 % parts)) return EIMS_ERR_ARG;  // 8 warps per block must split evenly over a row
+  static int per_sm = 0;  // resident blocks per SM the grid is sized for (tuning knob)
+  if (!per_sm) { const char* e = getenv("EIMS_SPMM_BLOCKS_PER_SM"); per_sm = e ? atoi(e) : 8; if (per_sm < 1) per_sm = 1; }
   int blocks = (max_nodes * parts + 7) / 8;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * per_sm) blocks = 148 * per_sm;
   if (blocks < 1) blocks = 1;
   const BnBwdFuse none{};
   // STATS: one wave of three blocks per SM (77 registers with one neighbour in flight per trip; measured at cfg 2:
