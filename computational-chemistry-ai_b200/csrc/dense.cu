@@ -289,6 +289,71 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_stats_kernel(const int* __restr
   }
 }
 
+// The same statistics for the layer under the readout, without touching the nodes.  There
+//   dh_i = dS_g (+ dMx_g at the arg-max node)        [sum; mean: dS_g / n_g; max: only the second term]
+// so   sum_i dh_i       = sum_g ( n_g dS_g + dMx_g )
+//      sum_i dh_i xhat_i = sum_g ( dS_g * Zsum_g + dMx_g * Zmax_g ) * invstd
+// with Zsum_g = sum_{i in g} (z_i - mu) and Zmax_g = z_argmax - mu, which the readout kernel left in zstat:
+// O(B*H) work instead of a pass over all N*H activations.  Thread = (column quad, graph lane).
+__global__ void __launch_bounds__(256) bn_bwd_stats_top_kernel(const int* __restrict__ dims, const float* __restrict__ dG,
+                                                               const float* __restrict__ zstat, const int* __restrict__ gptr,
+                                                               int pooling, int H, const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, float* __restrict__ means,
+                                                               float* __restrict__ scratch) {
+  pdl_sync();
+  const int B = dims[DIM_B], N = dims[DIM_N];
+  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
+  double* acc = reinterpret_cast<double*>(scratch + 16);
+  const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int c0 = blockIdx.x * kSlab, c = c0 + cl * 4;
+  const int pd = pooling == EIMS_POOL_COMBINED ? 2 * H : H;
+  double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+  if (c < H) {
+    const float4 is = ldg4(invstd + c);
+    for (int g = blockIdx.y * kRowLanes + rl; g < B; g += gridDim.y * kRowLanes) {
+      const float n = (float)(__ldg(gptr + g + 1) - __ldg(gptr + g));
+      if (pooling != EIMS_POOL_MAX) {
+        float4 d = ldg4(dG + (int64_t)g * pd + c);
+        const float4 zs = ldg4(zstat + (int64_t)g * 2 * H + c);
+        if (pooling == EIMS_POOL_MEAN) { d.x /= n; d.y /= n; d.z /= n; d.w /= n; }  // every node of the graph gets dS / n
+        a[0] += (double)d.x * n; a[1] += (double)d.y * n; a[2] += (double)d.z * n; a[3] += (double)d.w * n;
+        b[0] += (double)d.x * (double)(zs.x * is.x); b[1] += (double)d.y * (double)(zs.y * is.y);
+        b[2] += (double)d.z * (double)(zs.z * is.z); b[3] += (double)d.w * (double)(zs.w * is.w);
+      }
+      if ((pooling == EIMS_POOL_MAX || pooling == EIMS_POOL_COMBINED) && n > 0.f) {
+        const float4 m = ldg4(dG + (int64_t)g * pd + (pooling == EIMS_POOL_COMBINED ? H : 0) + c);
+        const float4 zm = ldg4(zstat + (int64_t)g * 2 * H + H + c);
+        a[0] += (double)m.x; a[1] += (double)m.y; a[2] += (double)m.z; a[3] += (double)m.w;
+        b[0] += (double)m.x * (double)(zm.x * is.x); b[1] += (double)m.y * (double)(zm.y * is.y);
+        b[2] += (double)m.z * (double)(zm.z * is.z); b[3] += (double)m.w * (double)(zm.w * is.w);
+      }
+    }
+  }
+  slab_reduce_atomic(a, b, H, c0, cl, rl, acc);
+  if (!last_block_ticket(counter, gridDim.x * gridDim.y)) return;
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    const double sa = bn_acc_take(acc, H, 0, k), sb = bn_acc_take(acc, H, 1, k);
+    dbeta[k] += (float)sa;
+    dgamma[k] += (float)sb;
+    means[k] = N > 0 ? (float)(sa / N) : 0.f;
+    means[H + k] = N > 0 ? (float)(sb / N) : 0.f;
+  }
+}
+
+int launch_bn_bwd_stats_top(const int* dims, const float* dG, const float* zstat, const int* gptr, int pooling, int H,
+                            const float* mean, const float* invstd, float* dgamma, float* dbeta, float* means,
+                            float* partials, int max_graphs, cudaStream_t st) {
+  if (H % 4 || H > 4096) return EIMS_ERR_ARG;
+  const int slabs = (H + kSlab - 1) / kSlab;
+  int rg = (max_graphs + 4 * kRowLanes - 1) / (4 * kRowLanes);  // >= 4 graphs per thread
+  if (rg > 37) rg = 37;
+  if (rg < 1) rg = 1;
+  launch_pdl(bn_bwd_stats_top_kernel, dim3(slabs, rg), dim3(256), 0, st, dims, dG, zstat, gptr, pooling, H, mean, invstd, dgamma, dbeta,
+             means, partials);
+  return 0;
+}
+
 // pass 2: q = gamma*invstd*(dh - mean(dh) - xhat*mean(dh*xhat)) * [z>0] * c_i ;  dbias += colsum(dr)
 // LAYER0: the first GraphConv has no input gradient, so q is consumed on the spot by its weight
 // gradient dW0[f,k] += sum_i a0[i,f] * q[i,k] (F <= 8 rows) and never written.

@@ -561,9 +561,10 @@ __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ di
                                                       const float* __restrict__ z, int H,
                                                       const float* __restrict__ bn_scale,
                                                       const float* __restrict__ bn_shift, int pooling,
-                                                      float* __restrict__ out, int* __restrict__ argmax) {
+                                                      float* __restrict__ out, int* __restrict__ argmax,
+                                                      float* __restrict__ zstat, const float* __restrict__ bn_mean) {
   pdl_sync();
-  __shared__ float4 ssum[256], smax[256];
+  __shared__ float4 ssum[256], smax[256], szs[256];
   __shared__ int4 sarg[256];
   const int B = dims[DIM_B];
   const int g = blockIdx.x;
@@ -580,13 +581,17 @@ __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ di
     const int c = (cb + cl) * 4;
     const bool on = rl < RL && cb + cl < cpl;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), mx = make_float4(ninf, ninf, ninf, ninf);
+    float4 zs = make_float4(0.f, 0.f, 0.f, 0.f);  // column sums of (z - batch mean) over the graph, for zstat
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f);
     int4 am = make_int4(r0, r0, r0, r0);
     if (on) {
       float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
       if (has_bn) { sc = ldg4(bn_scale + c); sh = ldg4(bn_shift + c); }
+      if (zstat) mu = ldg4(bn_mean + c);
 #pragma unroll 4
       for (int i = r0 + rl; i < r1; i += RL) {
         float4 v = ldg4(z + (int64_t)i * H + c);
+        zs.x += v.x - mu.x; zs.y += v.y - mu.y; zs.z += v.z - mu.z; zs.w += v.w - mu.w;
         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
         v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -597,12 +602,14 @@ __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ di
       }
     }
     __syncthreads();
-    ssum[threadIdx.x] = s; smax[threadIdx.x] = mx; sarg[threadIdx.x] = am;
+    ssum[threadIdx.x] = s; smax[threadIdx.x] = mx; sarg[threadIdx.x] = am; szs[threadIdx.x] = zs;
     __syncthreads();
     if (rl == 0 && on) {
       for (int k = 1; k < RL; ++k) {
         const float4 s2 = ssum[k * CL + cl], m2 = smax[k * CL + cl];
         const int4 a2 = sarg[k * CL + cl];
+        const float4 z2 = szs[k * CL + cl];
+        zs.x += z2.x; zs.y += z2.y; zs.z += z2.z; zs.w += z2.w;
         s.x += s2.x; s.y += s2.y; s.z += s2.z; s.w += s2.w;
         if (m2.x > mx.x || (m2.x == mx.x && a2.x < am.x)) { mx.x = m2.x; am.x = a2.x; }
         if (m2.y > mx.y || (m2.y == mx.y && a2.y < am.y)) { mx.y = m2.y; am.y = a2.y; }
@@ -619,14 +626,26 @@ __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ di
       if (pooling == EIMS_POOL_COMBINED) st4(o + H + c, mx);
       if (argmax && (pooling == EIMS_POOL_MAX || pooling == EIMS_POOL_COMBINED))
         *reinterpret_cast<int4*>(argmax + (int64_t)g * H + c) = am;
+      if (zstat) {
+        // what the BatchNorm-backward statistics of this layer need per graph (bn_bwd_stats_top_kernel):
+        // the column sums of z - mean (summed centred, so nearly constant columns keep their digits) and
+        // z - mean at the arg-max node
+        float* zo = zstat + (int64_t)g * 2 * H;
+        st4(zo + c, zs);
+        if (r1 > r0)
+          st4(zo + H + c, make_float4(__ldg(z + (int64_t)am.x * H + c) - mu.x, __ldg(z + (int64_t)am.y * H + c + 1) - mu.y,
+                                      __ldg(z + (int64_t)am.z * H + c + 2) - mu.z, __ldg(z + (int64_t)am.w * H + c + 3) - mu.w));
+      }
     }
   }
 }
 
 int launch_readout(const int* dims, const int* gptr, const float* z, int H, const float* bn_scale,
-                   const float* bn_shift, int pooling, float* out, int* argmax, int max_graphs, cudaStream_t st) {
-  if (H % 4 || H < 4) return EIMS_ERR_ARG;
-  launch_pdl(readout_kernel, dim3(max_graphs < 1 ? 1 : max_graphs), dim3(256), 0, st, dims, gptr, z, H, bn_scale, bn_shift, pooling, out, argmax);
+                   const float* bn_shift, int pooling, float* out, int* argmax, int max_graphs, cudaStream_t st, float* zstat,
+                   const float* bn_mean) {
+  if (H % 4 || H < 4 || (zstat && !bn_mean)) return EIMS_ERR_ARG;
+  launch_pdl(readout_kernel, dim3(max_graphs < 1 ? 1 : max_graphs), dim3(256), 0, st, dims, gptr, z, H, bn_scale, bn_shift, pooling, out, argmax,
+             zstat, bn_mean);
   return 0;
 }
 

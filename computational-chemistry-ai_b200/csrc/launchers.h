@@ -26,7 +26,9 @@ int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const f
                      const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
                      int max_nodes, cudaStream_t st, const BnBwdFuse* bf = nullptr);
 int launch_readout(const int* dims, const int* gptr, const float* z, int H, const float* bn_scale,
-                   const float* bn_shift, int pooling, float* out, int* argmax, int max_graphs, cudaStream_t st);
+                   const float* bn_shift, int pooling, float* out, int* argmax, int max_graphs, cudaStream_t st,
+                   float* zstat = nullptr, const float* bn_mean = nullptr);  // zstat [B][2H]: per graph, column sums of
+                                                                             // z - bn_mean and z - bn_mean at the arg-max node (training)
 
 // dense.cu
 int launch_gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M,
@@ -44,6 +46,10 @@ int launch_bn_bwd_stats(const int* dims, const float* dh, const float* dG, const
                         const int* argmax, int pooling, const float* z, int H, const float* mean, const float* invstd,
                         float* dgamma, float* dbeta, float* means, float* partials, int max_nodes, cudaStream_t st,
                         const GatherSrc* gs = nullptr);
+// statistics of the TOP layer's BatchNorm backward from per-graph quantities (O(B*H) instead of O(N*H))
+int launch_bn_bwd_stats_top(const int* dims, const float* dG, const float* zstat, const int* gptr, int pooling, int H,
+                            const float* mean, const float* invstd, float* dgamma, float* dbeta, float* means,
+                            float* partials, int max_graphs, cudaStream_t st);
 int launch_bn_bwd_apply(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr,
                         const int* argmax, int pooling, const float* z, int H, const float* mean, const float* invstd,
                         const float* gamma, const float* norm, float* dbias, const float* means, float* q, int max_nodes,

@@ -84,6 +84,7 @@ struct eims_plan {
   // per-stage CUDA-event profiling (bench.py's roofline pass) and launch accounting
   eims_peaks peak_targets{};  // targets as peak lists (eims_plan_set_peak_targets); peak_ptr == NULL: unset
   bool pair_gemms = true;     // wgrad + dgrad of a layer share one launch (EIMS_PAIR_GEMMS=0: two launches)
+  bool top_stats_per_graph = true;  // BatchNorm-backward statistics of the top layer from per-graph quantities (EIMS_TOP_STATS_PER_GRAPH=0: node pass)
   bool fuse_bn_bwd_stats = true;  // BatchNorm-backward statistics come out of the SpMM that writes dh (EIMS_FUSE_BN_BWD_STATS=0: own pass)
   bool fuse_spmm_bwd = false;  // measured slower at cfg 2 (0.405 vs 0.386 ms/step): the slab-layout gather costs more than K2 saves
   int batch_seq = 0;  // K1 sequence number (tags the zero-degree flag, see k1_build_kernel)
@@ -315,6 +316,7 @@ int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, 
   p->gemm_backend = EIMS_GEMM_TCGEN05;
   if (const char* e = getenv("EIMS_FUSE_SPMM_BWD")) p->fuse_spmm_bwd = e[0] != '0';
   if (const char* e = getenv("EIMS_PAIR_GEMMS")) p->pair_gemms = e[0] != '0';
+  if (const char* e = getenv("EIMS_TOP_STATS_PER_GRAPH")) p->top_stats_per_graph = e[0] != '0';
   if (const char* e = getenv("EIMS_FUSE_BN_BWD_STATS")) p->fuse_bn_bwd_stats = e[0] != '0';
   p->ws_bytes = 0; p->bound = false; p->state = 0; p->last_training = 0;
   memset(&p->last_step, 0, sizeof(p->last_step));
@@ -338,6 +340,7 @@ int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, 
   add(p, "bn_means2", 2 * H * 4);
   add(p, "bn_partials", bn_scratch_floats(d->hidden_dim, p->Nc) * 4);
   add(p, "readout", B * P * 4);
+  add(p, "zstat", B * 2 * H * 4);  // per graph: raw column sums and raw arg-max values of the top layer (training)
   // outputs of the split-K head GEMMs, contiguous: a training forward zeroes the whole range once
   // (inside the layer-0 kernel) instead of one memset per GEMM, which would also break the
   // programmatic-dependent-launch chain six times per step
@@ -469,7 +472,8 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
   // forwards keep plain stores and are bit-reproducible.
   const int head_acc = training ? 3 : 0;  // 3 = split-K allowed, C already zeroed (by the layer-0 kernel)
   STAGE(ST_READOUT, 1, launch_readout(dims, p->i("gptr"), p->f(L_("z", L - 1)), H, p->f(L_("bn_scale", L - 1)),
-                          p->f(L_("bn_shift", L - 1)), d.pooling, p->f("readout"), p->i("argmax"), p->Bc, st));
+                          p->f(L_("bn_shift", L - 1)), d.pooling, p->f("readout"), p->i("argmax"), p->Bc, st,
+                          training ? p->f("zstat") : nullptr, training ? p->f(L_("bn_mean", L - 1)) : nullptr));
   STAGE(ST_GEMM_HEAD_FWD, 1, gemm(p, p->f("readout"), P, 0, params + p->off_head(0), P, 0, p->f("u1"), 2 * H, p->Bc, 2 * H, P,
                 dims + DIM_B, nullptr, nullptr, params + p->off_head(1), 0, head_acc, st));
   STAGE(ST_LN_FWD, 1, launch_ln_fwd(dims, p->f("u1"), 2 * H, params + p->off_head(2), params + p->off_head(3),
@@ -572,7 +576,11 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
     GatherSrc gsrc{p->f("da"), p->i("rowptr"), p->i("col"), p->f("norm"), make_drop(drop_p, seed, step, l)};
     const GatherSrc* gs = gather ? &gsrc : nullptr;
     // the statistics pass of layer l < L-1 rides on the SpMM that wrote its dh (see below)
-    if (from_readout || gather || !p->fuse_bn_bwd_stats)
+    if (from_readout && p->top_stats_per_graph)
+      STAGE(ST_BN_BWD_STATS, 1, launch_bn_bwd_stats_top(dims, p->f("dG"), p->f("zstat"), p->i("gptr"), d.pooling, H, p->f(L_("bn_mean", l)),
+                                   p->f(L_("bn_invstd", l)), grads + p->off_bn_g(l), grads + p->off_bn_b(l), p->f("bn_means2"),
+                                   p->f("bn_partials"), p->Bc, st));
+    else if (from_readout || gather || !p->fuse_bn_bwd_stats)
     STAGE(ST_BN_BWD_STATS, 1, launch_bn_bwd_stats(dims, dh_in, p->f("dG"), p->i("gid"), p->i("gptr"), p->i("argmax"), d.pooling,
                                  p->f(L_("z", l)), H, p->f(L_("bn_mean", l)), p->f(L_("bn_invstd", l)), grads + p->off_bn_g(l),
                                  grads + p->off_bn_b(l), p->f("bn_means2"), p->f("bn_partials"), p->Nc, st, gs));
