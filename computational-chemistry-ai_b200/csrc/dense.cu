@@ -107,9 +107,10 @@ int launch_gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb,
 // the launch can be replayed.
 constexpr int kSlab = 64, kRowLanes = 16;
 
-static inline dim3 bn_grid(int H, int max_nodes) {
+// per_sm = blocks per SM in total: 4 (all resident at 64 registers) unless the kernel says otherwise
+static inline dim3 bn_grid(int H, int max_nodes, int per_sm = 4) {
   const int slabs = (H + kSlab - 1) / kSlab;
-  int rg = (148 * 4 + slabs - 1) / slabs;                       // ~4 blocks per SM in total
+  int rg = (148 * per_sm + slabs - 1) / slabs;
   const int need = (max_nodes + 4 * kRowLanes - 1) / (4 * kRowLanes);  // >= 4 rows per thread
   if (rg > need) rg = need;
   if (rg < 1) rg = 1;
@@ -449,8 +450,11 @@ int launch_bn_bwd_apply(const int* dims, const float* dh, const float* dG, const
   DhSrc src{dh, dG, gid, gptr, argmax, pooling, nullptr, nullptr, nullptr, nullptr, DropCfg{}};
   if (gs) { src.da = gs->da; src.rowptr = gs->rowptr; src.col = gs->col; src.norm = gs->norm; src.drop = gs->drop; }
   const dim3 grid = bn_grid(H, max_nodes);
+  // the layer-0 variant (104 registers: two resident blocks per SM) is launched as one wave: 12.7 us against 16.3
+  static int l0_per_sm = 0;
+  if (!l0_per_sm) { const char* e = getenv("EIMS_BN_L0_BLOCKS_PER_SM"); l0_per_sm = e ? atoi(e) : 2; if (l0_per_sm < 1) l0_per_sm = 1; }
   if (dW0)
-    launch_pdl(bn_bwd_apply_kernel<true>, grid, dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, a0, F, dW0);
+    launch_pdl(bn_bwd_apply_kernel<true>, bn_grid(H, max_nodes, l0_per_sm), dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, a0, F, dW0);
   else
     launch_pdl(bn_bwd_apply_kernel<false>, grid, dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, nullptr, 0, nullptr);
   return 0;

@@ -280,7 +280,7 @@ int launch_csr_build(const eims_dataset* ds, const int32_t* ids, int B, int F, i
 // z0 = relu((a0 W0) * c + b0), the transform done in registers, with the BatchNorm statistics
 // of z0 fused in (training).  Column-slab decomposition: grid = (H/64, row groups), thread =
 // (4 columns, 1 of 16 row lanes).
-constexpr int kL0Rows = 256;  // rows of a0 / norm a block stages in shared memory
+constexpr int kL0Rows = 512;  // rows of a0 / norm a block stages in shared memory
 
 __global__ void __launch_bounds__(256) layer0_fwd_kernel(const int* __restrict__ dims, const float* __restrict__ norm,
                                                          const float* __restrict__ a0, int F, const float* __restrict__ W,
@@ -350,8 +350,10 @@ int launch_layer0_fwd(const int* dims, const float* norm, const float* a0, int F
                       int H, float* z, int max_nodes, cudaStream_t st, const BnFuse* bn, float* zero, int64_t zero_n4) {
   if (F > kMaxF0 || H % 4) return EIMS_ERR_ARG;
   const int slabs = (H + 63) / 64;
-  static int per_sm = 0;  // blocks per SM in total (tuning knob)
-  if (!per_sm) { const char* e = getenv("EIMS_L0_BLOCKS_PER_SM"); per_sm = e ? atoi(e) : 4; if (per_sm < 1) per_sm = 1; }
+  // one wave: the kernel needs 104 registers, so two blocks are resident per SM (measured at cfg 2: 13.7 us with
+  // 2 blocks per SM, 16.7-17.5 us with 3 or 4, i.e. a second wave)
+  static int per_sm = 0;
+  if (!per_sm) { const char* e = getenv("EIMS_L0_BLOCKS_PER_SM"); per_sm = e ? atoi(e) : 2; if (per_sm < 1) per_sm = 1; }
   int rg = (148 * per_sm + slabs - 1) / slabs;
   const int need = (max_nodes + kL0Rows - 1) / kL0Rows;  // a block stages at most kL0Rows rows
   if (rg < need) rg = need;
