@@ -615,7 +615,9 @@ int launch_ln_bwd(const int* dims, const float* u, const float* y, const float* 
                   const float* stats, float drop_scale, float* du, float* dgamma, float* dbeta, float* dbias,
                   int max_graphs, cudaStream_t st) {
   if (W % 4 || W > 2048 || W < 4) return EIMS_ERR_ARG;
-  int blocks = (max_graphs + 15) / 16;  // ~2 rows per warp
+  static int rpb = 0;  // rows per block (8 warps): one row per warp measured best (cfg 2: 9.7 us for the two launches, 11.9 with two rows)
+  if (!rpb) { const char* e = getenv("EIMS_LN_BWD_ROWS_PER_BLOCK"); rpb = e ? atoi(e) : 8; if (rpb < 1) rpb = 1; }
+  int blocks = (max_graphs + rpb - 1) / rpb;
   if (blocks < 1) blocks = 1;
   if (blocks > 148) blocks = 148;
   size_t smem = (size_t)8 * 3 * W * sizeof(float);
