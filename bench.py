@@ -132,7 +132,7 @@ def stage_work(N, E, B, P, H=H, L=L):
         "colsum": ("hbm", 4 * B * M),
         "gemm_head_dgrad": ("tensor", gemm_head),
         "ln_bwd": ("hbm", 16 * B * (2 * H + H)),
-        "bn_bwd_stats": ("hbm", 4 * N * H),                      # own pass for the top layer only (z; dh comes from dG on the fly)
+        "bn_bwd_stats": ("hbm", 4 * B * (pd + 2 * H)),           # top layer only, from per-graph quantities: dG [B,2H] + zstat [B,2H]
         "bn_bwd_apply": ("hbm", L * 12 * N * H - 8 * N * H),     # dh + z read, q written (layer 0 writes no q)
         "gemm_gcn_wgrad": ("tensor", (L - 1) * 2 * N * H * H),
         "gemm_gcn_dgrad": ("tensor", (L - 1) * 2 * N * H * H),
