@@ -121,3 +121,25 @@ def test_onecycle_schedule_equals_torch():
     for total in (4, 20, 37, 300):
         np.testing.assert_allclose(np.array(onecycle_schedule(total)), np.array(O.onecycle_table(total)), rtol=1e-12)
     assert len(state_dict_order(ModelDims())) == 31
+
+
+def test_bench_knows_the_work_of_every_stage():
+    """bench.py reports achieved GB/s / TFLOP/s per stage: every stage name the library can time must have an
+    algorithmic-work entry (a missing one would silently drop that stage from the roofline table)."""
+    import ctypes as C
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from eims_b200 import _lib
+    lib = _lib.load()
+    lib.eims_plan_stage_name.restype = C.c_char_p
+    names = [lib.eims_plan_stage_name(k).decode() for k in range(lib.eims_plan_num_stages())]
+    work = bench.stage_work(16896.0, 34806.0, 512, 787432)
+    assert set(names) <= set(work), sorted(set(names) - set(work))
+    for name, (bound, w) in work.items():
+        assert bound in ("hbm", "tensor") and w >= 0, name
+    # the grouped launches count both gradients
+    assert work["gemm_gcn_bwd"][1] == work["gemm_gcn_wgrad"][1] + work["gemm_gcn_dgrad"][1]
