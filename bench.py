@@ -132,11 +132,13 @@ def stage_work(N, E, B, P, H=H, L=L):
         "colsum": ("hbm", 4 * B * M),
         "gemm_head_dgrad": ("tensor", gemm_head),
         "ln_bwd": ("hbm", 16 * B * (2 * H + H)),
-        "bn_bwd_stats": ("hbm", 4 * B * (pd + 2 * H)),           # top layer only, from per-graph quantities: dG [B,2H] + zstat [B,2H]
+        # top layer from per-graph quantities (dG [B,2H] + zstat [B,2H]); the layers below ride on K2 when H <= 256,
+        # else they are node passes over dh and z
+        "bn_bwd_stats": ("hbm", 4 * B * (pd + 2 * H) + (0 if H <= 256 else (L - 1) * 8 * N * H)),
         "bn_bwd_apply": ("hbm", L * 12 * N * H - 8 * N * H),     # dh + z read, q written (layer 0 writes no q)
         "gemm_gcn_wgrad": ("tensor", (L - 1) * 2 * N * H * H),
         "gemm_gcn_dgrad": ("tensor", (L - 1) * 2 * N * H * H),
-        "spmm_bwd": ("hbm", (L - 1) * (12 * N * H + 4 * E + 8 * N)),  # + the z row of the BatchNorm below (fused backward statistics)
+        "spmm_bwd": ("hbm", (L - 1) * ((12 if H <= 256 else 8) * N * H + 4 * E + 8 * N)),  # H <= 256: + the z row of the BatchNorm below (fused backward statistics)
         "layer0_wgrad": ("hbm", 4 * N * H + 4 * N * F0),
         "adamw": ("hbm", 28 * P),
         "elementwise": ("hbm", 0),

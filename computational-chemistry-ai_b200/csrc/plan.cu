@@ -317,6 +317,9 @@ int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, 
   if (const char* e = getenv("EIMS_FUSE_SPMM_BWD")) p->fuse_spmm_bwd = e[0] != '0';
   if (const char* e = getenv("EIMS_PAIR_GEMMS")) p->pair_gemms = e[0] != '0';
   if (const char* e = getenv("EIMS_TOP_STATS_PER_GRAPH")) p->top_stats_per_graph = e[0] != '0';
+  // (beyond 256 columns the statistics variant of K2 needs 172 registers - one block per SM - and measured slower
+  // than K2 plus the separate statistics pass: cfg 5, 0.99 + 0.02 ms against 0.38 + 0.43 ms per step)
+  p->fuse_bn_bwd_stats = d->hidden_dim <= 256;
   if (const char* e = getenv("EIMS_FUSE_BN_BWD_STATS")) p->fuse_bn_bwd_stats = e[0] != '0';
   p->ws_bytes = 0; p->bound = false; p->state = 0; p->last_training = 0;
   memset(&p->last_step, 0, sizeof(p->last_step));
