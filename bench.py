@@ -432,7 +432,7 @@ def run_ours(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(40, 1, BATCH, time_budget=20.0)
+        r = cpu_reference_run(120, 1, BATCH, time_budget=20.0)  # ~15 s of host work
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"{r['steps']} optimiser steps of batch {BATCH} from 4096 synthetic molecules in {r['seconds']:.1f} s (oracle/gcn_oracle.py, torch-CPU fp32, all host threads)"}
     line = {
