@@ -272,14 +272,26 @@ def segment_max_first(h, g: Graph):
 
 
 def forward(sd, g: Graph, feat, d: Dims, training: bool, *, dropout_masks=None, update_running=True,
-            dtype=torch.float32, keep=False):
+            dtype=torch.float32, keep=False, decisions=None):
     """Returns (spectrum[B,M], aux).  `sd` maps state-dict names to tensors (leaf tensors
     with requires_grad for the trainable ones when gradients are wanted).  In training
     mode BN uses batch statistics and (when `update_running`) updates the running buffers
     in place exactly as nn.BatchNorm1d does.  `dropout_masks`: optional dict
     {('gcn', l): keep[N,H], ('head', i): keep[B,*]} of 0/1 masks; when absent and
-    d.dropout > 0 in training, torch's own dropout is used (not reproducible on the GPU)."""
+    d.dropout > 0 in training, torch's own dropout is used (not reproducible on the GPU).
+    `decisions` (the flip-aware protocol): optional dict of DISCRETE choices taken
+    from another run of the same network, which replace this run's own - {('relu', l): bool[N,H]}
+    (z = r * mask instead of max(r, 0)), {('head_relu', i): bool[B,*]} and {'argmax': int64[B,H]}
+    (max-pool gathers that node).  With them two implementations differentiate the same
+    piecewise-linear branch, so their gradients are comparable at 1e-4 even when a pre-activation
+    within rounding distance of 0 falls on different sides."""
     L, p = d.num_gcn_layers, d.dropout
+    dec = decisions or {}
+
+    def relu(x, key):
+        if key in dec:
+            return x * dec[key].to(x.dtype)
+        return F.relu(x)
     aux = {}
     cast = (lambda t: t.to(dtype)) if dtype != torch.float32 else (lambda t: t)
     h = cast(feat)
@@ -293,7 +305,7 @@ def forward(sd, g: Graph, feat, d: Dims, training: bool, *, dropout_masks=None, 
 
     for l in range(L):
         r, a = graph_conv(g, h, cast(sd[f"gcn_layers.{l}.weight"]), cast(sd[f"gcn_layers.{l}.bias"]))
-        z = F.relu(r)
+        z = relu(r, ("relu", l))
         rm, rv = sd[f"batch_norms.{l}.running_mean"], sd[f"batch_norms.{l}.running_var"]
         if training and update_running and dtype == torch.float32:
             sd[f"batch_norms.{l}.num_batches_tracked"] += 1
@@ -312,6 +324,9 @@ def forward(sd, g: Graph, feat, d: Dims, training: bool, *, dropout_masks=None, 
         S = torch.zeros(B, H, dtype=h.dtype).index_add_(0, g.gid, h)
     if d.pooling in ("max", "combined"):
         Mx, arg = segment_max_first(h, g)
+        if "argmax" in dec:
+            arg = dec["argmax"].to(torch.int64)
+            Mx = h.gather(0, arg)
         aux["argmax"] = arg
     if d.pooling == "sum":
         G = S
@@ -323,9 +338,9 @@ def forward(sd, g: Graph, feat, d: Dims, training: bool, *, dropout_masks=None, 
         G = torch.cat([S, Mx], dim=1)
     sp = "spectrum_predictor"
     u1 = F.linear(G, cast(sd[f"{sp}.0.weight"]), cast(sd[f"{sp}.0.bias"]))
-    y1 = drop(F.relu(F.layer_norm(u1, (u1.shape[1],), cast(sd[f"{sp}.1.weight"]), cast(sd[f"{sp}.1.bias"]), 1e-5)), ("head", 0))
+    y1 = drop(relu(F.layer_norm(u1, (u1.shape[1],), cast(sd[f"{sp}.1.weight"]), cast(sd[f"{sp}.1.bias"]), 1e-5), ("head_relu", 0)), ("head", 0))
     u2 = F.linear(y1, cast(sd[f"{sp}.4.weight"]), cast(sd[f"{sp}.4.bias"]))
-    y2 = drop(F.relu(F.layer_norm(u2, (u2.shape[1],), cast(sd[f"{sp}.5.weight"]), cast(sd[f"{sp}.5.bias"]), 1e-5)), ("head", 1))
+    y2 = drop(relu(F.layer_norm(u2, (u2.shape[1],), cast(sd[f"{sp}.5.weight"]), cast(sd[f"{sp}.5.bias"]), 1e-5), ("head_relu", 1)), ("head", 1))
     u3 = F.linear(y2, cast(sd[f"{sp}.8.weight"]), cast(sd[f"{sp}.8.bias"]))
     P = torch.sigmoid(u3)
     if keep:
@@ -349,7 +364,7 @@ def trainable(sd):
 
 
 def loss_and_grads(sd, g, feat, target, d: Dims, *, training=True, dropout_masks=None, loss_kind="mse",
-                   dtype=torch.float32, update_running=False, keep=False):
+                   dtype=torch.float32, update_running=False, keep=False, decisions=None):
     """One forward + autograd backward.  Returns (pred, loss, grads dict, aux)."""
     work = OrderedDict()
     for n, t in sd.items():
@@ -358,7 +373,7 @@ def loss_and_grads(sd, g, feat, target, d: Dims, *, training=True, dropout_masks
         else:
             work[n] = t.detach().to(dtype).clone().requires_grad_(True)
     pred, aux = forward(work, g, feat, d, training, dropout_masks=dropout_masks,
-                        update_running=update_running, dtype=dtype, keep=keep)
+                        update_running=update_running, dtype=dtype, keep=keep, decisions=decisions)
     tgt = target.to(dtype)
     loss = mse_loss(pred, tgt) if loss_kind == "mse" else cosine_loss(pred, tgt)
     names = trainable(work)
