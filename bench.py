@@ -9,8 +9,13 @@
 A "step" is one optimiser step of the reference's hot path (GCN:410-431) over one batch of
 512 synthetic molecules: batch build (K1) -> GCNSpectrum forward -> MSE loss + cosine metric
 -> backward -> AdamW, with H=256, L=3, 1000 m/z bins, dropout 0.2, fp32 (BASELINE.json
-configs[1]; at N>1 configs[3]: 1 M molecules sharded over the ranks, batch 512 per GPU,
-gradient all-reduce over NCCL).  One JSON line is printed by rank 0.
+configs[1]; at N>1 configs[3]: 1 M molecules, batch 512 per GPU, one gradient exchange per
+step).  One JSON line is printed by rank 0.
+
+Timing protocol (the driver's): W warm-up steps, then exactly K steps between two CUDA events,
+bracketed by a barrier + synchronize on both sides; max over ranks.  At N>1 the clock sampler is
+started BEFORE the barrier and a device-side all-reduce sits immediately in front of the first
+event, so every rank's timed region starts within microseconds of the others'.
 """
 import argparse
 import json
@@ -18,6 +23,7 @@ import os
 import sys
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -28,6 +34,12 @@ sys.path.insert(0, os.path.join(ROOT, "computational-chemistry-ai_b200"))
 METRIC = "gcn_eims_train_molecules_per_sec"
 UNIT = "molecules/s"
 BATCH, H, L, M, F0, DROPOUT, MAX_ATOMS = 512, 256, 3, 1000, 6, 0.2, 64
+# the two training workloads of BASELINE.json: configs[1]/[3] ("train") and configs[4] ("wide")
+WORKLOADS = {
+    "train": dict(batch=BATCH, hid=H, layers=L, atoms=MAX_ATOMS, mols1=100_000, molsN=1_000_000),
+    "wide": dict(batch=BATCH, hid=1024, layers=6, atoms=128, mols1=20_000, molsN=160_000),
+}
+SAMPLINGS = ("global_uniform_balanced", "rank_strided_uniform", "stratified")
 
 
 def parse():
@@ -36,25 +48,29 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--molecules", type=int, default=0, help="molecules per rank (0 = BASELINE config)")
+    ap.add_argument("--molecules", type=int, default=0, help="molecules in the resident set (0 = BASELINE config)")
     ap.add_argument("--gemm", default="tcgen05", choices=["tcgen05", "simt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-stratify", action="store_true", help="N>1: plain random batches instead of equal-work (size-stratified) ones")
-    ap.add_argument("--no-prefetch", action="store_true", help="N=1: build each batch inside its own step instead of one step ahead")
+    ap.add_argument("--no-extra", action="store_true", help="N=1: skip the configs[2] / configs[4] measurements (extra_workloads)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel of a step from the host instead of replaying the captured CUDA graphs")
+    ap.add_argument("--sampling", default=SAMPLINGS[0], choices=SAMPLINGS,
+                    help="N>1: which molecules a rank's batch holds. global_uniform_balanced (default): the global batch is the "
+                         "reference's uniform shuffle (GCN:561-568) at batch world*512, dealt to the ranks so that atom counts are equal; "
+                         "rank_strided_uniform: the same global batch, every world-th molecule per rank (DistributedSampler); "
+                         "stratified: size-stratified batches (every batch the same work). The other two are timed as sampling_variants")
+    ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="eager N=1: build each batch inside its own step instead of one step ahead")
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"], help="N>1: gradient exchange implementation")
-    ap.add_argument("--dp-overlap", action="store_true",
-                    help="fused path: exchange the head bucket early on a side stream (measured slower at N=2: the step then "
-                         "needs four C calls instead of one)")
-    ap.add_argument("--no-overlap", action="store_true", help="N>1: one-shot all-reduce after backward instead of two overlapped buckets")
+    ap.add_argument("--dp-overlap", action="store_true", help="eager fused path: exchange the head bucket early on a side stream")
+    ap.add_argument("--no-overlap", action="store_true", help="nccl path: one-shot all-reduce after backward instead of two overlapped buckets")
     ap.add_argument("--targets", default="dense", choices=["dense", "peaks"],
                     help="target spectra as dense rows (what the reference's dataset holds, GCN:256) or as the peak lists they are "
                          "binned from, binned inside the loss kernel (~0.9 KB instead of 4 KB per molecule in HBM and over PCIe)")
     ap.add_argument("--profile-steps", type=int, default=20)
     ap.add_argument("--workload", default="train", choices=["train", "infer", "wide"],
-                    help="train = BASELINE configs[1]/[3] (the metric); infer = configs[2] (batch 4096 eval forward); "
-                         "wide = configs[4] (6 layers, hidden 1024, <=128 atoms). infer/wide are extra measurements: "
-                         "they print their own JSON line with the workload named in config")
+                    help="train = BASELINE configs[1]/[3] (the metric); wide = configs[4] (6 layers, hidden 1024, <=128 atoms; "
+                         "data-parallel under torchrun like train); infer = configs[2] (batch 4096 eval forward, 1 GPU)")
     return ap.parse_args()
 
 
@@ -99,14 +115,15 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=2)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
 
 
 # ------------------------------------------------------------------------------------------
@@ -207,41 +224,236 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = BATCH if args.steps <= 300 else 128
-    r = cpu_reference_run(args.steps, max(args.warmup, 1), batch)
-    sample = f"{r['steps']} optimiser steps of batch {batch} drawn from 4096 synthetic molecules (same generator, H={H}, L={L}, M={M}, dropout {DROPOUT})"
+    # always the configured batch of 512; a long --steps request is bounded by time (180 s), never by a smaller batch
+    r = cpu_reference_run(args.steps, max(args.warmup, 1), BATCH, time_budget=180.0)
+    sample = (f"{r['steps']} optimiser steps of batch {BATCH} drawn from 4096 synthetic molecules (same generator, H={H}, L={L}, M={M}, "
+              f"dropout {DROPOUT})" + ("" if r["steps"] == args.steps else f"; stopped at the 180 s budget, {args.steps} were asked for"))
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": r["steps"], "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * r["seconds"] / r["steps"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.gpus, "train"),
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "oracle/gcn_oracle.py (torch-CPU restatement of the reference script; dgl/cupy/rdkit are not installable offline) on the box's host cores",
+        "note": "oracle/gcn_oracle.py (torch-CPU restatement of the reference script; dgl/cupy/rdkit are not installable offline) on the box's host cores; host collate inside the timed loop",
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
-    if n_gpus == 1:
+def workload_config(n_gpus, workload="train", sampling=None):
+    c = WORKLOADS[workload]
+    if workload == "wide":
+        wl = (f"BASELINE configs[4]: wide/deep variant, 6 GCN layers, hidden 1024, molecules up to 128 heavy atoms, batch 512/GPU, "
+              f"training on {n_gpus} B200" + (" (data-parallel, fused NVLink gradient exchange)" if n_gpus > 1 else ""))
+    elif n_gpus == 1:
         wl = "BASELINE configs[1]: GCN EI-MS training, 100k synthetic molecules (<=64 heavy atoms), batch 512, 3 GCN layers, hidden 256, 1000 m/z bins, fp32, single B200"
     else:
-        wl = f"BASELINE configs[3]: data-parallel GCN EI-MS training, 1M synthetic molecules sharded over {n_gpus} B200, batch 512/GPU, NCCL gradient all-reduce"
-    return {"workload": wl, "batch_per_gpu": BATCH, "hidden_dim": H, "num_gcn_layers": L, "max_mz": M,
-            "dropout": DROPOUT, "loss": "mse", "optimizer": "AdamW+OneCycleLR",
-            "l2_policy": "no explicit flush: every step reads a fresh batch from a device-resident set (graph tables + 4 KB/molecule targets, >= 0.5 GB) larger than the 126 MB L2; activations are produced and consumed inside the step",
-            "parallelism": f"dp{n_gpus}"}
+        wl = f"BASELINE configs[3]: data-parallel GCN EI-MS training, 1M synthetic molecules on {n_gpus} B200, batch 512/GPU, one gradient all-reduce per step over NVLink"
+    out = {"workload": wl, "batch_per_gpu": c["batch"], "hidden_dim": c["hid"], "num_gcn_layers": c["layers"], "max_mz": M,
+           "dropout": DROPOUT, "loss": "mse", "optimizer": "AdamW+OneCycleLR",
+           "l2_policy": "no explicit flush: every step reads a fresh batch from a device-resident set (graph tables + 4 KB/molecule targets, >= 0.5 GB) larger than the 126 MB L2; activations are produced and consumed inside the step",
+           "parallelism": f"dp{n_gpus}"}
+    if sampling and n_gpus > 1:
+        out["sampling"] = sampling
+    return out
 
 
 # ------------------------------------------------------------------------------------------
+# data: the resident molecule set
+# ------------------------------------------------------------------------------------------
+def build_dataset(cfg, n_mols, world, rank, dev, targets_mode):
+    """Returns (device data set holding ALL n_mols molecules, atoms per molecule [n_mols] (host), this rank's own
+    host shard (table, peak lists) for the host-buffer e2e path).
+
+    N=1: the set is generated on the host and uploaded.  N>1: every rank generates 1/world of the molecules (its own
+    seed), the flat arrays are all-gathered over NCCL so that each rank holds the whole set in HBM (1 M molecules
+    ~ 1 GB of graph tables + 4 GB of dense targets: 3 % of a B200) - which lets any rank process any molecule of the
+    global batch (see --sampling) - and the dense target rows are binned on the device from the gathered peak lists by
+    the product's own `eims_peaks_to_spectrum` kernel (bit-exact with the reference's peaks_to_spectrum_batch)."""
+    import torch
+    import torch.distributed as dist
+    from eims_b200.engine import DeviceDataset, DevicePeaks
+    from eims_b200.synth import dense_spectra, synth_molecules, synth_peaks
+    n_local = n_mols // world
+    table = synth_molecules(n_local, max_atoms=cfg["atoms"], seed=1234 + 7919 * rank)
+    pk = synth_peaks(n_local, M, seed=4321 + 7919 * rank)
+    if world == 1:
+        if targets_mode == "peaks":
+            ds = DeviceDataset(table, None, dev, peaks=DevicePeaks(*pk, dev))
+        else:
+            ds = DeviceDataset(table, dense_spectra(*pk, M), dev)
+        return ds, np.diff(table.node_ptr), (table, pk)
+
+    def gather_cat(a, dt):
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+        n = torch.tensor([t.numel()], device=dev, dtype=torch.int64)
+        ns = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(ns, n)
+        ns = [int(x.item()) for x in ns]
+        pad = torch.zeros(max(ns), dtype=dt, device=dev)
+        pad[: t.numel()] = t
+        out = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(out, pad)
+        return torch.cat([o[:k] for o, k in zip(out, ns)])
+
+    ptr_of = lambda counts: torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(counts, 0)])
+    node_ptr = ptr_of(gather_cat(np.diff(table.node_ptr), torch.int64))
+    bond_ptr = ptr_of(gather_cat(np.diff(table.bond_ptr), torch.int64))
+    feat = gather_cat(table.feat.reshape(-1), torch.float32)
+    bb, be = gather_cat(table.bond_begin, torch.int32), gather_cat(table.bond_end, torch.int32)
+    peak_ptr = ptr_of(gather_cat(np.diff(pk[0]), torch.int64))
+    mz, inten = gather_cat(pk[1], torch.float64), gather_cat(pk[2], torch.float32)
+    dpk = DevicePeaks.from_device(peak_ptr, mz, inten)
+    dense = None if targets_mode == "peaks" else dpk.to_spectrum(M)
+    ds = DeviceDataset.from_device(node_ptr, bond_ptr, feat, bb, be, targets=dense, peaks=dpk if dense is None else None)
+    torch.cuda.synchronize()
+    return ds, ds.host_num_atoms, (table, pk)
+
+
+def make_ids(sampling, sizes, world, rank, batch, n_steps, seed):
+    """int32 [n_steps + 1, batch] molecule ids of this rank (one spare batch: the graph replay builds one ahead)."""
+    from eims_b200.dist import global_batches, stratified_epoch
+    out, ep = [], 0
+    need = n_steps + 1
+    while sum(len(o) for o in out) < need:
+        if sampling == "stratified":
+            # size-stratified batches over this rank's strided share of the set: every batch carries the same work
+            mine = np.arange(rank, len(sizes), world)
+            out.append(mine[stratified_epoch(sizes[mine], batch, ep, seed=seed + rank)].astype(np.int32))
+        else:
+            out.append(global_batches(sizes, world, rank, batch, ep, seed=seed, balance=(sampling == "global_uniform_balanced")))
+        ep += 1
+    return np.concatenate(out)[:need]
+
+
+# ------------------------------------------------------------------------------------------
+# one training workload, timed
+# ------------------------------------------------------------------------------------------
+class TrainBench:
+    def __init__(self, args, workload, world, rank, dev, n_mols=None):
+        import torch
+        from eims_b200.dist import FusedP2PAdamW, GradReducer, broadcast_params
+        from eims_b200.engine import FlatParams, ModelDims, Plan, onecycle_schedule
+        self.args, self.world, self.rank, self.dev, self.workload = args, world, rank, dev, workload
+        cfg = self.cfg = WORKLOADS[workload]
+        self.batch = cfg["batch"]
+        n_mols = n_mols or args.molecules or (cfg["mols1"] if world == 1 else cfg["molsN"])
+        n_mols = max(n_mols // world, self.batch) * world
+        self.ds, self.sizes, self.host_shard = build_dataset(cfg, n_mols, world, rank, dev, args.targets)
+        self.n_mols = n_mols
+        self.d = ModelDims(F0, cfg["hid"], cfg["layers"], M, "combined", DROPOUT)
+        cap_nodes = self.batch * cfg["atoms"]
+        self.plan = Plan(self.d, self.batch, cap_nodes, 2 * (cap_nodes + 3 * self.batch), dev, gemm_backend=args.gemm)
+        self.fp = FlatParams(self.d, dev)
+        init_weights(self.fp, self.d)
+        broadcast_params(self.fp)
+        self.reducer = GradReducer(self.fp.offsets, cfg["layers"], overlap=not args.no_overlap)
+        self.fused, self.dp_note = None, "single GPU"
+        if world > 1:
+            self.dp_note = "NCCL all-reduce (two buckets) + AdamW kernel"
+            if args.dp == "fused":
+                try:
+                    self.fused = FusedP2PAdamW(self.fp, cfg["layers"], overlap=args.dp_overlap and args.no_graph)
+                    self.dp_note = ("one fused kernel: all-reduce + AdamW + parameter broadcast over NVLink peer memory ("
+                                    + ("NVSwitch multimem" if self.fused.multicast else "peer loads/stores") + ")")
+                except Exception as exc:  # symmetric memory unavailable: say so, use the NCCL path
+                    self.dp_note += f" [fused path unavailable: {type(exc).__name__}: {exc}]"
+        self.metrics = torch.zeros(8, device=dev)
+        self.gscale = 1.0 / world
+        self.k = 0            # optimiser steps taken
+        self.graphed = None
+        self.graph_note = "eager launches"
+        self.sched = onecycle_schedule(4096)
+        self.launches_per_step = None
+
+    def step_scalars(self, k=None):
+        from eims_b200.engine import make_step
+        k = self.k if k is None else k
+        lr, b1 = self.sched[min(k, len(self.sched) - 1)]
+        return make_step(lr=lr, beta1=b1, grad_scale=self.gscale, step=k + 1, seed=2024 + self.rank)
+
+    def eager_step(self, ids, next_ids):
+        from eims_b200.dist import train_step_dp, train_step_fused
+        st = self.step_scalars()
+        if self.world == 1:
+            if self.args.no_prefetch:
+                self.plan.train_step(self.ds, ids, self.fp, st, self.metrics)
+            else:  # K1 of the next batch is built on a side stream while this step runs
+                self.plan.train_step_prefetch(self.ds, ids, next_ids, self.fp, st, self.metrics)
+        elif self.fused is not None:
+            train_step_fused(self.plan, self.ds, ids, self.fp, st, self.fused, self.metrics, next_ids=next_ids)
+        else:
+            train_step_dp(self.plan, self.ds, ids, self.fp, st, self.reducer, self.metrics)
+        self.k += 1
+
+    def try_capture(self, first_ids):
+        """Two eager steps have run (modules loaded, one-time attributes set): capture the step graphs."""
+        from eims_b200.engine import GraphedTrainStep
+        if self.args.no_graph or (self.world > 1 and self.fused is None):
+            return
+        try:
+            self.plan.profile(False)
+            g = GraphedTrainStep(self.plan, self.ds, self.fp, self.batch, self.metrics, fused=self.fused)
+            g.capture(first_ids, self.step_scalars())
+            _, n = self.plan.profile_read()
+            self.launches_per_step = n // 2 + 1 + (1 if self.fused is not None else 0)   # + step-block upload (+ exchange kernel)
+            self.graphed = g
+            self.graph_note = "two alternating captured CUDA graphs (step || next batch build), one step-block upload + one graph launch per step"
+        except Exception as exc:
+            self.graph_note = f"eager launches [graph capture failed: {type(exc).__name__}: {str(exc)[:200]}]"
+            self.graphed = None
+
+    def step(self, ids, next_ids):
+        if self.graphed is not None:
+            self.graphed.step(self.step_scalars(), next_ids)
+            self.k += 1
+        else:
+            self.eager_step(ids, next_ids)
+
+    def device_barrier(self):
+        """All ranks leave together, ON THE DEVICE: a tiny all-reduce on the compute stream; what is enqueued next
+        (the first timing event) executes only after every rank has arrived."""
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            t = torch.zeros(1, device=self.dev)
+            dist.all_reduce(t)
+
+    def timed(self, ids_dev, i0, n_steps, with_sampler=False):
+        """Times steps i0 .. i0+n_steps-1 of ids_dev (device int32 [*, batch]); the batch of step i0 must be the one
+        built last.  Returns (total ms (max over ranks), per-step ms of this rank, clocks)."""
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        sampler = ClockSampler(self.dev.index or 0) if with_sampler else None   # NVML init happens here, BEFORE the barrier
+        if sampler:
+            sampler.start()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps + 1)]
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        self.device_barrier()
+        evs[0].record()
+        for j in range(n_steps):
+            self.step(ids_dev[i0 + j], ids_dev[i0 + j + 1])
+            evs[j + 1].record()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = evs[0].elapsed_time(evs[-1])
+        per = np.array([evs[j].elapsed_time(evs[j + 1]) for j in range(n_steps)])
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, per, clocks
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from eims_b200.dist import FusedP2PAdamW, GradReducer, broadcast_params, stratified_epoch, train_step_dp, train_step_fused
-    from eims_b200.engine import DeviceDataset, DevicePeaks, FlatParams, ModelDims, Plan, make_step, onecycle_schedule
-    from eims_b200.hostpath import HostBatchRunner, PackedHostBatch
-    from eims_b200.synth import dense_spectra, synth_molecules, synth_peaks
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -251,200 +463,345 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n_mols = args.molecules or (100_000 if world == 1 else 1_000_000 // world)
-    steps_total = args.warmup + args.steps
-    n_mols = max(n_mols, BATCH)
-
-    # ---- synthetic data, device resident
-    table = synth_molecules(n_mols, max_atoms=MAX_ATOMS, seed=1234 + 7919 * rank)
-    pk = synth_peaks(n_mols, M, seed=4321 + 7919 * rank)
-    targets = dense_spectra(*pk, M)
-    if args.targets == "peaks":
-        ds = DeviceDataset(table, None, dev, peaks=DevicePeaks(*pk, dev))
-    else:
-        ds = DeviceDataset(table, targets, dev)
-    d = ModelDims(F0, H, L, M, "combined", DROPOUT)
-    rng = np.random.default_rng(99 + rank)
-    n_epochs = (steps_total * BATCH) // n_mols + 2
-    if world > 1 and not args.no_stratify:
-        # equal-work batches on every rank (see dist.stratified_epoch): no straggler tax
-        sizes = np.diff(table.node_ptr)
-        perm_host = np.concatenate([stratified_epoch(sizes, BATCH, ep, seed=99 + rank).reshape(-1) for ep in range(n_epochs)]).astype(np.int32)
-    else:
-        perm_host = np.concatenate([rng.permutation(n_mols) for _ in range(n_epochs)]).astype(np.int32)
-    cap_nodes = BATCH * MAX_ATOMS
-    cap_edges = 2 * (cap_nodes + 3 * BATCH)
-    plan = Plan(d, BATCH, cap_nodes, cap_edges, dev, gemm_backend=args.gemm)
-    fp = FlatParams(d, dev)
-    init_weights(fp, d)
-    broadcast_params(fp)
-    reducer = GradReducer(fp.offsets, L, overlap=not args.no_overlap)
-    fused, dp_note = None, "single GPU"
-    if world > 1:
-        dp_note = "NCCL all-reduce (two buckets) + AdamW kernel"
-        if args.dp == "fused":
-            try:
-                fused = FusedP2PAdamW(fp, L, overlap=args.dp_overlap)
-                dp_note = ("one fused kernel: all-reduce + AdamW + parameter broadcast over NVLink peer memory ("
-                           + ("NVSwitch multimem" if fused.multicast else "peer loads/stores") + ")")
-            except Exception as exc:  # symmetric memory unavailable: say so, use the NCCL path
-                dp_note += f" [fused path unavailable: {type(exc).__name__}: {exc}]"
-    perm = torch.from_numpy(perm_host).to(dev)
-    sched = onecycle_schedule(max(steps_total * 4, 100))
-    metrics = torch.zeros(8, device=dev)
-    gscale = 1.0 / world
-
-    def step_fn(i, k):
-        ids = perm[i * BATCH:(i + 1) * BATCH]
-        st = make_step(lr=sched[k][0], beta1=sched[k][1], grad_scale=gscale, step=k + 1, seed=2024 + rank)
-        if world == 1 and not args.no_prefetch:
-            # K1 of the next batch is built on a side stream while this step runs
-            plan.train_step_prefetch(ds, ids, perm[(i + 1) * BATCH:(i + 2) * BATCH], fp, st, metrics)
-        elif fused is not None:
-            train_step_fused(plan, ds, ids, fp, st, fused, metrics, next_ids=perm[(i + 1) * BATCH:(i + 2) * BATCH])
-        else:
-            train_step_dp(plan, ds, ids, fp, st, reducer, metrics)
+    tb = TrainBench(args, args.workload, world, rank, dev)
+    K, W = args.steps, max(args.warmup, 3)
+    variants = [s for s in SAMPLINGS if s != args.sampling] if (world > 1 and not args.no_variants) else []
+    Kv = min(K, 50)
+    ids_main = make_ids(args.sampling, tb.sizes, world, rank, tb.batch, W + K, seed=99)
+    segs = [ids_main[:-1]] + [make_ids(s, tb.sizes, world, rank, tb.batch, Kv, seed=199)[:-1] for s in variants]
+    ids_host = np.concatenate(segs + [ids_main[-1:]])
+    ids_dev = torch.from_numpy(ids_host).to(dev)
 
     # The step runs on a high-priority stream, so that its kernels win over the batch build of the NEXT
-    # step (default-priority side stream) whenever both have blocks to place: measured 0.353 -> 0.349 ms/step.
+    # step (default-priority side stream) whenever both have blocks to place.
     torch.cuda.synchronize()
     if os.environ.get("EIMS_BENCH_DEFAULT_STREAM", "0") != "1":
         torch.cuda.set_stream(torch.cuda.Stream(dev, priority=-1))
-    k = 0
-    for i in range(args.warmup):
-        step_fn(i, k)
-        k += 1
-    plan.check()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
-    plan.profile(False)  # resets the launch counter
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.warmup, steps_total):
-        step_fn(i, k)
-        k += 1
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    _, launches = plan.profile_read()
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    plan.check()
-    value = args.steps * BATCH * world / (ms * 1e-3)
-    final_loss = float(metrics[4].item())
+    # ---- warm-up: two eager steps, graph capture, the rest replayed
+    for i in range(2):
+        tb.eager_step(ids_dev[i], ids_dev[i + 1])
+    tb.plan.check()
+    tb.try_capture(ids_dev[2])
+    if tb.graphed is None and world == 1 and not args.no_prefetch:
+        pass  # the eager prefetch path already built batch 2
+    for i in range(2, W):
+        tb.step(ids_dev[i], ids_dev[i + 1])
+    tb.plan.check()
+    # ---- the timed region
+    tb.plan.profile(False)  # resets the launch counter
+    ms, per_step, clocks = tb.timed(ids_dev, W, K, with_sampler=True)
+    _, launches = tb.plan.profile_read()
+    if tb.graphed is not None:
+        launches = K * tb.launches_per_step
+    tb.plan.check()
+    if tb.fused is not None and tb.fused.lost_peer():
+        raise SystemExit(f"rank {rank}: a peer did not arrive at the gradient exchange (sequence {tb.fused.lost_peer()})")
+    value = K * tb.batch * world / (ms * 1e-3)
+    final_loss = float(tb.metrics[4].item())
+    nonfinite_steps = int(tb.metrics[6].item())
 
-    # ---- per-stage pass (same steps, CUDA events around every launch, not used for `value`)
+    # ---- per-rank step times (who is the straggler?)
+    step_times = None
+    if world > 1:
+        allp = [torch.zeros(K, device=dev) for _ in range(world)]
+        dist.all_gather(allp, torch.from_numpy(per_step).float().to(dev))
+        allp = torch.stack(allp).cpu().numpy()
+        wr, ws = np.unravel_index(np.argmax(allp), allp.shape)
+        atoms = [int(tb.sizes[ids_host[W + j]].sum()) for j in range(K)]
+        step_times = {"median_ms_per_rank": [round(float(np.median(r)), 4) for r in allp],
+                      "max_ms_per_rank": [round(float(r.max()), 4) for r in allp],
+                      "worst": {"rank": int(wr), "step": int(ws), "ms": round(float(allp[wr, ws]), 4)},
+                      "rank0_atoms_per_batch_min_max": [min(atoms), max(atoms)]}
+    else:
+        step_times = {"median_ms": round(float(np.median(per_step)), 4), "max_ms": round(float(per_step.max()), 4)}
+
+    # ---- the other sampling policies, same protocol, shorter (N>1)
+    sampling_variants = None
+    if variants:
+        sampling_variants = {args.sampling: {"value": value, "ms_per_step": ms / K, "steps": K}}
+        off = W + K
+        for s in variants:
+            # the batch built last belongs to the previous segment's successor row = first row of this segment
+            vms, _, _ = tb.timed(ids_dev, off, Kv)
+            sampling_variants[s] = {"value": Kv * tb.batch * world / (vms * 1e-3), "ms_per_step": vms / Kv, "steps": Kv}
+            off += Kv
+
+    # ---- per-stage pass (same steps launched eagerly with CUDA events around every launch; not used for `value`)
     roofline, stages_out = None, None
     if rank == 0 and args.profile_steps > 0:
-        pk_ = peaks()
-        plan.profile(True)
-        Ns, Es = [], []
-        for j in range(args.profile_steps):
-            i = (steps_total + j) % (len(perm_host) // BATCH)
-            ids_h = perm_host[i * BATCH:(i + 1) * BATCH]
-            n_, e_ = ds.batch_counts(ids_h)
-            Ns.append(n_)
-            Es.append(e_)
-            st = make_step(lr=sched[k][0], beta1=sched[k][1], grad_scale=gscale, step=k + 1, seed=2024)
-            plan.train_step(ds, perm[i * BATCH:(i + 1) * BATCH], fp, st, metrics)
-            k += 1
-        prof, _ = plan.profile_read()
-        plan.profile(False)
-        work = stage_work(float(np.mean(Ns)), float(np.mean(Es)), BATCH, fp.numel)
-        stages_out = stage_report(prof, work, args.profile_steps, pk_)
-        dom = max(stages_out, key=lambda n: stages_out[n]["ms_per_step"])
-        s = stages_out[dom]
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(dom)  # bytes per launch, ncu dram__bytes_read + dram__bytes_write
-        roofline = {"kernel": dom, "bound": s["bound"], "achieved": s["achieved"], "peak": peaks()["hbm_gbs"] if s["bound"] == "hbm" else peaks()["bf16_tflops"],
-                    "unit": s["unit"], "frac": s["frac"], "traffic": traffic,
-                    "peak_source": f"{pk_['source']} ({'copy bandwidth' if s['bound'] == 'hbm' else 'cuBLAS bf16 burst; tf32 is half of it and the kernel runs 3 tf32 passes, so 1/6 is the ceiling'})",
-                    "launch_ms": round(s["ms_per_step"] / s["launches_per_step"], 5)}
+        roofline, stages_out = stage_pass(tb, ids_host, ids_dev, args.profile_steps)
 
-    # ---- e2e: the same step through the host-buffer call (H2D of inputs + D2H of loss inside)
-    e2e = None
-    if not args.no_e2e:
-        n_e2e = min(args.steps, 100)
-        hbs = []
-        for j in range(n_e2e + 3):
-            ids_h = perm_host[j * BATCH:(j + 1) * BATCH]
-            if args.targets == "peaks":
-                kk = np.diff(pk[0])[ids_h]
-                pp = np.zeros(len(ids_h) + 1, np.int64)
-                np.cumsum(kk, out=pp[1:])
-                from eims_b200.synth import _ranges
-                sel = _ranges(pk[0][ids_h], kk)
-                hbs.append(PackedHostBatch(table.select(ids_h), None, peaks=(pp, pk[1][sel], pk[2][sel])))
-            else:
-                hbs.append(PackedHostBatch(table.select(ids_h), targets[ids_h]))
-        runner = HostBatchRunner(plan, fp, max(h.nbytes for h in hbs) + 4096)
+    # ---- e2e: the same step through the host-buffer call (collate + H2D of inputs + D2H of loss inside)
+    e2e = None if args.no_e2e else e2e_pass(tb, min(K, 100))
 
-        def e2e_step(j, slot_next):
-            st = make_step(lr=sched[k + j][0], beta1=sched[k + j][1], grad_scale=gscale, step=k + j + 1, seed=2024 + rank)
-            slot = slot_next
-            if world == 1:
-                runner.train_step(slot, hbs[j], st)
-            else:
-                raise NotImplementedError
-            # enqueue the next batch's H2D copy (+ its K1) after this step: it runs on the copy stream
-            # as soon as the step that last used that slot has finished, i.e. concurrently with this one
-            return runner.upload(hbs[j + 1], build=not args.no_prefetch) if j + 1 < len(hbs) else None
-
-        if world == 1:
-            slot = runner.upload(hbs[0], build=not args.no_prefetch)
-            for j in range(3):
-                slot = e2e_step(j, slot)
-            torch.cuda.synchronize()
-            runner.h2d_bytes = runner.d2h_bytes = 0
-            t0 = time.perf_counter()
-            e0.record()
-            for j in range(3, 3 + n_e2e):
-                slot = e2e_step(j, slot)
-                if j > 3:
-                    _ = runner.host_metrics[4].item()  # read the previous step's loss on the host
-            loss_e2e, _ = runner.result()
-            e1.record()
-            torch.cuda.synchronize()
-            wall = time.perf_counter() - t0
-            e2e = {"value": n_e2e * BATCH / wall, "unit": UNIT, "h2d_bytes_per_step": int(runner.h2d_bytes / n_e2e),
-                   "d2h_bytes_per_step": int(runner.d2h_bytes / n_e2e), "steps": n_e2e,
-                   "timing": "host wall clock around the loop (device events agree: %.1f ms)" % e0.elapsed_time(e1),
-                   "last_loss": loss_e2e}
-        else:
-            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                   "note": "e2e is measured on the N=1 run"}
+    extra = None
+    if world == 1 and args.workload == "train" and not args.no_extra:
+        del tb.graphed
+        extra = extra_workloads(args, dev)
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "train":
         r = cpu_reference_run(120, 1, BATCH, time_budget=20.0)  # ~15 s of host work
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                "sample": f"{r['steps']} optimiser steps of batch {BATCH} from 4096 synthetic molecules in {r['seconds']:.1f} s (oracle/gcn_oracle.py, torch-CPU fp32, all host threads)"}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(world), "gemm": args.gemm,
-        "targets": args.targets, "gpu_launches": int(launches), "data_parallel": dp_note, "clocks": clocks, "final_loss": final_loss,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "stages": stages_out,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(world, args.workload, args.sampling), "gemm": args.gemm,
+        "targets": args.targets, "gpu_launches": int(launches), "launch_mode": tb.graph_note, "data_parallel": tb.dp_note,
+        "clocks": clocks, "final_loss": final_loss, "nonfinite_loss_steps": nonfinite_steps, "resident_molecules": tb.n_mols,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "step_times": step_times, "sampling_variants": sampling_variants,
+        "extra_workloads": extra, "stages": stages_out,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def stage_pass(tb, ids_host, ids_dev, n_prof):
+    pk_ = peaks()
+    plan, ds, fp = tb.plan, tb.ds, tb.fp
+    plan.profile(True)
+    Ns, Es = [], []
+    for j in range(n_prof):
+        i = j % (len(ids_host) - 1)
+        n_, e_ = ds.batch_counts(ids_host[i])
+        Ns.append(n_)
+        Es.append(e_)
+        plan.train_step(ds, ids_dev[i], fp, tb.step_scalars(), tb.metrics)
+        tb.k += 1
+    prof, _ = plan.profile_read()
+    plan.profile(False)
+    work = stage_work(float(np.mean(Ns)), float(np.mean(Es)), tb.batch, fp.numel, tb.cfg["hid"], tb.cfg["layers"])
+    stages_out = stage_report(prof, work, n_prof, pk_)
+    dom = max(stages_out, key=lambda n: stages_out[n]["ms_per_step"])
+    s = stages_out[dom]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp) and tb.workload == "train":
+        traffic = json.load(open(tp)).get(dom)  # bytes per launch, ncu dram__bytes_read + dram__bytes_write (cold-cache capture, see profiles/)
+    roofline = {"kernel": dom, "bound": s["bound"], "achieved": s["achieved"], "peak": pk_["hbm_gbs"] if s["bound"] == "hbm" else pk_["bf16_tflops"],
+                "unit": s["unit"], "frac": s["frac"], "traffic": traffic,
+                "peak_source": f"{pk_['source']} ({'copy bandwidth' if s['bound'] == 'hbm' else 'cuBLAS bf16 burst; tf32 is half of it and the kernel runs 3 tf32 passes, so 1/6 is the ceiling'})",
+                "launch_ms": round(s["ms_per_step"] / s["launches_per_step"], 5)}
+    return roofline, stages_out
+
+
+def e2e_pass(tb, n_e2e):
+    """The reference-facing call with HOST buffers, per step and inside the timed region: collate of the batch from the
+    host-resident set into pinned memory (`eims_host_pack_batch`, C, on 4 worker threads - the reference's DataLoader
+    uses num_workers=4, GCN:100 - prefetching 4 batches ahead), ONE H2D copy, K1 + step, D2H of the step's loss / cosine,
+    which the host reads one step behind.  N>1: every rank feeds from its own host shard (uniform shuffle) and the
+    gradients go through the same fused exchange kernel."""
+    import torch
+    import torch.distributed as dist
+    from eims_b200.dist import train_step_fused  # noqa: F401
+    from eims_b200.hostpath import HostBatchRunner, HostDataset, HostPacker
+    from eims_b200.synth import dense_spectra
+    if tb.world > 1 and tb.fused is None:
+        return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "e2e needs the fused exchange path at N>1"}
+    table, pk = tb.host_shard
+    n_local = table.num_mols
+    if tb.args.targets == "peaks":
+        hds = HostDataset(table, None, peaks=pk)
+    else:
+        hds = HostDataset(table, dense_spectra(*pk, M))
+    depth, workers = 4, 4
+    cap = tb.batch * (tb.cfg["atoms"] * (F0 * 4 + 8 + 10) + 4 * M + 64) + (1 << 16)
+    packer = HostPacker(hds, M, cap, n_buffers=depth + 3)
+    runner = HostBatchRunner(tb.plan, tb.fp, cap)
+    rng = np.random.default_rng(7 + tb.rank)
+    n_total = n_e2e + 3
+    order = np.concatenate([rng.permutation(n_local) for _ in range(n_total * tb.batch // n_local + 2)]).astype(np.int32)
+    pool = ThreadPoolExecutor(workers)
+    lock = threading.Lock()
+
+    def submit(j):
+        with lock:   # ring-slot assignment is serial; the gather itself (ctypes releases the GIL) runs in parallel
+            k = packer._i % len(packer.bufs)
+            packer._i += 1
+        ids = order[j * tb.batch:(j + 1) * tb.batch]
+
+        def work():
+            packer2 = packer
+            if packer2.events[k] is not None:
+                packer2.events[k].synchronize()
+            return pack_into(packer2, k, ids)
+        return pool.submit(work)
+
+    futs = {j: submit(j) for j in range(min(depth, n_total))}
+
+    def one(j, slot):
+        st = tb.step_scalars()
+        hb_next = None
+        if tb.world == 1:
+            runner.train_step(slot, cur_hb[0], st)
+        else:
+            tb.fused.begin_step()
+            runner.train_step(slot, cur_hb[0], st, optimizer=False)
+            tb.fused.finish(st, tb.plan.stream)
+        tb.k += 1
+        if j + depth < n_total:
+            futs[j + depth] = submit(j + depth)
+        if j + 1 < n_total:
+            hb_next = futs.pop(j + 1).result()
+            nslot = runner.upload(hb_next, build=not tb.args.no_prefetch)
+            cur_hb[0] = hb_next
+            return nslot
+        return None
+
+    cur_hb = [futs.pop(0).result()]
+    slot = runner.upload(cur_hb[0], build=not tb.args.no_prefetch)
+    for j in range(3):
+        slot = one(j, slot)
+    torch.cuda.synchronize()
+    if tb.world > 1:
+        dist.barrier()
+    runner.h2d_bytes = runner.d2h_bytes = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tb.device_barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    last = None
+    for j in range(3, 3 + n_e2e):
+        slot = one(j, slot)
+        last = runner.read(1) or last   # the previous step's loss on the host (waits for ITS copy only)
+    loss_e2e, _ = runner.result()
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if tb.world > 1:
+        t = torch.tensor([wall], device=tb.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    pool.shutdown(wait=True)
+    return {"value": n_e2e * tb.batch * tb.world / wall, "unit": UNIT, "h2d_bytes_per_step": int(runner.h2d_bytes / n_e2e),
+            "d2h_bytes_per_step": int(runner.d2h_bytes / n_e2e), "steps": n_e2e,
+            "timing": ("host wall clock around the loop, max over ranks (device events: %.1f ms); INSIDE the timed region per step: host collate of "
+                       "the batch into pinned memory (C, %d worker threads, %d batches ahead), one H2D copy, K1 + step%s, D2H of loss/cosine "
+                       "read by the host one step behind" % (e0.elapsed_time(e1), workers, depth, " + fused gradient exchange" if tb.world > 1 else "")),
+            "last_loss": loss_e2e}
+
+
+def pack_into(packer, k, ids):
+    """HostPacker.pack with the ring slot chosen by the caller (worker threads)."""
+    import ctypes as C
+    from eims_b200 import _lib
+    from eims_b200.hostpath import PackedHostBatch
+    import torch
+    ids = np.ascontiguousarray(ids, np.int32)
+    lay = _lib.HostBatchLayout()
+    buf = packer.bufs[k]
+    _lib.check(packer.lib.eims_host_pack_batch(C.byref(packer.hds.struct), C.c_void_p(ids.ctypes.data), len(ids), packer.hds.feat_dim,
+                                               packer.max_mz, C.c_void_p(buf.data_ptr()), buf.numel(), C.byref(lay)))
+    hb = PackedHostBatch.__new__(PackedHostBatch)
+    hb.offsets = {n: getattr(lay, n) for n in ("node_ptr", "bond_ptr", "bond_begin", "bond_end", "feat", "targets", "peak_ptr",
+                                               "peak_mz", "peak_inten") if getattr(lay, n) >= 0}
+    hb.nbytes, hb.buf, hb.mz_is_f64 = int(lay.nbytes), buf, int(lay.mz_is_f64)
+    hb.num_graphs, hb.num_nodes, hb.num_edges, hb.feat_dim = lay.num_graphs, lay.num_nodes, lay.num_edges, lay.feat_dim
+    hb.has_targets, hb.has_peaks = lay.targets >= 0, lay.peak_ptr >= 0
+    if packer.events[k] is None:
+        packer.events[k] = torch.cuda.Event()
+    hb._ring_event = packer.events[k]
+    return hb
+
+
+# ------------------------------------------------------------------------------------------
+# configs[2] and configs[4] on one GPU: secondary numbers carried by the N=1 line
+# ------------------------------------------------------------------------------------------
+def infer_bench(args, dev, n_mols, batch=4096, with_stages=True):
+    """BASELINE configs[2]: one pass of batched eval-mode prediction over n_mols resident molecules."""
+    import torch
+    from eims_b200.engine import DeviceDataset, FlatParams, ModelDims, Plan
+    from eims_b200.synth import synth_molecules
+    table = synth_molecules(n_mols, max_atoms=MAX_ATOMS, seed=1234)
+    ds = DeviceDataset(table, None, dev)
+    d = ModelDims(F0, H, L, M, "combined", DROPOUT)
+    plan = Plan(d, batch, batch * MAX_ATOMS, 2 * (batch * MAX_ATOMS + 3 * batch), dev)
+    fp = FlatParams(d, dev)
+    init_weights(fp, d)
+    n_batches = n_mols // batch
+    perm_h = np.random.default_rng(5).permutation(n_mols).astype(np.int32)
+    perm = torch.from_numpy(perm_h).to(dev)
+    out = torch.empty(batch, M, device=dev)
+    for i in range(3):
+        plan.infer_batch(ds, perm[i * batch:(i + 1) * batch], fp, out)
+    plan.check()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_batches):
+        plan.infer_batch(ds, perm[i * batch:(i + 1) * batch], fp, out)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    res = {"metric": "gcn_eims_infer_molecules_per_sec", "value": n_batches * batch / (ms * 1e-3), "unit": UNIT, "ms_per_batch": ms / n_batches,
+           "batches": n_batches, "batch": batch, "resident_molecules": n_mols, "clocks": clocks,
+           "workload": f"BASELINE configs[2]: inference-only spectrum prediction for {n_mols} synthetic molecules (<=64 heavy atoms), batch {batch}, single B200; one pass over the resident set, spectra written to HBM"}
+    if with_stages:
+        plan.profile(True)
+        n_prof = 5
+        Ns, Es = [], []
+        for j in range(n_prof):
+            n_, e_ = ds.batch_counts(perm_h[j * batch:(j + 1) * batch])
+            Ns.append(n_)
+            Es.append(e_)
+            plan.infer_batch(ds, perm[j * batch:(j + 1) * batch], fp, out)
+        prof, _ = plan.profile_read()
+        plan.profile(False)
+        work = stage_work(float(np.mean(Ns)), float(np.mean(Es)), batch, fp.numel, H, L)
+        work["bn_stats"] = ("hbm", L * 6 * H * 4)   # eval mode: running buffers -> scale / shift
+        work["elementwise"] = ("hbm", 8 * batch * M)  # the sigmoid
+        st = stage_report(prof, work, n_prof, peaks())
+        res["top_stages"] = {k: st[k] for k in sorted(st, key=lambda n: -st[n]["ms_per_step"])[:3]}
+        res["stages"] = st
+    return res
+
+
+def extra_workloads(args, dev):
+    """Time-capped secondary measurements for the driver-visible N=1 line."""
+    import torch
+    out = {}
+    t0 = time.perf_counter()
+    try:
+        r = infer_bench(args, dev, 1_000_000)
+        r.pop("stages", None)
+        out["infer"] = r
+    except Exception as exc:
+        out["infer"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+    torch.cuda.empty_cache()
+    try:
+        sub = argparse.Namespace(**vars(args))
+        sub.molecules, sub.targets = 0, "dense"
+        tb = TrainBench(sub, "wide", 1, 0, dev)
+        Kw, Ww = 20, 3
+        ids_h = make_ids("rank_strided_uniform", tb.sizes, 1, 0, tb.batch, Ww + Kw, seed=5)
+        ids_d = torch.from_numpy(ids_h).to(dev)
+        for i in range(2):
+            tb.eager_step(ids_d[i], ids_d[i + 1])
+        tb.try_capture(ids_d[2])
+        for i in range(2, Ww):
+            tb.step(ids_d[i], ids_d[i + 1])
+        ms, per, clocks = tb.timed(ids_d, Ww, Kw, with_sampler=True)
+        _, st = stage_pass(tb, ids_h, ids_d, 5)
+        out["wide"] = {"metric": METRIC, "value": Kw * tb.batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / Kw, "steps": Kw,
+                       "clocks": clocks, "launch_mode": tb.graph_note, "workload": workload_config(1, "wide")["workload"],
+                       "top_stages": {k: st[k] for k in sorted(st, key=lambda n: -st[n]["ms_per_step"])[:3]}}
+        del tb
+    except Exception as exc:
+        out["wide"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+    out["seconds"] = round(time.perf_counter() - t0, 1)
+    return out
 
 
 def init_weights(fp, d):
@@ -485,85 +842,23 @@ def _claim_stdout():
     print = _print
 
 
-def run_extra(args):
-    """configs[2] (inference, batch 4096) and configs[4] (wide/deep training) on this rank's GPU:
-    secondary measurements, same timing rules (CUDA events, warm-up, device-resident molecules)."""
+def run_infer(args):
     import torch
-    from eims_b200.engine import DeviceDataset, FlatParams, ModelDims, Plan, make_step, onecycle_schedule
-    from eims_b200.synth import dense_spectra, synth_molecules, synth_peaks
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    infer = args.workload == "infer"
-    batch, hid, layers, atoms = (4096, H, L, MAX_ATOMS) if infer else (BATCH, 1024, 6, 128)
-    n_mols = args.molecules or (262_144 if infer else 20_000)
-    table = synth_molecules(n_mols, max_atoms=atoms, seed=1234)
-    targets = None if infer else dense_spectra(*synth_peaks(n_mols, M, seed=4321), M)
-    ds = DeviceDataset(table, targets, dev)
-    d = ModelDims(F0, hid, layers, M, "combined", DROPOUT)
-    plan = Plan(d, batch, batch * atoms, 2 * (batch * atoms + 3 * batch), dev)
-    fp = FlatParams(d, dev)
-    init_weights(fp, d)
-    rng = np.random.default_rng(5)
-    total = args.warmup + args.steps
-    perm = torch.from_numpy(np.concatenate([rng.permutation(n_mols) for _ in range(total * batch // n_mols + 2)]).astype(np.int32)).to(dev)
-    sched = onecycle_schedule(max(4 * total, 100))
-    metrics = torch.zeros(8, device=dev)
-    out = torch.empty(batch, M, device=dev) if infer else None
-
-    def step(i):
-        ids = perm[i * batch:(i + 1) * batch]
-        if infer:
-            plan.infer_batch(ds, ids, fp, out)
-        else:
-            plan.train_step(ds, ids, fp, make_step(lr=sched[i][0], beta1=sched[i][1], step=i + 1, seed=7), metrics)
-
-    for i in range(args.warmup):
-        step(i)
-    plan.check()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(dev.index or 0)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.warmup, total):
-        step(i)
-    e1.record()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    stages_out = None
-    if args.profile_steps > 0:
-        plan.profile(True)
-        n_prof = min(args.profile_steps, 10)
-        Ns, Es = [], []
-        perm_h = perm.cpu().numpy()
-        for j in range(n_prof):
-            n_, e_ = ds.batch_counts(perm_h[j * batch:(j + 1) * batch])
-            Ns.append(n_)
-            Es.append(e_)
-            step(j)
-        prof, _ = plan.profile_read()
-        plan.profile(False)
-        work = stage_work(float(np.mean(Ns)), float(np.mean(Es)), batch, fp.numel, hid, layers)
-        if infer:  # eval mode: "bn_stats" only turns the running buffers into scale / shift; "elementwise" is the sigmoid
-            work["bn_stats"] = ("hbm", layers * 6 * hid * 4)
-            work["elementwise"] = ("hbm", 8 * batch * M)
-        stages_out = stage_report(prof, work, n_prof, peaks())
-    wl = ("BASELINE configs[2]: inference-only spectrum prediction, synthetic molecules (<=64 heavy atoms), batch 4096, single B200"
-          if infer else "BASELINE configs[4] shapes on one B200: 6 GCN layers, hidden 1024, molecules up to 128 heavy atoms, batch 512, training")
-    print(json.dumps({"metric": "gcn_eims_infer_molecules_per_sec" if infer else METRIC, "value": args.steps * batch / (ms * 1e-3),
-                      "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                      "higher_is_better": True, "dtype": "f32", "data": "synthetic", "clocks": clocks,
-                      "config": {"workload": wl, "batch_per_gpu": batch, "hidden_dim": hid, "num_gcn_layers": layers, "max_mz": M,
-                                 "resident_molecules": n_mols}, "stages": stages_out}))
+    r = infer_bench(args, dev, args.molecules or 1_000_000)
+    print(json.dumps({"metric": r["metric"], "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": r["batches"], "warmup": 3,
+                      "ms_per_step": r["ms_per_batch"], "higher_is_better": True, "dtype": "f32", "data": "synthetic", "clocks": r["clocks"],
+                      "config": {"workload": r["workload"], "batch_per_gpu": r["batch"], "hidden_dim": H, "num_gcn_layers": L, "max_mz": M,
+                                 "resident_molecules": r["resident_molecules"]}, "stages": r.get("stages")}))
 
 
 if __name__ == "__main__":
     _claim_stdout()
     a = parse()
-    if a.workload != "train" and a.impl == "ours":
-        run_extra(a)
-    elif a.impl == "reference":
+    if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "infer":
+        run_infer(a)
     else:
         run_ours(a)

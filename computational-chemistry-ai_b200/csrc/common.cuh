@@ -5,6 +5,7 @@
 
 #include "../../include/eims_b200.h"
 
+#include <cmath>
 #include <cstdlib>
 
 namespace eims {
@@ -28,6 +29,7 @@ struct DropCfg {
   uint32_t threshold;  // keep iff 16-bit word >= threshold ; threshold = round(p * 65536)
   float scale;         // 1/(1-p)
   uint64_t key;
+  const uint64_t* key_dev;  // non-null: the key is read from the device-resident step block (captured CUDA graphs)
   __host__ __device__ bool active() const { return threshold != 0; }
 };
 
@@ -37,14 +39,56 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   return z ^ (z >> 31);
 }
 
+static inline uint64_t drop_key(uint64_t seed, int step, int site) {
+  return mix64(mix64(seed) ^ (((uint64_t)(uint32_t)step << 32) | (uint32_t)site));
+}
+
 static inline DropCfg make_drop(float p, uint64_t seed, int step, int site) {
   DropCfg d;
   double t = (double)p * 65536.0 + 0.5;
   d.threshold = p <= 0.f ? 0u : (t >= 65535.0 ? 65535u : (uint32_t)t);
   d.scale = p <= 0.f ? 1.f : 1.f / (1.f - p);
-  d.key = mix64(mix64(seed) ^ (((uint64_t)(uint32_t)step << 32) | (uint32_t)site));
+  d.key = drop_key(seed, step, site);
+  d.key_dev = nullptr;
   return d;
 }
+
+// the kernel-side view: after the grid-dependency wait, take the key from the step block if there is one
+__device__ __forceinline__ DropCfg resolve_drop(DropCfg d) {
+  if (d.key_dev && d.threshold != 0u) d.key = __ldg(d.key_dev);
+  return d;
+}
+
+// ---- device-resident per-step scalars ("step block")
+// A captured CUDA graph freezes kernel parameters, so everything that changes from one optimiser step to
+// the next - the molecule ids of the batch being built, the AdamW scalars (lr and beta1 follow the
+// one-cycle schedule, GCN:386-391), the dropout keys, the data-parallel sequence number - lives in one
+// small device struct that a 1-block kernel (parameters by value, so no host-buffer lifetime to manage)
+// rewrites before every graph launch; the step's kernels read it instead of kernel parameters.
+constexpr int kMaxDropSites = 24;
+struct AdamK { float decay, one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps, grad_scale; };
+// AdamW step scalars exactly as torch computes them (GCN:429): bias corrections with the CURRENT beta1
+static inline AdamK make_adam_k(const eims_step* s) {
+  const double b1 = s->beta1, b2 = s->beta2;
+  const double bc1 = 1.0 - pow(b1, (double)s->step), bc2 = 1.0 - pow(b2, (double)s->step);
+  AdamK k;
+  k.decay = (float)(1.0 - (double)s->lr * (double)s->weight_decay);
+  k.one_minus_b1 = (float)(1.0 - b1);
+  k.b2 = (float)b2;
+  k.one_minus_b2 = (float)(1.0 - b2);
+  k.step_size = (float)((double)s->lr / bc1);
+  k.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  k.eps = s->eps;
+  k.grad_scale = s->grad_scale;
+  return k;
+}
+struct StepBlock {
+  const int32_t* ids;      // ids of the batch the indirect K1 builds
+  AdamK adam;
+  uint64_t drop_key[kMaxDropSites];
+  uint32_t dp_seq;         // sequence number of the fused data-parallel exchange
+  int32_t k1_seq;          // batch sequence number (tags the zero-degree flag)
+};
 
 // 32-bit finaliser (two multiply / xor-shift rounds, the "lowbias32" constants of the hash-prospector
 // search): ~8 integer instructions, against ~25 for a 64-bit SplitMix round on this machine - the forward

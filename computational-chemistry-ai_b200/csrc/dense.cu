@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_stats_kernel(const int* __restr
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            float* __restrict__ means /*[2][H]*/, float* __restrict__ scratch) {
   pdl_sync();
+  src.drop = resolve_drop(src.drop);
   const int N = dims[DIM_N];
   unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
   double* acc = reinterpret_cast<double*>(scratch + 16);
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(256, LAYER0 ? 2 : 4) bn_bwd_apply_kernel(
     const float* __restrict__ norm, float* __restrict__ q, float* __restrict__ dbias, const float* __restrict__ a0,
     int F, float* __restrict__ dW0) {
   pdl_sync();
+  src.drop = resolve_drop(src.drop);
   __shared__ float red[kRowLanes][kSlab];
   const int N = dims[DIM_N];
   const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
@@ -468,6 +470,7 @@ __global__ void __launch_bounds__(256) ln_relu_drop_fwd_kernel(const int* __rest
                                                                const float* __restrict__ beta, DropCfg drop,
                                                                float* __restrict__ y, float* __restrict__ stats) {
   pdl_sync();
+  drop = resolve_drop(drop);
   const int B = dims[DIM_B];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -665,6 +668,7 @@ __device__ __forceinline__ void metrics_reduce(int B, const float* row_loss, con
     const float cosm = (float)(s2[0] / (double)B);
     metrics[0] += loss; metrics[1] += cosm; metrics[2] += 1.f;
     metrics[4] = loss; metrics[5] = cosm;  // last step's values
+    if (!isfinite(loss)) metrics[6] += 1.f;  // NaN / Inf guard: steps whose loss was not finite (read once per epoch)
   }
 }
 
@@ -954,11 +958,11 @@ int launch_colsum(const int* dims, int dim_slot, const float* in, int C, int ld,
 }
 
 // =========================================================================== K8 AdamW
-struct AdamK { float decay, one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps, grad_scale; };
-
+// k_dev != null: the scalars come from the device-resident step block (captured CUDA graphs)
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                                    float* __restrict__ v, int64_t n, AdamK k) {
+                                                    float* __restrict__ v, int64_t n, AdamK k, const AdamK* __restrict__ k_dev) {
   pdl_sync();
+  if (k_dev) k = *k_dev;
   const int64_t n4 = n >> 2;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pp = *reinterpret_cast<float4*>(p + 4 * i), gg = *reinterpret_cast<float4*>(g + 4 * i);
@@ -987,26 +991,27 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float
     }
 }
 
-int launch_adamw(float* p, float* g, float* m, float* v, int64_t n, const eims_step* s, cudaStream_t st) {
-  if (!s || s->step < 1) return EIMS_ERR_ARG;
-  const double b1 = s->beta1, b2 = s->beta2;
-  const double bc1 = 1.0 - pow(b1, (double)s->step), bc2 = 1.0 - pow(b2, (double)s->step);
-  AdamK k;
-  k.decay = (float)(1.0 - (double)s->lr * (double)s->weight_decay);
-  k.one_minus_b1 = (float)(1.0 - b1);
-  k.b2 = (float)b2;
-  k.one_minus_b2 = (float)(1.0 - b2);
-  k.step_size = (float)((double)s->lr / bc1);
-  k.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-  k.eps = s->eps;
-  k.grad_scale = s->grad_scale;
-  launch_pdl(adamw_kernel, dim3(ew_blocks(n / 4)), dim3(256), 0, st, p, g, m, v, n, k);
+int launch_adamw(float* p, float* g, float* m, float* v, int64_t n, const eims_step* s, cudaStream_t st, const StepBlock* blk) {
+  if (!blk && (!s || s->step < 1)) return EIMS_ERR_ARG;
+  const AdamK k = blk ? AdamK{} : make_adam_k(s);
+  launch_pdl(adamw_kernel, dim3(ew_blocks(n / 4)), dim3(256), 0, st, p, g, m, v, n, k, blk ? &blk->adam : nullptr);
+  return 0;
+}
+
+// ---- step block upload: one block stores the by-value struct (see StepBlock in common.cuh)
+__global__ void step_block_store_kernel(StepBlock v, StepBlock* __restrict__ dst) {
+  pdl_sync();
+  if (threadIdx.x == 0) *dst = v;
+}
+int launch_step_block_store(const StepBlock& v, StepBlock* dst, cudaStream_t st) {
+  launch_pdl(step_block_store_kernel, dim3(1), dim3(32), 0, st, v, dst);
   return 0;
 }
 
 // =========================================================================== dropout mask (tests)
 __global__ void dropout_mask_kernel(DropCfg d, int64_t n4, float* __restrict__ out) {
   pdl_sync();
+  d = resolve_drop(d);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 m = drop_mask4(d, (uint64_t)i * 4);
     m.x = m.x != 0.f; m.y = m.y != 0.f; m.z = m.z != 0.f; m.w = m.w != 0.f;

@@ -31,8 +31,6 @@ struct DpPeers {
   float* params_mc;              // multicast address of the parameter buffers, or null
 };
 
-struct AdamKd { float decay, one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps, grad_scale; };
-
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -55,13 +53,25 @@ __device__ __forceinline__ void multimem_st(float* mc, float4 v) {
                : "memory");
 }
 
-// wait until every rank has written `seq` (or later) into this rank's pad row `phase`
-__device__ __forceinline__ void wait_all(const uint32_t* my_pad, int row, int world, uint32_t seq) {
+// Wait until every rank has written `seq` (or later) into this rank's pad row `row`.  A peer may be late for a
+// long time for honest reasons (rank 0 writing a checkpoint or running the eval pass, an I/O stall, lazy module
+// loading on the first step), so the wait is long (EIMS_DP_TIMEOUT_S, default 600 s, measured on %globaltimer)
+// and running out of it is reported, not trapped: the waiting thread records the sequence number in `*status`
+// (read by the host with the per-epoch flag check) and the kernel carries on, so the context survives and the
+// job can stop with an error message instead of a sticky CUDA fault on every rank.
+__device__ __forceinline__ void wait_all(const uint32_t* my_pad, int row, int world, uint32_t seq, unsigned long long timeout_ns,
+                                         uint32_t* status) {
   if ((int)threadIdx.x < world) {
     const uint32_t* p = my_pad + row * kMaxRanks + threadIdx.x;
-    const long long t0 = clock64();
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
     while ((int32_t)(ld_acquire_sys(p) - seq) < 0) {
-      if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s: a lost rank must not hang the GPU for ever
+      if ((++spins & 0x3ffu) == 0) {  // look at the clock every 1024 polls
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > timeout_ns) { atomicMax(status, seq ? seq : 1u); break; }
+      }
     }
   }
   __syncthreads();
@@ -74,15 +84,18 @@ __device__ __forceinline__ void wait_all(const uint32_t* my_pad, int row, int wo
 __global__ void __launch_bounds__(256) dp_adamw_kernel(DpPeers pr, int rank, int world, float* __restrict__ m,
                                                        float* __restrict__ v, float* __restrict__ zero_buf,
                                                        int64_t base4, int64_t n4, int64_t per, uint32_t seq, int row,
-                                                       unsigned int* ticket, AdamKd k) {
+                                                       unsigned int* ticket, AdamK k, const StepBlock* __restrict__ blk,
+                                                       unsigned long long timeout_ns) {
   pdl_sync();
+  if (blk) { k = blk->adam; seq = blk->dp_seq; }  // captured graph: this step's scalars / sequence number
+  uint32_t* status = ticket + 1;
   uint32_t* my_pad = pr.signals[rank];
   // ---- phase 0: my gradients are complete (stream order) -> tell everyone, wait for everyone
   if (blockIdx.x == 0 && (int)threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(pr.signals[threadIdx.x] + (2 * row) * kMaxRanks + rank, seq);
   }
-  wait_all(my_pad, 2 * row, world, seq);
+  wait_all(my_pad, 2 * row, world, seq, timeout_ns, status);
   // ---- phase 1: reduce + AdamW + broadcast of the own slice
   const int64_t s0 = base4 + (int64_t)rank * per, s1 = min(base4 + n4, s0 + per);
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
@@ -144,7 +157,7 @@ __global__ void __launch_bounds__(256) dp_adamw_kernel(DpPeers pr, int rank, int
   __threadfence_system();
   if (!last_block_ticket(ticket, gridDim.x)) return;
   if ((int)threadIdx.x < world) st_release_sys(pr.signals[threadIdx.x] + (2 * row + 1) * kMaxRanks + rank, seq);
-  wait_all(my_pad, 2 * row + 1, world, seq);
+  wait_all(my_pad, 2 * row + 1, world, seq, timeout_ns, status);
 }
 
 }  // namespace eims
@@ -157,8 +170,17 @@ extern "C" int eims_dp_adamw_fused(int32_t rank, int32_t world, const uint64_t* 
                                    float* m_slice, float* v_slice, float* zero_buf, int64_t range_off,
                                    int64_t range_len, const eims_step* s, uint32_t seq, int32_t bucket,
                                    uint32_t* ticket, eims_stream_t stream) {
-  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !grad_ptrs || !param_ptrs || !signal_ptrs || !s ||
-      s->step < 1 || range_off < 0 || range_off % 4 || range_len <= 0 || range_len % (4 * (int64_t)world) || bucket < 0 ||
+  return eims_dp_adamw_fused_blk(rank, world, grad_ptrs, param_ptrs, signal_ptrs, grads_multicast, params_multicast, m_slice,
+                                 v_slice, zero_buf, range_off, range_len, s, seq, bucket, ticket, nullptr, stream);
+}
+
+extern "C" int eims_dp_adamw_fused_blk(int32_t rank, int32_t world, const uint64_t* grad_ptrs, const uint64_t* param_ptrs,
+                                       const uint64_t* signal_ptrs, uint64_t grads_multicast, uint64_t params_multicast,
+                                       float* m_slice, float* v_slice, float* zero_buf, int64_t range_off,
+                                       int64_t range_len, const eims_step* s, uint32_t seq, int32_t bucket,
+                                       uint32_t* ticket, const void* step_block, eims_stream_t stream) {
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !grad_ptrs || !param_ptrs || !signal_ptrs ||
+      (!step_block && (!s || s->step < 1)) || range_off < 0 || range_off % 4 || range_len <= 0 || range_len % (4 * (int64_t)world) || bucket < 0 ||
       bucket > 3 || !ticket)
     return EIMS_ERR_ARG;
   DpPeers pr{};
@@ -169,22 +191,19 @@ extern "C" int eims_dp_adamw_fused(int32_t rank, int32_t world, const uint64_t* 
   }
   pr.grads_mc = reinterpret_cast<float*>(grads_multicast);
   pr.params_mc = reinterpret_cast<float*>(params_multicast);
-  const double b1 = s->beta1, b2 = s->beta2;
-  const double bc1 = 1.0 - pow(b1, (double)s->step), bc2 = 1.0 - pow(b2, (double)s->step);
-  AdamKd k;
-  k.decay = (float)(1.0 - (double)s->lr * (double)s->weight_decay);
-  k.one_minus_b1 = (float)(1.0 - b1);
-  k.b2 = (float)b2;
-  k.one_minus_b2 = (float)(1.0 - b2);
-  k.step_size = (float)((double)s->lr / bc1);
-  k.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-  k.eps = s->eps;
-  k.grad_scale = s->grad_scale;
+  const AdamK k = step_block ? AdamK{} : make_adam_k(s);
+  static unsigned long long timeout_ns = 0;
+  if (!timeout_ns) {
+    const char* e = getenv("EIMS_DP_TIMEOUT_S");
+    const double sec = e ? atof(e) : 600.0;
+    timeout_ns = (unsigned long long)((sec > 0.001 ? sec : 0.001) * 1e9);
+  }
   const int64_t n4 = range_len / 4, per = n4 / world;
   int64_t blocks = (n4 + 255) / 256;   // the zeroing pass covers the whole range
   if (blocks > 148) blocks = 148;  // one block per SM: the early bucket shares the GPU with the backward pass
   launch_pdl(dp_adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, pr, rank, world, m_slice, v_slice,
-             zero_buf, range_off / 4, n4, per, seq, (int)bucket, ticket, k);
+             zero_buf, range_off / 4, n4, per, seq, (int)bucket, ticket, k, reinterpret_cast<const StepBlock*>(step_block),
+             timeout_ns);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : EIMS_ERR_CUDA;
 }
 #pragma GCC visibility pop

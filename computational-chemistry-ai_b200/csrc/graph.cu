@@ -28,8 +28,10 @@ __global__ void __launch_bounds__(1024) k1_scan_kernel(const int64_t* __restrict
                                                        const int64_t* __restrict__ bond_ptr,
                                                        const int32_t* __restrict__ ids, int B, int max_nodes,
                                                        int max_edges, int* __restrict__ gptr, int* __restrict__ eptr,
-                                                       int* __restrict__ rowptr, int* __restrict__ dims, int seq) {
+                                                       int* __restrict__ rowptr, int* __restrict__ dims, int seq,
+                                                       const StepBlock* __restrict__ blk) {
   pdl_sync();
+  if (blk) { ids = blk->ids; seq = blk->k1_seq; }  // captured graph: this step's ids / sequence number
   __shared__ int wn[32], we[32];
   __shared__ int carry_n, carry_e;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -96,8 +98,10 @@ __global__ void __launch_bounds__(kK1Warps * 32) k1_build_kernel(
     const int32_t* __restrict__ bond_begin, const int32_t* __restrict__ bond_end, const int32_t* __restrict__ ids, int B,
     int F, int max_nodes, int max_edges, int seq, int* __restrict__ gptr, int* __restrict__ eptr, int* __restrict__ gid,
     int* __restrict__ src, int* __restrict__ dst, int* __restrict__ rowptr, int* __restrict__ col,
-    float* __restrict__ norm, float* __restrict__ x, float* __restrict__ a0, int* __restrict__ dims, int prescanned) {
+    float* __restrict__ norm, float* __restrict__ x, float* __restrict__ a0, int* __restrict__ dims, int prescanned,
+    const StepBlock* __restrict__ blk, int* __restrict__ bids) {
   pdl_sync();
+  if (blk) { ids = blk->ids; seq = blk->k1_seq; }  // captured graph: this step's ids / sequence number
   __shared__ long long red[kK1Warps][4];
   __shared__ int cnt_n[kK1Warps], cnt_e[kK1Warps];
   __shared__ K1Stage stage[kK1Warps];
@@ -183,6 +187,7 @@ __global__ void __launch_bounds__(kK1Warps * 32) k1_build_kernel(
   const float* px = staged ? S.sx : x + (int64_t)o * F;
   const int rowbase = staged ? 0 : eo, colbase = staged ? 0 : o;
   if (lane == 0 && !prescanned) { gptr[g] = o; eptr[g] = eo; }
+  if (lane == 0 && bids) bids[g] = (int)id;  // the batch's molecule ids = the target rows of the loss kernel
   for (int t = lane; t < n * F; t += 32) {
     const float v = __ldg(feat + a_0 * F + t);
     x[(int64_t)o * F + t] = v;
@@ -262,16 +267,16 @@ __global__ void __launch_bounds__(kK1Warps * 32) k1_build_kernel(
 
 int launch_csr_build(const eims_dataset* ds, const int32_t* ids, int B, int F, int max_nodes, int max_edges,
                      int* gptr, int* eptr, int* gid, int* src, int* dst, int* rowptr, int* col, float* norm,
-                     float* x, int* dims, cudaStream_t st, float* a0, int seq) {
+                     float* x, int* dims, cudaStream_t st, float* a0, int seq, const StepBlock* blk, int* bids) {
   if (F > kMaxF0) return EIMS_ERR_ARG;
   const int blocks = B > 0 ? (B + kK1Warps - 1) / kK1Warps : 1;
   const int prescanned = B > 1024;
   if (prescanned)
     launch_pdl(k1_scan_kernel, dim3(1), dim3(1024), 0, st, ds->node_ptr, ds->bond_ptr, ids, B, max_nodes, max_edges, gptr, eptr,
-               rowptr, dims, seq);
+               rowptr, dims, seq, blk);
   launch_pdl(k1_build_kernel, dim3(blocks), dim3(kK1Warps * 32), 0, st, ds->node_ptr, ds->bond_ptr, ds->feat, ds->bond_begin,
              ds->bond_end, ids, B, F, max_nodes, max_edges, seq, gptr, eptr, gid, src, dst, rowptr, col, norm, x, a0, dims,
-             prescanned);
+             prescanned, blk, bids);
   return 0;
 }
 
@@ -383,6 +388,7 @@ __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ 
                                                         float* __restrict__ out, int parts, BnBwdFuse bf) {
   extern __shared__ float s_stats[];  // STATS: [warps per block][2][128 * NV]
   pdl_sync();
+  drop = resolve_drop(drop);
   const int N = dims[DIM_N];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

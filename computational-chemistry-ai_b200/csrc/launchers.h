@@ -12,7 +12,9 @@ namespace eims {
 // graph.cu
 int launch_csr_build(const eims_dataset* ds, const int32_t* ids, int B, int F, int max_nodes, int max_edges,
                      int* gptr, int* eptr, int* gid, int* src, int* dst, int* rowptr, int* col, float* norm,
-                     float* x, int* dims, cudaStream_t st, float* a0 = nullptr, int seq = 1);
+                     float* x, int* dims, cudaStream_t st, float* a0 = nullptr, int seq = 1,
+                     const StepBlock* blk = nullptr,  // non-null: ids and seq are read from the device step block
+                     int* bids = nullptr);            // optional: copy of the batch's molecule ids [B]
 int launch_layer0_fwd(const int* dims, const float* norm, const float* a0, int F, const float* W, const float* bias,
                       int H, float* z, int max_nodes, cudaStream_t st, const BnFuse* bn = nullptr, float* zero = nullptr,
                       int64_t zero_n4 = 0);
@@ -71,7 +73,9 @@ int launch_dprob_to_dlogits(const int* dims, const float* prob, const float* dpr
                             int max_graphs, cudaStream_t st);
 int launch_metrics(const int* dims, const float* row_loss, const float* row_cos, int M, float* metrics, cudaStream_t st);
 int launch_colsum(const int* dims, int dim_slot, const float* in, int C, int ld, float* out, int max_rows, cudaStream_t st);
-int launch_adamw(float* p, float* g, float* m, float* v, int64_t n, const eims_step* s, cudaStream_t st);
+int launch_adamw(float* p, float* g, float* m, float* v, int64_t n, const eims_step* s, cudaStream_t st,
+                 const StepBlock* blk = nullptr);  // blk: the scalars are read from the device step block
+int launch_step_block_store(const StepBlock& v, StepBlock* dst, cudaStream_t st);
 int launch_dropout_mask(DropCfg d, int rows, int W, float* out, cudaStream_t st);
 
 // gemm_tc.cu  (tcgen05 / TMEM, 3xTF32)

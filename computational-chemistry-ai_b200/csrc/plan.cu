@@ -99,8 +99,18 @@ struct eims_plan {
   // set the kernels enqueued so far do NOT use and makes it current for what is enqueued next, so
   // the next batch can be built on a side stream while the current step is still running.
   int cur = 0;
+  // Device step block (eims_plan_set_step_block) and the mode of the call being enqueued: `indirect` calls take
+  // the batch's ids, the dropout keys and the AdamW scalars from it instead of from kernel parameters, so that
+  // the launches can be captured into a CUDA graph once and replayed for every step.
+  StepBlock* blk = nullptr;
+  bool indirect = false;
+  DropCfg drop(float prob, uint64_t seed, int step, int site) const {
+    DropCfg d = make_drop(prob, seed, step, site);
+    if (indirect && blk && site >= 0 && site < kMaxDropSites) d.key_dev = &blk->drop_key[site];
+    return d;
+  }
   static bool pingpong(const std::string& n) {
-    static const char* k[] = {"dims", "gptr", "eptr", "gid", "src", "dst", "rowptr", "col", "norm", "x", "a0"};
+    static const char* k[] = {"dims", "gptr", "eptr", "gid", "src", "dst", "rowptr", "col", "norm", "x", "a0", "bids"};
     for (const char* s : k) if (n == s) return true;
     return false;
   }
@@ -330,7 +340,7 @@ int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, 
   const int64_t B = p->Bc, N = p->Nc, E = p->Ec, H = d->hidden_dim, F = d->node_feat_dim, M = d->max_mz, L = d->num_gcn_layers;
   const int64_t P = p->pool_dim();
   add(p, "dims", 16 * 4); add(p, "flags", 16 * 4);
-  add(p, "gptr", (B + 1) * 4); add(p, "eptr", (B + 1) * 4); add(p, "gid", N * 4);
+  add(p, "gptr", (B + 1) * 4); add(p, "eptr", (B + 1) * 4); add(p, "gid", N * 4); add(p, "bids", B * 4);
   add(p, "src", E * 4); add(p, "dst", E * 4); add(p, "rowptr", (N + 1) * 4); add(p, "col", E * 4);
   add(p, "argmax", B * H * 4);
   add(p, "norm", N * 4); add(p, "x", N * F * 4); add(p, "a0", N * F * 4);
@@ -397,9 +407,10 @@ int eims_plan_buffer(eims_plan* p, const char* name, void** ptr, int64_t* bytes)
   return 0;
 }
 
-int eims_batch_build(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
-                     eims_stream_t stream) {
+static int batch_build_impl(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
+                            eims_stream_t stream, bool indirect) {
   if (!p || !p->bound) return fail(EIMS_ERR_STATE, "plan not bound");
+  if (indirect && !p->blk) return fail(EIMS_ERR_STATE, "no step block set (eims_plan_set_step_block)");
   if (!ds || num_graphs < 0) return fail(EIMS_ERR_ARG, "bad dataset / num_graphs");
   if (num_graphs > p->Bc) return fail(EIMS_ERR_CAPACITY, "num_graphs %d exceeds plan max_graphs %d", num_graphs, p->Bc);
   cudaStream_t st = (cudaStream_t)stream;
@@ -413,9 +424,41 @@ int eims_batch_build(eims_plan* p, const eims_dataset* ds, const int32_t* mol_id
   ++p->batch_seq;
   STAGE(ST_K1, num_graphs > 1024 ? 2 : 1, launch_csr_build(ds, mol_ids, num_graphs, p->d.node_feat_dim, p->Nc, p->Ec, p->i("gptr"), p->i("eptr"),
                             p->i("gid"), p->i("src"), p->i("dst"), p->i("rowptr"), p->i("col"), p->f("norm"),
-                            p->f("x"), p->i("dims"), st, p->f("a0"), p->batch_seq));
+                            p->f("x"), p->i("dims"), st, p->f("a0"), p->batch_seq, indirect ? p->blk : nullptr, p->i("bids")));
   p->state = 1;
   return check_launch("eims_batch_build");
+}
+
+int eims_batch_build(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
+                     eims_stream_t stream) {
+  return batch_build_impl(p, ds, mol_ids, num_graphs, stream, false);
+}
+
+int eims_batch_build_indirect(eims_plan* p, const eims_dataset* ds, int32_t num_graphs, eims_stream_t stream) {
+  return batch_build_impl(p, ds, nullptr, num_graphs, stream, true);
+}
+
+int eims_plan_set_step_block(eims_plan* p, void* dev_block, int64_t bytes) {
+  if (!p) return fail(EIMS_ERR_ARG, "plan is NULL");
+  if (dev_block && (bytes < (int64_t)sizeof(StepBlock) || (reinterpret_cast<uintptr_t>(dev_block) & 15)))
+    return fail(EIMS_ERR_ARG, "step block needs %d bytes, 16-byte aligned", (int)sizeof(StepBlock));
+  p->blk = reinterpret_cast<StepBlock*>(dev_block);
+  return 0;
+}
+int64_t eims_step_block_bytes(void) { return (int64_t)sizeof(StepBlock); }
+
+int eims_step_block_upload(eims_plan* p, const eims_step* s, const int32_t* mol_ids, uint32_t dp_seq, eims_stream_t stream) {
+  if (!p || !p->blk) return fail(EIMS_ERR_STATE, "no step block set (eims_plan_set_step_block)");
+  if (!s || s->step < 1) return fail(EIMS_ERR_ARG, "step scalars are NULL / step < 1");
+  StepBlock v{};
+  v.ids = mol_ids;
+  v.adam = make_adam_k(s);
+  const int sites = p->d.num_gcn_layers + 2;
+  for (int k = 0; k < sites && k < kMaxDropSites; ++k) v.drop_key[k] = drop_key(s->seed, s->step, k);
+  v.dp_seq = dp_seq;
+  v.k1_seq = 1 + (s->step & 0x3fffffff);
+  EIMS_TRY(launch_step_block_store(v, p->blk, (cudaStream_t)stream));
+  return check_launch("eims_step_block_upload");
 }
 
 int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t training, const eims_step* s,
@@ -465,7 +508,7 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
     if (fuse_bn) bf = fuse(l);
     STAGE(ST_SPMM_FWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f(L_("z", l - 1)), H,
                               p->f(L_("bn_scale", l - 1)), p->f(L_("bn_shift", l - 1)),
-                              make_drop(drop_p, seed, step, l - 1), 0, p->f(L_("a", l)), p->Nc, st));
+                              p->drop(drop_p, seed, step, l - 1), 0, p->f(L_("a", l)), p->Nc, st));
     STAGE(ST_GEMM_GCN_FWD, 1, gemm(p, p->f(L_("a", l)), H, 0, params + p->off_gcn_w(l), H, 1, p->f(L_("z", l)), H, p->Nc, H, H,
                   dims + DIM_N, nullptr, p->f("norm"), params + p->off_gcn_b(l), 1, 0, st, fuse_bn ? &bf : nullptr));
     if (!fuse_bn) STAGE(ST_BN_STATS, 1, bn(l));
@@ -480,11 +523,11 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
   STAGE(ST_GEMM_HEAD_FWD, 1, gemm(p, p->f("readout"), P, 0, params + p->off_head(0), P, 0, p->f("u1"), 2 * H, p->Bc, 2 * H, P,
                 dims + DIM_B, nullptr, nullptr, params + p->off_head(1), 0, head_acc, st));
   STAGE(ST_LN_FWD, 1, launch_ln_fwd(dims, p->f("u1"), 2 * H, params + p->off_head(2), params + p->off_head(3),
-                         make_drop(drop_p, seed, step, L), p->f("y1"), p->f("ln1"), p->Bc, st));
+                         p->drop(drop_p, seed, step, L), p->f("y1"), p->f("ln1"), p->Bc, st));
   STAGE(ST_GEMM_HEAD_FWD, 1, gemm(p, p->f("y1"), 2 * H, 0, params + p->off_head(4), 2 * H, 0, p->f("u2"), H, p->Bc, H, 2 * H,
                 dims + DIM_B, nullptr, nullptr, params + p->off_head(5), 0, head_acc, st));
   STAGE(ST_LN_FWD, 1, launch_ln_fwd(dims, p->f("u2"), H, params + p->off_head(6), params + p->off_head(7),
-                         make_drop(drop_p, seed, step, L + 1), p->f("y2"), p->f("ln2"), p->Bc, st));
+                         p->drop(drop_p, seed, step, L + 1), p->f("y2"), p->f("ln2"), p->Bc, st));
   STAGE(ST_GEMM_HEAD_FWD, 1, gemm(p, p->f("y2"), H, 0, params + p->off_head(8), H, 0, p->f("logits"), M, p->Bc, M, H, dims + DIM_B,
                 nullptr, nullptr, params + p->off_head(9), 0, head_acc, st));
   p->state = training ? 2 : 1;
@@ -576,7 +619,7 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
     // the fly inside both BatchNorm-backward passes when EIMS_FUSE_SPMM_BWD=1; by default K2 materialises it
     const bool gather = !from_readout && p->fuse_spmm_bwd;
     const float* dh_in = (from_readout || gather) ? nullptr : p->f("dh");
-    GatherSrc gsrc{p->f("da"), p->i("rowptr"), p->i("col"), p->f("norm"), make_drop(drop_p, seed, step, l)};
+    GatherSrc gsrc{p->f("da"), p->i("rowptr"), p->i("col"), p->f("norm"), p->drop(drop_p, seed, step, l)};
     const GatherSrc* gs = gather ? &gsrc : nullptr;
     // the statistics pass of layer l < L-1 rides on the SpMM that wrote its dh (see below)
     if (from_readout && p->top_stats_per_graph)
@@ -601,7 +644,7 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
                      reinterpret_cast<double*>(scratch + 16), reinterpret_cast<unsigned int*>(scratch),
                      grads + p->off_bn_g(l - 1), grads + p->off_bn_b(l - 1), p->f("bn_means2")};
         STAGE(ST_SPMM_BWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("da"), H, nullptr, nullptr,
-                                  make_drop(drop_p, seed, step, l - 1), 1, p->f("dh"), p->Nc, st,
+                                  p->drop(drop_p, seed, step, l - 1), 1, p->f("dh"), p->Nc, st,
                                   p->fuse_bn_bwd_stats ? &bf : nullptr));
       }
     }  // l == 0: dW0 came out of the BatchNorm-backward apply pass above (q_0 is never materialised)
@@ -650,6 +693,25 @@ int eims_train_step_built(eims_plan* p, const float* targets, const int32_t* tar
     STAGE(ST_ADAMW, 1, launch_adamw(params, grads, adam_m, adam_v, p->poff.back(), s, st));
   }
   return 0;
+}
+
+int eims_train_step_built_indirect(eims_plan* p, const float* targets, float* params, float* grads, float* adam_m,
+                                   float* adam_v, float* bn_running, int32_t loss_kind, float* metrics, eims_stream_t stream) {
+  if (!p || !p->blk) return fail(EIMS_ERR_STATE, "no step block set (eims_plan_set_step_block)");
+  if (!targets && !p->peak_targets.peak_ptr) return fail(EIMS_ERR_ARG, "training needs target spectra");
+  eims_step dummy{};  // seed / step are not used: the dropout keys come from the step block
+  p->indirect = true;
+  int rc = eims_forward(p, params, bn_running, 1, &dummy, stream);
+  if (!rc) rc = loss_impl(p, targets, p->i("bids"), loss_kind, 1, metrics, stream);
+  if (!rc) rc = eims_backward(p, params, nullptr, grads, stream);
+  if (!rc && adam_m && adam_v) {
+    cudaStream_t st = (cudaStream_t)stream;
+    prof_begin(p, ST_ADAMW, 1, st);
+    rc = launch_adamw(params, grads, adam_m, adam_v, p->poff.back(), nullptr, st, p->blk);
+    prof_end(p, st);
+  }
+  p->indirect = false;
+  return rc;
 }
 
 int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,

@@ -46,6 +46,12 @@ class Dataset(C.Structure):
                 ("num_mols", C.c_int64), ("peaks", C.POINTER(Peaks))]
 
 
+class HostBatchLayout(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("node_ptr", "bond_ptr", "bond_begin", "bond_end", "feat", "targets", "peak_ptr",
+                                         "peak_mz", "peak_inten", "nbytes")] + \
+               [(n, C.c_int32) for n in ("num_graphs", "num_nodes", "num_edges", "feat_dim", "mz_is_f64")]
+
+
 class Step(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("weight_decay", C.c_float), ("grad_scale", C.c_float), ("step", C.c_int32), ("seed", C.c_uint64)]
@@ -89,6 +95,14 @@ _SIGS = {
     "eims_infer_batch": (C.c_int, [_vp, C.POINTER(Dataset), _vp, _i32, _vp, _vp, _vp, _vp]),
     "eims_dp_adamw_fused": (C.c_int, [_i32, _i32, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _u64, _u64, _vp, _vp, _vp,
                                       _i64, _i64, C.POINTER(Step), C.c_uint32, _i32, _vp, _vp]),
+    "eims_dp_adamw_fused_blk": (C.c_int, [_i32, _i32, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _u64, _u64, _vp, _vp, _vp,
+                                          _i64, _i64, C.POINTER(Step), C.c_uint32, _i32, _vp, _vp, _vp]),
+    "eims_host_pack_batch": (C.c_int, [C.POINTER(Dataset), _vp, _i32, _i32, _i32, _vp, _i64, C.POINTER(HostBatchLayout)]),
+    "eims_step_block_bytes": (_i64, []),
+    "eims_plan_set_step_block": (C.c_int, [_vp, _vp, _i64]),
+    "eims_step_block_upload": (C.c_int, [_vp, C.POINTER(Step), _vp, C.c_uint32, _vp]),
+    "eims_batch_build_indirect": (C.c_int, [_vp, C.POINTER(Dataset), _i32, _vp]),
+    "eims_train_step_built_indirect": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "eims_plan_profile": (C.c_int, [_vp, _i32]),
     "eims_plan_profile_read": (C.c_int, [_vp, C.POINTER(_f32), C.POINTER(_i32), _i32, C.POINTER(_i64)]),
     "eims_plan_num_stages": (C.c_int, []),

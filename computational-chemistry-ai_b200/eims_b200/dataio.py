@@ -138,7 +138,9 @@ def write_reference_msp(path, rec):
                 f.write(f"{k}: {v}\n")
         f.write(f"Num Peaks: {len(rec['peaks'])}\n")
         for mz, inten in rec["peaks"]:
-            f.write(f"{mz:g} {inten:g}\n")
+            # repr() round-trips a float exactly: "{:g}" keeps 6 significant digits, which moved 101.49996 to
+            # "101.5" (bin 102 instead of 101) and truncated intensities above 1e6
+            f.write(f"{float(mz)!r} {float(inten)!r}\n")
 
 
 def preprocess(msp_file, mol_dir, data_dir, verbose=True):

@@ -70,6 +70,37 @@ def stratified_epoch(sizes, batch: int, epoch: int, seed: int = 0):
     return out
 
 
+def global_batches(sizes, world: int, rank: int, batch: int, epoch: int, seed: int = 0, balance: bool = True, steps: int | None = None):
+    """Molecule ids of every step of `rank` in `epoch` when every rank holds the WHOLE data set: int32 [steps, batch].
+
+    The global batch of step k is `perm[k*world*batch : (k+1)*world*batch]` of one uniform permutation per epoch
+    shared by all ranks - exactly the batches the reference's `DataLoader(shuffle=True)` (GCN:561-568) draws at batch
+    size world*batch.  Only the ASSIGNMENT of those molecules to ranks is free, and the gradient (the mean over the
+    global batch, equal counts per rank) does not depend on it:
+      balance=False  rank r takes every world-th molecule of the global batch (torch's DistributedSampler);
+      balance=True   the global batch is sorted by atom count and dealt out in snake order (r, 2W-1-r, 2W+r, ...),
+                     so that every rank gets the same number of molecules AND almost the same number of atoms.
+    A synchronous step runs at the pace of the slowest rank and a step's cost follows its atom count (std ~2.4 % for
+    512 random molecules of 2..64 atoms: a 3-4 % straggler tax at 8 ranks); the balanced deal removes it without
+    touching what is sampled."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    sizes = np.asarray(sizes)
+    n = len(sizes)
+    gb = world * batch
+    total = n // gb
+    if total == 0:
+        raise ValueError(f"{n} molecules do not fill one batch of {batch} on each of {world} ranks")
+    steps = total if steps is None else min(int(steps), total)
+    perm = np.random.Generator(np.random.PCG64([seed, epoch])).permutation(n)[: steps * gb].reshape(steps, gb)
+    if not balance or world == 1:
+        return np.ascontiguousarray(perm[:, rank::world]).astype(np.int32)
+    order = np.argsort(-sizes[perm], axis=1, kind="stable")              # largest first, per global batch
+    srt = np.take_along_axis(perm, order, axis=1).reshape(steps, batch, world)
+    col = np.where(np.arange(batch) % 2 == 0, rank, world - 1 - rank)    # snake: even rounds forwards, odd rounds backwards
+    return np.ascontiguousarray(srt[:, np.arange(batch), col]).astype(np.int32)
+
+
 def head_split(offsets, num_gcn_layers: int) -> int:
     """Flat-buffer offset where the spectrum_predictor tensors start (parameters() order:
     2L GraphConv tensors, 2L BatchNorm tensors, then the 10 head tensors)."""
@@ -138,7 +169,7 @@ class FusedP2PAdamW:
 
     SIGNAL_OFFSET = 8192  # bytes into torch's signal pad (its own barriers use the front)
 
-    def __init__(self, fp, num_gcn_layers=None, group=None, overlap=True):
+    def __init__(self, fp, num_gcn_layers=None, group=None, overlap=True, use_multicast=True):
         import ctypes as C
         import torch.distributed._symmetric_memory as symm
         from . import _lib
@@ -168,7 +199,8 @@ class FusedP2PAdamW:
         self.signal_ptrs = arr(self.h_params.signal_pad_ptrs, self.SIGNAL_OFFSET)
         mc = lambda h: int(getattr(h, "multicast_ptr", 0) or 0)
         self.params_mc, self.grads_mc = mc(self.h_params), [mc(h) for h in self.h_grads]
-        self.multicast = bool(self.params_mc and all(self.grads_mc))
+        # use_multicast=False forces the peer-load / peer-store branch of the kernel (tests cover both)
+        self.multicast = bool(use_multicast and self.params_mc and all(self.grads_mc))
         # buckets: [0, split) = GraphConv + BatchNorm tensors (final at the end of backward),
         # [split, n_pad) = the head (final before the GCN layers are differentiated); the split is
         # rounded UP to the slice granularity so nothing unfinished lands in the early bucket
@@ -191,16 +223,23 @@ class FusedP2PAdamW:
         self.fp.grads = self.sym_grads[self.seq % 2][: self.fp.numel]
         self.seq += 1
 
-    def _launch(self, bucket, step, stream):
+    def _launch(self, bucket, step, stream, step_block=None):
         from ._lib import check, ptr
         C = self.C
         cur = (self.seq - 1) % 2
         off, ln = self.buckets[bucket]
-        check(self.lib.eims_dp_adamw_fused(self.rank, self.world, self.grad_ptrs[cur], self.param_ptrs, self.signal_ptrs,
-                                           C.c_uint64(self.grads_mc[cur] if self.multicast else 0),
-                                           C.c_uint64(self.params_mc if self.multicast else 0), ptr(self.m[bucket]),
-                                           ptr(self.v[bucket]), ptr(self.sym_grads[1 - cur]), off, ln, C.byref(step),
-                                           C.c_uint32(self.seq), bucket, C.c_void_p(self.ticket.data_ptr() + 16 * bucket), stream))
+        check(self.lib.eims_dp_adamw_fused_blk(self.rank, self.world, self.grad_ptrs[cur], self.param_ptrs, self.signal_ptrs,
+                                               C.c_uint64(self.grads_mc[cur] if self.multicast else 0),
+                                               C.c_uint64(self.params_mc if self.multicast else 0), ptr(self.m[bucket]),
+                                               ptr(self.v[bucket]), ptr(self.sym_grads[1 - cur]), off, ln,
+                                               C.byref(step) if step is not None else None,
+                                               C.c_uint32(self.seq), bucket, C.c_void_p(self.ticket.data_ptr() + 16 * bucket),
+                                               ptr(step_block), stream))
+
+    def lost_peer(self):
+        """Sequence number at which this rank gave up waiting for a peer (EIMS_DP_TIMEOUT_S), or 0.  One small
+        synchronous read: call it once per epoch, not per step."""
+        return int(self.ticket.view(-1, 4)[:, 1].max().item())
 
     def head_ready(self, step):
         """Call when the head gradients are final (between the two parts of backward): exchanges and
@@ -213,13 +252,14 @@ class FusedP2PAdamW:
         self.side_done = torch.cuda.Event()
         self.side_done.record(self.side)
 
-    def finish(self, step, stream):
+    def finish(self, step, stream, step_block=None):
         """Exchange + update of the remaining bucket(s) on the compute stream; afterwards the new
-        parameters of every bucket are in place for the next forward."""
-        self._launch(0, step, stream)
+        parameters of every bucket are in place for the next forward.  step_block: the device step block
+        the kernel reads its scalars and sequence number from (captured graphs) instead of `step`."""
+        self._launch(0, step, stream, step_block)
         if self.side is not None:
             if self.side_done is None:      # head_ready was not called: do that bucket here
-                self._launch(1, step, stream)
+                self._launch(1, step, stream, step_block)
             else:
                 torch.cuda.current_stream(self.fp.params.device).wait_event(self.side_done)
                 self.side_done = None

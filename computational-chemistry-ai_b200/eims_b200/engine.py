@@ -168,6 +168,22 @@ class DevicePeaks:
                                   int(mz.dtype == np.float64), self.num_spectra)
 
     @classmethod
+    def from_device(cls, peak_ptr, mz, intensity):
+        """Peak lists whose flat arrays are device tensors already (mz float32 or float64)."""
+        self = cls.__new__(cls)
+        self.device = peak_ptr.device
+        self.peak_ptr = peak_ptr.to(torch.int64).contiguous()
+        self.num_spectra = self.peak_ptr.numel() - 1
+        self.num_peaks = int(self.peak_ptr[-1]) if self.peak_ptr.numel() else 0
+        if mz.dtype not in (torch.float32, torch.float64):
+            mz = mz.to(torch.float64)
+        self.mz = mz.contiguous() if mz.numel() else torch.zeros(1, dtype=mz.dtype, device=self.device)
+        self.intensity = intensity.to(torch.float32).contiguous() if intensity.numel() else torch.zeros(1, device=self.device)
+        self._struct = _lib.Peaks(self.peak_ptr.data_ptr(), self.mz.data_ptr(), self.intensity.data_ptr(),
+                                  int(self.mz.dtype == torch.float64), self.num_spectra)
+        return self
+
+    @classmethod
     def from_lists(cls, peaks_list, device="cuda"):
         """From the reference's list-of-lists-of-(mz, intensity) form (GCN:166, 260-278)."""
         lens = np.fromiter((len(p) for p in peaks_list), np.int64, len(peaks_list))
@@ -221,8 +237,32 @@ class DeviceDataset:
         self.feat = up(table.feat.reshape(-1), torch.float32) if table.feat.size else torch.zeros(1, device=self.device)
         self.bond_begin = up(table.bond_begin, torch.int32) if table.bond_begin.size else torch.zeros(1, dtype=torch.int32, device=self.device)
         self.bond_end = up(table.bond_end, torch.int32) if table.bond_end.size else torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.targets = None if targets is None else up(np.asarray(targets, np.float32), torch.float32)
+        if isinstance(targets, torch.Tensor):     # already resident (e.g. binned on the device from peak lists)
+            self.targets = targets.to(self.device, torch.float32).contiguous()
+        else:
+            self.targets = None if targets is None else up(np.asarray(targets, np.float32), torch.float32)
         self.peaks = peaks
+        self._make_struct()
+
+    @classmethod
+    def from_device(cls, node_ptr, bond_ptr, feat, bond_begin, bond_end, targets=None, peaks: "DevicePeaks" = None):
+        """A data set whose flat arrays are device tensors already (assembled on the GPU, e.g. from the shards the
+        ranks of a data-parallel job generated)."""
+        self = cls.__new__(cls)
+        self.device = node_ptr.device
+        self.num_mols = node_ptr.numel() - 1
+        self.node_ptr, self.bond_ptr = node_ptr.to(torch.int64).contiguous(), bond_ptr.to(torch.int64).contiguous()
+        self.host_num_atoms = torch.diff(self.node_ptr).cpu().numpy().astype(np.int64)
+        self.host_num_bonds = torch.diff(self.bond_ptr).cpu().numpy().astype(np.int64)
+        self.feat = feat.to(torch.float32).contiguous().view(-1)
+        self.bond_begin, self.bond_end = bond_begin.to(torch.int32).contiguous(), bond_end.to(torch.int32).contiguous()
+        self.targets = None if targets is None else targets.to(torch.float32).contiguous()
+        self.peaks = peaks
+        self._make_struct()
+        return self
+
+    def _make_struct(self):
+        peaks = self.peaks
         self._struct = Dataset(self.node_ptr.data_ptr(), self.bond_ptr.data_ptr(), self.feat.data_ptr(),
                                self.bond_begin.data_ptr(), self.bond_end.data_ptr(),
                                0 if self.targets is None else self.targets.data_ptr(), self.num_mols,
@@ -436,6 +476,30 @@ class Plan:
         for l in range(self.d.num_gcn_layers):
             fp.num_batches_tracked[l] += 1
 
+    # -- device step block / CUDA-graph replay (include/eims_b200.h, "one optimiser step as a replayable CUDA graph")
+    def enable_step_block(self):
+        if getattr(self, "_step_block", None) is None:
+            n = int(self.lib.eims_step_block_bytes())
+            self._step_block = torch.zeros((n + 15) // 16 * 16, dtype=torch.uint8, device=self.device)
+            check(self.lib.eims_plan_set_step_block(self.h, ptr(self._step_block), self._step_block.numel()))
+        return self._step_block
+
+    def step_block_upload(self, step: Step, ids, dp_seq: int = 0):
+        """Rewrite the device step block: AdamW scalars + dropout keys of `step`, the ids the next indirect batch
+        build reads, the data-parallel sequence number.  One 1-block kernel on the current stream."""
+        check(self.lib.eims_step_block_upload(self.h, C.byref(step), ptr(ids), C.c_uint32(int(dp_seq) & 0xffffffff), self.stream))
+
+    def batch_build_indirect(self, ds: DeviceDataset, num_graphs: int):
+        check(self.lib.eims_batch_build_indirect(self.h, C.byref(ds.struct), int(num_graphs), self.stream))
+        self.num_graphs = int(num_graphs)
+
+    def train_step_built_indirect(self, ds: DeviceDataset, fp: FlatParams, metrics=None, loss_kind="mse", optimizer=True):
+        if optimizer:
+            fp.ensure_adam()
+        check(self.lib.eims_train_step_built_indirect(self.h, ptr(self._targets(ds)), ptr(fp.params), ptr(fp.grads),
+                                                      ptr(fp.adam_m) if optimizer else None, ptr(fp.adam_v) if optimizer else None,
+                                                      ptr(fp.bn_running), _lib.LOSS[loss_kind], ptr(metrics), self.stream))
+
     # -- per-stage profiling (bench.py) ------------------------------------------------
     def profile(self, enable: bool):
         check(self.lib.eims_plan_profile(self.h, int(enable)))
@@ -454,3 +518,69 @@ class Plan:
                                         ptr(out), self.stream))
         self.num_graphs = n
         return out if out is not None else self.buffer("prob", torch.float32, (n, self.d.max_mz))
+
+
+class GraphedTrainStep:
+    """One optimiser step (GCN:410-431) as a replayed CUDA graph: per step the host issues one tiny
+    kernel (the step-block upload) and one cudaGraphLaunch instead of ~30 kernel launches, so a
+    descheduled Python thread no longer stalls the GPU - which matters most in data-parallel runs,
+    where every rank waits for the slowest one at the gradient exchange.
+
+    Graph k (k = 0, 1; the plan double-buffers its batch tables) holds
+        main stream:  forward + loss + backward + AdamW on table set k   [+ fused exchange kernel]
+        side stream:  K1 batch build of the NEXT batch into table set 1-k
+    and the two alternate.  torch is plumbing here (stream capture, graph launch)."""
+
+    def __init__(self, plan: Plan, ds: DeviceDataset, fp: FlatParams, batch: int, metrics=None, loss_kind="mse", fused=None):
+        self.plan, self.ds, self.fp, self.batch, self.metrics, self.loss_kind, self.fused = plan, ds, fp, int(batch), metrics, loss_kind, fused
+        self.graphs, self.k, self.primed = [], 0, False
+        self.side = torch.cuda.Stream(plan.device)
+        plan.enable_step_block()
+        if fused is None:
+            fp.ensure_adam()
+
+    def _enqueue(self, step_for_fused=None):
+        plan, cur = self.plan, torch.cuda.current_stream(self.plan.device)
+        self.side.wait_stream(cur)                       # fork: the build may start with the step
+        if self.fused is not None:
+            self.fused.begin_step()
+        plan.train_step_built_indirect(self.ds, self.fp, self.metrics, self.loss_kind, optimizer=self.fused is None)
+        if self.fused is not None:
+            self.fused.finish(step_for_fused, plan.stream, step_block=plan._step_block)
+        with torch.cuda.stream(self.side):
+            plan.batch_build_indirect(self.ds, self.batch)
+        cur.wait_stream(self.side)                       # join
+
+    def capture(self, first_ids, step: Step):
+        """Builds batch `first_ids` for real (cold start), then captures the two graphs.  Call after a few
+        eager warm-up steps (module loading and one-time attribute calls must not happen under capture)."""
+        plan = self.plan
+        plan.step_block_upload(step, first_ids, 0)       # also loads the upload kernel before capture
+        plan.batch_build(self.ds, first_ids, self.batch)
+        torch.cuda.synchronize(plan.device)
+        seq0 = self.fused.seq if self.fused is not None else 0
+        for _ in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue(step)
+            self.graphs.append(g)
+        if self.fused is not None:
+            self.fused.seq = seq0                        # capture enqueued nothing
+        self._keep = first_ids
+        self.k, self.primed = 0, True
+
+    def step(self, step: Step, next_ids):
+        """Runs the step on the batch built last and builds `next_ids` (same length as every batch) for the
+        following call."""
+        if not self.primed:
+            raise RuntimeError("GraphedTrainStep.capture() first")
+        dp_seq = 0
+        if self.fused is not None:
+            self.fused.seq += 1
+            dp_seq = self.fused.seq
+        self.plan.step_block_upload(step, next_ids, dp_seq)
+        self._keep = next_ids
+        self.graphs[self.k].replay()
+        self.k ^= 1
+        for l in range(self.plan.d.num_gcn_layers):
+            self.fp.num_batches_tracked[l] += 1

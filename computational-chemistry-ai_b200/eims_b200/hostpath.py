@@ -30,7 +30,15 @@ class PackedHostBatch:
     [... | feat f32 | peak_ptr i64 | peak_mz f32/f64 | peak_inten f32]  (binned on the device inside
     the loss kernel: ~1 KB instead of 4*max_mz bytes per molecule over PCIe)."""
 
-    def __init__(self, table: MolTable, targets: np.ndarray | None, pin=True, peaks=None):
+    @staticmethod
+    def bytes_needed(table: MolTable, max_mz: int) -> int:
+        """Size of the packed buffer of `table` with dense [B, max_mz] targets."""
+        B, N, nb = table.num_mols, int(table.node_ptr[-1]), int(table.bond_ptr[-1])
+        F = table.feat.shape[1] if table.feat.ndim == 2 else 6
+        return sum(_align(x) for x in (8 * (B + 1), 8 * (B + 1), 4 * nb, 4 * nb, 4 * N * F, 4 * B * int(max_mz)))
+
+    def __init__(self, table: MolTable, targets: np.ndarray | None, pin=True, peaks=None, out=None):
+        """out: an existing (pinned) uint8 buffer of at least the packed size to write into instead of allocating."""
         B, N, nb = table.num_mols, int(table.node_ptr[-1]), int(table.bond_ptr[-1])
         F = table.feat.shape[1] if table.feat.ndim == 2 else 6
         parts = [("node_ptr", table.node_ptr.astype(np.int64)), ("bond_ptr", table.bond_ptr.astype(np.int64)),
@@ -53,7 +61,12 @@ class PackedHostBatch:
             self.offsets[name] = off
             off = _align(off + a.nbytes)
         self.nbytes = off
-        self.buf = torch.empty(off, dtype=torch.uint8, pin_memory=pin)
+        if out is not None:
+            if out.numel() < off:
+                raise ValueError(f"staging buffer too small: {out.numel()} < {off}")
+            self.buf = out
+        else:
+            self.buf = torch.empty(off, dtype=torch.uint8, pin_memory=pin)
         view = self.buf.numpy()
         for name, a in parts:
             o = self.offsets[name]
@@ -63,10 +76,76 @@ class PackedHostBatch:
         self.has_peaks = targets is None and peaks is not None
 
 
+class HostDataset:
+    """A MolTable (+ dense target rows or peak lists) in HOST memory behind an `eims_dataset` of host pointers:
+    what the reference's `OptimizedEIMSDataset` holds (GCN:227-258), packed."""
+
+    def __init__(self, table: MolTable, targets: np.ndarray | None = None, peaks=None):
+        c = np.ascontiguousarray
+        self.node_ptr, self.bond_ptr = c(table.node_ptr, np.int64), c(table.bond_ptr, np.int64)
+        self.feat = c(table.feat, np.float32).reshape(-1, table.feat.shape[1] if table.feat.ndim == 2 else 6)
+        self.bond_begin, self.bond_end = c(table.bond_begin, np.int32), c(table.bond_end, np.int32)
+        self.feat_dim = self.feat.shape[1]
+        self.targets = None if targets is None else c(targets, np.float32)
+        self.max_mz = 0 if self.targets is None else self.targets.shape[1]
+        self.num_mols = len(self.node_ptr) - 1
+        self._peaks = None
+        a = lambda x: x.ctypes.data if x is not None and x.size else None
+        if targets is None and peaks is not None:
+            pptr, mz, inten = peaks
+            mz = c(mz)
+            if mz.dtype != np.float32:
+                mz = mz.astype(np.float64)
+            self._pk_arrays = (c(pptr, np.int64), mz if mz.size else np.zeros(1, mz.dtype),
+                               c(inten, np.float32) if len(inten) else np.zeros(1, np.float32))
+            self._peaks = _lib.Peaks(self._pk_arrays[0].ctypes.data, self._pk_arrays[1].ctypes.data,
+                                     self._pk_arrays[2].ctypes.data, int(mz.dtype == np.float64), self.num_mols)
+        self.struct = Dataset(self.node_ptr.ctypes.data, self.bond_ptr.ctypes.data, self.feat.ctypes.data,
+                              a(self.bond_begin) or self.node_ptr.ctypes.data, a(self.bond_end) or self.node_ptr.ctypes.data,
+                              a(self.targets), self.num_mols, C.pointer(self._peaks) if self._peaks is not None else None)
+
+
+class HostPacker:
+    """`collate_fn` (GCN:292-297) + pin_memory (GCN:567) as one C call (`eims_host_pack_batch`): gathers a batch of
+    molecule ids from a HostDataset straight into a pinned buffer of a small ring, ready for ONE H2D copy.
+    The ring buffer handed out by `pack` is reused `n_buffers` calls later; by then its upload
+    (`HostBatchRunner.upload`, which records the buffer's event) has long finished, and `pack` waits if not."""
+
+    def __init__(self, hds: HostDataset, max_mz: int, capacity_bytes: int, n_buffers: int = 4, pin: bool = True):
+        self.hds, self.max_mz = hds, int(max_mz or hds.max_mz)
+        self.lib = _lib.load()
+        self.bufs = [torch.empty(int(capacity_bytes), dtype=torch.uint8, pin_memory=pin) for _ in range(n_buffers)]
+        self.events = [None] * n_buffers
+        self._i = 0
+
+    def pack(self, ids: np.ndarray) -> PackedHostBatch:
+        k = self._i % len(self.bufs)
+        self._i += 1
+        if self.events[k] is not None:
+            self.events[k].synchronize()      # the H2D copy that read this buffer has completed
+        ids = np.ascontiguousarray(ids, np.int32)
+        lay = _lib.HostBatchLayout()
+        buf = self.bufs[k]
+        check(self.lib.eims_host_pack_batch(C.byref(self.hds.struct), C.c_void_p(ids.ctypes.data), len(ids), self.hds.feat_dim,
+                                            self.max_mz, C.c_void_p(buf.data_ptr()), buf.numel(), C.byref(lay)))
+        hb = PackedHostBatch.__new__(PackedHostBatch)
+        hb.offsets = {n: getattr(lay, n) for n in ("node_ptr", "bond_ptr", "bond_begin", "bond_end", "feat", "targets", "peak_ptr",
+                                                   "peak_mz", "peak_inten") if getattr(lay, n) >= 0}
+        hb.nbytes, hb.buf, hb.mz_is_f64 = int(lay.nbytes), buf, int(lay.mz_is_f64)
+        hb.num_graphs, hb.num_nodes, hb.num_edges, hb.feat_dim = lay.num_graphs, lay.num_nodes, lay.num_edges, lay.feat_dim
+        hb.has_targets, hb.has_peaks = lay.targets >= 0, lay.peak_ptr >= 0
+        if buf.is_pinned() and torch.cuda.is_available():
+            if self.events[k] is None:
+                self.events[k] = torch.cuda.Event()
+            hb._ring_event = self.events[k]
+        return hb
+
+
 class HostBatchRunner:
     """Runs training / inference steps whose inputs start in (pinned) host memory."""
 
-    def __init__(self, plan, fp, capacity_bytes, n_slots=2):
+    def __init__(self, plan, fp, capacity_bytes, n_slots=2, metrics=None):
+        """metrics: the caller's device tensor [8] the steps accumulate into (kept across runner rebuilds)."""
         self.plan, self.fp = plan, fp
         dev = plan.device
         self.slots = [torch.empty(capacity_bytes, dtype=torch.uint8, device=dev) for _ in range(n_slots)]
@@ -74,8 +153,12 @@ class HostBatchRunner:
         self.copied = [torch.cuda.Event() for _ in range(n_slots)]
         self.consumed = [None] * n_slots
         self.built = [False] * n_slots
-        self.metrics = torch.zeros(8, dtype=torch.float32, device=dev)
-        self.host_metrics = torch.zeros(8, dtype=torch.float32, pin_memory=True)
+        self.metrics = metrics if metrics is not None else torch.zeros(8, dtype=torch.float32, device=dev)
+        # the per-step loss / cosine come back through two pinned buffers used in turn, each with the event of its
+        # device-to-host copy: the host reads a step's values only after that event (`read`), one step behind the GPU
+        self.host_ring = [torch.zeros(8, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        self.d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self._n = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._i = 0
@@ -113,6 +196,8 @@ class HostBatchRunner:
                                                      C.c_void_p(self.copy_stream.cuda_stream)))
             self.built[slot] = build
             self.copied[slot].record(self.copy_stream)
+            if getattr(hb, "_ring_event", None) is not None:
+                hb._ring_event.record(self.copy_stream)   # the pinned ring buffer may be repacked after this
         self.h2d_bytes += hb.nbytes
         return slot
 
@@ -146,7 +231,10 @@ class HostBatchRunner:
         ev = torch.cuda.Event()
         ev.record(cur)
         self.consumed[slot] = ev
-        self.host_metrics.copy_(self.metrics, non_blocking=True)
+        k = self._n % 2
+        self.host_ring[k].copy_(self.metrics, non_blocking=True)
+        self.d2h_done[k].record(cur)
+        self._n += 1
         self.d2h_bytes += self.metrics.numel() * 4
         for l in range(self.plan.d.num_gcn_layers):
             fp.num_batches_tracked[l] += 1
@@ -165,7 +253,15 @@ class HostBatchRunner:
         out_host[:hb.num_graphs].copy_(prob, non_blocking=True)
         self.d2h_bytes += prob.numel() * 4
 
+    def read(self, lag: int = 1):
+        """(loss, cosine) of the training step `lag` steps before the one enqueued last (lag 0 or 1), after waiting
+        for THAT step's device-to-host copy only - with lag 1 the GPU keeps running the current step meanwhile."""
+        if self._n - 1 - lag < 0:
+            return None
+        k = (self._n - 1 - lag) % 2
+        self.d2h_done[k].synchronize()
+        return float(self.host_ring[k][4]), float(self.host_ring[k][5])
+
     def result(self):
-        """(loss, cosine) of the last finished training step (host sync)."""
-        torch.cuda.current_stream(self.plan.device).synchronize()
-        return float(self.host_metrics[4]), float(self.host_metrics[5])
+        """(loss, cosine) of the last enqueued training step (waits for it)."""
+        return self.read(0)

@@ -450,12 +450,56 @@ class GCNSpectrum(nn.Module):
 
 
 # ------------------------------------------------------------------------------ training (GCN:382-488)
+def _zero_in_degree(table: MolTable) -> bool:
+    """True when some atom of the batch has no bond: DGL's GraphConv (allow_zero_in_degree=False, the default the
+    reference uses, GCN:316,321) raises DGLError on the first forward of such a batch."""
+    n = int(table.node_ptr[-1])
+    if n == 0:
+        return False
+    off = np.repeat(table.node_ptr[:-1], np.diff(table.bond_ptr))
+    deg = np.bincount(table.bond_begin + off, minlength=n) + np.bincount(table.bond_end + off, minlength=n)
+    return bool((deg == 0).any())
+
+
+def _loader_capacity(loaders, fallback):
+    """(graphs, atoms, directed edges, bytes of a dense-target batch) no batch of these loaders can exceed: the
+    batch_size largest molecules of the underlying data set.  Sizes the plan and the staging buffers ONCE, before
+    the first step.  None when the loaders do not expose a dataset of MolGraphs (then `fallback` grows on demand)."""
+    try:
+        bs, atoms, bonds, M = 0, [], [], 0
+        for ld in loaders:
+            ds = ld.dataset
+            base, idx = (ds.dataset, ds.indices) if hasattr(ds, "indices") else (ds, range(len(ds)))
+            graphs = base.graphs
+            if not all(isinstance(graphs[i], MolGraph) for i in list(idx)[:4]):
+                return None
+            bs = max(bs, int(ld.batch_size))
+            atoms += [graphs[i].num_nodes() for i in idx]
+            bonds += [len(graphs[i]._bb) for i in idx]
+            M = max(M, int(np.asarray(base.spectra).shape[1]))
+        top = lambda v: int(np.sort(np.asarray(v))[::-1][:bs].sum())
+        n, b = top(atoms), top(bonds)
+        nbytes = 16 * (bs + 1) + 8 * b + 24 * n + 4 * bs * M + 8 * 256
+        return bs, n, 2 * b, nbytes
+    except Exception:
+        return fallback
+
+
 def train_model(model, train_loader, val_loader, config, loss="mse", world_size=1, allreduce=None, verbose=True):
     """AdamW(lr, weight_decay) + OneCycleLR(max_lr=lr, epochs, steps_per_epoch) + MSE loss, the
     cosine metric per step, an eval pass per epoch, the same history dict and prints
     (GCN:382-488).  Differences by construction: one fused call per step (K1, forward, loss +
     metric, backward, AdamW) and the running loss / cosine stay on the device until the end of
-    the epoch instead of three `.item()` syncs per step."""
+    the epoch instead of three `.item()` syncs per step; the device-side flags (isolated atoms, capacity, non-finite
+    loss, a lost data-parallel peer) are read with them, once per epoch.
+
+    Data parallel (new: the reference is single-GPU, GCN:63): under torchrun with an initialised process group and
+    world_size > 1 every rank calls this with ITS shard's loader (same number of steps on every rank, e.g.
+    `dist.shard_epoch`); gradients are exchanged and the optimiser applied by the fused NVLink kernel
+    (`dist.FusedP2PAdamW`), all ranks hold bit-identical weights, BatchNorm statistics stay rank-local (DDP without
+    SyncBN) and every rank runs the (replicated) validation pass.  `allreduce` (a callable on the flat gradient
+    tensor) selects the plain all-reduce + AdamW path instead."""
+    import torch.distributed as tdist
     from .hostpath import HostBatchRunner
     dev = model.flat.device
     steps_per_epoch = len(train_loader)
@@ -463,22 +507,48 @@ def train_model(model, train_loader, val_loader, config, loss="mse", world_size=
     history = {"train_loss": [], "val_loss": [], "train_cosine": [], "val_cosine": []}
     best_val_cosine = 0
     k = 0
-    runner = None
+    runner, fused = None, None
+    metrics = torch.zeros(8, dtype=torch.float32, device=dev)   # epoch sums live here, whatever happens to the runner
+    cap = _loader_capacity((train_loader, val_loader), None)
+    if cap is not None:   # size the plan and the staging slots once, from the data set's maxima: nothing regrows mid-epoch
+        model._engine(cap[0], cap[1], cap[2])
+    pinned, pinned_ev = [], [None, None, None]   # ring of pinned staging buffers, reused (a fresh cudaHostAlloc per step costs
+                                                 # more than the step); a buffer is repacked only after the copy that read it
+    use_fused = world_size > 1 and allreduce is None and tdist.is_available() and tdist.is_initialized()
     for epoch in range(config.num_epochs):
         model.train()
-        metrics_sum = None
+        metrics.zero_()
         for batch_graph, batch_spectra in train_loader:
-            hb = PackedHostBatch(batch_graph.table, batch_spectra.numpy(), pin=True)
+            if _zero_in_degree(batch_graph.table):
+                raise _lib.ZeroInDegreeError(_lib.ERR_ZERO_DEGREE, "There are 0-in-degree nodes in the graph (DGL GraphConv would raise)")
+            ring = k % 3
+            if pinned_ev[ring] is not None:
+                pinned_ev[ring].synchronize()
+            else:
+                pinned_ev[ring] = torch.cuda.Event()
+            need = PackedHostBatch.bytes_needed(batch_graph.table, batch_spectra.shape[1])
+            if len(pinned) <= ring or pinned[ring].numel() < need:
+                size = max(need, cap[3] if cap else 0)
+                buf = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+                pinned[ring:ring + 1] = [buf]
+            hb = PackedHostBatch(batch_graph.table, batch_spectra.numpy(), out=pinned[ring])
+            hb._ring_event = pinned_ev[ring]   # recorded by runner.upload after the H2D copy
             plan, fp = model._engine(hb.num_graphs, hb.num_nodes, hb.num_edges)
             if runner is None or runner.plan is not plan or runner.slots[0].numel() < hb.nbytes:
-                runner = HostBatchRunner(plan, fp, max(2 * hb.nbytes, 1 << 20))
-            if metrics_sum is None:
-                runner.metrics.zero_()
-                metrics_sum = runner.metrics
+                runner = HostBatchRunner(plan, fp, max(2 * hb.nbytes, cap[3] if cap else 0, 1 << 20), metrics=metrics)
+            if use_fused and fused is None:
+                from .dist import FusedP2PAdamW, broadcast_params
+                broadcast_params(fp)
+                fused = FusedP2PAdamW(fp, model.dims.num_gcn_layers, overlap=False)
+                model.flat.data = fp.params        # the parameters now live in the symmetric (peer-mapped) buffer
             st = make_step(lr=sched[k][0], beta1=sched[k][1], weight_decay=config.weight_decay, step=k + 1,
                            seed=model._seed, grad_scale=1.0 / world_size)
             slot = runner.upload(hb)
-            if allreduce is None:
+            if fused is not None:
+                fused.begin_step()
+                runner.train_step(slot, hb, st, loss, optimizer=False)
+                fused.finish(st, plan.stream)
+            elif allreduce is None:
                 runner.train_step(slot, hb, st, loss)
             else:
                 runner.train_step(slot, hb, st, loss, optimizer=False)
@@ -486,7 +556,13 @@ def train_model(model, train_loader, val_loader, config, loss="mse", world_size=
                 plan.adamw(fp, st)
             model._step = k + 1
             k += 1
-        m = runner.metrics.cpu().numpy()
+        m = metrics.cpu().numpy()
+        if runner is not None:
+            runner.plan.check()    # capacity / isolated-atom flags K1 left on the device (raises like DGL's GraphConv)
+        if m[6] > 0:
+            raise FloatingPointError(f"the training loss was NaN / Inf in {int(m[6])} step(s) of epoch {epoch + 1}")
+        if fused is not None and fused.lost_peer():
+            raise RuntimeError(f"a data-parallel peer did not arrive at the gradient exchange (sequence {fused.lost_peer()})")
         train_loss, train_cosine = float(m[0] / max(m[2], 1)), float(m[1] / max(m[2], 1))
         model.eval()
         vm = torch.zeros(8, device=dev)
@@ -576,6 +652,43 @@ def predict_graphs(model, graphs, batch_size=4096, top_k=0):
             np.concatenate(vals) if vals else np.zeros((0, top_k), np.float32))
 
 
+# ------------------------------------------------------------------------------ data parallel (new; the reference is single-GPU)
+def _init_data_parallel():
+    """(world, rank).  Under torchrun (WORLD_SIZE > 1 in the environment) joins the NCCL process group, one process
+    per GPU; otherwise (1, 0) and nothing is initialised - the script behaves exactly like the reference."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1 or not torch.cuda.is_available():
+        return 1, 0
+    import torch.distributed as tdist
+    global device
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if not tdist.is_initialized():
+        tdist.init_process_group("nccl", device_id=device)
+    return world, tdist.get_rank()
+
+
+class ShardedLoader:
+    """The train loader of one rank of a data-parallel run: every epoch one shuffle shared by all ranks
+    (`dist.shard_epoch`: rank r takes every world-th element, the tail that does not fill a batch on every rank is
+    dropped so that all ranks take the same number of steps), collated like the reference's DataLoader (GCN:561-568)."""
+
+    def __init__(self, dataset, batch_size, world, rank, seed=0):
+        self.dataset, self.batch_size, self.world, self.rank, self.seed, self.epoch = dataset, int(batch_size), world, rank, seed, 0
+        from .dist import shard_epoch
+        self._shard = shard_epoch
+
+    def __len__(self):
+        return len(self.dataset) // (self.world * self.batch_size)
+
+    def __iter__(self):
+        ids = self._shard(len(self.dataset), self.world, self.rank, self.batch_size, self.epoch, self.seed)
+        self.epoch += 1
+        for row in ids:
+            yield collate_fn([self.dataset[int(i)] for i in row])
+
+
 # ------------------------------------------------------------------------------ CLI (GCN:517-633)
 def build_parser():
     parser = argparse.ArgumentParser(description="GCN-based EI-MS Spectrum Prediction")
@@ -604,15 +717,26 @@ def main(argv=None):
         print(f"Found {len(mol_files)} molecule files")
         dataset = OptimizedEIMSDataset(mol_files, msp_files, config)
         train_idx, val_idx = train_test_split(range(len(dataset)), test_size=0.2, random_state=42)
+        world, rank = _init_data_parallel()
         mk = lambda idx, shuffle: torch.utils.data.DataLoader(torch.utils.data.Subset(dataset, idx), batch_size=config.batch_size,
-                                                              shuffle=shuffle, collate_fn=collate_fn, num_workers=config.num_workers)
-        train_loader, val_loader = mk(train_idx, True), mk(val_idx, False)
+                                                              shuffle=shuffle, collate_fn=collate_fn, num_workers=config.num_workers,
+                                                              pin_memory=False)  # the step packs straight into its own pinned ring (GCN:567)
+        if world > 1:
+            # one process per GPU (torchrun): rank r trains on its shard of every epoch's shuffle, same step count on every rank
+            train_loader = ShardedLoader(torch.utils.data.Subset(dataset, train_idx), config.batch_size, world, rank)
+        else:
+            train_loader = mk(train_idx, True)
+        val_loader = mk(val_idx, False)
         sample_graph, _ = dataset[0]
         model = GCNSpectrum(sample_graph.ndata["feat"].shape[1], config).to(device)
         print(f"Model parameters: {sum(p.numel() for p in model.parameters())}")
-        model, history = train_model(model, train_loader, val_loader, config)
-        torch.save({"model_state_dict": model.state_dict(), "config": config.__dict__, "history": history}, config.model_save_path)
-        print(f"Model saved to {config.model_save_path}")
+        model, history = train_model(model, train_loader, val_loader, config, world_size=world, verbose=(rank == 0))
+        if rank == 0:   # every rank holds the same weights; rank 0 writes the reference-format checkpoint (GCN:589-593)
+            torch.save({"model_state_dict": model.state_dict(), "config": config.__dict__, "history": history}, config.model_save_path)
+            print(f"Model saved to {config.model_save_path}")
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
     elif args.mode == "predict":
         if args.smiles:
             checkpoint = torch.load(config.model_save_path)

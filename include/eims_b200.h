@@ -190,6 +190,20 @@ int eims_adamw_flat(float* p, float* g, float* m, float* v, int64_t n, const eim
 int eims_dropout_mask(float drop_p, uint64_t seed, int32_t step, int32_t site,
                       int32_t rows, int32_t width, float* out, eims_stream_t stream);
 
+/* ---------------------------------------------------------------- host-side collate
+ * For callers whose data set lives in HOST memory (the reference's case): replaces collate_fn -> dgl.batch +
+ * torch.stack (GCN:292-297) and the DataLoader's pin_memory copy (GCN:567).  `ds` holds HOST pointers here; the
+ * batch `ids` (NULL = 0..n-1) is gathered into the caller's (pinned) buffer `out` in the packed layout that
+ * eims_batch_build reads after ONE host-to-device copy of `lay->nbytes` bytes; section offsets (bytes, 256-aligned,
+ * -1 = absent) come back in `lay`.  Targets: dense rows when ds->targets != NULL, else the peak lists of ds->peaks.
+ * Returns EIMS_ERR_CAPACITY (with lay->nbytes = the size needed) when `out` is too small.  Pure host code. */
+typedef struct {
+  int64_t node_ptr, bond_ptr, bond_begin, bond_end, feat, targets, peak_ptr, peak_mz, peak_inten, nbytes;
+  int32_t num_graphs, num_nodes, num_edges, feat_dim, mz_is_f64;
+} eims_host_batch;
+int eims_host_pack_batch(const eims_dataset* ds, const int32_t* ids, int32_t n, int32_t node_feat_dim, int32_t max_mz,
+                         void* out, int64_t capacity, eims_host_batch* lay);
+
 /* ---------------------------------------------------------------- plan: the whole path */
 int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, int32_t max_edges,
                      eims_plan** out);
@@ -234,7 +248,8 @@ int eims_backward(eims_plan* p, const float* params, const float* dprob, float* 
 int eims_backward_part(eims_plan* p, const float* params, const float* dprob, float* grads, int32_t part,
                        eims_stream_t stream);
 /* metrics[8] (device): [0..2] += {sum_b row_loss/(B*M), mean_b row_cos, 1}; [4],[5] = this step's loss / cosine  - the per-step
- * `loss.item()` / `cos_sim.mean().item()` of GCN:436-437 without the host syncs. */
+ * `loss.item()` / `cos_sim.mean().item()` of GCN:436-437 without the host syncs; [6] += 1 for every step whose loss
+ * was NaN / Inf (a guard the caller reads once per epoch together with the sums). */
 int eims_metrics_accumulate(eims_plan* p, float* metrics, eims_stream_t stream);
 
 /* One optimiser step: batch build + forward + loss + backward [+ AdamW when adam_m != NULL]. */
@@ -249,6 +264,24 @@ int eims_train_step(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids
 int eims_train_step_built(eims_plan* p, const float* targets, const int32_t* target_rows, float* params, float* grads,
                           float* adam_m, float* adam_v, float* bn_running, int32_t loss_kind, const eims_step* s,
                           float* metrics, eims_stream_t stream);
+/* ---- one optimiser step as a replayable CUDA graph (new: the reference launches ~150 library kernels per step
+ * from Python, GCN:410-431).  A captured graph freezes kernel parameters, so what changes from step to step - the
+ * ids of the batch to build, the AdamW scalars of the one-cycle schedule (GCN:386-391, 429-431), the dropout keys,
+ * the data-parallel sequence number - is kept in a small device "step block" (eims_step_block_bytes() bytes, caller
+ * owned, 16-byte aligned).  eims_step_block_upload rewrites it with ONE tiny kernel that takes the values as launch
+ * parameters (no host buffer has to stay alive); the *_indirect calls enqueue the same kernels as their plain
+ * namesakes but those read the step block at execution time.  Usage: capture
+ *     eims_train_step_built_indirect (main stream)  ||  eims_batch_build_indirect (side stream: next batch)
+ * once per table set (the plan double-buffers the batch tables, so two graphs alternate), then per step:
+ *     eims_step_block_upload(scalars of step t, ids of batch t+1) ; cudaGraphLaunch.
+ * The target row of graph b is the molecule id it was built from (the ids K1 read). */
+int64_t eims_step_block_bytes(void);
+int eims_plan_set_step_block(eims_plan* p, void* dev_block, int64_t bytes); /* NULL: indirect calls disabled */
+int eims_step_block_upload(eims_plan* p, const eims_step* s, const int32_t* mol_ids, uint32_t dp_seq, eims_stream_t stream);
+int eims_batch_build_indirect(eims_plan* p, const eims_dataset* ds, int32_t num_graphs, eims_stream_t stream);
+int eims_train_step_built_indirect(eims_plan* p, const float* targets, float* params, float* grads, float* adam_m,
+                                   float* adam_v, float* bn_running, int32_t loss_kind, float* metrics, eims_stream_t stream);
+
 /* predict_spectrum (GCN:494-511) for a batch: batch build + eval forward + sigmoid. */
 int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
                      const float* params, const float* bn_running, float* prob_out, eims_stream_t stream);
@@ -265,11 +298,20 @@ int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_id
  * and m_slice / v_slice / ticket belong to the bucket (range_len/world floats; one zeroed word).
  * zero_buf: this rank's OTHER gradient buffer (gradients are double-buffered because peers read
  * them); its range is zeroed here.  seq: 1, 2, 3, ... the same on every rank.
- * s->grad_scale = 1/world. */
+ * s->grad_scale = 1/world.  `ticket` points at 4 zeroed words of the bucket: word 0 is the grid ticket, word 1 a
+ * status word - a rank that waited longer than EIMS_DP_TIMEOUT_S (default 600 s) for a peer stores the sequence
+ * number there and carries on (no trap: the context stays usable and the host reports the lost peer).
+ * _blk: the same with the AdamW scalars and the sequence number read from a device step block (s, seq ignored when
+ * step_block != NULL) so that the launch can sit inside a captured CUDA graph. */
 int eims_dp_adamw_fused(int32_t rank, int32_t world, const uint64_t* grad_ptrs, const uint64_t* param_ptrs,
                         const uint64_t* signal_ptrs, uint64_t grads_multicast, uint64_t params_multicast,
                         float* m_slice, float* v_slice, float* zero_buf, int64_t range_off, int64_t range_len,
                         const eims_step* s, uint32_t seq, int32_t bucket, uint32_t* ticket, eims_stream_t stream);
+int eims_dp_adamw_fused_blk(int32_t rank, int32_t world, const uint64_t* grad_ptrs, const uint64_t* param_ptrs,
+                            const uint64_t* signal_ptrs, uint64_t grads_multicast, uint64_t params_multicast,
+                            float* m_slice, float* v_slice, float* zero_buf, int64_t range_off, int64_t range_len,
+                            const eims_step* s, uint32_t seq, int32_t bucket, uint32_t* ticket, const void* step_block,
+                            eims_stream_t stream);
 
 /* Per-stage device timing for the roofline report (bench.py): when enabled every kernel
  * launch of the plan is bracketed by CUDA events on the launching stream.  _read

@@ -92,3 +92,13 @@ def test_packed_cache_round_trip(tmp_path):
     assert np.array_equal(g.ndata["feat"].numpy(), table.mol(5)[0])
     from eims_b200.synth import dense_spectra
     assert np.array_equal(spec.numpy(), dense_spectra(ptr, mz, inten, 100)[5])
+
+
+def test_reference_msp_writer_round_trips_floats_exactly(tmp_path):
+    """`{:g}` rounded 101.49996 to '101.5' (bin 102 instead of 101) and truncated large intensities."""
+    from eims_b200.dataio import load_peaks_reference, write_reference_msp
+    peaks = [(101.49996, 1234567.25), (57.0, 999.0), (0.1 + 0.2, 1e-7), (300.5000001, 3.0)]
+    path = str(tmp_path / "x.msp")
+    write_reference_msp(path, {"fields": {"Name": "x"}, "peaks": peaks})
+    back = load_peaks_reference(path)
+    assert [(float(a), float(b)) for a, b in back] == [(float(a), float(b)) for a, b in peaks]

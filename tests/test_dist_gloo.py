@@ -139,3 +139,28 @@ def test_two_rank_gradient_average_equals_sequential_oracle(tmp_path):
     ref = (acc / WORLD).astype(np.float32)
     # fp32 round-off only (the in-process oracle may use a different torch thread count)
     assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-30)
+
+
+def test_global_batches_keep_the_uniform_global_batch_and_balance_atoms():
+    from eims_b200.dist import global_batches
+    table = synth_molecules(8 * 128 * 6 + 91, max_atoms=64, seed=8)
+    sizes = np.diff(table.node_ptr)
+    W, B = 8, 128
+    bal = [global_batches(sizes, W, r, B, epoch=4, seed=2) for r in range(W)]
+    ddp = [global_batches(sizes, W, r, B, epoch=4, seed=2, balance=False) for r in range(W)]
+    perm = np.random.Generator(np.random.PCG64([2, 4])).permutation(len(sizes))
+    assert all(b.shape == (6, B) and b.dtype == np.int32 for b in bal + ddp)
+    for k in range(6):
+        chunk = np.sort(perm[k * W * B:(k + 1) * W * B])
+        # the SET of molecules in the global batch is the reference's uniform draw, whatever the assignment
+        assert np.array_equal(np.sort(np.concatenate([b[k] for b in bal])), chunk)
+        assert np.array_equal(np.sort(np.concatenate([b[k] for b in ddp])), chunk)
+        assert np.array_equal(ddp[3][k], perm[k * W * B:(k + 1) * W * B][3::W])      # DistributedSampler order
+        wb = np.array([sizes[b[k]].sum() for b in bal])
+        wd = np.array([sizes[b[k]].sum() for b in ddp])
+        assert wb.max() - wb.min() <= 0.003 * wb.mean()                              # atoms per rank within 0.3 %
+        assert wd.max() - wd.min() > 5 * (wb.max() - wb.min())
+    assert np.array_equal(global_batches(sizes, 1, 0, B, 0, 2), global_batches(sizes, 1, 0, B, 0, 2, balance=False))
+    assert global_batches(sizes, W, 0, B, 0, 2, steps=2).shape == (2, B)
+    with pytest.raises(ValueError):
+        global_batches(sizes[:100], W, 0, B, 0)

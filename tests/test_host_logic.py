@@ -162,3 +162,44 @@ def test_bench_knows_the_work_of_every_stage():
         assert bound in ("hbm", "tensor") and w >= 0, name
     # the grouped launches count both gradients
     assert work["gemm_gcn_bwd"][1] == work["gemm_gcn_wgrad"][1] + work["gemm_gcn_dgrad"][1]
+
+
+def test_host_packer_equals_python_collate():
+    """`eims_host_pack_batch` (C, one call) produces byte for byte the packed batch the Python collate
+    (MolTable.select + PackedHostBatch) builds: dense targets and both peak-list precisions; capacity errors."""
+    import numpy as np
+    from eims_b200 import _lib
+    from eims_b200.hostpath import HostDataset, HostPacker, PackedHostBatch
+    from eims_b200.synth import _ranges, dense_spectra, synth_molecules, synth_peaks
+    n, M = 300, 200
+    table = synth_molecules(n, max_atoms=24, seed=5)
+    pk = synth_peaks(n, M, seed=6)
+    dense = dense_spectra(*pk, M)
+    ids = np.random.default_rng(1).permutation(n)[:77].astype(np.int32)
+    ref = PackedHostBatch(table.select(ids), dense[ids], pin=False)
+    got = HostPacker(HostDataset(table, dense), M, 1 << 20, n_buffers=2, pin=False).pack(ids)
+    assert got.nbytes == ref.nbytes and {k: v for k, v in got.offsets.items()} == ref.offsets
+    assert (got.num_graphs, got.num_nodes, got.num_edges, got.feat_dim) == (ref.num_graphs, ref.num_nodes, ref.num_edges, ref.feat_dim)
+    for name, o in ref.offsets.items():   # compare the live bytes of every section (padding is unspecified)
+        nxt = min([v for v in ref.offsets.values() if v > o] + [ref.nbytes])
+        live = {"node_ptr": 8 * 78, "bond_ptr": 8 * 78, "bond_begin": 2 * ref.num_edges, "bond_end": 2 * ref.num_edges,
+                "feat": 4 * ref.num_nodes * 6, "targets": 4 * 77 * M}[name]
+        assert live <= nxt - o
+        assert np.array_equal(got.buf.numpy()[o:o + live], ref.buf.numpy()[o:o + live]), name
+    for mz_dt in (np.float32, np.float64):
+        kk = np.diff(pk[0])[ids]
+        pp = np.zeros(len(ids) + 1, np.int64)
+        np.cumsum(kk, out=pp[1:])
+        sel = _ranges(pk[0][ids], kk)
+        refp = PackedHostBatch(table.select(ids), None, pin=False, peaks=(pp, pk[1][sel].astype(mz_dt), pk[2][sel]))
+        gotp = HostPacker(HostDataset(table, None, peaks=(pk[0], pk[1].astype(mz_dt), pk[2])), M, 1 << 20, 2, pin=False).pack(ids)
+        assert gotp.has_peaks and not gotp.has_targets and gotp.mz_is_f64 == int(mz_dt == np.float64)
+        assert gotp.nbytes == refp.nbytes and gotp.offsets == refp.offsets
+        nb = int(pp[-1])
+        for name, live in (("peak_ptr", 8 * 78), ("peak_mz", np.dtype(mz_dt).itemsize * nb), ("peak_inten", 4 * nb)):
+            o = refp.offsets[name]
+            assert np.array_equal(gotp.buf.numpy()[o:o + live], refp.buf.numpy()[o:o + live]), name
+    with pytest.raises(_lib.EimsError):
+        HostPacker(HostDataset(table, dense), M, 1024, 1, pin=False).pack(ids)
+    with pytest.raises(_lib.EimsError):
+        HostPacker(HostDataset(table, dense), M, 1 << 20, 1, pin=False).pack(np.array([n], np.int32))
