@@ -17,7 +17,7 @@ namespace eims {
 // aggregate a0 = A (x * c) of GraphConv (GCN:359, i = 0), which only needs the molecule itself.
 // dims[DIM_ZERO_DEG] holds the sequence number of the last batch that had an isolated atom and
 // dims[5] the current sequence number (no reset race between blocks).
-constexpr int kK1Warps = 4;
+constexpr int kK1Warps = 2;  // 256 blocks for a batch of 512: more than one per SM
 constexpr int kMaxF0 = 8;
 
 // Large batches (inference, thousands of molecules): the per-block batch reduction of the fused
@@ -89,6 +89,7 @@ struct K1Stage {  // per-warp staging
   int sb[kK1MaxB], se[kK1MaxB];   // bond ends (molecule-local)
   int scol[2 * kK1MaxB];          // CSR columns (molecule-local source atom)
   int srow[kK1MaxN + 1];          // row starts (molecule-local edge offset)
+  int scnt[kK1MaxN];              // per-atom counters of the counting sort (degree, then fill cursor)
   float snorm[kK1MaxN];
   float sx[kK1MaxN * kMaxF0];
 };
@@ -194,19 +195,38 @@ __global__ void __launch_bounds__(kK1Warps * 32) k1_build_kernel(
     if (staged) S.sx[t] = v;
   }
   for (int k = lane; k < nb; k += 32) {
-    const int bgn = __ldg(bond_begin + b_0 + k), end = __ldg(bond_end + b_0 + k);
+    int bgn = __ldg(bond_begin + b_0 + k), end = __ldg(bond_end + b_0 + k);
+    if ((unsigned)bgn >= (unsigned)n || (unsigned)end >= (unsigned)n) {  // corrupt table: flag it, stay in bounds
+      dims[DIM_OVERFLOW] = 1;
+      bgn = min(max(bgn, 0), n - 1);
+      end = min(max(end, 0), n - 1);
+    }
     if (staged) { S.sb[k] = bgn; S.se[k] = end; }
     src[eo + 2 * k] = o + bgn; dst[eo + 2 * k] = o + end;          // GCN:142-143: [b->e, e->b]
     src[eo + 2 * k + 1] = o + end; dst[eo + 2 * k + 1] = o + bgn;
   }
   __syncwarp();
-  // degrees (lane per atom) -> row starts, degree normalisation
+  // ---- counting sort of the directed edges by destination, in shared memory (staged molecules):
+  //   1. degree of every atom: one shared-memory atomic per bond end (lanes over bonds)
+  //   2. row starts: exclusive warp scan of the degrees (lanes over atoms), degree normalisation
+  //   3. every edge takes the next free slot of its destination row (lanes over edges, any order) ...
+  //   4. ... and every row sorts its <= deg slots by edge id (lanes over atoms): ascending edge id inside a row,
+  //      which is the order torch's index_add_ adds in.
+  // Oversized molecules (beyond the staging arrays) keep the O(bonds) scans per atom / per edge on global memory.
+  if (staged) {
+    for (int i = lane; i < n; i += 32) S.scnt[i] = 0;
+    __syncwarp();
+    for (int k = lane; k < nb; k += 32) { atomicAdd(&S.scnt[S.sb[k]], 1); atomicAdd(&S.scnt[S.se[k]], 1); }
+    __syncwarp();
+  }
   int run = 0;
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
     int deg = 0;
-    if (i < n)
-      for (int k = 0; k < nb; ++k) deg += (pe_[k] == i) + (pb[k] == i);
+    if (i < n) {
+      if (staged) { deg = S.scnt[i]; S.scnt[i] = 0; }  // the counter becomes the row's fill cursor
+      else for (int k = 0; k < nb; ++k) deg += (pe_[k] == i) + (pb[k] == i);
+    }
     int inc = deg;
 #pragma unroll
     for (int sft = 1; sft < 32; sft <<= 1) {
@@ -229,17 +249,40 @@ __global__ void __launch_bounds__(kK1Warps * 32) k1_build_kernel(
   if (staged && lane == 0) S.srow[n] = ne;
   __syncwarp();
   if (!staged) __threadfence_block();
-  // CSR columns (lane per directed edge): edge e = 2k (b->e) or 2k+1 (e->b) lands in row dst(e) at
-  // the rank it has among the edges with the same destination, i.e. in ascending edge id
-  for (int e = lane; e < ne; e += 32) {
-    const int k = e >> 1;
-    const int d = (e & 1) ? pb[k] : pe_[k], sv = (e & 1) ? pe_[k] : pb[k];
-    int rank = 0;
-    for (int k2 = 0; k2 < k; ++k2) rank += (pe_[k2] == d) + (pb[k2] == d);
-    if (e & 1) rank += (pe_[k] == d);  // edge 2k precedes edge 2k+1 (only matters for a self-bond)
-    const int pos = prow[d] - rowbase + rank;  // molecule-local edge offset
-    col[eo + pos] = o + sv;
-    if (staged) S.scol[pos] = sv;
+  if (staged) {
+    for (int e = lane; e < ne; e += 32) {   // edge e = 2k (b->e) or 2k+1 (e->b): destination = the other end
+      const int k = e >> 1;
+      const int d = (e & 1) ? S.sb[k] : S.se[k];
+      S.scol[S.srow[d] + atomicAdd(&S.scnt[d], 1)] = e;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const int a = S.srow[i], b = S.srow[i + 1];
+      for (int x = a + 1; x < b; ++x) {     // insertion sort of the row's edge ids (deg is a handful)
+        const int v = S.scol[x];
+        int y = x - 1;
+        while (y >= a && S.scol[y] > v) { S.scol[y + 1] = S.scol[y]; --y; }
+        S.scol[y + 1] = v;
+      }
+      for (int x = a; x < b; ++x) {          // edge id -> source atom
+        const int e = S.scol[x], k = e >> 1;
+        const int sv = (e & 1) ? S.se[k] : S.sb[k];
+        S.scol[x] = sv;
+        col[eo + x] = o + sv;
+      }
+    }
+  } else {
+    // CSR columns (lane per directed edge): edge e lands in row dst(e) at the rank it has among the edges with the
+    // same destination, i.e. in ascending edge id
+    for (int e = lane; e < ne; e += 32) {
+      const int k = e >> 1;
+      const int d = (e & 1) ? pb[k] : pe_[k], sv = (e & 1) ? pe_[k] : pb[k];
+      int rank = 0;
+      for (int k2 = 0; k2 < k; ++k2) rank += (pe_[k2] == d) + (pb[k2] == d);
+      if (e & 1) rank += (pe_[k] == d);  // edge 2k precedes edge 2k+1 (only matters for a self-bond)
+      const int pos = prow[d] - rowbase + rank;  // molecule-local edge offset
+      col[eo + pos] = o + sv;
+    }
   }
   if (!a0) return;
   __syncwarp();
@@ -528,11 +571,287 @@ __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------ K2, molecule tiles
+// The same aggregation with the neighbour rows STAGED IN SHARED MEMORY.  A batched graph is block diagonal and K1
+// lays the atoms of a molecule out contiguously, so everything row i of molecule g can reach is the contiguous
+// [n_g, H] tile h[gptr[g] .. gptr[g+1]): one block takes one molecule at a time, brings the tile in with the bulk
+// async-copy engine (cp.async.bulk global -> shared, completion on an mbarrier: ONE copy per molecule when the block
+// owns all H columns, else one per row of its column chunk), applies the per-row transform (BatchNorm apply, dropout,
+// source-side degree norm) ONCE per element in place, and sums the neighbours of every row out of shared memory.
+// Against the gather kernel above: every row of h is read from L2 once instead of deg ~ 2.06 times, and the
+// transform - the dropout hash made the forward gather instruction-issue bound - runs once per element instead of
+// once per gathered element.  Same neighbour order, same roundings: bit-identical output.
+// Molecules too large for the tile (n_g > cap_rows or more directed edges than cap_edges) take the gather path
+// inside the same kernel.  STATS as above (backward form only).
+constexpr int kMolThreads = 256;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init1(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a protocol bug must not hang the GPU
+  }
+}
+
+template <int NV, bool STATS>
+__global__ void __launch_bounds__(kMolThreads) spmm_mol_kernel(const int* __restrict__ dims, const int* __restrict__ gptr,
+                                                               const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                               const float* __restrict__ norm, const float* __restrict__ h, int H,
+                                                               const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
+                                                               DropCfg drop, int out_mode, float* __restrict__ out, int cap_rows,
+                                                               int cap_edges, BnBwdFuse bf) {
+  constexpr int HC = 128 * NV;  // columns a block owns
+  extern __shared__ __align__(128) uint8_t mol_smem[];
+  float* tile = reinterpret_cast<float*>(mol_smem);                    // [cap_rows][HC]
+  int* scol = reinterpret_cast<int*>(tile + (size_t)cap_rows * HC);    // [cap_edges] molecule-local source rows
+  int* srow = scol + cap_edges;                                        // [cap_rows + 1] molecule-local edge offsets
+  float* snorm = reinterpret_cast<float*>(srow + cap_rows + 1);        // [cap_rows]
+  float* s_stats = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(snorm + cap_rows) + 15) & ~(uintptr_t)15);  // STATS: [8 warps][2][HC]
+  __shared__ __align__(8) uint64_t bar_storage;
+  const uint32_t bar = smem_addr(&bar_storage);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) mbar_init1(bar);
+  __syncthreads();
+  pdl_sync();
+  drop = resolve_drop(drop);
+  const int B = dims[DIM_B], N = dims[DIM_N];
+  const int c0 = blockIdx.y * HC;
+  const bool has_bn = bn_scale != nullptr;
+  const bool in_drop = drop.active() && out_mode == 0;
+  const bool out_drop = drop.active() && out_mode == 1;
+  float4 sc[NV], sh[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = c0 + (v * 32 + lane) * 4;
+    sc[v] = make_float4(1.f, 1.f, 1.f, 1.f);
+    sh[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_bn && c < H) { sc[v] = ldg4(bn_scale + c); sh[v] = ldg4(bn_shift + c); }
+  }
+  // the transform pass maps threads to columns differently: float4 column tq of the chunk, fixed per thread
+  const int tq = tid % (HC / 4);
+  float4 ta = make_float4(1.f, 1.f, 1.f, 1.f), tb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (has_bn && c0 + tq * 4 < H) { ta = ldg4(bn_scale + c0 + tq * 4); tb = ldg4(bn_shift + c0 + tq * 4); }
+  float4 s1[STATS ? NV : 1], s2[STATS ? NV : 1];
+  if (STATS) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s1[v] = s2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  uint32_t phase = 0;
+  for (int g = blockIdx.x; g < B; g += gridDim.x) {
+    const int r0 = __ldg(gptr + g), r1 = __ldg(gptr + g + 1), n = r1 - r0;
+    if (n <= 0) continue;
+    const int e0 = __ldg(rowptr + r0), e1 = __ldg(rowptr + r1), ne = e1 - e0;
+    const bool staged = n <= cap_rows && ne <= cap_edges;
+    if (staged) {
+      // ---- stage: the tile through the bulk-copy engine, the molecule's CSR slice through ordinary loads
+      if (warp == 0) {
+        if (H == HC) {  // the block owns whole rows: the tile is one contiguous range of h
+          if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses to the tile precede the async write
+            mbar_expect_tx(bar, (uint32_t)n * HC * 4u);
+            bulk_g2s(smem_addr(tile), h + (size_t)r0 * H, (uint32_t)n * HC * 4u, bar);
+          }
+        } else {
+          if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, (uint32_t)n * HC * 4u);
+          }
+          __syncwarp();
+          for (int i = lane; i < n; i += 32) bulk_g2s(smem_addr(tile + (size_t)i * HC), h + (size_t)(r0 + i) * H + c0, HC * 4u, bar);
+        }
+      }
+      for (int e = tid; e < ne; e += kMolThreads) scol[e] = __ldg(col + e0 + e) - r0;
+      for (int i = tid; i <= n; i += kMolThreads) srow[i] = __ldg(rowptr + r0 + i) - e0;
+      for (int i = tid; i < n; i += kMolThreads) snorm[i] = __ldg(norm + r0 + i);
+      mbar_wait_parity(bar, phase);
+      phase ^= 1u;
+      if (out_mode == 0) {
+        __syncthreads();  // snorm visible
+        // ---- transform in place, once per element: fl( drop(bn(h_j)) * c_j ).  A thread keeps one float4 column
+        // (kMolThreads is a multiple of HC/4) and walks down the rows.
+        for (int j = tid / (HC / 4); j < n; j += kMolThreads / (HC / 4)) {
+          float4 x = *reinterpret_cast<float4*>(tile + (size_t)j * HC + tq * 4);
+          if (has_bn) {
+            x.x = fmaf(x.x, ta.x, tb.x); x.y = fmaf(x.y, ta.y, tb.y); x.z = fmaf(x.z, ta.z, tb.z); x.w = fmaf(x.w, ta.w, tb.w);
+          }
+          if (in_drop) {
+            const float4 m = drop_mask4(drop, (uint64_t)(r0 + j) * H + c0 + tq * 4);
+            x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+          }
+          const float cj = snorm[j];
+          x.x = __fmul_rn(x.x, cj); x.y = __fmul_rn(x.y, cj); x.z = __fmul_rn(x.z, cj); x.w = __fmul_rn(x.w, cj);
+          *reinterpret_cast<float4*>(tile + (size_t)j * HC + tq * 4) = x;
+        }
+      }
+      __syncthreads();
+    }
+    // ---- aggregate: warp per destination row, neighbours in ascending edge id
+    for (int i = warp; i < n; i += kMolThreads / 32) {
+      const int row = r0 + i;
+      float4 zrow[STATS ? NV : 1];
+      if (STATS) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c = c0 + (v * 32 + lane) * 4;
+          zrow[v] = c < H ? ldg4(bf.z + (int64_t)row * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      float4 acc[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (staged) {
+        const int a0 = srow[i], a1 = srow[i + 1];
+        for (int e = a0; e < a1; ++e) {
+          const float* src = tile + (size_t)scol[e] * HC;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const float4 x = *reinterpret_cast<const float4*>(src + (v * 32 + lane) * 4);
+            acc[v].x = __fadd_rn(acc[v].x, x.x); acc[v].y = __fadd_rn(acc[v].y, x.y);
+            acc[v].z = __fadd_rn(acc[v].z, x.z); acc[v].w = __fadd_rn(acc[v].w, x.w);
+          }
+        }
+      } else {  // oversized molecule: gather from global, transform on the fly (as spmm_norm_kernel does)
+        const int a0 = __ldg(rowptr + row), a1 = __ldg(rowptr + row + 1);
+        for (int e = a0; e < a1; ++e) {
+          const int j = __ldg(col + e);
+          const float cj = out_mode == 0 ? __ldg(norm + j) : 1.f;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            const int c = c0 + (v * 32 + lane) * 4;
+            if (c >= H) continue;
+            float4 x = ldg4(h + (int64_t)j * H + c);
+            if (has_bn) {
+              x.x = fmaf(x.x, sc[v].x, sh[v].x); x.y = fmaf(x.y, sc[v].y, sh[v].y);
+              x.z = fmaf(x.z, sc[v].z, sh[v].z); x.w = fmaf(x.w, sc[v].w, sh[v].w);
+            }
+            if (in_drop) {
+              const float4 m = drop_mask4(drop, (uint64_t)j * H + c);
+              x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+            }
+            if (out_mode == 0) {
+              x.x = __fmul_rn(x.x, cj); x.y = __fmul_rn(x.y, cj); x.z = __fmul_rn(x.z, cj); x.w = __fmul_rn(x.w, cj);
+            }
+            acc[v].x = __fadd_rn(acc[v].x, x.x); acc[v].y = __fadd_rn(acc[v].y, x.y);
+            acc[v].z = __fadd_rn(acc[v].z, x.z); acc[v].w = __fadd_rn(acc[v].w, x.w);
+          }
+        }
+      }
+      const float ci = out_mode == 1 ? (staged ? snorm[i] : __ldg(norm + row)) : 1.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = c0 + (v * 32 + lane) * 4;
+        if (c >= H) continue;
+        float4 a = acc[v];
+        if (out_mode == 1) {
+          a.x *= ci; a.y *= ci; a.z *= ci; a.w *= ci;
+          if (out_drop) {
+            const float4 m = drop_mask4(drop, (uint64_t)row * H + c);
+            a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w;
+          }
+        }
+        st4(out + (int64_t)row * H + c, a);
+        if (STATS) {
+          const float4 mu = ldg4(bf.mean + c), is = ldg4(bf.invstd + c);
+          s1[v].x += a.x; s1[v].y += a.y; s1[v].z += a.z; s1[v].w += a.w;
+          s2[v].x = fmaf(a.x, (zrow[v].x - mu.x) * is.x, s2[v].x); s2[v].y = fmaf(a.y, (zrow[v].y - mu.y) * is.y, s2[v].y);
+          s2[v].z = fmaf(a.z, (zrow[v].z - mu.z) * is.z, s2[v].z); s2[v].w = fmaf(a.w, (zrow[v].w - mu.w) * is.w, s2[v].w);
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with the tile and the index arrays before the next molecule overwrites them
+  }
+  if (STATS) {
+    // combine the block's warps in shared memory, one fp32 atomic per column and statistic into one of the
+    // replicas, finalise in the last block (same scheme as spmm_norm_kernel<.., true>; gridDim.y == 1 here)
+    float* mine = s_stats + warp * 2 * HC;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      st4(mine + (v * 32 + lane) * 4, s1[v]);
+      st4(mine + HC + (v * 32 + lane) * 4, s2[v]);
+    }
+    __syncthreads();
+    float* facc = reinterpret_cast<float*>(bf.acc);
+    for (int k = tid; k < 2 * H; k += kMolThreads) {
+      const int which = k / H, cc = k % H;
+      float t = 0.f;
+      for (int w = 0; w < kMolThreads / 32; ++w) t += s_stats[(w * 2 + which) * HC + cc];
+      atomicAdd(facc + (size_t)(blockIdx.x % kBnReplicas) * 2 * H + k, t);
+    }
+    if (!last_block_ticket(bf.ticket, gridDim.x)) return;
+    for (int k = tid; k < H; k += kMolThreads) {
+      double sa = 0.0, sb = 0.0;
+#pragma unroll
+      for (int r = 0; r < kBnReplicas; ++r) {
+        float* q = facc + (size_t)r * 2 * H;
+        sa += (double)__ldcg(q + k);
+        sb += (double)__ldcg(q + H + k);
+        q[k] = 0.f;
+        q[H + k] = 0.f;
+      }
+      bf.dbeta[k] += (float)sa;
+      bf.dgamma[k] += (float)sb;
+      bf.means[k] = N > 0 ? (float)(sa / N) : 0.f;
+      bf.means[H + k] = N > 0 ? (float)(sb / N) : 0.f;
+    }
+  }
+}
+
+static int launch_spmm_mol(const int* dims, const int* gptr, const int* rowptr, const int* col, const float* norm, const float* h,
+                           int H, const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
+                           int max_graphs, int tile_rows, cudaStream_t st, const BnBwdFuse* bf) {
+  // a block owns 256 columns when that keeps the tile at <= 64 KB (three blocks per SM), else 128
+  const int NV = (H % 256 == 0 && (size_t)tile_rows * 256 * 4 <= 64 * 1024) ? 2 : 1;
+  const int HC = 128 * NV;
+  if (H % HC) return EIMS_ERR_ARG;
+  if (bf && H != HC) return EIMS_ERR_ARG;  // the statistics variant owns whole rows
+  const int cap_edges = 4 * tile_rows + 64;
+  size_t smem = (size_t)tile_rows * HC * 4 + (size_t)cap_edges * 4 + (size_t)(tile_rows + 1) * 4 + (size_t)tile_rows * 4;
+  smem = (smem + 15) & ~(size_t)15;
+  if (bf) smem += (size_t)8 * 2 * HC * 4;
+  int gx = max_graphs < 1 ? 1 : max_graphs;
+  const int chunks = H / HC;
+  const int cap = 148 * 16 / chunks;   // grid-stride beyond a few waves (inference batches)
+  if (gx > cap) gx = cap > 0 ? cap : 1;
+  const BnBwdFuse none{};
+#define EIMS_MOL(NVv, ST)                                                                                                   \
+  do {                                                                                                                      \
+    static bool attr = false;                                                                                               \
+    if (!attr) { cudaFuncSetAttribute(spmm_mol_kernel<NVv, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; } \
+    launch_pdl(spmm_mol_kernel<NVv, ST>, dim3(gx, chunks), dim3(kMolThreads), smem, st, dims, gptr, rowptr, col, norm, h, H, bn_scale, \
+               bn_shift, drop, out_mode, out, tile_rows, cap_edges, bf ? *bf : none);                                        \
+  } while (0)
+  if (NV == 2) { if (bf) EIMS_MOL(2, true); else EIMS_MOL(2, false); }
+  else { if (bf) EIMS_MOL(1, true); else EIMS_MOL(1, false); }
+#undef EIMS_MOL
+  return 0;
+}
+
 int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const float* norm, const float* h, int H,
                      const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
-                     int max_nodes, cudaStream_t st, const BnBwdFuse* bf) {
+                     int max_nodes, cudaStream_t st, const BnBwdFuse* bf, const int* gptr, int max_graphs, int tile_rows) {
   if (H % 4) return EIMS_ERR_ARG;
   if (bf && out_mode != 1) return EIMS_ERR_ARG;
+  // molecule-tile kernel (neighbour rows staged in shared memory by the bulk-copy engine) when the caller knows the
+  // batch's graph offsets; EIMS_SPMM_MOL=0 keeps the gather kernel (A/B timing)
+  static int mol_on = -1;
+  if (mol_on < 0) { const char* e = getenv("EIMS_SPMM_MOL"); mol_on = (e && e[0] == '0') ? 0 : 1; }
+  if (mol_on && gptr && tile_rows > 0 && H % 128 == 0 && (!bf || H == 128 || (H == 256 && tile_rows <= 64)))
+    return launch_spmm_mol(dims, gptr, rowptr, col, norm, h, H, bn_scale, bn_shift, drop, out_mode, out, max_graphs, tile_rows, st, bf);
   const int parts = H <= 512 ? 1 : (H + 511) / 512;
   if (parts > 8 || (8 % parts)) return EIMS_ERR_ARG;  // 8 warps per block must split evenly over a row
   static int per_sm = 0;  // resident blocks per SM the grid is sized for (tuning knob)
@@ -570,10 +889,16 @@ __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ di
                                                       const float* __restrict__ bn_scale,
                                                       const float* __restrict__ bn_shift, int pooling,
                                                       float* __restrict__ out, int* __restrict__ argmax,
-                                                      float* __restrict__ zstat, const float* __restrict__ bn_mean) {
-  pdl_sync();
+                                                      float* __restrict__ zstat, const float* __restrict__ bn_mean,
+                                                      int tile_bytes) {
+  extern __shared__ __align__(128) uint8_t ro_smem[];  // the graph's [n_g, H] tile of z when it fits tile_bytes
+  __shared__ __align__(8) uint64_t bar_storage;
   __shared__ float4 ssum[256], smax[256], szs[256];
   __shared__ int4 sarg[256];
+  const uint32_t bar = smem_addr(&bar_storage);
+  if (threadIdx.x == 0 && tile_bytes > 0) mbar_init1(bar);
+  __syncthreads();
+  pdl_sync();
   const int B = dims[DIM_B];
   const int g = blockIdx.x;
   if (g >= B) return;
@@ -585,6 +910,18 @@ __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ di
   const bool has_bn = bn_scale != nullptr;
   const int r0 = __ldg(gptr + g), r1 = __ldg(gptr + g + 1);
   const float ninf = -__int_as_float(0x7f800000);
+  // The graph's rows are contiguous: one bulk async copy brings the whole tile into shared memory and the row
+  // lanes then stride over it there instead of issuing a chain of dependent L2 loads each (n_g / RL deep).
+  const bool staged = tile_bytes > 0 && r1 > r0 && (int64_t)(r1 - r0) * H * 4 <= (int64_t)tile_bytes;
+  const float* zt = z;          // row i of the graph is at zt + i * H
+  if (staged) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, (uint32_t)(r1 - r0) * H * 4u);
+      bulk_g2s(smem_addr(ro_smem), z + (int64_t)r0 * H, (uint32_t)(r1 - r0) * H * 4u, bar);
+    }
+    mbar_wait_parity(bar, 0);
+    zt = reinterpret_cast<const float*>(ro_smem) - (int64_t)r0 * H;
+  }
   for (int cb = 0; cb < cpl; cb += CL) {
     const int c = (cb + cl) * 4;
     const bool on = rl < RL && cb + cl < cpl;
@@ -598,7 +935,7 @@ __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ di
       if (zstat) mu = ldg4(bn_mean + c);
 #pragma unroll 4
       for (int i = r0 + rl; i < r1; i += RL) {
-        float4 v = ldg4(z + (int64_t)i * H + c);
+        float4 v = staged ? *reinterpret_cast<const float4*>(zt + (int64_t)i * H + c) : ldg4(z + (int64_t)i * H + c);
         zs.x += v.x - mu.x; zs.y += v.y - mu.y; zs.z += v.z - mu.z; zs.w += v.w - mu.w;
         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
         v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
@@ -641,8 +978,8 @@ __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ di
         float* zo = zstat + (int64_t)g * 2 * H;
         st4(zo + c, zs);
         if (r1 > r0)
-          st4(zo + H + c, make_float4(__ldg(z + (int64_t)am.x * H + c) - mu.x, __ldg(z + (int64_t)am.y * H + c + 1) - mu.y,
-                                      __ldg(z + (int64_t)am.z * H + c + 2) - mu.z, __ldg(z + (int64_t)am.w * H + c + 3) - mu.w));
+          st4(zo + H + c, make_float4(zt[(int64_t)am.x * H + c] - mu.x, zt[(int64_t)am.y * H + c + 1] - mu.y,
+                                      zt[(int64_t)am.z * H + c + 2] - mu.z, zt[(int64_t)am.w * H + c + 3] - mu.w));
       }
     }
   }
@@ -652,8 +989,15 @@ int launch_readout(const int* dims, const int* gptr, const float* z, int H, cons
                    const float* bn_shift, int pooling, float* out, int* argmax, int max_graphs, cudaStream_t st, float* zstat,
                    const float* bn_mean) {
   if (H % 4 || H < 4 || (zstat && !bn_mean)) return EIMS_ERR_ARG;
-  launch_pdl(readout_kernel, dim3(max_graphs < 1 ? 1 : max_graphs), dim3(256), 0, st, dims, gptr, z, H, bn_scale, bn_shift, pooling, out, argmax,
-             zstat, bn_mean);
+  // shared-memory tile for the graph's rows (bulk async copy): 64 KB holds 64 atoms at H = 256; graphs that do not
+  // fit read their rows from global memory as before.  EIMS_READOUT_TILE_KB=0 turns the staging off (A/B timing).
+  static int tile_kb = -1;
+  if (tile_kb < 0) { const char* e = getenv("EIMS_READOUT_TILE_KB"); tile_kb = e ? atoi(e) : 64; if (tile_kb < 0 || tile_kb > 200) tile_kb = 64; }
+  const int tile_bytes = (H * 4) % 16 == 0 ? tile_kb * 1024 : 0;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(readout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  launch_pdl(readout_kernel, dim3(max_graphs < 1 ? 1 : max_graphs), dim3(256), (size_t)tile_bytes, st, dims, gptr, z, H, bn_scale, bn_shift,
+             pooling, out, argmax, zstat, bn_mean, tile_bytes);
   return 0;
 }
 

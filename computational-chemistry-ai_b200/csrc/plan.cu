@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only (dlopens the injection library when a profiler is attached)
+
 #include "common.cuh"
 #include "launchers.h"
 
@@ -95,6 +97,10 @@ struct eims_plan {
   int64_t launches = 0;
   eims_step last_step;
   int pool_dim() const { return d.pooling == EIMS_POOL_COMBINED ? 2 * d.hidden_dim : d.hidden_dim; }
+  // rows of the shared-memory molecule tile of the aggregation / readout kernels: sized from the plan's own
+  // atoms-per-molecule capacity (64 KB of tile: 64 rows x 256 columns or 128 rows x 128 columns); bigger molecules
+  // take the gather path inside the same kernels
+  int tile_rows() const { return (Nc + Bc - 1) / Bc <= 64 ? 64 : 128; }
   // The batch tables K1 writes exist twice ("name#0" / "name#1"): eims_batch_build always fills the
   // set the kernels enqueued so far do NOT use and makes it current for what is enqueued next, so
   // the next batch can be built on a side stream while the current step is still running.
@@ -157,8 +163,17 @@ const char* kStageNames[ST_COUNT] = {
   "metrics", "gemm_head_wgrad", "colsum", "gemm_head_dgrad", "ln_bwd", "bn_bwd_stats", "bn_bwd_apply", "gemm_gcn_wgrad",
   "gemm_gcn_dgrad", "spmm_bwd", "layer0_wgrad", "adamw", "elementwise", "gemm_head_bwd", "gemm_gcn_bwd"};
 
+// NVTX range per kernel class (stage) around its launches, for nsys / ncu timelines: EIMS_NVTX=1.  Off by default:
+// the ranges are host-side calls on the launch path.
+bool nvtx_on() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("EIMS_NVTX"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on != 0;
+}
+
 void prof_begin(eims_plan* p, int stage, int nkernels, cudaStream_t st) {
   p->launches += nkernels;
+  if (nvtx_on()) nvtxRangePushA(kStageNames[stage]);
   if (!p->prof) return;
   if (p->prof_used == p->prof_recs.size()) {
     eims_plan::ProfRec r;
@@ -171,6 +186,7 @@ void prof_begin(eims_plan* p, int stage, int nkernels, cudaStream_t st) {
   cudaEventRecord(p->prof_recs[p->prof_used].a, st);
 }
 void prof_end(eims_plan* p, cudaStream_t st) {
+  if (nvtx_on()) nvtxRangePop();
   if (!p->prof) return;
   cudaEventRecord(p->prof_recs[p->prof_used].b, st);
   ++p->prof_used;
@@ -249,6 +265,16 @@ int eims_spmm_norm(const int32_t* dims, const int32_t* rowptr, const int32_t* co
   EIMS_TRY(launch_spmm_norm(dims, rowptr, col, norm, h, width, bn_scale, bn_shift, make_drop(drop_p, seed, step, site),
                             out_scale_norm ? 1 : 0, out, max_nodes, (cudaStream_t)stream));
   return check_launch("eims_spmm_norm");
+}
+
+int eims_spmm_norm_mol(const int32_t* dims, const int32_t* gptr, const int32_t* rowptr, const int32_t* col, const float* norm,
+                       const float* h, int32_t width, const float* bn_scale, const float* bn_shift, float drop_p, uint64_t seed,
+                       int32_t step, int32_t site, int32_t out_scale_norm, float* out, int32_t max_nodes, int32_t max_graphs,
+                       int32_t tile_rows, eims_stream_t stream) {
+  if (!gptr || tile_rows < 1 || tile_rows > 128 || width % 128) return fail(EIMS_ERR_ARG, "gptr / tile_rows in [1,128] / width %% 128");
+  EIMS_TRY(launch_spmm_norm(dims, rowptr, col, norm, h, width, bn_scale, bn_shift, make_drop(drop_p, seed, step, site),
+                            out_scale_norm ? 1 : 0, out, max_nodes, (cudaStream_t)stream, nullptr, gptr, max_graphs, tile_rows));
+  return check_launch("eims_spmm_norm_mol");
 }
 
 int eims_gemm(int32_t backend, const float* A, int32_t lda, int32_t a_mn_major, const float* B, int32_t ldb,
@@ -508,7 +534,8 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
     if (fuse_bn) bf = fuse(l);
     STAGE(ST_SPMM_FWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f(L_("z", l - 1)), H,
                               p->f(L_("bn_scale", l - 1)), p->f(L_("bn_shift", l - 1)),
-                              p->drop(drop_p, seed, step, l - 1), 0, p->f(L_("a", l)), p->Nc, st));
+                              p->drop(drop_p, seed, step, l - 1), 0, p->f(L_("a", l)), p->Nc, st, nullptr, p->i("gptr"), p->Bc,
+                              p->tile_rows()));
     STAGE(ST_GEMM_GCN_FWD, 1, gemm(p, p->f(L_("a", l)), H, 0, params + p->off_gcn_w(l), H, 1, p->f(L_("z", l)), H, p->Nc, H, H,
                   dims + DIM_N, nullptr, p->f("norm"), params + p->off_gcn_b(l), 1, 0, st, fuse_bn ? &bf : nullptr));
     if (!fuse_bn) STAGE(ST_BN_STATS, 1, bn(l));
@@ -645,7 +672,7 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
                      grads + p->off_bn_g(l - 1), grads + p->off_bn_b(l - 1), p->f("bn_means2")};
         STAGE(ST_SPMM_BWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f("da"), H, nullptr, nullptr,
                                   p->drop(drop_p, seed, step, l - 1), 1, p->f("dh"), p->Nc, st,
-                                  p->fuse_bn_bwd_stats ? &bf : nullptr));
+                                  p->fuse_bn_bwd_stats ? &bf : nullptr, p->i("gptr"), p->Bc, p->tile_rows()));
       }
     }  // l == 0: dW0 came out of the BatchNorm-backward apply pass above (q_0 is never materialised)
   }
@@ -760,7 +787,7 @@ int eims_plan_check(eims_plan* p, int32_t* num_nodes, int32_t* num_edges, eims_s
     return fail(EIMS_ERR_CUDA, "dims read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (num_nodes) *num_nodes = h[DIM_N];
   if (num_edges) *num_edges = h[DIM_E];
-  if (h[DIM_OVERFLOW]) return fail(EIMS_ERR_CAPACITY, "batch exceeds plan capacity (max_nodes %d, max_edges %d)", p->Nc, p->Ec);
+  if (h[DIM_OVERFLOW]) return fail(EIMS_ERR_CAPACITY, "batch exceeds plan capacity (max_nodes %d, max_edges %d) or a bond names an atom outside its molecule", p->Nc, p->Ec);
   if (h[DIM_ZERO_DEG] != 0 && h[DIM_ZERO_DEG] == h[5]) return fail(EIMS_ERR_ZERO_DEGREE, "There are 0-in-degree nodes in the graph (DGL GraphConv would raise)");
   return 0;
 }

@@ -70,6 +70,7 @@ _SIGS = {
     "eims_plan_set_peak_targets": (C.c_int, [_vp, C.POINTER(Peaks)]),
     "eims_csr_build": (C.c_int, [C.POINTER(Dataset), _vp, _i32, _i32, _i32, _i32] + [_vp] * 10 + [_vp]),
     "eims_spmm_norm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "eims_spmm_norm_mol": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _u64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "eims_gemm": (C.c_int, [_i32, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "eims_bn_scratch_floats": (_i64, [_i32, _i32]),
     "eims_bn_stats": (C.c_int, [_vp, _vp, _i32] + [_vp] * 9 + [_i32, _vp]),

@@ -142,6 +142,16 @@ int eims_spmm_norm(const int32_t* dims, const int32_t* rowptr, const int32_t* co
                    float drop_p, uint64_t seed, int32_t step, int32_t site,
                    int32_t out_scale_norm, float* out, int32_t max_nodes, eims_stream_t stream);
 
+/* K2, molecule tiles: the same result bit for bit, computed block-per-molecule with the molecule's [n_g, width] tile
+ * of h staged in shared memory by the bulk async-copy engine (each row read once instead of once per neighbour; the
+ * BatchNorm / dropout / degree-norm transform applied once per element).  gptr[B+1] = node offset per graph (K1);
+ * tile_rows = rows of the shared tile (<= 128; molecules with more atoms take the gather path in the same kernel);
+ * width must be a multiple of 128.  This is what the plan's forward / backward use. */
+int eims_spmm_norm_mol(const int32_t* dims, const int32_t* gptr, const int32_t* rowptr, const int32_t* col, const float* norm,
+                       const float* h, int32_t width, const float* bn_scale, const float* bn_shift, float drop_p, uint64_t seed,
+                       int32_t step, int32_t site, int32_t out_scale_norm, float* out, int32_t max_nodes, int32_t max_graphs,
+                       int32_t tile_rows, eims_stream_t stream);
+
 /* K3/K6  C[M,N] = op(A)[M,K] * op(B)[K,N] in fp32-grade arithmetic.
  * a_mn_major: 0 -> A stored [M,K] row-major (lda), 1 -> stored [K,M] row-major (lda).
  * b_mn_major: 0 -> B stored [N,K] row-major (ldb) (nn.Linear weight), 1 -> stored [K,N]

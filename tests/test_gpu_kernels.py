@@ -237,6 +237,35 @@ def test_spmm_forward_backward(H):
 
 
 # ------------------------------------------------------------------------------- BN stats
+@pytest.mark.parametrize("H,tile_rows,max_atoms", [(256, 64, 64), (256, 16, 64), (128, 64, 40), (1024, 128, 128), (1024, 24, 128), (384, 64, 30)])
+def test_spmm_molecule_tiles_bit_identical_to_gather(H, tile_rows, max_atoms):
+    """The molecule-tile aggregation (neighbour rows staged in shared memory by cp.async.bulk) must reproduce the
+    gather kernel - itself pinned to torch's index_add_ order above - bit for bit: plain, with BatchNorm apply + dropout
+    (forward form) and in the backward form with the output mask; a small tile sends the bigger molecules down the
+    in-kernel gather path, so both paths and their mix are covered; empty trailing capacity stays untouched."""
+    n = 90
+    table = synth_molecules(n, max_atoms=max_atoms, seed=13)
+    b, rowptr, col, deg, norm = graph_arrays(table, np.arange(n))
+    N, E = b["num_nodes"], len(b["src"])
+    gptr = np.concatenate([[0], np.cumsum(b["batch_num_nodes"])]).astype(np.int32)
+    rng = np.random.default_rng(2)
+    hd = dev(rng.standard_normal((N, H)).astype(np.float32))
+    scale_d, shift_d = dev(rng.standard_normal(H).astype(np.float32)), dev(rng.standard_normal(H).astype(np.float32))
+    dims = make_dims(n, N, E)
+    args = (dims, dev(rowptr, torch.int32), dev(col, torch.int32), dev(norm))
+    gp = dev(gptr, torch.int32)
+    lib = _lib.load()
+    cases = [(None, None, 0.0, 0), (scale_d, shift_d, 0.0, 0), (scale_d, shift_d, 0.2, 0), (None, None, 0.0, 1), (None, None, 0.35, 1)]
+    for sc, sh, p, mode in cases:
+        ref = torch.full((N + 3, H), 7.0, device=DEV)
+        got = torch.full((N + 3, H), 7.0, device=DEV)
+        check(lib.eims_spmm_norm(*map(ptr, args), ptr(hd), H, ptr(sc), ptr(sh), p, 99, 5, 1, mode, ptr(ref), N, stream()))
+        check(lib.eims_spmm_norm_mol(ptr(dims), ptr(gp), *map(ptr, args[1:]), ptr(hd), H, ptr(sc), ptr(sh), p, 99, 5, 1, mode, ptr(got), N,
+                                     n + 5, tile_rows, stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(got.view(torch.int32), ref.view(torch.int32)), (H, tile_rows, p, mode)
+
+
 @pytest.mark.parametrize("N,H", [(1, 64), (2, 64), (1000, 256), (4097, 1024)])
 def test_bn_stats(N, H):
     rng = np.random.default_rng(2)
