@@ -583,7 +583,6 @@ __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ 
 // once per gathered element.  Same neighbour order, same roundings: bit-identical output.
 // Molecules too large for the tile (n_g > cap_rows or more directed edges than cap_edges) take the gather path
 // inside the same kernel.  STATS as above (backward form only).
-constexpr int kMolThreads = 256;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init1(uint32_t bar) {
@@ -608,8 +607,8 @@ __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) 
   }
 }
 
-template <int NV, bool STATS>
-__global__ void __launch_bounds__(kMolThreads) spmm_mol_kernel(const int* __restrict__ dims, const int* __restrict__ gptr,
+template <int NV, bool STATS, int THREADS>
+__global__ void __launch_bounds__(THREADS) spmm_mol_kernel(const int* __restrict__ dims, const int* __restrict__ gptr,
                                                                const int* __restrict__ rowptr, const int* __restrict__ col,
                                                                const float* __restrict__ norm, const float* __restrict__ h, int H,
                                                                const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
@@ -675,16 +674,16 @@ __global__ void __launch_bounds__(kMolThreads) spmm_mol_kernel(const int* __rest
           for (int i = lane; i < n; i += 32) bulk_g2s(smem_addr(tile + (size_t)i * HC), h + (size_t)(r0 + i) * H + c0, HC * 4u, bar);
         }
       }
-      for (int e = tid; e < ne; e += kMolThreads) scol[e] = __ldg(col + e0 + e) - r0;
-      for (int i = tid; i <= n; i += kMolThreads) srow[i] = __ldg(rowptr + r0 + i) - e0;
-      for (int i = tid; i < n; i += kMolThreads) snorm[i] = __ldg(norm + r0 + i);
+      for (int e = tid; e < ne; e += THREADS) scol[e] = __ldg(col + e0 + e) - r0;
+      for (int i = tid; i <= n; i += THREADS) srow[i] = __ldg(rowptr + r0 + i) - e0;
+      for (int i = tid; i < n; i += THREADS) snorm[i] = __ldg(norm + r0 + i);
       mbar_wait_parity(bar, phase);
       phase ^= 1u;
       if (out_mode == 0) {
         __syncthreads();  // snorm visible
         // ---- transform in place, once per element: fl( drop(bn(h_j)) * c_j ).  A thread keeps one float4 column
-        // (kMolThreads is a multiple of HC/4) and walks down the rows.
-        for (int j = tid / (HC / 4); j < n; j += kMolThreads / (HC / 4)) {
+        // (THREADS is a multiple of HC/4) and walks down the rows.
+        for (int j = tid / (HC / 4); j < n; j += THREADS / (HC / 4)) {
           float4 x = *reinterpret_cast<float4*>(tile + (size_t)j * HC + tq * 4);
           if (has_bn) {
             x.x = fmaf(x.x, ta.x, tb.x); x.y = fmaf(x.y, ta.y, tb.y); x.z = fmaf(x.z, ta.z, tb.z); x.w = fmaf(x.w, ta.w, tb.w);
@@ -701,7 +700,7 @@ __global__ void __launch_bounds__(kMolThreads) spmm_mol_kernel(const int* __rest
       __syncthreads();
     }
     // ---- aggregate: warp per destination row, neighbours in ascending edge id
-    for (int i = warp; i < n; i += kMolThreads / 32) {
+    for (int i = warp; i < n; i += THREADS / 32) {
       const int row = r0 + i;
       float4 zrow[STATS ? NV : 1];
       if (STATS) {
@@ -777,7 +776,7 @@ __global__ void __launch_bounds__(kMolThreads) spmm_mol_kernel(const int* __rest
   }
   if (STATS) {
     // combine the block's warps in shared memory, one fp32 atomic per column and statistic into one of the
-    // replicas, finalise in the last block (same scheme as spmm_norm_kernel<.., true>; gridDim.y == 1 here)
+    // replicas, finalise in the last block of the whole grid (same scheme as spmm_norm_kernel<.., true>)
     float* mine = s_stats + warp * 2 * HC;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -786,14 +785,15 @@ __global__ void __launch_bounds__(kMolThreads) spmm_mol_kernel(const int* __rest
     }
     __syncthreads();
     float* facc = reinterpret_cast<float*>(bf.acc);
-    for (int k = tid; k < 2 * H; k += kMolThreads) {
-      const int which = k / H, cc = k % H;
+    for (int k = tid; k < 2 * HC; k += THREADS) {   // this block's column chunk
+      const int which = k / HC, cc = k % HC;
+      if (c0 + cc >= H) continue;
       float t = 0.f;
-      for (int w = 0; w < kMolThreads / 32; ++w) t += s_stats[(w * 2 + which) * HC + cc];
-      atomicAdd(facc + (size_t)(blockIdx.x % kBnReplicas) * 2 * H + k, t);
+      for (int w = 0; w < THREADS / 32; ++w) t += s_stats[(w * 2 + which) * HC + cc];
+      atomicAdd(facc + (size_t)(blockIdx.x % kBnReplicas) * 2 * H + (size_t)which * H + c0 + cc, t);
     }
-    if (!last_block_ticket(bf.ticket, gridDim.x)) return;
-    for (int k = tid; k < H; k += kMolThreads) {
+    if (!last_block_ticket(bf.ticket, gridDim.x * gridDim.y)) return;
+    for (int k = tid; k < H; k += THREADS) {
       double sa = 0.0, sb = 0.0;
 #pragma unroll
       for (int r = 0; r < kBnReplicas; ++r) {
@@ -811,18 +811,22 @@ __global__ void __launch_bounds__(kMolThreads) spmm_mol_kernel(const int* __rest
   }
 }
 
-static int launch_spmm_mol(const int* dims, const int* gptr, const int* rowptr, const int* col, const float* norm, const float* h,
+int launch_spmm_mol(const int* dims, const int* gptr, const int* rowptr, const int* col, const float* norm, const float* h,
                            int H, const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
                            int max_graphs, int tile_rows, cudaStream_t st, const BnBwdFuse* bf) {
-  // a block owns 256 columns when that keeps the tile at <= 64 KB (three blocks per SM), else 128
-  const int NV = (H % 256 == 0 && (size_t)tile_rows * 256 * 4 <= 64 * 1024) ? 2 : 1;
-  const int HC = 128 * NV;
+  // Shape: a block owns HC = 128 columns (4 warps) or 256 columns (8 warps) of one molecule at a time.  The narrow
+  // shape keeps the tile at tile_rows x 512 bytes (32 KB at 64 rows), so ~7 blocks are resident per SM and the
+  // (molecules x column chunks) grid of a training batch - 512 x 2 at cfg 2 - fits in ONE wave; with 256-column
+  // blocks the same batch took 1.15 waves of 3 blocks per SM, i.e. twice the time (EIMS_SPMM_MOL_WIDE=1 for A/B).
+  static int wide = -1;
+  if (wide < 0) { const char* e = getenv("EIMS_SPMM_MOL_WIDE"); wide = (e && e[0] == '0') ? 0 : 1; }
+  const int NV = (wide && H % 256 == 0 && (size_t)tile_rows * 256 * 4 <= 64 * 1024) ? 2 : 1;
+  const int HC = 128 * NV, threads = 128 * NV;
   if (H % HC) return EIMS_ERR_ARG;
-  if (bf && H != HC) return EIMS_ERR_ARG;  // the statistics variant owns whole rows
   const int cap_edges = 4 * tile_rows + 64;
   size_t smem = (size_t)tile_rows * HC * 4 + (size_t)cap_edges * 4 + (size_t)(tile_rows + 1) * 4 + (size_t)tile_rows * 4;
   smem = (smem + 15) & ~(size_t)15;
-  if (bf) smem += (size_t)8 * 2 * HC * 4;
+  if (bf) smem += (size_t)(threads / 32) * 2 * HC * 4;
   int gx = max_graphs < 1 ? 1 : max_graphs;
   const int chunks = H / HC;
   const int cap = 148 * 16 / chunks;   // grid-stride beyond a few waves (inference batches)
@@ -831,8 +835,8 @@ static int launch_spmm_mol(const int* dims, const int* gptr, const int* rowptr, 
 #define EIMS_MOL(NVv, ST)                                                                                                   \
   do {                                                                                                                      \
     static bool attr = false;                                                                                               \
-    if (!attr) { cudaFuncSetAttribute(spmm_mol_kernel<NVv, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; } \
-    launch_pdl(spmm_mol_kernel<NVv, ST>, dim3(gx, chunks), dim3(kMolThreads), smem, st, dims, gptr, rowptr, col, norm, h, H, bn_scale, \
+    if (!attr) { cudaFuncSetAttribute(spmm_mol_kernel<NVv, ST, 128 * NVv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; } \
+    launch_pdl(spmm_mol_kernel<NVv, ST, 128 * NVv>, dim3(gx, chunks), dim3(128 * NVv), smem, st, dims, gptr, rowptr, col, norm, h, H, bn_scale, \
                bn_shift, drop, out_mode, out, tile_rows, cap_edges, bf ? *bf : none);                                        \
   } while (0)
   if (NV == 2) { if (bf) EIMS_MOL(2, true); else EIMS_MOL(2, false); }
@@ -846,11 +850,17 @@ int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const f
                      int max_nodes, cudaStream_t st, const BnBwdFuse* bf, const int* gptr, int max_graphs, int tile_rows) {
   if (H % 4) return EIMS_ERR_ARG;
   if (bf && out_mode != 1) return EIMS_ERR_ARG;
-  // molecule-tile kernel (neighbour rows staged in shared memory by the bulk-copy engine) when the caller knows the
-  // batch's graph offsets; EIMS_SPMM_MOL=0 keeps the gather kernel (A/B timing)
-  static int mol_on = -1;
-  if (mol_on < 0) { const char* e = getenv("EIMS_SPMM_MOL"); mol_on = (e && e[0] == '0') ? 0 : 1; }
-  if (mol_on && gptr && tile_rows > 0 && H % 128 == 0 && (!bf || H == 128 || (H == 256 && tile_rows <= 64)))
+  // Molecule-tile kernel (neighbour rows staged in shared memory by the bulk-copy engine) when the caller knows the
+  // batch's graph offsets AND the batch is large.  Measured on a B200 (profiles/r2_spmm_ab.md): with >= ~8 molecules
+  // per resident block (inference batches of 4096) staging wins, 0.128 vs 0.144 ms for the two cfg-3 launches (67 %
+  // vs 59 % of the measured copy bandwidth); at a training batch of 512 molecules a block sees one molecule, its
+  // phases (offsets -> bulk copy lands -> transform -> sum) cannot overlap, and the gather kernel - 9.5 k warps with
+  // independent rows in flight - is faster (17 vs 18-26 us per launch for three staged variants, software-pipelined
+  // producer/consumer ring included).  EIMS_SPMM_MOL=0 / 1 forces one or the other (A/B timing, tests).
+  static int mol_on = -2;
+  if (mol_on == -2) { const char* e = getenv("EIMS_SPMM_MOL"); mol_on = e ? (e[0] == '0' ? 0 : 1) : -1; }
+  const bool big_batch = max_graphs >= 2048 && !bf;
+  if ((mol_on == 1 || (mol_on == -1 && big_batch)) && gptr && tile_rows > 0 && H % 128 == 0)
     return launch_spmm_mol(dims, gptr, rowptr, col, norm, h, H, bn_scale, bn_shift, drop, out_mode, out, max_graphs, tile_rows, st, bf);
   const int parts = H <= 512 ? 1 : (H + 511) / 512;
   if (parts > 8 || (8 % parts)) return EIMS_ERR_ARG;  // 8 warps per block must split evenly over a row

@@ -28,6 +28,10 @@ int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const f
                      const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
                      int max_nodes, cudaStream_t st, const BnBwdFuse* bf = nullptr,
                      const int* gptr = nullptr, int max_graphs = 0, int tile_rows = 0);  // gptr + tile_rows: molecule-tile kernel
+// the molecule-tile kernel itself, whatever the batch size (launch_spmm_norm picks it for large batches only)
+int launch_spmm_mol(const int* dims, const int* gptr, const int* rowptr, const int* col, const float* norm, const float* h, int H,
+                    const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out, int max_graphs,
+                    int tile_rows, cudaStream_t st, const BnBwdFuse* bf);
 int launch_readout(const int* dims, const int* gptr, const float* z, int H, const float* bn_scale,
                    const float* bn_shift, int pooling, float* out, int* argmax, int max_graphs, cudaStream_t st,
                    float* zstat = nullptr, const float* bn_mean = nullptr);  // zstat [B][2H]: per graph, column sums of

@@ -272,8 +272,9 @@ int eims_spmm_norm_mol(const int32_t* dims, const int32_t* gptr, const int32_t* 
                        int32_t step, int32_t site, int32_t out_scale_norm, float* out, int32_t max_nodes, int32_t max_graphs,
                        int32_t tile_rows, eims_stream_t stream) {
   if (!gptr || tile_rows < 1 || tile_rows > 128 || width % 128) return fail(EIMS_ERR_ARG, "gptr / tile_rows in [1,128] / width %% 128");
-  EIMS_TRY(launch_spmm_norm(dims, rowptr, col, norm, h, width, bn_scale, bn_shift, make_drop(drop_p, seed, step, site),
-                            out_scale_norm ? 1 : 0, out, max_nodes, (cudaStream_t)stream, nullptr, gptr, max_graphs, tile_rows));
+  (void)max_nodes;
+  EIMS_TRY(launch_spmm_mol(dims, gptr, rowptr, col, norm, h, width, bn_scale, bn_shift, make_drop(drop_p, seed, step, site),
+                           out_scale_norm ? 1 : 0, out, max_graphs, tile_rows, (cudaStream_t)stream, nullptr));
   return check_launch("eims_spmm_norm_mol");
 }
 
