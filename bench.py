@@ -612,7 +612,8 @@ def e2e_pass(tb, n_e2e):
         hds = HostDataset(table, None, peaks=pk)
     else:
         hds = HostDataset(table, dense_spectra(*pk, M))
-    depth, workers = 4, 4
+    depth = 4
+    workers = max(1, min(4, (os.cpu_count() or 4) // tb.world - 1))   # the ranks share the box's host cores
     cap = tb.batch * (tb.cfg["atoms"] * (F0 * 4 + 8 + 10) + 4 * M + 64) + (1 << 16)
     packer = HostPacker(hds, M, cap, n_buffers=depth + 3)
     runner = HostBatchRunner(tb.plan, tb.fp, cap)

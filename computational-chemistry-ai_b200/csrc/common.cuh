@@ -197,6 +197,25 @@ __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// Batch sizes B / N / E of the current batch (dims[0..2], written by K1).  Every kernel needs them and used to read
+// them first thing after the grid-dependency wait - a dependent L2 round trip at the head of every launch of a
+// latency-bound step.  Under programmatic dependent launch a kernel that starts early overlaps only its immediate
+// predecessor, whose own wait guarantees that everything before THAT has completed; so unless the predecessor is K1
+// itself the sizes are already final when the kernel starts and can be loaded BEFORE the wait (`early` != 0).  The
+// plan sets the flag for every launch of a step except the first one after the batch build (dims_early_ref()).
+struct BatchDims { int B, N, E; };
+__device__ __forceinline__ BatchDims pdl_sync_dims(const int* __restrict__ dims, int early) {
+  int4 v = make_int4(0, 0, 0, 0);
+  if (early) v = __ldcg(reinterpret_cast<const int4*>(dims));
+  pdl_sync();
+  if (!early) v = __ldcg(reinterpret_cast<const int4*>(dims));
+  return BatchDims{v.x, v.y, v.z};
+}
+inline int& dims_early_ref() {
+  static thread_local int v = 0;
+  return v;
+}
+
 inline bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {

@@ -255,10 +255,10 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_stats_kernel(const int* __restr
                                                            const float* __restrict__ z, int H,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           float* __restrict__ means /*[2][H]*/, float* __restrict__ scratch) {
-  pdl_sync();
+                                                           float* __restrict__ means /*[2][H]*/, float* __restrict__ scratch,
+                                                           int early) {
+  const int N = pdl_sync_dims(dims, early).N;
   src.drop = resolve_drop(src.drop);
-  const int N = dims[DIM_N];
   unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
   double* acc = reinterpret_cast<double*>(scratch + 16);
   const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
@@ -302,9 +302,9 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_top_kernel(const int* __rest
                                                                int pooling, int H, const float* __restrict__ mean,
                                                                const float* __restrict__ invstd, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, float* __restrict__ means,
-                                                               float* __restrict__ scratch) {
-  pdl_sync();
-  const int B = dims[DIM_B], N = dims[DIM_N];
+                                                               float* __restrict__ scratch, int early) {
+  const BatchDims bd = pdl_sync_dims(dims, early);
+  const int B = bd.B, N = bd.N;
   unsigned int* counter = reinterpret_cast<unsigned int*>(scratch);
   double* acc = reinterpret_cast<double*>(scratch + 16);
   const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
@@ -352,7 +352,7 @@ int launch_bn_bwd_stats_top(const int* dims, const float* dG, const float* zstat
   if (rg > 37) rg = 37;
   if (rg < 1) rg = 1;
   launch_pdl(bn_bwd_stats_top_kernel, dim3(slabs, rg), dim3(256), 0, st, dims, dG, zstat, gptr, pooling, H, mean, invstd, dgamma, dbeta,
-             means, partials);
+             means, partials, dims_early_ref());
   return 0;
 }
 
@@ -366,11 +366,10 @@ __global__ void __launch_bounds__(256, LAYER0 ? 2 : 4) bn_bwd_apply_kernel(
     const int* __restrict__ dims, DhSrc src, const float* __restrict__ z, int H, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ means,
     const float* __restrict__ norm, float* __restrict__ q, float* __restrict__ dbias, const float* __restrict__ a0,
-    int F, float* __restrict__ dW0) {
-  pdl_sync();
+    int F, float* __restrict__ dW0, int early) {
+  const int N = pdl_sync_dims(dims, early).N;
   src.drop = resolve_drop(src.drop);
   __shared__ float red[kRowLanes][kSlab];
-  const int N = dims[DIM_N];
   const int cl = threadIdx.x & 15, rl = threadIdx.x >> 4;
   const int c0 = blockIdx.x * kSlab, c = c0 + cl * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -440,7 +439,8 @@ int launch_bn_bwd_stats(const int* dims, const float* dh, const float* dG, const
   if (H % 4 || H > 4096) return EIMS_ERR_ARG;
   DhSrc src{dh, dG, gid, gptr, argmax, pooling, nullptr, nullptr, nullptr, nullptr, DropCfg{}};
   if (gs) { src.da = gs->da; src.rowptr = gs->rowptr; src.col = gs->col; src.norm = gs->norm; src.drop = gs->drop; }
-  launch_pdl(bn_bwd_stats_kernel, bn_grid(H, max_nodes), dim3(256), 0, st, dims, src, z, H, mean, invstd, dgamma, dbeta, means, partials);
+  launch_pdl(bn_bwd_stats_kernel, bn_grid(H, max_nodes), dim3(256), 0, st, dims, src, z, H, mean, invstd, dgamma, dbeta, means, partials,
+             dims_early_ref());
   return 0;
 }
 
@@ -456,9 +456,9 @@ int launch_bn_bwd_apply(const int* dims, const float* dh, const float* dG, const
   static int l0_per_sm = 0;
   if (!l0_per_sm) { const char* e = getenv("EIMS_BN_L0_BLOCKS_PER_SM"); l0_per_sm = e ? atoi(e) : 2; if (l0_per_sm < 1) l0_per_sm = 1; }
   if (dW0)
-    launch_pdl(bn_bwd_apply_kernel<true>, bn_grid(H, max_nodes, l0_per_sm), dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, a0, F, dW0);
+    launch_pdl(bn_bwd_apply_kernel<true>, bn_grid(H, max_nodes, l0_per_sm), dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, a0, F, dW0, dims_early_ref());
   else
-    launch_pdl(bn_bwd_apply_kernel<false>, grid, dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, nullptr, 0, nullptr);
+    launch_pdl(bn_bwd_apply_kernel<false>, grid, dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, nullptr, 0, nullptr, dims_early_ref());
   return 0;
 }
 
@@ -468,10 +468,9 @@ template <int NV>
 __global__ void __launch_bounds__(256) ln_relu_drop_fwd_kernel(const int* __restrict__ dims, const float* __restrict__ u,
                                                                int W, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, DropCfg drop,
-                                                               float* __restrict__ y, float* __restrict__ stats) {
-  pdl_sync();
+                                                               float* __restrict__ y, float* __restrict__ stats, int early) {
+  const int B = pdl_sync_dims(dims, early).B;
   drop = resolve_drop(drop);
-  const int B = dims[DIM_B];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -530,7 +529,7 @@ int launch_ln_fwd(const int* dims, const float* u, int W, const float* gamma, co
   int blocks = (max_graphs + 7) / 8;
   if (blocks < 1) blocks = 1;
   switch (ln_nv(W)) {
-#define EIMS_LN_F(NV) case NV: launch_pdl(ln_relu_drop_fwd_kernel<NV>, dim3(blocks), dim3(256), 0, st, dims, u, W, gamma, beta, drop, y, stats); break;
+#define EIMS_LN_F(NV) case NV: launch_pdl(ln_relu_drop_fwd_kernel<NV>, dim3(blocks), dim3(256), 0, st, dims, u, W, gamma, beta, drop, y, stats, dims_early_ref()); break;
     EIMS_LN_F(1) EIMS_LN_F(2) EIMS_LN_F(4) EIMS_LN_F(8) EIMS_LN_F(16)
 #undef EIMS_LN_F
     default: return EIMS_ERR_ARG;
@@ -546,10 +545,9 @@ __global__ void __launch_bounds__(256) ln_relu_drop_bwd_kernel(const int* __rest
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ stats, float drop_scale,
                                                                float* du, float* __restrict__ dgamma,
-                                                               float* __restrict__ dbeta, float* __restrict__ dbias) {
-  pdl_sync();
+                                                               float* __restrict__ dbeta, float* __restrict__ dbias, int early) {
   extern __shared__ float smem[];  // [8 warps][3][W] : per-warp column partials of dgamma / dbeta / dbias
-  const int B = dims[DIM_B];
+  const int B = pdl_sync_dims(dims, early).B;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -629,7 +627,7 @@ int launch_ln_bwd(const int* dims, const float* u, const float* y, const float* 
   case NV:                                                                                                         \
     if (smem > 48 * 1024)                                                                                          \
       cudaFuncSetAttribute(ln_relu_drop_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    launch_pdl(ln_relu_drop_bwd_kernel<NV>, dim3(blocks), dim3(256), smem, st, dims, u, y, dy, W, gamma, stats, drop_scale, du, dgamma, dbeta, dbias); \
+    launch_pdl(ln_relu_drop_bwd_kernel<NV>, dim3(blocks), dim3(256), smem, st, dims, u, y, dy, W, gamma, stats, drop_scale, du, dgamma, dbeta, dbias, dims_early_ref()); \
     break;
     EIMS_LN_B(1) EIMS_LN_B(2) EIMS_LN_B(4) EIMS_LN_B(8) EIMS_LN_B(16)
 #undef EIMS_LN_B
@@ -729,11 +727,10 @@ __global__ void __launch_bounds__(128) loss_kernel(const int* __restrict__ dims,
                                                    int M, int loss_kind, float* __restrict__ prob,
                                                    float* __restrict__ dlogits, float* __restrict__ row_loss,
                                                    float* __restrict__ row_cos, float* __restrict__ metrics,
-                                                   unsigned int* __restrict__ ticket, PeakSrc pk) {
-  pdl_sync();
+                                                   unsigned int* __restrict__ ticket, PeakSrc pk, int early) {
   __shared__ float sh[4];
   __shared__ __align__(16) float bins[PEAKS ? 4 * 128 * kLossMaxV4 : 4];  // PEAKS: the target row is binned here
-  const int B = dims[DIM_B];
+  const int B = pdl_sync_dims(dims, early).B;
   const int nv4 = M >> 2;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     const int64_t trow = target_rows ? (int64_t)target_rows[b] : (int64_t)b;
@@ -808,10 +805,10 @@ int launch_loss(const int* dims, const float* logits, const float* targets, cons
   int blocks = max_graphs < 1 ? 1 : max_graphs;
   if (src.ptr)
     launch_pdl(loss_kernel<true>, dim3(blocks), dim3(128), 0, st, dims, logits, targets, target_rows, M, loss_kind, prob, dlogits,
-               row_loss, row_cos, metrics, ticket, src);
+               row_loss, row_cos, metrics, ticket, src, dims_early_ref());
   else
     launch_pdl(loss_kernel<false>, dim3(blocks), dim3(128), 0, st, dims, logits, targets, target_rows, M, loss_kind, prob, dlogits,
-               row_loss, row_cos, metrics, ticket, src);
+               row_loss, row_cos, metrics, ticket, src, dims_early_ref());
   return 0;
 }
 
@@ -877,9 +874,8 @@ int launch_topk_peaks(const float* spectra, int num_rows, int M, int k, int* idx
 
 // prob = sigmoid(logits) (inference) ; dlogits = dprob * p * (1-p) (autograd entry)
 __global__ void sigmoid_kernel(const int* __restrict__ dims, const float* __restrict__ logits, int M,
-                               float* __restrict__ prob) {
-  pdl_sync();
-  const int64_t n4 = (int64_t)dims[DIM_B] * M / 4;
+                               float* __restrict__ prob, int early) {
+  const int64_t n4 = (int64_t)pdl_sync_dims(dims, early).B * M / 4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 u = ldg4(logits + 4 * i), p;
     p.x = 1.f / (1.f + expf(-u.x)); p.y = 1.f / (1.f + expf(-u.y));
@@ -903,7 +899,7 @@ static inline int ew_blocks(int64_t n4) {
   return b < 1 ? 1 : (int)b;
 }
 int launch_sigmoid(const int* dims, const float* logits, int M, float* prob, int max_graphs, cudaStream_t st) {
-  launch_pdl(sigmoid_kernel, dim3(ew_blocks((int64_t)max_graphs * M / 4)), dim3(256), 0, st, dims, logits, M, prob);
+  launch_pdl(sigmoid_kernel, dim3(ew_blocks((int64_t)max_graphs * M / 4)), dim3(256), 0, st, dims, logits, M, prob, dims_early_ref());
   return 0;
 }
 int launch_dprob_to_dlogits(const int* dims, const float* prob, const float* dprob, int M, float* dlogits,
@@ -926,10 +922,10 @@ int launch_metrics(const int* dims, const float* row_loss, const float* row_cos,
 // =========================================================================== column sums (bias grads)
 // out[c] += sum_r in[r,c]  for r < dims[dim_slot]
 __global__ void __launch_bounds__(256) colsum_kernel(const int* __restrict__ dims, int dim_slot,
-                                                     const float* __restrict__ in, int C, int ld, float* __restrict__ out) {
-  pdl_sync();
+                                                     const float* __restrict__ in, int C, int ld, float* __restrict__ out, int early) {
   __shared__ float4 sh[4][64];
-  const int R = dims[dim_slot];
+  const BatchDims bd = pdl_sync_dims(dims, early);
+  const int R = dim_slot == DIM_B ? bd.B : (dim_slot == DIM_N ? bd.N : bd.E);
   const int cg = blockIdx.x * 64 + (threadIdx.x & 63), rs = threadIdx.x >> 6;
   const int rows_per = (R + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * rows_per, r1 = min(R, r0 + rows_per);
@@ -953,7 +949,7 @@ int launch_colsum(const int* dims, int dim_slot, const float* in, int C, int ld,
   if (gy > 64) gy = 64;
   if (gy < 1) gy = 1;
   dim3 grid((C / 4 + 63) / 64, gy);
-  launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, st, dims, dim_slot, in, C, ld, out);
+  launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, st, dims, dim_slot, in, C, ld, out, dims_early_ref());
   return 0;
 }
 

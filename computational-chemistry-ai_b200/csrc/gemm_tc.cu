@@ -132,6 +132,7 @@ struct Args {
   const int* m_dev; const int* k_dev;
   const float* row_scale; const float* bias;
   int relu, accumulate, vec_a, vec_b;
+  int early;  // m_dev / k_dev (the batch's sizes) may be read before the grid-dependency wait (see pdl_sync_dims)
   int nt, mt, splits;  // tile grid of this problem: CTA `local` -> (local % nt, local / nt % mt, local / (nt * mt))
   BnFuse bn;  // bn.acc != null: column sums of the stored C (after bias / ReLU) -> BatchNorm statistics
 };
@@ -317,11 +318,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(const __grid_c
   const uint32_t tmem_base = tmem_base_slot;
   const uint32_t smem_base = smem_u32(smem);
   if (warp == 0) TRACE(1);
+  int M = g.M, K = g.K;
+  if (g.early) { if (g.m_dev) M = __ldcg(g.m_dev); if (g.k_dev) K = __ldcg(g.k_dev); }
   pdl_sync();
   if (warp == 0) TRACE(2);
-
-  const int M = g.m_dev ? *g.m_dev : g.M;
-  const int K = g.k_dev ? *g.k_dev : g.K;
+  if (!g.early) { if (g.m_dev) M = __ldcg(g.m_dev); if (g.k_dev) K = __ldcg(g.k_dev); }
   const int N = g.N;
   const int m0 = by * BM, n0 = bx * BN;
   const int kblocks = (K + BK - 1) / BK;
@@ -659,14 +660,21 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_3xtf32_persistent_ker
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   const uint32_t smem_base = smem_u32(smem);
-  pdl_sync();
-  if (warp == 0) TRACE(0);
-
   int Mv[2], Kv[2];
+  const bool early = grp.g[0].early != 0;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
-    Mv[k] = grp.g[k].m_dev ? *grp.g[k].m_dev : grp.g[k].M;
-    Kv[k] = grp.g[k].k_dev ? *grp.g[k].k_dev : grp.g[k].K;
+    Mv[k] = grp.g[k].M; Kv[k] = grp.g[k].K;
+    if (early) { if (grp.g[k].m_dev) Mv[k] = __ldcg(grp.g[k].m_dev); if (grp.g[k].k_dev) Kv[k] = __ldcg(grp.g[k].k_dev); }
+  }
+  pdl_sync();
+  if (warp == 0) TRACE(0);
+  if (!early) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (grp.g[k].m_dev) Mv[k] = __ldcg(grp.g[k].m_dev);
+      if (grp.g[k].k_dev) Kv[k] = __ldcg(grp.g[k].k_dev);
+    }
   }
   const int T = grp.tiles, G = gridDim.x;
 
@@ -896,7 +904,7 @@ int launch_group(const tc::Group& grp_in, int ctas, bool wide, cudaStream_t st) 
 
 tc::Args make_args(const GemmProblem& q) {
   tc::Args g{q.A, q.B, q.C, q.lda, q.ldb, q.ldc, q.a_mn, q.b_mn, q.M, q.N, q.K, q.m_dev, q.k_dev, q.row_scale, q.bias,
-             q.relu, q.accumulate, 0, 0, 1, 1, 1, BnFuse{}};
+             q.relu, q.accumulate, 0, 0, dims_early_ref(), 1, 1, 1, BnFuse{}};
   if (q.bn) g.bn = *q.bn;
   return g;
 }

@@ -428,11 +428,10 @@ __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ 
                                                         const float* __restrict__ h, int H,
                                                         const float* __restrict__ bn_scale,
                                                         const float* __restrict__ bn_shift, DropCfg drop, int out_mode,
-                                                        float* __restrict__ out, int parts, BnBwdFuse bf) {
+                                                        float* __restrict__ out, int parts, BnBwdFuse bf, int early) {
   extern __shared__ float s_stats[];  // STATS: [warps per block][2][128 * NV]
-  pdl_sync();
+  const int N = pdl_sync_dims(dims, early).N;
   drop = resolve_drop(drop);
-  const int N = dims[DIM_N];
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -613,7 +612,7 @@ __global__ void __launch_bounds__(THREADS) spmm_mol_kernel(const int* __restrict
                                                                const float* __restrict__ norm, const float* __restrict__ h, int H,
                                                                const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
                                                                DropCfg drop, int out_mode, float* __restrict__ out, int cap_rows,
-                                                               int cap_edges, BnBwdFuse bf) {
+                                                               int cap_edges, BnBwdFuse bf, int early) {
   constexpr int HC = 128 * NV;  // columns a block owns
   extern __shared__ __align__(128) uint8_t mol_smem[];
   float* tile = reinterpret_cast<float*>(mol_smem);                    // [cap_rows][HC]
@@ -626,9 +625,9 @@ __global__ void __launch_bounds__(THREADS) spmm_mol_kernel(const int* __restrict
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) mbar_init1(bar);
   __syncthreads();
-  pdl_sync();
+  const BatchDims bd = pdl_sync_dims(dims, early);
   drop = resolve_drop(drop);
-  const int B = dims[DIM_B], N = dims[DIM_N];
+  const int B = bd.B, N = bd.N;
   const int c0 = blockIdx.y * HC;
   const bool has_bn = bn_scale != nullptr;
   const bool in_drop = drop.active() && out_mode == 0;
@@ -837,7 +836,7 @@ int launch_spmm_mol(const int* dims, const int* gptr, const int* rowptr, const i
     static bool attr = false;                                                                                               \
     if (!attr) { cudaFuncSetAttribute(spmm_mol_kernel<NVv, ST, 128 * NVv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; } \
     launch_pdl(spmm_mol_kernel<NVv, ST, 128 * NVv>, dim3(gx, chunks), dim3(128 * NVv), smem, st, dims, gptr, rowptr, col, norm, h, H, bn_scale, \
-               bn_shift, drop, out_mode, out, tile_rows, cap_edges, bf ? *bf : none);                                        \
+               bn_shift, drop, out_mode, out, tile_rows, cap_edges, bf ? *bf : none, dims_early_ref());                     \
   } while (0)
   if (NV == 2) { if (bf) EIMS_MOL(2, true); else EIMS_MOL(2, false); }
   else { if (bf) EIMS_MOL(1, true); else EIMS_MOL(1, false); }
@@ -878,9 +877,9 @@ int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const f
 #define EIMS_SPMM(NV, UE)                                                                                              \
   do {                                                                                                                 \
     if (bf) launch_pdl(spmm_norm_kernel<NV, 1, true>, dim3(blocks_s), dim3(256), (size_t)8 * 2 * 128 * NV * sizeof(float), st, dims, rowptr, col, norm, \
-                       h, H, bn_scale, bn_shift, drop, out_mode, out, parts, *bf);                                      \
+                       h, H, bn_scale, bn_shift, drop, out_mode, out, parts, *bf, dims_early_ref());                     \
     else launch_pdl(spmm_norm_kernel<NV, UE, false>, dim3(blocks), dim3(256), 0, st, dims, rowptr, col, norm, h, H, bn_scale,   \
-                    bn_shift, drop, out_mode, out, parts, none);                                                        \
+                    bn_shift, drop, out_mode, out, parts, none, dims_early_ref());                                       \
   } while (0)
   if (H <= 128) EIMS_SPMM(1, 4);
   else if (H <= 256) EIMS_SPMM(2, 2);
@@ -900,7 +899,7 @@ __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ di
                                                       const float* __restrict__ bn_shift, int pooling,
                                                       float* __restrict__ out, int* __restrict__ argmax,
                                                       float* __restrict__ zstat, const float* __restrict__ bn_mean,
-                                                      int tile_bytes) {
+                                                      int tile_bytes, int early) {
   extern __shared__ __align__(128) uint8_t ro_smem[];  // the graph's [n_g, H] tile of z when it fits tile_bytes
   __shared__ __align__(8) uint64_t bar_storage;
   __shared__ float4 ssum[256], smax[256], szs[256];
@@ -908,8 +907,7 @@ __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ di
   const uint32_t bar = smem_addr(&bar_storage);
   if (threadIdx.x == 0 && tile_bytes > 0) mbar_init1(bar);
   __syncthreads();
-  pdl_sync();
-  const int B = dims[DIM_B];
+  const int B = pdl_sync_dims(dims, early).B;
   const int g = blockIdx.x;
   if (g >= B) return;
   const int cpl = H >> 2;                       // float4 columns per row
@@ -1007,7 +1005,7 @@ int launch_readout(const int* dims, const int* gptr, const float* z, int H, cons
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(readout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
   launch_pdl(readout_kernel, dim3(max_graphs < 1 ? 1 : max_graphs), dim3(256), (size_t)tile_bytes, st, dims, gptr, z, H, bn_scale, bn_shift,
-             pooling, out, argmax, zstat, bn_mean, tile_bytes);
+             pooling, out, argmax, zstat, bn_mean, tile_bytes, dims_early_ref());
   return 0;
 }
 

@@ -191,6 +191,17 @@ void prof_end(eims_plan* p, cudaStream_t st) {
   cudaEventRecord(p->prof_recs[p->prof_used].b, st);
   ++p->prof_used;
 }
+// resets the "sizes may be read before the grid-dependency wait" flag however the function is left
+struct EarlyDimsScope {
+  explicit EarlyDimsScope(int v) { dims_early_ref() = v; }
+  ~EarlyDimsScope() { dims_early_ref() = 0; }
+};
+bool early_dims_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("EIMS_EARLY_DIMS"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+
 #define STAGE(id, nk, expr)          \
   do {                               \
     prof_begin(p, id, nk, st);       \
@@ -528,6 +539,8 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
                                H, p->f("z0"), p->Nc, st, training ? &bf : nullptr, zero, zero_bytes / 16));
     if (!training) STAGE(ST_BN_STATS, 1, bn(0));
   }
+  // every launch from here on is at least two kernels after the batch build: sizes before the grid-dependency wait
+  EarlyDimsScope early_scope(early_dims_enabled() ? 1 : 0);
   for (int l = 1; l < L; ++l) {
     // training on the tensor-core path: the BatchNorm statistics of z_l come out of the GEMM epilogue
     const bool fuse_bn = training && p->gemm_backend == EIMS_GEMM_TCGEN05;
@@ -583,6 +596,7 @@ static int loss_impl(eims_plan* p, const float* targets, const int32_t* target_r
   if (!targets && !peaks && p->peak_targets.peak_ptr) peaks = &p->peak_targets;
   if (!targets && !peaks) return fail(EIMS_ERR_ARG, "targets is NULL (and no peak-list targets are set)");
   cudaStream_t st = (cudaStream_t)stream;
+  EarlyDimsScope early_scope(early_dims_enabled() && p->state >= 2 ? 1 : 0);  // after a forward, never right after a batch build
   // metrics != NULL: the last block of the loss kernel also folds the row terms into the running
   // metrics (flags[0] is its ticket), which saves the separate one-block launch
   STAGE(ST_LOSS, 1, launch_loss(p->i("dims"), p->f("logits"), targets, target_rows, p->d.max_mz, loss_kind, p->f("prob"),
@@ -609,6 +623,7 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
   }
   if (!params || !grads) return fail(EIMS_ERR_ARG, "params / grads is NULL");
   cudaStream_t st = (cudaStream_t)stream;
+  EarlyDimsScope early_scope(early_dims_enabled() ? 1 : 0);  // backward always follows a forward (state >= 2)
   const eims_dims& d = p->d;
   const int H = d.hidden_dim, F = d.node_feat_dim, L = d.num_gcn_layers, M = d.max_mz, P = p->pool_dim();
   const int* dims = p->i("dims");
@@ -747,6 +762,7 @@ int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_id
   EIMS_TRY(eims_batch_build(p, ds, mol_ids, num_graphs, stream));
   EIMS_TRY(eims_forward(p, params, const_cast<float*>(bn_running), 0, nullptr, stream));
   cudaStream_t st = (cudaStream_t)stream;
+  EarlyDimsScope early_scope(early_dims_enabled() ? 1 : 0);
   STAGE(ST_ELEMENTWISE, 1, launch_sigmoid(p->i("dims"), p->f("logits"), p->d.max_mz, prob_out ? prob_out : p->f("prob"), p->Bc,
                           (cudaStream_t)stream));
   return check_launch("eims_infer_batch");

@@ -515,10 +515,17 @@ def train_model(model, train_loader, val_loader, config, loss="mse", world_size=
     pinned, pinned_ev = [], [None, None, None]   # ring of pinned staging buffers, reused (a fresh cudaHostAlloc per step costs
                                                  # more than the step); a buffer is repacked only after the copy that read it
     use_fused = world_size > 1 and allreduce is None and tdist.is_available() and tdist.is_initialized()
+    try:
+        from tqdm import tqdm
+    except Exception:  # pragma: no cover - tqdm is optional
+        tqdm = None
     for epoch in range(config.num_epochs):
         model.train()
         metrics.zero_()
-        for batch_graph, batch_spectra in train_loader:
+        # the reference's progress bar (GCN:409) with its loss / cosine postfix (GCN:439) - read one step behind the
+        # GPU through the runner's pinned ring, so the display costs no device synchronisation
+        bar = tqdm(train_loader, desc=f"Epoch {epoch+1}/{config.num_epochs}", leave=False) if (verbose and tqdm is not None) else None
+        for batch_graph, batch_spectra in (bar if bar is not None else train_loader):
             if _zero_in_degree(batch_graph.table):
                 raise _lib.ZeroInDegreeError(_lib.ERR_ZERO_DEGREE, "There are 0-in-degree nodes in the graph (DGL GraphConv would raise)")
             ring = k % 3
@@ -556,6 +563,10 @@ def train_model(model, train_loader, val_loader, config, loss="mse", world_size=
                 plan.adamw(fp, st)
             model._step = k + 1
             k += 1
+            if bar is not None and k % 16 == 0:
+                last = runner.read(1)
+                if last is not None:
+                    bar.set_postfix({"loss": f"{last[0]:.4f}", "cos": f"{last[1]:.4f}"})
         m = metrics.cpu().numpy()
         if runner is not None:
             runner.plan.check()    # capacity / isolated-atom flags K1 left on the device (raises like DGL's GraphConv)

@@ -133,3 +133,14 @@ def test_two_rank_fused_step_vs_shard_sequential_oracle(branch, tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     assert "DP PARITY OK" in r.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run via gpurun --gpus 2)")
+def test_two_rank_train_model_through_the_drop_in(tmp_path):
+    """`script.train_model(..., world_size=2)` under torchrun: bit-identical weights on both ranks, history and
+    validation against the shard-sequential oracle, reference-format checkpoint round trip (tools/dp_dropin.py)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "tools", "dp_dropin.py"), "--out", str(tmp_path / "dropin.json")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    assert "DP DROP-IN OK" in r.stdout
