@@ -582,12 +582,15 @@ def stage_pass(tb, ids_host, ids_dev, n_prof):
     stages_out = stage_report(prof, work, n_prof, pk_)
     dom = max(stages_out, key=lambda n: stages_out[n]["ms_per_step"])
     s = stages_out[dom]
-    traffic = None
+    traffic, l2_traffic = None, None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp) and tb.workload == "train":
-        traffic = json.load(open(tp)).get(dom)  # bytes per launch, ncu dram__bytes_read + dram__bytes_write (cold-cache capture, see profiles/)
+        tj = json.load(open(tp))
+        traffic = tj.get(dom)  # bytes per launch, ncu dram__bytes_read + dram__bytes_write (cold-cache capture of the same launch, see profiles/)
+        l2_traffic = tj.get("_l2_bytes_per_launch", {}).get(dom)  # lts__t_bytes.sum of that capture
     roofline = {"kernel": dom, "bound": s["bound"], "achieved": s["achieved"], "peak": pk_["hbm_gbs"] if s["bound"] == "hbm" else pk_["bf16_tflops"],
-                "unit": s["unit"], "frac": s["frac"], "traffic": traffic,
+                "unit": s["unit"], "frac": s["frac"], "traffic": traffic, "l2_traffic": l2_traffic,
+                "traffic_source": "profiles/ncu_traffic.json: one `ncu --set full` capture of this launch (round 2, cold cache), not measured by this run",
                 "peak_source": f"{pk_['source']} ({'copy bandwidth' if s['bound'] == 'hbm' else 'cuBLAS bf16 burst; tf32 is half of it and the kernel runs 3 tf32 passes, so 1/6 is the ceiling'})",
                 "launch_ms": round(s["ms_per_step"] / s["launches_per_step"], 5)}
     return roofline, stages_out

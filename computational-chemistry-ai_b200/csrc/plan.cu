@@ -110,6 +110,17 @@ struct eims_plan {
   // the launches can be captured into a CUDA graph once and replayed for every step.
   StepBlock* blk = nullptr;
   bool indirect = false;
+  // Side branch of a step (eims_train_step_built_indirect with a second stream): work that nothing on the chain
+  // waits for - the output-layer bias gradient (colsum) and the AdamW update of the head tensors, 84 % of the
+  // parameters - runs there while the GCN layers are differentiated on the main stream.  Fork / join are event
+  // record / wait pairs, which stream capture turns into graph edges.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int ensure_events() {
+    for (auto& e : ev)
+      if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return EIMS_ERR_CUDA;
+    return 0;
+  }
   DropCfg drop(float prob, uint64_t seed, int step, int site) const {
     DropCfg d = make_drop(prob, seed, step, site);
     if (indirect && blk && site >= 0 && site < kMaxDropSites) d.key_dev = &blk->drop_key[site];
@@ -408,6 +419,7 @@ int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, 
 
 int eims_plan_destroy(eims_plan* p) {
   if (p) for (auto& r : p->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  if (p) for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   delete p;
   return 0;
 }
@@ -637,7 +649,15 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
   float* dl = p->f("dlogits");
   // ---- head (GCN:341-352 backwards)
   const int* dB = dims + DIM_B;
-  STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, dl, M, M, grads + p->off_head(9), p->Bc, st));
+  if (p->side) {  // fork: the bias gradient of the output layer is needed by AdamW only
+    if (cudaEventRecord(p->ev[0], st) != cudaSuccess || cudaStreamWaitEvent(p->side, p->ev[0], 0) != cudaSuccess)
+      return fail(EIMS_ERR_CUDA, "side-branch fork failed: %s", cudaGetErrorString(cudaGetLastError()));
+    prof_begin(p, ST_COLSUM, 1, p->side);
+    EIMS_TRY(launch_colsum(dims, DIM_B, dl, M, M, grads + p->off_head(9), p->Bc, p->side));
+    prof_end(p, p->side);
+  } else {
+    STAGE(ST_COLSUM, 1, launch_colsum(dims, DIM_B, dl, M, M, grads + p->off_head(9), p->Bc, st));
+  }
   STAGE(ST_GEMM_HEAD_BWD, (p->pair_gemms && p->gemm_backend == EIMS_GEMM_TCGEN05) ? 1 : 2, gemm_pair(p,
         GemmProblem{dl, M, 1, p->f("y2"), H, 1, grads + p->off_head(8), H, M, H, p->Bc, nullptr, dB, nullptr, nullptr, 0, 1, nullptr},
         GemmProblem{dl, M, 0, params + p->off_head(8), H, 1, p->f("dy2"), H, p->Bc, H, M, dB, nullptr, nullptr, nullptr, 0, 3, nullptr}, st));
@@ -739,22 +759,56 @@ int eims_train_step_built(eims_plan* p, const float* targets, const int32_t* tar
 }
 
 int eims_train_step_built_indirect(eims_plan* p, const float* targets, float* params, float* grads, float* adam_m,
-                                   float* adam_v, float* bn_running, int32_t loss_kind, float* metrics, eims_stream_t stream) {
+                                   float* adam_v, float* bn_running, int32_t loss_kind, float* metrics, eims_stream_t stream,
+                                   eims_stream_t side_stream) {
   if (!p || !p->blk) return fail(EIMS_ERR_STATE, "no step block set (eims_plan_set_step_block)");
   if (!targets && !p->peak_targets.peak_ptr) return fail(EIMS_ERR_ARG, "training needs target spectra");
+  cudaStream_t st = (cudaStream_t)stream, side = (cudaStream_t)side_stream;
+  if (side && side != st && p->ensure_events()) return fail(EIMS_ERR_CUDA, "cudaEventCreate failed");
+  if (side == st) side = nullptr;
   eims_step dummy{};  // seed / step are not used: the dropout keys come from the step block
+  struct Scope {  // the plan's per-call mode must not leak out of this function
+    eims_plan* p;
+    ~Scope() { p->indirect = false; p->side = nullptr; }
+  } scope{p};
   p->indirect = true;
-  int rc = eims_forward(p, params, bn_running, 1, &dummy, stream);
-  if (!rc) rc = loss_impl(p, targets, p->i("bids"), loss_kind, 1, metrics, stream);
-  if (!rc) rc = eims_backward(p, params, nullptr, grads, stream);
-  if (!rc && adam_m && adam_v) {
-    cudaStream_t st = (cudaStream_t)stream;
+  p->side = side;
+  EIMS_TRY(eims_forward(p, params, bn_running, 1, &dummy, stream));
+  EIMS_TRY(loss_impl(p, targets, p->i("bids"), loss_kind, 1, metrics, stream));
+  const bool adam = adam_m && adam_v;
+  const int64_t P = p->poff.back();
+  int64_t split = p->off_head(0) & ~(int64_t)3;   // [0, split) GraphConv + BatchNorm tensors, [split, P) the head
+  if (!side || !adam) {
+    EIMS_TRY(eims_backward(p, params, nullptr, grads, stream));
+    if (adam) {
+      prof_begin(p, ST_ADAMW, 1, st);
+      EIMS_TRY(launch_adamw(params, grads, adam_m, adam_v, P, nullptr, st, p->blk));
+      prof_end(p, st);
+    }
+    if (side) {  // join the colsum branch
+      if (cudaEventRecord(p->ev[1], side) != cudaSuccess || cudaStreamWaitEvent(st, p->ev[1], 0) != cudaSuccess)
+        return fail(EIMS_ERR_CUDA, "side-branch join failed");
+    }
+    return 0;
+  }
+  // head part on the main stream (its bias-gradient colsum on the side branch), then
+  //   side: AdamW of the head range, as soon as the head gradients are final   ||   main: GCN layers backward
+  EIMS_TRY(eims_backward_part(p, params, nullptr, grads, EIMS_BWD_HEAD, stream));
+  if (cudaEventRecord(p->ev[2], st) != cudaSuccess || cudaStreamWaitEvent(side, p->ev[2], 0) != cudaSuccess)
+    return fail(EIMS_ERR_CUDA, "side-branch fork failed");
+  prof_begin(p, ST_ADAMW, 1, side);
+  EIMS_TRY(launch_adamw(params + split, grads + split, adam_m + split, adam_v + split, P - split, nullptr, side, p->blk));
+  prof_end(p, side);
+  if (cudaEventRecord(p->ev[1], side) != cudaSuccess) return fail(EIMS_ERR_CUDA, "cudaEventRecord failed");
+  p->side = nullptr;  // the GCN part has nothing for the side branch
+  EIMS_TRY(eims_backward_part(p, params, nullptr, grads, EIMS_BWD_GCN, stream));
+  if (split > 0) {
     prof_begin(p, ST_ADAMW, 1, st);
-    rc = launch_adamw(params, grads, adam_m, adam_v, p->poff.back(), nullptr, st, p->blk);
+    EIMS_TRY(launch_adamw(params, grads, adam_m, adam_v, split, nullptr, st, p->blk));
     prof_end(p, st);
   }
-  p->indirect = false;
-  return rc;
+  if (cudaStreamWaitEvent(st, p->ev[1], 0) != cudaSuccess) return fail(EIMS_ERR_CUDA, "side-branch join failed");
+  return 0;
 }
 
 int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,

@@ -493,12 +493,14 @@ class Plan:
         check(self.lib.eims_batch_build_indirect(self.h, C.byref(ds.struct), int(num_graphs), self.stream))
         self.num_graphs = int(num_graphs)
 
-    def train_step_built_indirect(self, ds: DeviceDataset, fp: FlatParams, metrics=None, loss_kind="mse", optimizer=True):
+    def train_step_built_indirect(self, ds: DeviceDataset, fp: FlatParams, metrics=None, loss_kind="mse", optimizer=True, side=None):
+        """side: a torch stream for the step's side branch (output-layer bias gradient, AdamW of the head tensors)."""
         if optimizer:
             fp.ensure_adam()
         check(self.lib.eims_train_step_built_indirect(self.h, ptr(self._targets(ds)), ptr(fp.params), ptr(fp.grads),
                                                       ptr(fp.adam_m) if optimizer else None, ptr(fp.adam_v) if optimizer else None,
-                                                      ptr(fp.bn_running), _lib.LOSS[loss_kind], ptr(metrics), self.stream))
+                                                      ptr(fp.bn_running), _lib.LOSS[loss_kind], ptr(metrics), self.stream,
+                                                      C.c_void_p(side.cuda_stream) if side is not None else None))
 
     # -- per-stage profiling (bench.py) ------------------------------------------------
     def profile(self, enable: bool):
@@ -535,6 +537,10 @@ class GraphedTrainStep:
         self.plan, self.ds, self.fp, self.batch, self.metrics, self.loss_kind, self.fused = plan, ds, fp, int(batch), metrics, loss_kind, fused
         self.graphs, self.k, self.primed = [], 0, False
         self.side = torch.cuda.Stream(plan.device)
+        # second side branch: the bias gradient of the output layer and the head's AdamW run off the chain (single GPU;
+        # in data-parallel runs the fused exchange kernel is the optimiser).  EIMS_STEP_SIDE_BRANCH=0 keeps one chain.
+        import os
+        self.side2 = torch.cuda.Stream(plan.device) if (fused is None and os.environ.get("EIMS_STEP_SIDE_BRANCH", "1") != "0") else None
         plan.enable_step_block()
         if fused is None:
             fp.ensure_adam()
@@ -544,7 +550,7 @@ class GraphedTrainStep:
         self.side.wait_stream(cur)                       # fork: the build may start with the step
         if self.fused is not None:
             self.fused.begin_step()
-        plan.train_step_built_indirect(self.ds, self.fp, self.metrics, self.loss_kind, optimizer=self.fused is None)
+        plan.train_step_built_indirect(self.ds, self.fp, self.metrics, self.loss_kind, optimizer=self.fused is None, side=self.side2)
         if self.fused is not None:
             self.fused.finish(step_for_fused, plan.stream, step_block=plan._step_block)
         with torch.cuda.stream(self.side):

@@ -289,8 +289,12 @@ int64_t eims_step_block_bytes(void);
 int eims_plan_set_step_block(eims_plan* p, void* dev_block, int64_t bytes); /* NULL: indirect calls disabled */
 int eims_step_block_upload(eims_plan* p, const eims_step* s, const int32_t* mol_ids, uint32_t dp_seq, eims_stream_t stream);
 int eims_batch_build_indirect(eims_plan* p, const eims_dataset* ds, int32_t num_graphs, eims_stream_t stream);
+/* side_stream (may be NULL): a second stream for the work nothing on the step's chain waits for - the bias gradient
+ * of the output layer and the AdamW update of the head tensors (84 % of the parameters) run there while the GCN layers
+ * are differentiated; forked from and joined back into `stream` with events, i.e. graph edges under capture. */
 int eims_train_step_built_indirect(eims_plan* p, const float* targets, float* params, float* grads, float* adam_m,
-                                   float* adam_v, float* bn_running, int32_t loss_kind, float* metrics, eims_stream_t stream);
+                                   float* adam_v, float* bn_running, int32_t loss_kind, float* metrics, eims_stream_t stream,
+                                   eims_stream_t side_stream);
 
 /* predict_spectrum (GCN:494-511) for a batch: batch build + eval forward + sigmoid. */
 int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
