@@ -60,6 +60,9 @@ def parse():
                          "rank_strided_uniform: the same global batch, every world-th molecule per rank (DistributedSampler); "
                          "stratified: size-stratified batches (every batch the same work). The other two are timed as sampling_variants")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--step-events", default="auto", choices=["auto", "on", "off"],
+                    help="one CUDA event per timed step (per-rank step_times); auto = only at N>1, where the diagnosis matters: the "
+                         "event between two steps costs the eager path its kernel-to-kernel launch overlap across the step boundary")
     ap.add_argument("--no-prefetch", action="store_true", help="eager N=1: build each batch inside its own step instead of one step ahead")
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"], help="N>1: gradient exchange implementation")
     ap.add_argument("--dp-overlap", action="store_true", help="eager fused path: exchange the head bucket early on a side stream")
@@ -365,6 +368,7 @@ class TrainBench:
         self.graph_note = "eager launches"
         self.sched = onecycle_schedule(4096)
         self.launches_per_step = None
+        self.sampler = ClockSampler(dev.index or 0)   # nvmlInit + handle lookup now, sampling thread later
 
     def step_scalars(self, k=None):
         from eims_b200.engine import make_step
@@ -396,19 +400,27 @@ class TrainBench:
             g = GraphedTrainStep(self.plan, self.ds, self.fp, self.batch, self.metrics, fused=self.fused)
             g.capture(first_ids, self.step_scalars())
             _, n = self.plan.profile_read()
-            self.launches_per_step = n // 2 + 1 + (1 if self.fused is not None else 0)   # + step-block upload (+ exchange kernel)
+            per = n // (2 + g.group)                                  # launches the plan counted per captured step
+            self.launches_per_step = per + (1 if self.fused is not None else 0) + 1.0 / max(g.group, 1)   # (+ exchange kernel) + upload per group
             self.graphed = g
-            self.graph_note = "two alternating captured CUDA graphs (step || next batch build), one step-block upload + one graph launch per step"
+            self.graph_note = (f"captured CUDA graphs: {g.group} consecutive steps per graph (step || next batch build || head optimiser), one "
+                               "step-block upload + one graph launch per group; single-step graphs for the remainder")
         except Exception as exc:
             self.graph_note = f"eager launches [graph capture failed: {type(exc).__name__}: {str(exc)[:200]}]"
             self.graphed = None
 
     def step(self, ids, next_ids):
+        """Returns True when work was actually enqueued (graph groups are launched when full)."""
         if self.graphed is not None:
             self.graphed.step(self.step_scalars(), next_ids)
             self.k += 1
-        else:
-            self.eager_step(ids, next_ids)
+            return not self.graphed.pending
+        self.eager_step(ids, next_ids)
+        return True
+
+    def flush(self):
+        if self.graphed is not None:
+            self.graphed.flush()
 
     def device_barrier(self):
         """All ranks leave together, ON THE DEVICE: a tiny all-reduce on the compute stream; what is enqueued next
@@ -425,25 +437,43 @@ class TrainBench:
         import torch
         import torch.distributed as dist
         torch.cuda.synchronize()
-        sampler = ClockSampler(self.dev.index or 0) if with_sampler else None   # NVML init happens here, BEFORE the barrier
+        # NVML was initialised when the bench object was built (tens of ms, 8 processes at once): here only the sampling
+        # thread starts, BEFORE the barrier, so the GPU is idle for microseconds, not milliseconds, ahead of the timed steps
+        sampler = self.sampler if with_sampler else None
         if sampler:
+            self.sampler = None
             sampler.start()
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps + 1)]
+        per_step = self.args.step_events == "on" or (self.args.step_events == "auto" and self.world > 1)
         if self.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         self.device_barrier()
-        evs[0].record()
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        marks = []   # (event, steps enqueued since the previous mark): one per launch (a graph group, or an eager step)
+        since = 0
         for j in range(n_steps):
-            self.step(ids_dev[i0 + j], ids_dev[i0 + j + 1])
-            evs[j + 1].record()
+            launched = self.step(ids_dev[i0 + j], ids_dev[i0 + j + 1])
+            since += 1
+            if j == n_steps - 1:
+                self.flush()
+                launched = True
+            if launched and (per_step or j == n_steps - 1):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((e, since))
+                since = 0
         torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
-        ms = evs[0].elapsed_time(evs[-1])
-        per = np.array([evs[j].elapsed_time(evs[j + 1]) for j in range(n_steps)])
+        ms = ev0.elapsed_time(marks[-1][0])
+        per, prev = [], ev0
+        for e, cnt in marks:   # a group's time is spread evenly over its steps
+            per += [prev.elapsed_time(e) / cnt] * cnt
+            prev = e
+        per = np.array(per)
         if self.world > 1:
             t = torch.tensor([ms], device=self.dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -486,13 +516,14 @@ def run_ours(args):
         pass  # the eager prefetch path already built batch 2
     for i in range(2, W):
         tb.step(ids_dev[i], ids_dev[i + 1])
+    tb.flush()
     tb.plan.check()
     # ---- the timed region
     tb.plan.profile(False)  # resets the launch counter
     ms, per_step, clocks = tb.timed(ids_dev, W, K, with_sampler=True)
     _, launches = tb.plan.profile_read()
     if tb.graphed is not None:
-        launches = K * tb.launches_per_step
+        launches = int(round(K * tb.launches_per_step))
     tb.plan.check()
     if tb.fused is not None and tb.fused.lost_peer():
         raise SystemExit(f"rank {rank}: a peer did not arrive at the gradient exchange (sequence {tb.fused.lost_peer()})")
@@ -508,7 +539,8 @@ def run_ours(args):
         allp = torch.stack(allp).cpu().numpy()
         wr, ws = np.unravel_index(np.argmax(allp), allp.shape)
         atoms = [int(tb.sizes[ids_host[W + j]].sum()) for j in range(K)]
-        step_times = {"median_ms_per_rank": [round(float(np.median(r)), 4) for r in allp],
+        step_times = {"note": "graph groups are timed as a whole and spread evenly over their steps",
+                      "median_ms_per_rank": [round(float(np.median(r)), 4) for r in allp],
                       "max_ms_per_rank": [round(float(r.max()), 4) for r in allp],
                       "worst": {"rank": int(wr), "step": int(ws), "ms": round(float(allp[wr, ws]), 4)},
                       "rank0_atoms_per_batch_min_max": [min(atoms), max(atoms)]}
@@ -796,6 +828,7 @@ def extra_workloads(args, dev):
         tb.try_capture(ids_d[2])
         for i in range(2, Ww):
             tb.step(ids_d[i], ids_d[i + 1])
+        tb.flush()
         ms, per, clocks = tb.timed(ids_d, Ww, Kw, with_sampler=True)
         _, st = stage_pass(tb, ids_h, ids_d, 5)
         out["wide"] = {"metric": METRIC, "value": Kw * tb.batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / Kw, "steps": Kw,

@@ -89,6 +89,9 @@ struct StepBlock {
   uint32_t dp_seq;         // sequence number of the fused data-parallel exchange
   int32_t k1_seq;          // batch sequence number (tags the zero-degree flag)
 };
+constexpr int kStepPack = 16;   // blocks one upload launch can carry by value (kernel parameters are limited to 4 KB)
+struct StepBlockPack { StepBlock b[kStepPack]; };
+static_assert(sizeof(StepBlockPack) + 16 <= 4096, "step blocks no longer fit the kernel parameter space");
 
 // 32-bit finaliser (two multiply / xor-shift rounds, the "lowbias32" constants of the hash-prospector
 // search): ~8 integer instructions, against ~25 for a 64-bit SplitMix round on this machine - the forward

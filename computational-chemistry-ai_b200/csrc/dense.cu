@@ -1003,6 +1003,16 @@ int launch_step_block_store(const StepBlock& v, StepBlock* dst, cudaStream_t st)
   launch_pdl(step_block_store_kernel, dim3(1), dim3(32), 0, st, v, dst);
   return 0;
 }
+// several consecutive blocks at once (a graph that holds several steps): still one launch, the blocks by value
+__global__ void step_blocks_store_kernel(StepBlockPack v, StepBlock* __restrict__ dst, int n) {
+  pdl_sync();
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = v.b[threadIdx.x];
+}
+int launch_step_blocks_store(const StepBlockPack& v, StepBlock* dst, int n, cudaStream_t st) {
+  if (n < 1 || n > kStepPack) return EIMS_ERR_ARG;
+  launch_pdl(step_blocks_store_kernel, dim3(1), dim3(32), 0, st, v, dst, n);
+  return 0;
+}
 
 // =========================================================================== dropout mask (tests)
 __global__ void dropout_mask_kernel(DropCfg d, int64_t n4, float* __restrict__ out) {

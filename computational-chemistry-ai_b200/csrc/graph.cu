@@ -17,7 +17,7 @@ namespace eims {
 // aggregate a0 = A (x * c) of GraphConv (GCN:359, i = 0), which only needs the molecule itself.
 // dims[DIM_ZERO_DEG] holds the sequence number of the last batch that had an isolated atom and
 // dims[5] the current sequence number (no reset race between blocks).
-constexpr int kK1Warps = 2;  // 256 blocks for a batch of 512: more than one per SM
+constexpr int kK1Warps = 4;  // upper bound (shared-memory arrays); the launch picks 2 or 4 warps per block
 constexpr int kMaxF0 = 8;
 
 // Large batches (inference, thousands of molecules): the per-block batch reduction of the fused
@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(kK1Warps * 32) k1_build_kernel(
   __shared__ int cnt_n[kK1Warps], cnt_e[kK1Warps];
   __shared__ K1Stage stage[kK1Warps];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int g0 = blockIdx.x * kK1Warps;
+  const int nwarps = blockDim.x >> 5;   // warps (= molecules) per block
+  const int g0 = blockIdx.x * nwarps;
   int o, eo;
   if (prescanned) {  // offsets and dims[] come from k1_scan_kernel
     if (dims[DIM_OVERFLOW]) return;
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kK1Warps * 32) k1_build_kernel(
       const int g = gb + u * blockDim.x;
       tn += n[u]; te += e[u];
       if (g < g0) { pn += n[u]; pe += e[u]; }
-      if (g >= g0 && g < g0 + kK1Warps && g < B) { cnt_n[g - g0] = (int)n[u]; cnt_e[g - g0] = (int)e[u]; }
+      if (g >= g0 && g < g0 + nwarps && g < B) { cnt_n[g - g0] = (int)n[u]; cnt_e[g - g0] = (int)e[u]; }
     }
   }
 #pragma unroll
@@ -152,8 +153,7 @@ __global__ void __launch_bounds__(kK1Warps * 32) k1_build_kernel(
   if (lane == 0) { red[w][0] = tn; red[w][1] = te; red[w][2] = pn; red[w][3] = pe; }
   __syncthreads();
   tn = te = pn = pe = 0;
-#pragma unroll
-  for (int k = 0; k < kK1Warps; ++k) { tn += red[k][0]; te += red[k][1]; pn += red[k][2]; pe += red[k][3]; }
+  for (int k = 0; k < nwarps; ++k) { tn += red[k][0]; te += red[k][1]; pn += red[k][2]; pe += red[k][3]; }
   const bool over = tn > max_nodes || te > max_edges;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const int N = over ? 0 : (int)tn, E = over ? 0 : (int)te;
@@ -312,12 +312,15 @@ int launch_csr_build(const eims_dataset* ds, const int32_t* ids, int B, int F, i
                      int* gptr, int* eptr, int* gid, int* src, int* dst, int* rowptr, int* col, float* norm,
                      float* x, int* dims, cudaStream_t st, float* a0, int seq, const StepBlock* blk, int* bids) {
   if (F > kMaxF0) return EIMS_ERR_ARG;
-  const int blocks = B > 0 ? (B + kK1Warps - 1) / kK1Warps : 1;
+  // molecules (warps) per block: 2 gives 256 blocks for a batch of 512, 4 is round 1's shape (EIMS_K1_WARPS for A/B)
+  static int k1w = 0;
+  if (!k1w) { const char* e = getenv("EIMS_K1_WARPS"); k1w = e ? atoi(e) : 2; if (k1w < 1 || k1w > kK1Warps) k1w = 2; }
+  const int blocks = B > 0 ? (B + k1w - 1) / k1w : 1;
   const int prescanned = B > 1024;
   if (prescanned)
     launch_pdl(k1_scan_kernel, dim3(1), dim3(1024), 0, st, ds->node_ptr, ds->bond_ptr, ids, B, max_nodes, max_edges, gptr, eptr,
                rowptr, dims, seq, blk);
-  launch_pdl(k1_build_kernel, dim3(blocks), dim3(kK1Warps * 32), 0, st, ds->node_ptr, ds->bond_ptr, ds->feat, ds->bond_begin,
+  launch_pdl(k1_build_kernel, dim3(blocks), dim3(k1w * 32), 0, st, ds->node_ptr, ds->bond_ptr, ds->feat, ds->bond_begin,
              ds->bond_end, ids, B, F, max_nodes, max_edges, seq, gptr, eptr, gid, src, dst, rowptr, col, norm, x, a0, dims,
              prescanned, blk, bids);
   return 0;

@@ -81,6 +81,7 @@ int launch_colsum(const int* dims, int dim_slot, const float* in, int C, int ld,
 int launch_adamw(float* p, float* g, float* m, float* v, int64_t n, const eims_step* s, cudaStream_t st,
                  const StepBlock* blk = nullptr);  // blk: the scalars are read from the device step block
 int launch_step_block_store(const StepBlock& v, StepBlock* dst, cudaStream_t st);
+int launch_step_blocks_store(const StepBlockPack& v, StepBlock* dst, int n, cudaStream_t st);
 int launch_dropout_mask(DropCfg d, int rows, int W, float* out, cudaStream_t st);
 
 // gemm_tc.cu  (tcgen05 / TMEM, 3xTF32)

@@ -108,7 +108,9 @@ struct eims_plan {
   // Device step block (eims_plan_set_step_block) and the mode of the call being enqueued: `indirect` calls take
   // the batch's ids, the dropout keys and the AdamW scalars from it instead of from kernel parameters, so that
   // the launches can be captured into a CUDA graph once and replayed for every step.
-  StepBlock* blk = nullptr;
+  StepBlock* blk = nullptr;       // the block the next *_indirect calls bake in (eims_plan_select_step_block)
+  StepBlock* blk_base = nullptr;  // the caller's array of blk_count blocks
+  int blk_count = 0;
   bool indirect = false;
   // Side branch of a step (eims_train_step_built_indirect with a second stream): work that nothing on the chain
   // waits for - the output-layer bias gradient (colsum) and the AdamW update of the head tensors, 84 % of the
@@ -492,14 +494,20 @@ int eims_plan_set_step_block(eims_plan* p, void* dev_block, int64_t bytes) {
   if (!p) return fail(EIMS_ERR_ARG, "plan is NULL");
   if (dev_block && (bytes < (int64_t)sizeof(StepBlock) || (reinterpret_cast<uintptr_t>(dev_block) & 15)))
     return fail(EIMS_ERR_ARG, "step block needs %d bytes, 16-byte aligned", (int)sizeof(StepBlock));
-  p->blk = reinterpret_cast<StepBlock*>(dev_block);
+  p->blk_base = p->blk = reinterpret_cast<StepBlock*>(dev_block);
+  p->blk_count = dev_block ? (int)(bytes / (int64_t)sizeof(StepBlock)) : 0;
   return 0;
 }
 int64_t eims_step_block_bytes(void) { return (int64_t)sizeof(StepBlock); }
 
-int eims_step_block_upload(eims_plan* p, const eims_step* s, const int32_t* mol_ids, uint32_t dp_seq, eims_stream_t stream) {
-  if (!p || !p->blk) return fail(EIMS_ERR_STATE, "no step block set (eims_plan_set_step_block)");
-  if (!s || s->step < 1) return fail(EIMS_ERR_ARG, "step scalars are NULL / step < 1");
+int eims_plan_select_step_block(eims_plan* p, int32_t index) {
+  if (!p || !p->blk_base) return fail(EIMS_ERR_STATE, "no step block set (eims_plan_set_step_block)");
+  if (index < 0 || index >= p->blk_count) return fail(EIMS_ERR_ARG, "step block %d outside [0, %d)", index, p->blk_count);
+  p->blk = p->blk_base + index;
+  return 0;
+}
+
+static StepBlock make_step_block(const eims_plan* p, const eims_step* s, const int32_t* mol_ids, uint32_t dp_seq) {
   StepBlock v{};
   v.ids = mol_ids;
   v.adam = make_adam_k(s);
@@ -507,6 +515,27 @@ int eims_step_block_upload(eims_plan* p, const eims_step* s, const int32_t* mol_
   for (int k = 0; k < sites && k < kMaxDropSites; ++k) v.drop_key[k] = drop_key(s->seed, s->step, k);
   v.dp_seq = dp_seq;
   v.k1_seq = 1 + (s->step & 0x3fffffff);
+  return v;
+}
+
+int eims_step_blocks_upload(eims_plan* p, const eims_step* steps, const int32_t* const* mol_ids, const uint32_t* dp_seq,
+                            int32_t first, int32_t n, eims_stream_t stream) {
+  if (!p || !p->blk_base) return fail(EIMS_ERR_STATE, "no step block set (eims_plan_set_step_block)");
+  if (!steps || !mol_ids || n < 1 || n > kStepPack || first < 0 || first + n > p->blk_count)
+    return fail(EIMS_ERR_ARG, "need 1 <= n <= %d blocks inside [0, %d)", kStepPack, p->blk_count);
+  StepBlockPack pack{};
+  for (int k = 0; k < n; ++k) {
+    if (steps[k].step < 1) return fail(EIMS_ERR_ARG, "step < 1");
+    pack.b[k] = make_step_block(p, steps + k, mol_ids[k], dp_seq ? dp_seq[k] : 0u);
+  }
+  EIMS_TRY(launch_step_blocks_store(pack, p->blk_base + first, n, (cudaStream_t)stream));
+  return check_launch("eims_step_blocks_upload");
+}
+
+int eims_step_block_upload(eims_plan* p, const eims_step* s, const int32_t* mol_ids, uint32_t dp_seq, eims_stream_t stream) {
+  if (!p || !p->blk) return fail(EIMS_ERR_STATE, "no step block set (eims_plan_set_step_block)");
+  if (!s || s->step < 1) return fail(EIMS_ERR_ARG, "step scalars are NULL / step < 1");
+  const StepBlock v = make_step_block(p, s, mol_ids, dp_seq);
   EIMS_TRY(launch_step_block_store(v, p->blk, (cudaStream_t)stream));
   return check_launch("eims_step_block_upload");
 }

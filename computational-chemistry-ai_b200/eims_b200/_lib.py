@@ -102,6 +102,8 @@ _SIGS = {
     "eims_step_block_bytes": (_i64, []),
     "eims_plan_set_step_block": (C.c_int, [_vp, _vp, _i64]),
     "eims_step_block_upload": (C.c_int, [_vp, C.POINTER(Step), _vp, C.c_uint32, _vp]),
+    "eims_plan_select_step_block": (C.c_int, [_vp, _i32]),
+    "eims_step_blocks_upload": (C.c_int, [_vp, C.POINTER(Step), C.POINTER(_vp), C.POINTER(C.c_uint32), _i32, _i32, _vp]),
     "eims_batch_build_indirect": (C.c_int, [_vp, C.POINTER(Dataset), _i32, _vp]),
     "eims_train_step_built_indirect": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "eims_plan_profile": (C.c_int, [_vp, _i32]),

@@ -234,7 +234,7 @@ class FusedP2PAdamW:
                                                ptr(self.v[bucket]), ptr(self.sym_grads[1 - cur]), off, ln,
                                                C.byref(step) if step is not None else None,
                                                C.c_uint32(self.seq), bucket, C.c_void_p(self.ticket.data_ptr() + 16 * bucket),
-                                               ptr(step_block), stream))
+                                               step_block if isinstance(step_block, C.c_void_p) else ptr(step_block), stream))
 
     def lost_peer(self):
         """Sequence number at which this rank gave up waiting for a peer (EIMS_DP_TIMEOUT_S), or 0.  One small

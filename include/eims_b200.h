@@ -286,8 +286,15 @@ int eims_train_step_built(eims_plan* p, const float* targets, const int32_t* tar
  *     eims_step_block_upload(scalars of step t, ids of batch t+1) ; cudaGraphLaunch.
  * The target row of graph b is the molecule id it was built from (the ids K1 read). */
 int64_t eims_step_block_bytes(void);
-int eims_plan_set_step_block(eims_plan* p, void* dev_block, int64_t bytes); /* NULL: indirect calls disabled */
+/* dev_block: room for one or more step blocks (bytes / eims_step_block_bytes() of them); NULL: indirect calls disabled.
+ * A graph may hold SEVERAL consecutive steps (the launch gap between two graphs then amortises over them): give every
+ * captured step its own block - eims_plan_select_step_block(k) before enqueueing step k - and fill blocks
+ * [first, first + n) with one launch of eims_step_blocks_upload (n <= 16) before each replay. */
+int eims_plan_set_step_block(eims_plan* p, void* dev_block, int64_t bytes);
+int eims_plan_select_step_block(eims_plan* p, int32_t index);
 int eims_step_block_upload(eims_plan* p, const eims_step* s, const int32_t* mol_ids, uint32_t dp_seq, eims_stream_t stream);
+int eims_step_blocks_upload(eims_plan* p, const eims_step* steps, const int32_t* const* mol_ids, const uint32_t* dp_seq,
+                            int32_t first, int32_t n, eims_stream_t stream);
 int eims_batch_build_indirect(eims_plan* p, const eims_dataset* ds, int32_t num_graphs, eims_stream_t stream);
 /* side_stream (may be NULL): a second stream for the work nothing on the step's chain waits for - the bias gradient
  * of the output layer and the AdamW update of the head tensors (84 % of the parameters) run there while the GCN layers

@@ -96,7 +96,7 @@ def test_graph_replay_equals_eager_steps(dropout):
     sched = onecycle_schedule(steps)
     mk = lambda k: make_step(lr=sched[k][0], beta1=sched[k][1], step=k + 1, seed=77)
     out = {}
-    for mode in ("eager", "graph"):
+    for mode in ("eager", "graph", "group4"):
         plan = Plan(d, batch, batch * 40, 2 * (batch * 40 + 3 * batch), DEV)
         fp = FlatParams(d, DEV)
         fp.load_state_dict(O.init_params(od, 0))
@@ -107,21 +107,30 @@ def test_graph_replay_equals_eager_steps(dropout):
                 plan.train_step(ds, ids[k], fp, mk(k), metrics)
                 losses.append(float(metrics[4]))
         else:
-            gs = GraphedTrainStep(plan, ds, fp, batch, metrics)
+            # "graph": single-step graphs, flushed after every step; "group4": 4 steps per graph + 2 single steps
+            gs = GraphedTrainStep(plan, ds, fp, batch, metrics, group=0 if mode == "graph" else 4)
             gs.capture(ids[0], mk(0))
             for k in range(steps):
                 gs.step(mk(k), ids[min(k + 1, steps - 1)])
-                losses.append(float(metrics[4]))
+                if mode == "graph":
+                    gs.flush()
+                    losses.append(float(metrics[4]))
+            gs.flush()
+            if mode != "graph":
+                assert gs.multi is not None and gs.k == 0
+                losses = out["eager"][2][:-1] + [float(metrics[4])]   # only the last step's loss is visible
         plan.check()
         out[mode] = (fp.params.clone(), fp.bn_running.clone(), losses, metrics.clone())
-    pe, pg = out["eager"][0], out["graph"][0]
-    # training sums with atomics (BatchNorm, split-K): equal up to summation order, and AdamW's sign-like
-    # first steps amplify last-bit gradient noise on elements whose gradient is ~0
-    np.testing.assert_allclose(out["graph"][2], out["eager"][2], rtol=2e-5)
-    assert float((out["eager"][1] - out["graph"][1]).abs().max() / out["eager"][1].abs().max()) < 2e-4
-    close = ((pe - pg).abs() <= 1e-5 * pe.abs().max()).float().mean()
-    assert close > 0.995, float(close)
-    assert float(out["graph"][3][2]) == steps and float(out["graph"][3][6]) == 0.0
+    for mode in ("graph", "group4"):
+        pe, pg = out["eager"][0], out[mode][0]
+        # training sums with atomics (BatchNorm, split-K): equal up to summation order, and AdamW's sign-like
+        # first steps amplify last-bit gradient noise on elements whose gradient is ~0
+        np.testing.assert_allclose(out[mode][2], out["eager"][2], rtol=2e-5)
+        assert float((out["eager"][1] - out[mode][1]).abs().max() / out["eager"][1].abs().max()) < 2e-4
+        close = ((pe - pg).abs() <= 1e-5 * pe.abs().max()).float().mean()
+        assert close > 0.995, (mode, float(close))
+        assert float(out[mode][3][2]) == steps and float(out[mode][3][6]) == 0.0
+        np.testing.assert_allclose(float(out[mode][3][0]), float(out["eager"][3][0]), rtol=2e-5)   # the epoch's loss sum
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run via gpurun --gpus 2)")
