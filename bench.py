@@ -632,7 +632,7 @@ def e2e_pass(tb, n_e2e):
     """The reference-facing call with HOST buffers, per step and inside the timed region: collate of the batch from the
     host-resident set into pinned memory (`eims_host_pack_batch`, C, on 4 worker threads - the reference's DataLoader
     uses num_workers=4, GCN:100 - prefetching 4 batches ahead), ONE H2D copy, K1 + step, D2H of the step's loss / cosine,
-    which the host reads one step behind.  N>1: every rank feeds from its own host shard (uniform shuffle) and the
+    which the host reads two steps behind.  N>1: every rank feeds from its own host shard (uniform shuffle) and the
     gradients go through the same fused exchange kernel."""
     import torch
     import torch.distributed as dist
@@ -708,7 +708,7 @@ def e2e_pass(tb, n_e2e):
     last = None
     for j in range(3, 3 + n_e2e):
         slot = one(j, slot)
-        last = runner.read(1) or last   # the previous step's loss on the host (waits for ITS copy only)
+        last = runner.read(2) or last   # a finished step's loss on the host, two steps behind the GPU (waits for ITS copy only)
     loss_e2e, _ = runner.result()
     e1.record()
     torch.cuda.synchronize()
@@ -722,7 +722,7 @@ def e2e_pass(tb, n_e2e):
             "d2h_bytes_per_step": int(runner.d2h_bytes / n_e2e), "steps": n_e2e,
             "timing": ("host wall clock around the loop, max over ranks (device events: %.1f ms); INSIDE the timed region per step: host collate of "
                        "the batch into pinned memory (C, %d worker threads, %d batches ahead), one H2D copy, K1 + step%s, D2H of loss/cosine "
-                       "read by the host one step behind" % (e0.elapsed_time(e1), workers, depth, " + fused gradient exchange" if tb.world > 1 else "")),
+                       "read by the host two steps behind" % (e0.elapsed_time(e1), workers, depth, " + fused gradient exchange" if tb.world > 1 else "")),
             "last_loss": loss_e2e}
 
 

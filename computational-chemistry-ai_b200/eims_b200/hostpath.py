@@ -156,8 +156,9 @@ class HostBatchRunner:
         self.metrics = metrics if metrics is not None else torch.zeros(8, dtype=torch.float32, device=dev)
         # the per-step loss / cosine come back through two pinned buffers used in turn, each with the event of its
         # device-to-host copy: the host reads a step's values only after that event (`read`), one step behind the GPU
-        self.host_ring = [torch.zeros(8, dtype=torch.float32, pin_memory=True) for _ in range(2)]
-        self.d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.RING = 4
+        self.host_ring = [torch.zeros(8, dtype=torch.float32, pin_memory=True) for _ in range(self.RING)]
+        self.d2h_done = [torch.cuda.Event() for _ in range(self.RING)]
         self._n = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -231,7 +232,7 @@ class HostBatchRunner:
         ev = torch.cuda.Event()
         ev.record(cur)
         self.consumed[slot] = ev
-        k = self._n % 2
+        k = self._n % self.RING
         self.host_ring[k].copy_(self.metrics, non_blocking=True)
         self.d2h_done[k].record(cur)
         self._n += 1
@@ -254,11 +255,11 @@ class HostBatchRunner:
         self.d2h_bytes += prob.numel() * 4
 
     def read(self, lag: int = 1):
-        """(loss, cosine) of the training step `lag` steps before the one enqueued last (lag 0 or 1), after waiting
-        for THAT step's device-to-host copy only - with lag 1 the GPU keeps running the current step meanwhile."""
-        if self._n - 1 - lag < 0:
+        """(loss, cosine) of the training step `lag` steps before the one enqueued last (0 <= lag < 4), after waiting
+        for THAT step's device-to-host copy only - with lag >= 1 the GPU keeps running the newer steps meanwhile."""
+        if self._n - 1 - lag < 0 or lag >= self.RING:
             return None
-        k = (self._n - 1 - lag) % 2
+        k = (self._n - 1 - lag) % self.RING
         self.d2h_done[k].synchronize()
         return float(self.host_ring[k][4]), float(self.host_ring[k][5])
 
