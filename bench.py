@@ -629,6 +629,87 @@ def stage_pass(tb, ids_host, ids_dev, n_prof):
 
 
 def e2e_pass(tb, n_e2e):
+    """The reference-facing path with HOST buffers.  Default: `GraphedHostTrainer` - the copies, K1 and the steps replayed
+    as CUDA graphs of 10 steps, the host collating into a pinned ring.  Falls back to the eagerly launched
+    `HostBatchRunner` loop (and says so) if the graphs cannot be captured or with --no-graph."""
+    if not tb.args.no_graph and (tb.world == 1 or tb.fused is not None):
+        try:
+            return e2e_graph_pass(tb, n_e2e)
+        except Exception as exc:
+            note = f"graph e2e path failed ({type(exc).__name__}: {str(exc)[:160]}); eager host-buffer loop instead"
+            out = e2e_eager_pass(tb, n_e2e)
+            out["note"] = note
+            return out
+    return e2e_eager_pass(tb, n_e2e)
+
+
+def e2e_graph_pass(tb, n_e2e):
+    import torch
+    import torch.distributed as dist
+    from eims_b200.hostpath import GraphedHostTrainer, HostDataset
+    from eims_b200.synth import dense_spectra
+    table, pk = tb.host_shard
+    n_local = table.num_mols
+    peaks_mode = tb.args.targets == "peaks"
+    hds = HostDataset(table, None, peaks=pk) if peaks_mode else HostDataset(table, dense_spectra(*pk, M))
+    G = 10
+    groups = max(1, n_e2e // G)
+    workers = max(1, min(4, (os.cpu_count() or 4) // tb.world - 1))   # the ranks share the box's host cores
+    cap_nodes = tb.batch * tb.cfg["atoms"]
+    tr = GraphedHostTrainer(tb.plan, tb.fp, hds, tb.batch, M, cap_nodes, cap_nodes + 3 * tb.batch, tb.batch * 150 if peaks_mode else 0,
+                            metrics=tb.metrics, fused=tb.fused, group=G, workers=workers)
+    rng = np.random.default_rng(7 + tb.rank)
+    n_batches = (groups + 2) * G + 2
+    order = np.concatenate([rng.permutation(n_local) for _ in range(n_batches * tb.batch // n_local + 2)]).astype(np.int32)
+    ids_of = lambda n: order[n * tb.batch:(n + 1) * tb.batch]
+    futs = {n: tr.pack_async(n, ids_of(n)) for n in range(G + 1)}
+    tr.prime(futs.pop(0))
+    tr.capture(tb.step_scalars())
+
+    def run_group(l):
+        steps = [tb.step_scalars(tb.k + j) for j in range(G)]
+        tb.k += G
+        li = tr.launch(steps, [futs.pop(n) for n in range(l * G + 1, l * G + G + 1)])
+        for n in range((l + 1) * G + 1, (l + 2) * G + 1):     # collate the next group's batches while this one runs
+            futs[n] = tr.pack_async(n, ids_of(n))
+        return li
+
+    run_group(0)                                              # untimed warm-up group
+    torch.cuda.synchronize()
+    if tb.world > 1:
+        dist.barrier()
+    tr.h2d_bytes = tr.d2h_bytes = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tb.device_barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    last = None
+    for l in range(1, groups + 1):
+        run_group(l)
+        if l > 1:
+            last = tr.results(l - 1)[-1]                      # the host reads a group's losses while the next group runs
+    last = tr.results(groups)[-1]
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if tb.world > 1:
+        t = torch.tensor([wall], device=tb.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    tr.close()
+    n_steps = groups * G
+    return {"value": n_steps * tb.batch * tb.world / wall, "unit": UNIT, "h2d_bytes_per_step": int(tr.h2d_bytes / n_steps),
+            "d2h_bytes_per_step": int(tr.d2h_bytes / n_steps), "steps": n_steps,
+            "timing": ("host wall clock around the loop, max over ranks (device events: %.1f ms); INSIDE the timed region per step: host collate "
+                       "of the batch from the host-resident set into a pinned ring (C, %d worker threads, one group of %d batches ahead), "
+                       "H2D copy of the batch (fixed-layout buffer), K1 + step%s, D2H of the step's loss/cosine; copies, K1 and steps are "
+                       "replayed from captured CUDA graphs of %d steps, the host reads each group's losses while the next group runs"
+                       % (e0.elapsed_time(e1), workers, G, " + fused gradient exchange" if tb.world > 1 else "", G)),
+            "last_loss": last[0]}
+
+
+def e2e_eager_pass(tb, n_e2e):
     """The reference-facing call with HOST buffers, per step and inside the timed region: collate of the batch from the
     host-resident set into pinned memory (`eims_host_pack_batch`, C, on 4 worker threads - the reference's DataLoader
     uses num_workers=4, GCN:100 - prefetching 4 batches ahead), ONE H2D copy, K1 + step, D2H of the step's loss / cosine,

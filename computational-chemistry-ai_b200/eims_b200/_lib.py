@@ -99,6 +99,7 @@ _SIGS = {
     "eims_dp_adamw_fused_blk": (C.c_int, [_i32, _i32, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _u64, _u64, _vp, _vp, _vp,
                                           _i64, _i64, C.POINTER(Step), C.c_uint32, _i32, _vp, _vp, _vp]),
     "eims_host_pack_batch": (C.c_int, [C.POINTER(Dataset), _vp, _i32, _i32, _i32, _vp, _i64, C.POINTER(HostBatchLayout)]),
+    "eims_host_pack_batch_fixed": (C.c_int, [C.POINTER(Dataset), _vp, _i32, _i32, _i32, _i64, _i64, _i64, _vp, _i64, C.POINTER(HostBatchLayout)]),
     "eims_step_block_bytes": (_i64, []),
     "eims_plan_set_step_block": (C.c_int, [_vp, _vp, _i64]),
     "eims_step_block_upload": (C.c_int, [_vp, C.POINTER(Step), _vp, C.c_uint32, _vp]),

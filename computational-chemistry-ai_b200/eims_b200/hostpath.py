@@ -266,3 +266,157 @@ class HostBatchRunner:
     def result(self):
         """(loss, cosine) of the last enqueued training step (waits for it)."""
         return self.read(0)
+
+
+class GraphedHostTrainer:
+    """Training steps fed from HOST-resident data, replayed as CUDA graphs: per step the graph holds the H2D copy of
+    the NEXT batch from a pinned ring buffer into one of two device slots + its K1 batch build (copy stream), the step
+    itself on the batch built one step earlier (forward, loss, backward, AdamW or the fused data-parallel exchange),
+    and the D2H copy of the step's loss / cosine into a pinned result ring.  The host's part per GROUP of `group` steps:
+    collate `group` batches into the pinned ring (`eims_host_pack_batch_fixed`, C, worker threads - the fixed layout
+    keeps every device pointer constant, which is what lets the copies and K1 sit inside a graph), one step-block
+    upload, one graph launch.  This is what `collate_fn` + `.to(device)` + one `train_model` iteration + `loss.item()`
+    are in the reference (GCN:292-297, 411-439), with the launches taken off the host.
+
+    Ring discipline: batch n lives in pinned buffer n % (2*group); launch l runs steps l*group .. l*group+group-1 and
+    copies batches l*group+1 .. l*group+group; buffer n % (2*group) may be repacked once the launch that copied batch
+    n - 2*group has completed (`done` events)."""
+
+    def __init__(self, plan, fp, hds: HostDataset, batch: int, max_mz: int, cap_nodes: int, cap_bonds: int, cap_peaks: int = 0,
+                 metrics=None, loss_kind="mse", fused=None, group: int = 10, workers: int = 4):
+        from concurrent.futures import ThreadPoolExecutor
+        self.plan, self.fp, self.hds, self.batch, self.max_mz = plan, fp, hds, int(batch), int(max_mz)
+        self.caps = (int(cap_nodes), int(cap_bonds), int(cap_peaks))
+        self.loss_kind, self.fused = loss_kind, fused
+        self.G = max(2, min(16, int(group))) // 2 * 2
+        self.lib = _lib.load()
+        dev = plan.device
+        self.metrics = metrics if metrics is not None else torch.zeros(8, dtype=torch.float32, device=dev)
+        # the fixed layout: probe it with the first `batch` molecules
+        lay = _lib.HostBatchLayout()
+        probe = np.arange(self.batch, dtype=np.int32)
+        rc = self.lib.eims_host_pack_batch_fixed(C.byref(hds.struct), C.c_void_p(probe.ctypes.data), self.batch, hds.feat_dim, self.max_mz,
+                                                 *self.caps, None, 0, C.byref(lay))
+        if rc not in (0, _lib.ERR_CAPACITY) or lay.nbytes <= 0:
+            check(rc if rc else _lib.ERR_ARG)
+        self.lay, self.nbytes = lay, int(lay.nbytes)
+        self.pinned = [torch.empty(self.nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(2 * self.G)]
+        self.slots = [torch.empty(self.nbytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.out_host = torch.zeros(2 * self.G, 8, dtype=torch.float32, pin_memory=True)
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.side2 = torch.cuda.Stream(dev) if fused is None else None
+        self.pool = ThreadPoolExecutor(max(1, int(workers)))
+        self.h2d_bytes = self.d2h_bytes = 0
+        self.graphs, self.done, self.launches = [], {}, 0
+        self._ds, self._pk = [], []
+        for s in range(2):
+            base = self.slots[s].data_ptr()
+            pk = None
+            if lay.peak_ptr >= 0:
+                pk = _lib.Peaks(base + lay.peak_ptr, base + lay.peak_mz, base + lay.peak_inten, lay.mz_is_f64, self.batch)
+            self._pk.append(pk)
+            self._ds.append(Dataset(base + lay.node_ptr, base + lay.bond_ptr, base + lay.feat, base + lay.bond_begin, base + lay.bond_end,
+                                    (base + lay.targets) if lay.targets >= 0 else None, self.batch, C.pointer(pk) if pk is not None else None))
+        plan.enable_step_block(self.G)
+        if fused is None:
+            fp.ensure_adam()
+
+    # -- host side ------------------------------------------------------------------------
+    def pack_async(self, n: int, ids: np.ndarray):
+        """Collate batch n into its pinned ring buffer on a worker thread (returns a future)."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        buf = self.pinned[n % (2 * self.G)]
+        need = (n - 2 * self.G - 1) // self.G if n - 2 * self.G >= 1 else -1   # the launch that copied this buffer's previous batch
+        ev = self.done.get(need)
+
+        def work():
+            if ev is not None:
+                ev.synchronize()
+            lay = _lib.HostBatchLayout()
+            check(self.lib.eims_host_pack_batch_fixed(C.byref(self.hds.struct), C.c_void_p(ids.ctypes.data), len(ids), self.hds.feat_dim,
+                                                      self.max_mz, *self.caps, C.c_void_p(buf.data_ptr()), buf.numel(), C.byref(lay)))
+            return n
+        return self.pool.submit(work)
+
+    def prime(self, fut0):
+        """Batch 0 (already submitted with pack_async) is uploaded and built eagerly on the current stream."""
+        fut0.result()
+        self.slots[0].copy_(self.pinned[0], non_blocking=True)
+        check(self.lib.eims_batch_build(self.plan.h, C.byref(self._ds[0]), None, self.batch, self.plan.stream))
+        self.h2d_bytes += self.nbytes
+
+    def _enqueue(self, n_local: int, block: int, step):
+        plan, cur = self.plan, torch.cuda.current_stream(self.plan.device)
+        slot, nxt = n_local % 2, (n_local + 1) % 2
+        plan.select_step_block(block)
+        self.copy_stream.wait_stream(cur)            # the next batch's slot was last read by the previous step: fork here
+        if self.fused is not None:
+            self.fused.begin_step()
+        check(self.lib.eims_plan_set_peak_targets(plan.h, C.byref(self._pk[slot]) if self._pk[slot] is not None else None))
+        plan._peak_targets = None
+        fp, opt = self.fp, self.fused is None
+        tgt = self._ds[slot].targets
+        check(self.lib.eims_train_step_built_indirect(plan.h, C.c_void_p(tgt) if tgt else None, _lib.ptr(fp.params), _lib.ptr(fp.grads),
+                                                      _lib.ptr(fp.adam_m) if opt else None, _lib.ptr(fp.adam_v) if opt else None,
+                                                      _lib.ptr(fp.bn_running), _lib.LOSS[self.loss_kind], _lib.ptr(self.metrics), plan.stream,
+                                                      C.c_void_p(self.side2.cuda_stream) if self.side2 is not None else None))
+        if self.fused is not None:
+            self.fused.finish(step, plan.stream, step_block=plan.step_block_ptr(block))
+        self.out_host[n_local].copy_(self.metrics, non_blocking=True)      # the step's loss / cosine back to the host
+        with torch.cuda.stream(self.copy_stream):
+            self.slots[nxt].copy_(self.pinned[(n_local + 1) % (2 * self.G)], non_blocking=True)
+            check(self.lib.eims_batch_build(plan.h, C.byref(self._ds[nxt]), None, self.batch, C.c_void_p(self.copy_stream.cuda_stream)))
+        cur.wait_stream(self.copy_stream)            # join
+
+    def capture(self, step):
+        """After prime() and a few eager steps elsewhere (modules loaded): capture the two group graphs."""
+        plan = self.plan
+        plan.select_step_block(0)
+        plan.step_blocks_upload([step], [self.slots[0]], [0], 0)   # loads the upload kernel (ids unused: K1 is not indirect here)
+        torch.cuda.synchronize(plan.device)
+        seq0 = self.fused.seq if self.fused is not None else 0
+        for s in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for j in range(self.G):
+                    self._enqueue(s * self.G + j, j, step)
+            self.graphs.append(g)
+        if self.fused is not None:
+            self.fused.seq = seq0
+        plan.select_step_block(0)
+
+    def launch(self, steps, futures):
+        """Run the next group: `steps` = its `group` Step structs, `futures` = the pack futures of the `group` batches it
+        uploads (batches l*group+1 .. l*group+group).  Returns the launch index."""
+        assert len(steps) == self.G
+        for f in futures:
+            f.result()
+        l = self.launches
+        seqs = []
+        for _ in steps:
+            if self.fused is not None:
+                self.fused.seq += 1
+                seqs.append(self.fused.seq)
+            else:
+                seqs.append(0)
+        self.plan.step_blocks_upload(list(steps), [self.slots[0]] * self.G, seqs, 0)
+        self.graphs[l % 2].replay()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.plan.device))
+        self.done[l] = ev
+        self.done.pop(l - 4, None)
+        self.launches += 1
+        self.h2d_bytes += self.G * self.nbytes
+        self.d2h_bytes += self.G * 32
+        for k in range(self.plan.d.num_gcn_layers):
+            self.fp.num_batches_tracked[k] += self.G
+        return l
+
+    def results(self, l: int):
+        """(loss, cosine) of every step of launch l (waits for that launch)."""
+        self.done[l].synchronize()
+        rows = self.out_host[(l % 2) * self.G:(l % 2 + 1) * self.G]
+        return [(float(r[4]), float(r[5])) for r in rows]
+
+    def close(self):
+        self.pool.shutdown(wait=True)
