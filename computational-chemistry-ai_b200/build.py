@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "eims_b200", "libeims_b200.so")
-SOURCES = ["graph.cu", "dense.cu", "gemm_tc.cu", "dp_fused.cu", "plan.cu", "hostpack.cu"]
+SOURCES = ["graph.cu", "dense.cu", "gemm_tc.cu", "gemm_tma.cu", "dp_fused.cu", "plan.cu", "hostpack.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

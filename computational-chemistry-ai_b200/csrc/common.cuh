@@ -137,6 +137,18 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// 3xTF32 operand split, the planes form (gemm_tma.cu): hi = rna_tf32(x), lo = rna_tf32(x - hi), both kept as fp32 bit
+// patterns with the 13 low mantissa bits clear.  Round-to-nearest-away on the magnitude bits (+2^12, clear 13 bits):
+// identical to cvt.rna.tf32.f32 for every finite input, and to the in-register split of gemm_tc.cu.
+__device__ __forceinline__ void split_tf32_planes(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void split_tf32_planes4(float4 v, float4& h, float4& l) {
+  split_tf32_planes(v.x, h.x, l.x); split_tf32_planes(v.y, h.y, l.y);
+  split_tf32_planes(v.z, h.z, l.z); split_tf32_planes(v.w, h.w, l.w);
+}
+
 // Grid-wide "last block reduces" ticket.  Returns true in exactly one block (the last to
 // arrive) after all earlier blocks' global writes are visible; resets the counter so the
 // kernel can be relaunched / replayed from a CUDA graph.

@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(256, LAYER0 ? 2 : 4) bn_bwd_apply_kernel(
     const int* __restrict__ dims, DhSrc src, const float* __restrict__ z, int H, const float* __restrict__ mean,
     const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ means,
     const float* __restrict__ norm, float* __restrict__ q, float* __restrict__ dbias, const float* __restrict__ a0,
-    int F, float* __restrict__ dW0, int early) {
+    int F, float* __restrict__ dW0, int early, int64_t q_lo_off) {
   const int N = pdl_sync_dims(dims, early).N;
   src.drop = resolve_drop(src.drop);
   __shared__ float red[kRowLanes][kSlab];
@@ -400,8 +400,19 @@ __global__ void __launch_bounds__(256, LAYER0 ? 2 : 4) bn_bwd_apply_kernel(
             w[f].x = fmaf(a, o.x, w[f].x); w[f].y = fmaf(a, o.y, w[f].y);
             w[f].z = fmaf(a, o.z, w[f].z); w[f].w = fmaf(a, o.w, w[f].w);
           }
+      } else if (q_lo_off) {  // q as stacked tf32 hi / lo planes: the operand layout of gemm_tma.cu
+        float4 hi4, lo4;
+        split_tf32_planes4(o, hi4, lo4);
+        st4(q + (int64_t)r * H + c, hi4);
+        st4(q + q_lo_off + (int64_t)r * H + c, lo4);
       } else {
         st4(q + (int64_t)r * H + c, o);
+      }
+    }
+    if (!LAYER0 && q_lo_off) {  // rows [N, next multiple of 32): zero in both planes (whole k-blocks of the weight gradient)
+      for (int r = N + blockIdx.y * kRowLanes + rl; r < ((N + 31) & ~31); r += stride) {
+        st4(q + (int64_t)r * H + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        st4(q + q_lo_off + (int64_t)r * H + c, make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
   }
@@ -447,8 +458,8 @@ int launch_bn_bwd_stats(const int* dims, const float* dh, const float* dG, const
 int launch_bn_bwd_apply(const int* dims, const float* dh, const float* dG, const int* gid, const int* gptr,
                         const int* argmax, int pooling, const float* z, int H, const float* mean, const float* invstd,
                         const float* gamma, const float* norm, float* dbias, const float* means, float* q, int max_nodes,
-                        cudaStream_t st, const float* a0, int F, float* dW0, const GatherSrc* gs) {
-  if (H % 4 || H > 4096 || (dW0 && (F < 1 || F > kMaxF0d))) return EIMS_ERR_ARG;
+                        cudaStream_t st, const float* a0, int F, float* dW0, const GatherSrc* gs, int64_t q_lo_off) {
+  if (H % 4 || H > 4096 || (dW0 && (F < 1 || F > kMaxF0d)) || (q_lo_off & 3) || (dW0 && q_lo_off)) return EIMS_ERR_ARG;
   DhSrc src{dh, dG, gid, gptr, argmax, pooling, nullptr, nullptr, nullptr, nullptr, DropCfg{}};
   if (gs) { src.da = gs->da; src.rowptr = gs->rowptr; src.col = gs->col; src.norm = gs->norm; src.drop = gs->drop; }
   const dim3 grid = bn_grid(H, max_nodes);
@@ -456,9 +467,9 @@ int launch_bn_bwd_apply(const int* dims, const float* dh, const float* dG, const
   static int l0_per_sm = 0;
   if (!l0_per_sm) { const char* e = getenv("EIMS_BN_L0_BLOCKS_PER_SM"); l0_per_sm = e ? atoi(e) : 2; if (l0_per_sm < 1) l0_per_sm = 1; }
   if (dW0)
-    launch_pdl(bn_bwd_apply_kernel<true>, bn_grid(H, max_nodes, l0_per_sm), dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, a0, F, dW0, dims_early_ref());
+    launch_pdl(bn_bwd_apply_kernel<true>, bn_grid(H, max_nodes, l0_per_sm), dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, a0, F, dW0, dims_early_ref(), (int64_t)0);
   else
-    launch_pdl(bn_bwd_apply_kernel<false>, grid, dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, nullptr, 0, nullptr, dims_early_ref());
+    launch_pdl(bn_bwd_apply_kernel<false>, grid, dim3(256), 0, st, dims, src, z, H, mean, invstd, gamma, means, norm, q, dbias, nullptr, 0, nullptr, dims_early_ref(), q_lo_off);
   return 0;
 }
 

@@ -163,6 +163,25 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// explicit shared-space accesses for the epilogue's staging tile: through a pointer derived from the rounded-up dynamic
+// shared-memory base the compiler emits GENERIC loads / stores (LD.E / ST.E instead of LDS / STS), ~4x the latency
+__device__ __forceinline__ void sts_f4(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t saddr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(saddr), "d"(v) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t saddr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void store_split(uint32_t hi_saddr, uint32_t lo_saddr, float4 v) {
   uint4 h, l;
   split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
@@ -375,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(const __grid_c
     tc_fence_after();
     if (warp == 0) TRACE(3);
     constexpr int LDS = BN + 4;  // padded row stride (floats): conflict-free float4 row writes
-    float* stage = reinterpret_cast<float*>(smem);
+    const uint32_t stage = smem_base;  // shared-space byte address of the staging tile (the pipeline stages are free by now)
     {
       const int q = warp & 3;
       const int row = q * 32 + lane, m = m0 + row;
@@ -394,11 +413,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(const __grid_c
             for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(c[j]));
           }
         }
-        float* dst = stage + row * LDS + col0;
+        const uint32_t dst = stage + (uint32_t)(row * LDS + col0) * 4u;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          st4(dst + j, make_float4(__uint_as_float(r[j]) * rs, __uint_as_float(r[j + 1]) * rs,
-                                   __uint_as_float(r[j + 2]) * rs, __uint_as_float(r[j + 3]) * rs));
+          sts_f4(dst + j * 4, make_float4(__uint_as_float(r[j]) * rs, __uint_as_float(r[j + 1]) * rs,
+                                          __uint_as_float(r[j + 2]) * rs, __uint_as_float(r[j + 3]) * rs));
       }
     }
     tc_fence_before();
@@ -434,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(const __grid_c
         for (int row = warp; row < BM; row += kProducerWarps) {
           const int m = m0 + row;
           if (m >= M) break;
-          float4 v = *reinterpret_cast<const float4*>(stage + row * LDS + c);
+          float4 v = lds_f4(stage + (uint32_t)(row * LDS + c) * 4u);
           v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
           if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
           if (stats) {
@@ -467,21 +486,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(const __grid_c
         // combine the 16 warps in shared memory (the staging tile is dead once every warp has read
         // its rows), then one fp64 atomic per column and statistic
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        double* red = reinterpret_cast<double*>(smem);  // [16 warps][2][BN]
+        const uint32_t red = smem_base;  // double [16 warps][2][BN]
 #pragma unroll
         for (int qd = 0; qd < QUADS; ++qd)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int c = 4 * lane + qd * 128 + e;
-            red[(warp * 2 + 0) * BN + c] = s1[qd][e];
-            red[(warp * 2 + 1) * BN + c] = s2[qd][e];
+            sts_f64(red + (uint32_t)((warp * 2 + 0) * BN + c) * 8u, s1[qd][e]);
+            sts_f64(red + (uint32_t)((warp * 2 + 1) * BN + c) * 8u, s2[qd][e]);
           }
         asm volatile("bar.sync 1, 512;" ::: "memory");
         for (int k = threadIdx.x; k < 2 * BN; k += kProducerWarps * 32) {
           const int which = k / BN, cc = k % BN;
           double tsum = 0.0;
 #pragma unroll
-          for (int w = 0; w < kProducerWarps; ++w) tsum += red[(w * 2 + which) * BN + cc];
+          for (int w = 0; w < kProducerWarps; ++w) tsum += lds_f64(red + (uint32_t)((w * 2 + which) * BN + cc) * 8u);
           if (n0 + cc < N) atomicAdd(bn_acc_slot(g.bn.acc, g.bn.H, blockIdx.x, which, n0 + cc), tsum);
         }
       }
@@ -751,7 +770,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_3xtf32_persistent_ker
       // stored straight from registers every instruction touches 32 different lines, and the load/store
       // pipe it shares with the producers became the bottleneck - measured 116 us against 110 us for the
       // cfg-3 forward, with 16- or 32-byte stores alike.)
-      float* patch = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + (warp - kProducerWarps - 1) * (32 * 36);
+      const uint32_t patch = smem_base + STAGES * STAGE_BYTES + (uint32_t)(warp - kProducerWarps - 1) * (32 * 36 * 4);  // shared-space byte address
 #pragma unroll 1
       for (int col0 = 0; col0 < BN; col0 += 32) {
         uint32_t r[32];
@@ -759,8 +778,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_3xtf32_persistent_ker
         __syncwarp();  // the previous block's reads of the patch are done
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          st4(patch + lane * 36 + j, make_float4(__uint_as_float(r[j]) * rs, __uint_as_float(r[j + 1]) * rs,
-                                                 __uint_as_float(r[j + 2]) * rs, __uint_as_float(r[j + 3]) * rs));
+          sts_f4(patch + (uint32_t)(lane * 36 + j) * 4u, make_float4(__uint_as_float(r[j]) * rs, __uint_as_float(r[j + 1]) * rs,
+                                                                     __uint_as_float(r[j + 2]) * rs, __uint_as_float(r[j + 3]) * rs));
         __syncwarp();
         const int cc = (lane & 7) * 4;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -770,7 +789,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_3xtf32_persistent_ker
           const int rr = it * 4 + (lane >> 3);
           const int mm = ti.m0 + q * 32 + rr;
           if (mm >= ti.M) continue;
-          float4 v = *reinterpret_cast<const float4*>(patch + rr * 36 + cc);
+          float4 v = lds_f4(patch + (uint32_t)(rr * 36 + cc) * 4u);
           v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
           if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
           float* dst = g.C + (int64_t)mm * g.ldc + ti.n0 + col0 + cc;

@@ -431,9 +431,15 @@ __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ 
                                                         const float* __restrict__ h, int H,
                                                         const float* __restrict__ bn_scale,
                                                         const float* __restrict__ bn_shift, DropCfg drop, int out_mode,
-                                                        float* __restrict__ out, int parts, BnBwdFuse bf, int early) {
+                                                        float* __restrict__ out, int parts, BnBwdFuse bf, int early,
+                                                        int64_t lo_off) {
   extern __shared__ float s_stats[];  // STATS: [warps per block][2][128 * NV]
   const int N = pdl_sync_dims(dims, early).N;
+  // lo_off != 0: `out` is the hi plane of a stacked tf32 hi / lo pair (gemm_tma.cu), the lo plane lo_off floats
+  // behind it; the rows up to the next multiple of 32 are zeroed (the weight gradient reduces over whole 32-row k-blocks)
+  // (compiled out of the STATS instantiation, whose register count decides whether its one-wave grid fits: 80 vs 94)
+  const int64_t lo = STATS ? (int64_t)0 : lo_off;
+  const int Nw = lo ? ((N + 31) & ~31) : N;
   drop = resolve_drop(drop);
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -459,7 +465,17 @@ __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ 
 #pragma unroll
     for (int v = 0; v < NV; ++v) s1[v] = s2[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int i = warp / parts; i < N; i += nwarps / parts) {
+  for (int i = warp / parts; i < Nw; i += nwarps / parts) {
+    if (!STATS && i >= N) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c = cbase + (v * 32 + lane) * 4;
+        if (c >= H) continue;
+        st4(out + (int64_t)i * H + c, make_float4(0.f, 0.f, 0.f, 0.f));
+        st4(out + lo + (int64_t)i * H + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
+      continue;
+    }
     const int e0 = __ldg(rowptr + i), e1 = __ldg(rowptr + i + 1);
     float4 zrow[STATS ? NV : 1];
     if (STATS) {  // issued before the gather so that it is in flight with it
@@ -526,7 +542,14 @@ __global__ void __launch_bounds__(256) spmm_norm_kernel(const int* __restrict__ 
           a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w;
         }
       }
-      st4(out + (int64_t)i * H + c, a);
+      if (!STATS && lo) {
+        float4 hi4, lo4;
+        split_tf32_planes4(a, hi4, lo4);
+        st4(out + (int64_t)i * H + c, hi4);
+        st4(out + lo + (int64_t)i * H + c, lo4);
+      } else {
+        st4(out + (int64_t)i * H + c, a);
+      }
       if (STATS) {
         const float4 mu = ldg4(bf.mean + c), is = ldg4(bf.invstd + c);
         s1[v].x += a.x; s1[v].y += a.y; s1[v].z += a.z; s1[v].w += a.w;
@@ -615,7 +638,7 @@ __global__ void __launch_bounds__(THREADS) spmm_mol_kernel(const int* __restrict
                                                                const float* __restrict__ norm, const float* __restrict__ h, int H,
                                                                const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
                                                                DropCfg drop, int out_mode, float* __restrict__ out, int cap_rows,
-                                                               int cap_edges, BnBwdFuse bf, int early) {
+                                                               int cap_edges, BnBwdFuse bf, int early, int64_t lo_off) {
   constexpr int HC = 128 * NV;  // columns a block owns
   extern __shared__ __align__(128) uint8_t mol_smem[];
   float* tile = reinterpret_cast<float*>(mol_smem);                    // [cap_rows][HC]
@@ -765,7 +788,14 @@ __global__ void __launch_bounds__(THREADS) spmm_mol_kernel(const int* __restrict
             a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w;
           }
         }
-        st4(out + (int64_t)row * H + c, a);
+        if (!STATS && lo_off) {  // stacked tf32 hi / lo planes (see spmm_norm_kernel)
+          float4 hi4, lo4;
+          split_tf32_planes4(a, hi4, lo4);
+          st4(out + (int64_t)row * H + c, hi4);
+          st4(out + lo_off + (int64_t)row * H + c, lo4);
+        } else {
+          st4(out + (int64_t)row * H + c, a);
+        }
         if (STATS) {
           const float4 mu = ldg4(bf.mean + c), is = ldg4(bf.invstd + c);
           s1[v].x += a.x; s1[v].y += a.y; s1[v].z += a.z; s1[v].w += a.w;
@@ -775,6 +805,15 @@ __global__ void __launch_bounds__(THREADS) spmm_mol_kernel(const int* __restrict
       }
     }
     __syncthreads();  // everyone is done with the tile and the index arrays before the next molecule overwrites them
+  }
+  if (!STATS && lo_off && blockIdx.x == 0) {  // rows [N, next multiple of 32) of both planes: zero (k-blocks of the weight gradient)
+    const int Nw = (N + 31) & ~31;
+    for (int k = tid; k < (Nw - N) * (HC / 4); k += THREADS) {
+      const int row = N + k / (HC / 4), c = c0 + (k % (HC / 4)) * 4;
+      if (c >= H) continue;
+      st4(out + (int64_t)row * H + c, make_float4(0.f, 0.f, 0.f, 0.f));
+      st4(out + lo_off + (int64_t)row * H + c, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
   }
   if (STATS) {
     // combine the block's warps in shared memory, one fp32 atomic per column and statistic into one of the
@@ -815,7 +854,7 @@ __global__ void __launch_bounds__(THREADS) spmm_mol_kernel(const int* __restrict
 
 int launch_spmm_mol(const int* dims, const int* gptr, const int* rowptr, const int* col, const float* norm, const float* h,
                            int H, const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
-                           int max_graphs, int tile_rows, cudaStream_t st, const BnBwdFuse* bf) {
+                           int max_graphs, int tile_rows, cudaStream_t st, const BnBwdFuse* bf, int64_t lo_off) {
   // Shape: a block owns HC = 128 columns (4 warps) or 256 columns (8 warps) of one molecule at a time.  The narrow
   // shape keeps the tile at tile_rows x 512 bytes (32 KB at 64 rows), so ~7 blocks are resident per SM and the
   // (molecules x column chunks) grid of a training batch - 512 x 2 at cfg 2 - fits in ONE wave; with 256-column
@@ -839,7 +878,7 @@ int launch_spmm_mol(const int* dims, const int* gptr, const int* rowptr, const i
     static bool attr = false;                                                                                               \
     if (!attr) { cudaFuncSetAttribute(spmm_mol_kernel<NVv, ST, 128 * NVv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; } \
     launch_pdl(spmm_mol_kernel<NVv, ST, 128 * NVv>, dim3(gx, chunks), dim3(128 * NVv), smem, st, dims, gptr, rowptr, col, norm, h, H, bn_scale, \
-               bn_shift, drop, out_mode, out, tile_rows, cap_edges, bf ? *bf : none, dims_early_ref());                     \
+               bn_shift, drop, out_mode, out, tile_rows, cap_edges, bf ? *bf : none, dims_early_ref(), lo_off);             \
   } while (0)
   if (NV == 2) { if (bf) EIMS_MOL(2, true); else EIMS_MOL(2, false); }
   else { if (bf) EIMS_MOL(1, true); else EIMS_MOL(1, false); }
@@ -849,9 +888,11 @@ int launch_spmm_mol(const int* dims, const int* gptr, const int* rowptr, const i
 
 int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const float* norm, const float* h, int H,
                      const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
-                     int max_nodes, cudaStream_t st, const BnBwdFuse* bf, const int* gptr, int max_graphs, int tile_rows) {
+                     int max_nodes, cudaStream_t st, const BnBwdFuse* bf, const int* gptr, int max_graphs, int tile_rows,
+                     int64_t lo_off) {
   if (H % 4) return EIMS_ERR_ARG;
   if (bf && out_mode != 1) return EIMS_ERR_ARG;
+  if (lo_off && (bf || (lo_off & 3))) return EIMS_ERR_ARG;
   // Molecule-tile kernel (neighbour rows staged in shared memory by the bulk-copy engine) when the caller knows the
   // batch's graph offsets AND the batch is large.  Measured on a B200 (profiles/r2_spmm_ab.md): with >= ~8 molecules
   // per resident block (inference batches of 4096) staging wins, 0.128 vs 0.144 ms for the two cfg-3 launches (67 %
@@ -863,7 +904,7 @@ int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const f
   if (mol_on == -2) { const char* e = getenv("EIMS_SPMM_MOL"); mol_on = e ? (e[0] == '0' ? 0 : 1) : -1; }
   const bool big_batch = max_graphs >= 2048 && !bf;
   if ((mol_on == 1 || (mol_on == -1 && big_batch)) && gptr && tile_rows > 0 && H % 128 == 0)
-    return launch_spmm_mol(dims, gptr, rowptr, col, norm, h, H, bn_scale, bn_shift, drop, out_mode, out, max_graphs, tile_rows, st, bf);
+    return launch_spmm_mol(dims, gptr, rowptr, col, norm, h, H, bn_scale, bn_shift, drop, out_mode, out, max_graphs, tile_rows, st, bf, lo_off);
   const int parts = H <= 512 ? 1 : (H + 511) / 512;
   if (parts > 8 || (8 % parts)) return EIMS_ERR_ARG;  // 8 warps per block must split evenly over a row
   static int per_sm = 0;  // resident blocks per SM the grid is sized for (tuning knob)
@@ -880,9 +921,9 @@ int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const f
 #define EIMS_SPMM(NV, UE)                                                                                              \
   do {                                                                                                                 \
     if (bf) launch_pdl(spmm_norm_kernel<NV, 1, true>, dim3(blocks_s), dim3(256), (size_t)8 * 2 * 128 * NV * sizeof(float), st, dims, rowptr, col, norm, \
-                       h, H, bn_scale, bn_shift, drop, out_mode, out, parts, *bf, dims_early_ref());                     \
+                       h, H, bn_scale, bn_shift, drop, out_mode, out, parts, *bf, dims_early_ref(), (int64_t)0);         \
     else launch_pdl(spmm_norm_kernel<NV, UE, false>, dim3(blocks), dim3(256), 0, st, dims, rowptr, col, norm, h, H, bn_scale,   \
-                    bn_shift, drop, out_mode, out, parts, none, dims_early_ref());                                       \
+                    bn_shift, drop, out_mode, out, parts, none, dims_early_ref(), lo_off);                               \
   } while (0)
   if (H <= 128) EIMS_SPMM(1, 4);
   else if (H <= 256) EIMS_SPMM(2, 2);
@@ -925,6 +966,7 @@ __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ di
   // lanes then stride over it there instead of issuing a chain of dependent L2 loads each (n_g / RL deep).
   const bool staged = tile_bytes > 0 && r1 > r0 && (int64_t)(r1 - r0) * H * 4 <= (int64_t)tile_bytes;
   const float* zt = z;          // row i of the graph is at zt + i * H
+  const uint32_t tile_sa = smem_addr(ro_smem);
   if (staged) {
     if (threadIdx.x == 0) {
       mbar_expect_tx(bar, (uint32_t)(r1 - r0) * H * 4u);
@@ -946,7 +988,13 @@ __global__ void __launch_bounds__(256) readout_kernel(const int* __restrict__ di
       if (zstat) mu = ldg4(bn_mean + c);
 #pragma unroll 4
       for (int i = r0 + rl; i < r1; i += RL) {
-        float4 v = staged ? *reinterpret_cast<const float4*>(zt + (int64_t)i * H + c) : ldg4(z + (int64_t)i * H + c);
+        float4 v;
+        if (staged) {  // explicit shared-space load (through the generic pointer zt this is LD.E, several times the latency of LDS)
+          const uint32_t sa = tile_sa + (uint32_t)((i - r0) * H + c) * 4u;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sa) : "memory");
+        } else {
+          v = ldg4(z + (int64_t)i * H + c);
+        }
         zs.x += v.x - mu.x; zs.y += v.y - mu.y; zs.z += v.z - mu.z; zs.w += v.w - mu.w;
         v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
         v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);

@@ -27,11 +27,12 @@ struct BnBwdFuse {
 int launch_spmm_norm(const int* dims, const int* rowptr, const int* col, const float* norm, const float* h, int H,
                      const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out,
                      int max_nodes, cudaStream_t st, const BnBwdFuse* bf = nullptr,
-                     const int* gptr = nullptr, int max_graphs = 0, int tile_rows = 0);  // gptr + tile_rows: molecule-tile kernel
+                     const int* gptr = nullptr, int max_graphs = 0, int tile_rows = 0,   // gptr + tile_rows: molecule-tile kernel
+                     int64_t lo_off = 0);  // != 0: out = hi plane, out + lo_off = lo plane of a stacked tf32 pair (gemm_tma.cu)
 // the molecule-tile kernel itself, whatever the batch size (launch_spmm_norm picks it for large batches only)
 int launch_spmm_mol(const int* dims, const int* gptr, const int* rowptr, const int* col, const float* norm, const float* h, int H,
                     const float* bn_scale, const float* bn_shift, DropCfg drop, int out_mode, float* out, int max_graphs,
-                    int tile_rows, cudaStream_t st, const BnBwdFuse* bf);
+                    int tile_rows, cudaStream_t st, const BnBwdFuse* bf, int64_t lo_off = 0);
 int launch_readout(const int* dims, const int* gptr, const float* z, int H, const float* bn_scale,
                    const float* bn_shift, int pooling, float* out, int* argmax, int max_graphs, cudaStream_t st,
                    float* zstat = nullptr, const float* bn_mean = nullptr);  // zstat [B][2H]: per graph, column sums of
@@ -61,7 +62,7 @@ int launch_bn_bwd_apply(const int* dims, const float* dh, const float* dG, const
                         const int* argmax, int pooling, const float* z, int H, const float* mean, const float* invstd,
                         const float* gamma, const float* norm, float* dbias, const float* means, float* q, int max_nodes,
                         cudaStream_t st, const float* a0 = nullptr, int F = 0, float* dW0 = nullptr,
-                        const GatherSrc* gs = nullptr);
+                        const GatherSrc* gs = nullptr, int64_t q_lo_off = 0);  // != 0: q as stacked tf32 hi / lo planes
 int launch_ln_fwd(const int* dims, const float* u, int W, const float* gamma, const float* beta, DropCfg drop, float* y,
                   float* stats, int max_graphs, cudaStream_t st);
 int launch_ln_bwd(const int* dims, const float* u, const float* y, const float* dy, int W, const float* gamma,
@@ -93,5 +94,23 @@ struct GemmProblem {
   const int* m_dev; const int* k_dev; const float* row_scale; const float* bias; int relu, accumulate; const BnFuse* bn;
 };
 int launch_gemm_tc_pair(const GemmProblem& p0, const GemmProblem& p1, cudaStream_t st);
+
+// gemm_tma.cu  (tcgen05 / TMEM, 3xTF32 on pre-split hi / lo operand planes fed by the tensor-map copy engine, persistent)
+struct alignas(64) TmaMap { uint8_t bytes[128]; };  // a CUtensorMap (driver type) kept opaque outside gemm_tma.cu
+// map over the stacked planes [2][rows][ld] (plane_stride floats apart) of a row-major operand with `cols` columns:
+// mn_major = 0 -> the rows are the operand's M / N index (box_rows of them per tile), 1 -> the rows are its K index
+int tma_make_map(TmaMap* out, const float* planes, int64_t plane_stride, int rows, int cols, int ld, int box_rows, int mn_major);
+bool gemm_tma_enabled();  // EIMS_GEMM_TMA=0 turns the planes path off (A/B timing)
+bool gemm_tma_forced();   // EIMS_GEMM_TMA=1: use it wherever the shapes allow (default: large batches only, see plan.cu)
+int gemm_tma_pair();      // 2: CTA pairs (tcgen05.mma.cta_group::2), 1: one CTA per tile (EIMS_GEMM_PAIR=1)
+int gemm_tma_b_rows();    // box rows of a K-major B map for that mode (256 / pair)
+struct GemmTmaProblem {
+  const TmaMap* ta; const TmaMap* tb; float* C; int ldc, a_mn, b_mn, M, N, K;
+  const int* m_dev; const int* k_dev; const float* row_scale; const float* bias; int relu, red; const BnFuse* bn;
+};
+bool gemm_tma_supports(const GemmTmaProblem& q);
+// one launch: a store problem (red = 0) and / or a split-K problem (red = 1: partial sums added into C)
+int launch_gemm_tma(const GemmTmaProblem* p0, const GemmTmaProblem* p1, cudaStream_t st);
+int launch_split_planes(const float* src, float* hi, float* lo, int64_t n, cudaStream_t st, bool chained);
 
 }  // namespace eims

@@ -96,6 +96,31 @@ struct eims_plan {
   size_t prof_used = 0;
   int64_t launches = 0;
   eims_step last_step;
+  // Planes path of the GraphConv products (csrc/gemm_tma.cu): a_l, q and the GraphConv weights exist as stacked tf32
+  // hi / lo planes [2][rows][H] and the GEMMs are fed by the tensor-map copy engine.  planes_cap: the shapes allow it
+  // (H a multiple of 256, <= 512) and the workspace was sized for it; planes_on(): ... and the tensor-core backend is
+  // selected and the path is not switched off (EIMS_GEMM_TMA=0).
+  bool planes_cap = false;
+  int64_t act_plane = 0;   // floats between the hi and the lo plane of a_l / q ( = rows_alloc * H )
+  int64_t w_plane = 0;     // floats between the hi and the lo plane of the weight range [W_1 .. W_{L-1}]
+  std::vector<TmaMap> maps;  // per layer l >= 1: a_l K-major, a_l MN-major, W_l MN-major (forward B), W_l K-major (dgrad B); then q K-major, q MN-major
+  const TmaMap* map_a_k(int l) const { return &maps[4 * (l - 1) + 0]; }
+  const TmaMap* map_a_mn(int l) const { return &maps[4 * (l - 1) + 1]; }
+  const TmaMap* map_w_mn(int l) const { return &maps[4 * (l - 1) + 2]; }
+  const TmaMap* map_w_k(int l) const { return &maps[4 * (l - 1) + 3]; }
+  const TmaMap* map_q_k() const { return &maps[4 * (d.num_gcn_layers - 1) + 0]; }
+  const TmaMap* map_q_mn() const { return &maps[4 * (d.num_gcn_layers - 1) + 1]; }
+  // Measured on a B200 (profiles/r2_gemm_planes.md): with >= ~4 output tiles per SM (inference batches of 4096) the
+  // persistent planes kernel hides every tile's epilogue under the next tile's main loop and runs at the MMA issue rate
+  // (cfg 3: 6.9 -> 7.4 M molecules/s); at a training batch of 512 a launch is ONE tile per SM, nothing overlaps, and
+  // what the planes cost (a second plane written by the producers, the weight split, twice the operand bytes from L2)
+  // outweighs the faster main loop: 0.363 against 0.342 ms per step.  So: large batches only, unless EIMS_GEMM_TMA=1.
+  bool planes_on() const {
+    if (!(planes_cap && gemm_backend == EIMS_GEMM_TCGEN05 && gemm_tma_enabled() && !maps.empty())) return false;
+    if (planes_mode >= 0) return planes_mode != 0;
+    return gemm_tma_forced() || Nc >= 4 * 148 * 128;
+  }
+  int planes_mode = -1;  // eims_plan_set_gemm_planes
   int pool_dim() const { return d.pooling == EIMS_POOL_COMBINED ? 2 * d.hidden_dim : d.hidden_dim; }
   // rows of the shared-memory molecule tile of the aggregation / readout kernels: sized from the plan's own
   // atoms-per-molecule capacity (64 KB of tile: 64 rows x 256 columns or 128 rows x 128 columns); bigger molecules
@@ -315,6 +340,51 @@ int eims_gemm(int32_t backend, const float* A, int32_t lda, int32_t a_mn_major, 
   return check_launch("eims_gemm");
 }
 
+// stand-alone form of the planes GEMM: split both operands of each problem into scratch, encode the maps, launch
+static int64_t planes_rows(const eims_gemm_problem* q, bool b) {
+  return b ? (q->b_mn_major ? q->K : q->N) : (q->a_mn_major ? q->K : q->M);
+}
+int64_t eims_gemm_planes_scratch_bytes(const eims_gemm_problem* p0, const eims_gemm_problem* p1) {
+  int64_t bytes = 0;
+  for (const eims_gemm_problem* q : {p0, p1})
+    if (q) bytes += 2 * 4 * (planes_rows(q, false) * q->lda + planes_rows(q, true) * q->ldb) + 512;
+  return bytes;
+}
+int eims_gemm_planes(const eims_gemm_problem* p0, const eims_gemm_problem* p1, void* scratch, int64_t scratch_bytes,
+                     eims_stream_t stream) {
+  if (!p0 || !scratch) return fail(EIMS_ERR_ARG, "problem / scratch is NULL");
+  if (scratch_bytes < eims_gemm_planes_scratch_bytes(p0, p1)) return fail(EIMS_ERR_ARG, "scratch too small");
+  if (reinterpret_cast<uintptr_t>(scratch) & 255) return fail(EIMS_ERR_ARG, "scratch must be 256-byte aligned");
+  if (!gemm_tma_enabled()) return fail(EIMS_ERR_STATE, "the planes GEMM is unavailable (EIMS_GEMM_TMA=0 or no cuTensorMapEncodeTiled)");
+  cudaStream_t st = (cudaStream_t)stream;
+  TmaMap maps[4];
+  GemmTmaProblem gp[2];
+  char* c = reinterpret_cast<char*>(scratch);
+  int n = 0;
+  for (const eims_gemm_problem* q : {p0, p1}) {
+    if (!q) continue;
+    if (!q->A || !q->B || !q->C || (q->lda & 3) || (q->ldb & 3)) return fail(EIMS_ERR_ARG, "operands NULL or lda / ldb not a multiple of 4");
+    const float* src[2] = {q->A, q->B};
+    const int64_t rows[2] = {planes_rows(q, false), planes_rows(q, true)};
+    const int ld[2] = {q->lda, q->ldb}, mn[2] = {q->a_mn_major, q->b_mn_major};
+    const int cols[2] = {q->a_mn_major ? q->M : q->K, q->b_mn_major ? q->N : q->K};
+    for (int o = 0; o < 2; ++o) {
+      const int64_t plane = rows[o] * ld[o];
+      float* hi = reinterpret_cast<float*>(c);
+      // EIMS_PLANES_SKIP_SPLIT (diagnostic timing only): reuse the planes the previous call left in scratch
+      if (!getenv("EIMS_PLANES_SKIP_SPLIT")) EIMS_TRY(launch_split_planes(src[o], hi, hi + plane, plane, st, false));
+      EIMS_TRY(tma_make_map(&maps[2 * n + o], hi, plane, (int)rows[o], cols[o], ld[o], o ? gemm_tma_b_rows() : 128, mn[o]));
+      c += ((2 * 4 * plane + 255) & ~(int64_t)255);
+    }
+    gp[n] = GemmTmaProblem{&maps[2 * n], &maps[2 * n + 1], q->C, q->ldc, q->a_mn_major, q->b_mn_major, q->M, q->N, q->K, q->m_dev,
+                           q->k_dev, q->row_scale, q->bias, q->relu, q->accumulate ? 1 : 0, nullptr};
+    if (!gemm_tma_supports(gp[n])) return fail(EIMS_ERR_ARG, "shape not supported by the planes GEMM (N %% 256, ldc %% 4, K <= 512 unless split-K)");
+    ++n;
+  }
+  EIMS_TRY(launch_gemm_tma(&gp[0], n > 1 ? &gp[1] : nullptr, st));
+  return check_launch("eims_gemm_planes");
+}
+
 int64_t eims_bn_scratch_floats(int32_t width, int32_t max_nodes) { return bn_scratch_floats(width, max_nodes); }
 
 int eims_bn_stats(const int32_t* dims, const float* z, int32_t width, const float* gamma, const float* beta,
@@ -395,7 +465,14 @@ int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, 
   add(p, "src", E * 4); add(p, "dst", E * 4); add(p, "rowptr", (N + 1) * 4); add(p, "col", E * 4);
   add(p, "argmax", B * H * 4);
   add(p, "norm", N * 4); add(p, "x", N * F * 4); add(p, "a0", N * F * 4);
-  for (int l = 1; l < L; ++l) add(p, "a" + std::to_string(l), N * H * 4);
+  // a_l and q hold two planes (tf32 hi / lo) when the GraphConv GEMMs may take the planes path; rows padded to 32
+  p->planes_cap = gemm_tma_enabled() && H % 256 == 0 && H <= 512 && L > 1;
+  const int64_t Np = (N + 31) & ~(int64_t)31;
+  p->act_plane = Np * H;
+  p->w_plane = p->planes_cap ? (p->off_gcn_w(L - 1) + H * H - p->off_gcn_w(1)) : 0;
+  const int64_t act_bytes = p->planes_cap ? 2 * Np * H * 4 : N * H * 4;
+  for (int l = 1; l < L; ++l) add(p, "a" + std::to_string(l), act_bytes);
+  if (p->planes_cap) add(p, "wplanes", 2 * p->w_plane * 4);
   for (int l = 0; l < L; ++l) add(p, "z" + std::to_string(l), N * H * 4);
   for (int l = 0; l < L; ++l) {
     add(p, "bn_mean" + std::to_string(l), H * 4); add(p, "bn_invstd" + std::to_string(l), H * 4);
@@ -414,7 +491,7 @@ int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, 
   add(p, "y2", B * H * 4); add(p, "ln2", B * 2 * 4);
   add(p, "prob", B * M * 4); add(p, "dlogits", B * M * 4);
   add(p, "row_loss", B * 4); add(p, "row_cos", B * 4);
-  add(p, "dh", N * H * 4); add(p, "q", N * H * 4); add(p, "da", N * H * 4);
+  add(p, "dh", N * H * 4); add(p, "q", act_bytes); add(p, "da", N * H * 4);
   *out = p;
   return 0;
 }
@@ -439,6 +516,26 @@ int eims_plan_bind(eims_plan* p, void* workspace, int64_t bytes) {
       cudaMemset(p->buf["flags"].ptr, 0, p->buf["flags"].bytes) != cudaSuccess ||
       cudaMemset(p->buf["bn_partials"].ptr, 0, p->buf["bn_partials"].bytes) != cudaSuccess)
     return fail(EIMS_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(cudaGetLastError()));
+  p->maps.clear();
+  if (p->planes_cap) {
+    const int L = p->d.num_gcn_layers, H = p->d.hidden_dim;
+    const int rows = (int)(p->act_plane / H);
+    p->maps.resize(4 * (L - 1) + 2);
+    int rc = 0;
+    float* wpl = reinterpret_cast<float*>(p->buf["wplanes"].ptr);
+    for (int l = 1; l < L && !rc; ++l) {
+      float* a = reinterpret_cast<float*>(p->buf["a" + std::to_string(l)].ptr);
+      float* w = wpl + (p->off_gcn_w(l) - p->off_gcn_w(1));
+      rc = tma_make_map(&p->maps[4 * (l - 1) + 0], a, p->act_plane, rows, H, H, 128, 0);
+      if (!rc) rc = tma_make_map(&p->maps[4 * (l - 1) + 1], a, p->act_plane, rows, H, H, 128, 1);
+      if (!rc) rc = tma_make_map(&p->maps[4 * (l - 1) + 2], w, p->w_plane, H, H, H, gemm_tma_b_rows(), 1);
+      if (!rc) rc = tma_make_map(&p->maps[4 * (l - 1) + 3], w, p->w_plane, H, H, H, gemm_tma_b_rows(), 0);
+    }
+    float* q = reinterpret_cast<float*>(p->buf["q"].ptr);
+    if (!rc) rc = tma_make_map(&p->maps[4 * (L - 1) + 0], q, p->act_plane, rows, H, H, 128, 0);
+    if (!rc) rc = tma_make_map(&p->maps[4 * (L - 1) + 1], q, p->act_plane, rows, H, H, 128, 1);
+    if (rc) p->maps.clear();  // the encoder refused: the in-kernel-split GEMMs take over (planes_on() is false)
+  }
   p->bound = true;
   p->state = 0;
   return 0;
@@ -447,6 +544,14 @@ int eims_plan_bind(eims_plan* p, void* workspace, int64_t bytes) {
 int eims_plan_set_gemm_backend(eims_plan* p, int32_t backend) {
   if (!p || (backend != EIMS_GEMM_TCGEN05 && backend != EIMS_GEMM_FP32_SIMT)) return fail(EIMS_ERR_ARG, "bad backend");
   p->gemm_backend = backend;
+  return 0;
+}
+
+int eims_plan_set_gemm_planes(eims_plan* p, int32_t mode) {
+  if (!p || mode < -1 || mode > 1) return fail(EIMS_ERR_ARG, "mode must be one of EIMS_PLANES_*");
+  if (mode == 1 && !(p->planes_cap && (!p->bound || !p->maps.empty())))
+    return fail(EIMS_ERR_STATE, "the planes GEMM needs hidden_dim %% 256 == 0, hidden_dim <= 512, >= 2 GCN layers and cuTensorMapEncodeTiled");
+  p->planes_mode = mode;
   return 0;
 }
 
@@ -582,6 +687,9 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
   }
   // every launch from here on is at least two kernels after the batch build: sizes before the grid-dependency wait
   EarlyDimsScope early_scope(early_dims_enabled() ? 1 : 0);
+  const bool planes = p->planes_on();
+  if (planes)  // hi / lo planes of the GraphConv weights W_1 .. W_{L-1} (one pass over the range that holds them)
+    STAGE(ST_ELEMENTWISE, 1, launch_split_planes(params + p->off_gcn_w(1), p->f("wplanes"), p->f("wplanes") + p->w_plane, p->w_plane, st, true));
   for (int l = 1; l < L; ++l) {
     // training on the tensor-core path: the BatchNorm statistics of z_l come out of the GEMM epilogue
     const bool fuse_bn = training && p->gemm_backend == EIMS_GEMM_TCGEN05;
@@ -590,9 +698,15 @@ int eims_forward(eims_plan* p, const float* params, float* bn_running, int32_t t
     STAGE(ST_SPMM_FWD, 1, launch_spmm_norm(dims, p->i("rowptr"), p->i("col"), p->f("norm"), p->f(L_("z", l - 1)), H,
                               p->f(L_("bn_scale", l - 1)), p->f(L_("bn_shift", l - 1)),
                               p->drop(drop_p, seed, step, l - 1), 0, p->f(L_("a", l)), p->Nc, st, nullptr, p->i("gptr"), p->Bc,
-                              p->tile_rows()));
-    STAGE(ST_GEMM_GCN_FWD, 1, gemm(p, p->f(L_("a", l)), H, 0, params + p->off_gcn_w(l), H, 1, p->f(L_("z", l)), H, p->Nc, H, H,
-                  dims + DIM_N, nullptr, p->f("norm"), params + p->off_gcn_b(l), 1, 0, st, fuse_bn ? &bf : nullptr));
+                              p->tile_rows(), planes ? p->act_plane : 0));
+    if (planes) {
+      GemmTmaProblem fw{p->map_a_k(l), p->map_w_mn(l), p->f(L_("z", l)), H, 0, 1, p->Nc, H, H, dims + DIM_N, nullptr, p->f("norm"),
+                        params + p->off_gcn_b(l), 1, 0, fuse_bn ? &bf : nullptr};
+      STAGE(ST_GEMM_GCN_FWD, 1, launch_gemm_tma(&fw, nullptr, st));
+    } else {
+      STAGE(ST_GEMM_GCN_FWD, 1, gemm(p, p->f(L_("a", l)), H, 0, params + p->off_gcn_w(l), H, 1, p->f(L_("z", l)), H, p->Nc, H, H,
+                    dims + DIM_N, nullptr, p->f("norm"), params + p->off_gcn_b(l), 1, 0, st, fuse_bn ? &bf : nullptr));
+    }
     if (!fuse_bn) STAGE(ST_BN_STATS, 1, bn(l));
   }
   // The 512-row head GEMMs cannot fill 148 SMs with output tiles, so in training they split K and
@@ -672,6 +786,7 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
   const float drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const uint64_t seed = p->last_step.seed;
   const int step = p->last_step.step;
+  const bool planes = p->planes_on();  // as in the forward that produced a_l (the backend must not change in between)
   auto L_ = [&](const char* b, int l) { return std::string(b) + std::to_string(l); };
   if (part != EIMS_BWD_GCN) {
   if (dprob) STAGE(ST_ELEMENTWISE, 1, launch_dprob_to_dlogits(dims, p->f("prob"), dprob, M, p->f("dlogits"), p->Bc, st));
@@ -725,11 +840,19 @@ int eims_backward_part(eims_plan* p, const float* params, const float* dprob, fl
     STAGE(ST_BN_BWD_APPLY, 1, launch_bn_bwd_apply(dims, dh_in, p->f("dG"), p->i("gid"), p->i("gptr"), p->i("argmax"), d.pooling,
                                  p->f(L_("z", l)), H, p->f(L_("bn_mean", l)), p->f(L_("bn_invstd", l)), params + p->off_bn_g(l),
                                  p->f("norm"), grads + p->off_gcn_b(l), p->f("bn_means2"), p->f("q"), p->Nc, st,
-                                 l == 0 ? p->f("a0") : nullptr, F, l == 0 ? grads + p->off_gcn_w(0) : nullptr, gs));
-    if (l > 0) {
+                                 l == 0 ? p->f("a0") : nullptr, F, l == 0 ? grads + p->off_gcn_w(0) : nullptr, gs,
+                                 (planes && l > 0) ? p->act_plane : 0));
+    if (l > 0 && planes) {
+      // one persistent launch: data gradient tiles (stores) + weight gradient k-slices (red.add), balanced on the device
+      GemmTmaProblem dg{p->map_q_k(), p->map_w_k(l), p->f("da"), H, 0, 0, p->Nc, H, H, dims + DIM_N, nullptr, nullptr, nullptr, 0, 0, nullptr};
+      GemmTmaProblem wg{p->map_a_mn(l), p->map_q_mn(), grads + p->off_gcn_w(l), H, 1, 1, H, H, p->Nc, nullptr, dims + DIM_N, nullptr, nullptr, 0, 1, nullptr};
+      STAGE(ST_GEMM_GCN_BWD, 1, launch_gemm_tma(&dg, &wg, st));
+    } else if (l > 0) {
       STAGE(ST_GEMM_GCN_BWD, (p->pair_gemms && p->gemm_backend == EIMS_GEMM_TCGEN05) ? 1 : 2, gemm_pair(p,
             GemmProblem{p->f(L_("a", l)), H, 1, p->f("q"), H, 1, grads + p->off_gcn_w(l), H, H, H, p->Nc, nullptr, dims + DIM_N, nullptr, nullptr, 0, 1, nullptr},
             GemmProblem{p->f("q"), H, 0, params + p->off_gcn_w(l), H, 0, p->f("da"), H, p->Nc, H, H, dims + DIM_N, nullptr, nullptr, nullptr, 0, 0, nullptr}, st));
+    }
+    if (l > 0) {
       if (!p->fuse_spmm_bwd) {
         float* scratch = p->f("bn_partials");
         BnBwdFuse bf{p->f(L_("z", l - 1)), p->f(L_("bn_mean", l - 1)), p->f(L_("bn_invstd", l - 1)),

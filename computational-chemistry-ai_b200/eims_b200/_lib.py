@@ -52,6 +52,16 @@ class HostBatchLayout(C.Structure):
                [(n, C.c_int32) for n in ("num_graphs", "num_nodes", "num_edges", "feat_dim", "mz_is_f64")]
 
 
+class GemmProblem(C.Structure):
+    """eims_gemm_problem: one product of eims_gemm_planes."""
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int32), ("a_mn_major", C.c_int32),
+                ("B", C.c_void_p), ("ldb", C.c_int32), ("b_mn_major", C.c_int32),
+                ("C", C.c_void_p), ("ldc", C.c_int32),
+                ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+                ("m_dev", C.c_void_p), ("k_dev", C.c_void_p), ("row_scale", C.c_void_p), ("bias", C.c_void_p),
+                ("relu", C.c_int32), ("accumulate", C.c_int32)]
+
+
 class Step(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("weight_decay", C.c_float), ("grad_scale", C.c_float), ("step", C.c_int32), ("seed", C.c_uint64)]
@@ -72,6 +82,8 @@ _SIGS = {
     "eims_spmm_norm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _u64, _i32, _i32, _i32, _vp, _i32, _vp]),
     "eims_spmm_norm_mol": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _f32, _u64, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "eims_gemm": (C.c_int, [_i32, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "eims_gemm_planes_scratch_bytes": (_i64, [C.POINTER(GemmProblem), C.POINTER(GemmProblem)]),
+    "eims_gemm_planes": (C.c_int, [C.POINTER(GemmProblem), C.POINTER(GemmProblem), _vp, _i64, _vp]),
     "eims_bn_scratch_floats": (_i64, [_i32, _i32]),
     "eims_bn_stats": (C.c_int, [_vp, _vp, _i32] + [_vp] * 9 + [_i32, _vp]),
     "eims_readout": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
@@ -83,6 +95,7 @@ _SIGS = {
     "eims_plan_workspace_bytes": (_i64, [_vp]),
     "eims_plan_bind": (C.c_int, [_vp, _vp, _i64]),
     "eims_plan_set_gemm_backend": (C.c_int, [_vp, _i32]),
+    "eims_plan_set_gemm_planes": (C.c_int, [_vp, _i32]),
     "eims_plan_buffer": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_i64)]),
     "eims_batch_build": (C.c_int, [_vp, C.POINTER(Dataset), _vp, _i32, _vp]),
     "eims_forward": (C.c_int, [_vp, _vp, _vp, _i32, C.POINTER(Step), _vp]),

@@ -337,6 +337,11 @@ class Plan:
         except Exception:
             pass
 
+    def set_gemm_planes(self, mode):
+        """'auto' (default) / 'off' / 'on': which kernel runs the GraphConv products (eims_plan_set_gemm_planes)."""
+        m = {"auto": -1, "off": 0, "on": 1}.get(mode, mode)
+        check(self.lib.eims_plan_set_gemm_planes(self.h, int(m)))
+
     def set_gemm_backend(self, backend):
         b = {"tcgen05": _lib.GEMM_TCGEN05, "simt": _lib.GEMM_FP32_SIMT}.get(backend, backend)
         check(self.lib.eims_plan_set_gemm_backend(self.h, int(b)))

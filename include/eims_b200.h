@@ -167,6 +167,27 @@ int eims_gemm(int32_t backend, const float* A, int32_t lda, int32_t a_mn_major,
               const float* row_scale, const float* bias, int32_t relu, int32_t accumulate,
               eims_stream_t stream);
 
+/* K3/K6 on pre-split operand planes (csrc/gemm_tma.cu): the same products as eims_gemm, computed by the persistent
+ * kernel that the plan uses for the GraphConv layers (GCN:316,359 forward, and their weight / data gradients): every
+ * operand is first split into stacked tf32 hi / lo planes (inside `scratch`; in the plan the kernels that produce the
+ * operands write the planes directly), the planes travel global -> shared by cp.async.bulk.tensor, and one CTA per SM
+ * walks over the output tiles of a store problem (accumulate = 0) and / or the k-slices of a split-K problem
+ * (accumulate = 1, partial sums added into C), dealt out on the device from the live sizes.  p1 may be NULL; with two
+ * problems exactly one must have accumulate = 1.  Needs N % 256 == 0, ldc % 4 == 0, K <= 512 for the store problem, lda /
+ * ldb % 4 == 0; for a split-K problem with a live k_dev < K the operand rows in [k_dev, K) must be finite. */
+typedef struct {
+  const float* A; int32_t lda, a_mn_major;
+  const float* B; int32_t ldb, b_mn_major;
+  float* C; int32_t ldc;
+  int32_t M, N, K;
+  const int32_t* m_dev; const int32_t* k_dev;
+  const float* row_scale; const float* bias;
+  int32_t relu, accumulate;
+} eims_gemm_problem;
+int64_t eims_gemm_planes_scratch_bytes(const eims_gemm_problem* p0, const eims_gemm_problem* p1);
+int eims_gemm_planes(const eims_gemm_problem* p0, const eims_gemm_problem* p1, void* scratch, int64_t scratch_bytes,
+                     eims_stream_t stream);
+
 /* BatchNorm1d training statistics over the N atoms of the batch (GCN:361):
  * mean / biased var per column -> scale = gamma*invstd, shift = beta - mean*scale,
  * saved mean & invstd, running stats update (momentum 0.1, unbiased var).  `partials`
@@ -227,6 +248,15 @@ int eims_plan_destroy(eims_plan* p);
 int64_t eims_plan_workspace_bytes(const eims_plan* p);
 int eims_plan_bind(eims_plan* p, void* workspace, int64_t bytes);
 int eims_plan_set_gemm_backend(eims_plan* p, int32_t backend);
+/* Which kernel runs the GraphConv products (GCN:316,359 and their gradients) on the tensor-core backend:
+ * EIMS_PLANES_AUTO (default) - the persistent planes kernel (csrc/gemm_tma.cu: operands pre-split into tf32 hi / lo
+ * planes by their producers, fed by cp.async.bulk.tensor, CTA pairs) for plans sized for large batches (>= 4 output
+ * tiles per SM), the in-kernel-split kernel (csrc/gemm_tc.cu) otherwise; EIMS_PLANES_OFF / EIMS_PLANES_ON force one.
+ * EIMS_ERR_STATE if the planes path is asked for but the plan's shapes do not allow it (hidden_dim % 256, > 512). */
+#define EIMS_PLANES_AUTO (-1)
+#define EIMS_PLANES_OFF 0
+#define EIMS_PLANES_ON 1
+int eims_plan_set_gemm_planes(eims_plan* p, int32_t mode);
 
 /* Named views into the bound workspace (tests / host layer).  Names: "dims","gptr","eptr",
  * "gid","src","dst","rowptr","col","norm","x","prob","logits","row_loss","row_cos",

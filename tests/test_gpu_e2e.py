@@ -35,7 +35,11 @@ def setup(d, n_mols, max_atoms, seed, backend, wseed=0):
     table = synth_molecules(n_mols, max_atoms=max_atoms, seed=seed)
     targets = dense_spectra(*synth_peaks(n_mols, d.max_mz, seed=seed + 1), d.max_mz)
     N, E = int(table.node_ptr[-1]), int(2 * table.bond_ptr[-1])
-    plan = Plan(d, n_mols, N, E, DEV, gemm_backend=backend)
+    # "tcgen05+planes": the tensor-core backend with the planes kernel forced for the GraphConv products (a plan of
+    # this size would pick the in-kernel-split kernel on its own)
+    plan = Plan(d, n_mols, N, E, DEV, gemm_backend=backend.split("+")[0])
+    if backend.endswith("+planes"):
+        plan.set_gemm_planes("on")
     ds = DeviceDataset(table, targets, DEV)
     fp = FlatParams(d, DEV)
     sd = O.init_params(odims(d), wseed)
@@ -312,7 +316,7 @@ def gpu_decisions(plan, B, N, d):
     return dec
 
 
-@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("backend", BACKENDS + (["tcgen05+planes"] if "tcgen05" in BACKENDS else []))
 def test_full_size_flip_aware_gradients(backend):
     """BASELINE cfg-2 shapes (batch 512, H 256, M 1000), ALL 22 gradient tensors at 1e-4 against the fp64 oracle.
 
