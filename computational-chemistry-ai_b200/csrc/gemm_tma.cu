@@ -48,6 +48,7 @@ constexpr int kEpiWarps = 4, kThreads = (2 + kEpiWarps) * 32;
 constexpr int kPatchFloats = 32 * 36;                              // padded 32 x 32 staging patch per epilogue warp
 constexpr int kStatCols = 128;                                     // BatchNorm partial sums are flushed per half tile
 constexpr int kMaxKbPerItem = 16;                                  // single accumulator per item: K <= 512 (see gemm_tc.cu)
+constexpr int kMaxKbDeep = 64;                                     // "deep" launches (main + correction accumulator): K <= 2048
 // PAIR = 1: one CTA per 128 x 256 tile.  PAIR = 2: a CTA pair (cluster of two SMs) works on a 256 x 256 tile with
 // tcgen05.mma.cta_group::2 - each CTA stages its own 128 rows of A and HALF of B (128 of the 256 columns), the tensor
 // cores of both SMs read both halves: per CTA and k-block 64 KB instead of 96 KB enter shared memory and 96 KB instead
@@ -182,7 +183,11 @@ struct Prob {
 struct Group {
   Prob g[2];
   int nprob, early, ovh;               // ovh: fixed cost of one item in k-block units (balances the two problems)
-  int dbg;                             // diagnostic (EIMS_GEMM_TMA_DBG): 1 = no global stores, 2 = stores straight from registers
+  // deep != 0 (a store problem with K > 512): every item of the launch uses BOTH 256-column accumulators - the A_hi*B_hi
+  // products in one, the two correction products in the other, summed in the epilogue - because the tensor core truncates
+  // on every accumulation and one accumulator over K = 1024 carries a bias of ~1e-5 (gemm_tc.cu, measured); the epilogue
+  // of an item then no longer overlaps the next item's main loop, which at >= 32 k-blocks per item costs ~10 %.
+  int deep;
 };
 
 // ---- CTA-pair plumbing (PAIR = 2)
@@ -346,7 +351,7 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
                : "memory");
 }
 
-template <bool RED, bool STAT, bool FULL>
+template <bool RED, bool STAT, bool FULL, bool DEEP>
 __device__ __forceinline__ void epilogue_tile(const EpiCtx& cx) {
   const int lane = cx.lane, cc = (lane & 7) * 4, r8 = lane >> 3;
   const uint32_t wr = cx.patch + lane * 144;                 // this thread's row of the patch (36 floats)
@@ -354,11 +359,18 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& cx) {
   float* const dst0 = cx.Cq + (int64_t)r8 * cx.ldc + cc;     // + t8 * 4 * ldc, + col0
   const int64_t step = (int64_t)4 * cx.ldc;
   uint32_t r[32];
+  uint32_t rc[32];   // DEEP only (dead otherwise): the correction accumulator, 256 columns further
   tmem_ld32_issue(cx.taddr, r);
+  if constexpr (DEEP) tmem_ld32_issue(cx.taddr + BN, rc);
   tmem_ld32_wait(r);
 #pragma unroll 1
   for (int cb = 0; cb < BN / 32; ++cb) {
     const int col0 = cb * 32;
+    if constexpr (DEEP) {
+      tmem_ld32_wait(rc);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(rc[j]) + __uint_as_float(r[j]));
+    }
     __syncwarp();  // the previous block's reads of the patch are done
 #pragma unroll
     for (int j = 0; j < 32; j += 4)
@@ -367,6 +379,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& cx) {
     __syncwarp();
     if (cb + 1 < BN / 32) {
       tmem_ld32_issue(cx.taddr + (uint32_t)(col0 + 32), r);   // in flight under the stores of this block
+      if constexpr (DEEP) tmem_ld32_issue(cx.taddr + BN + (uint32_t)(col0 + 32), rc);
     } else {
       // the whole accumulator has left TMEM: hand the buffer back before the last block's stores
       tc_fence_before();
@@ -553,11 +566,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_planes_kernel(const __grid_c
         const uint32_t b_lbo = b_mn ? 8192u : 16u, b_sbo = b_mn ? 512u : 1024u, b_kstep = b_mn ? 1024u : 32u;
         const uint32_t a_lo_off = a_mn ? 4096u : (uint32_t)C::A_PLANE, b_lo_off = b_mn ? 4096u : (uint32_t)C::B_PLANE;
         const uint32_t a_lt = a_mn ? 1u : 2u, b_lt = b_mn ? 1u : 2u;
-        const uint32_t b = tcount & 1u;
-        mbar_wait(acce0 + 8 * b, ((tcount >> 1) & 1u) ^ 1u);  // accumulator b drained by the epilogue warps (of both CTAs)
+        const uint32_t b = grp.deep ? 0u : (tcount & 1u);
+        const uint32_t bph = grp.deep ? (tcount & 1u) : ((tcount >> 1) & 1u);
+        mbar_wait(acce0 + 8 * b, bph ^ 1u);  // accumulator b drained by the epilogue warps (of both CTAs)
         tc_fence_after();
         PTRACE(8 + tcount * 8 + 1);   // accumulator free
         const uint32_t acc = tmem_base + b * BN;
+        const uint32_t acc_corr = grp.deep ? tmem_base + BN : acc;   // deep: the correction products have their own accumulator
         for (int i = 0; i < it.nkb; ++i, ++n) {
           const uint32_t s = n % S;
           mbar_wait(full0 + 8 * s, (n / S) & 1u);
@@ -573,14 +588,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_planes_kernel(const __grid_c
               const uint64_t dbh = make_desc(sb + ks * b_kstep, b_lbo, b_sbo, b_lt);
               const uint64_t dbl = make_desc(sb + b_lo_off + ks * b_kstep, b_lbo, b_sbo, b_lt);
               const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
+              const uint32_t mfirst = grp.deep ? first : 1u;   // deep: the main accumulator starts with this product
               if (PAIR == 2) {
-                umma_tf32_pair(acc, dal, dbh, idesc, first);  // smallest terms first
-                umma_tf32_pair(acc, dah, dbl, idesc, 1u);
-                umma_tf32_pair(acc, dah, dbh, idesc, 1u);
+                umma_tf32_pair(acc_corr, dal, dbh, idesc, first);  // smallest terms first
+                umma_tf32_pair(acc_corr, dah, dbl, idesc, 1u);
+                umma_tf32_pair(acc, dah, dbh, idesc, mfirst);
               } else {
-                umma_tf32(acc, dal, dbh, idesc, first);
-                umma_tf32(acc, dah, dbl, idesc, 1u);
-                umma_tf32(acc, dah, dbh, idesc, 1u);
+                umma_tf32(acc_corr, dal, dbh, idesc, first);
+                umma_tf32(acc_corr, dah, dbl, idesc, 1u);
+                umma_tf32(acc, dah, dbh, idesc, mfirst);
               }
             }
             if (PAIR == 2) {
@@ -618,7 +634,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_planes_kernel(const __grid_c
       const int ldc = p1 ? grp.g[1].ldc : grp.g[0].ldc;
       const int M = p1 ? Mv[1] : Mv[0];
       const int m_own = it.m0 + (int)rank * BM;
-      const uint32_t b = tcount & 1u;
+      const uint32_t b = grp.deep ? 0u : (tcount & 1u);
+      const uint32_t bph = grp.deep ? (tcount & 1u) : ((tcount >> 1) & 1u);
       cx.m_q0 = m_own + q * 32;
       cx.M = M;
       cx.n0 = it.n0;
@@ -631,18 +648,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_planes_kernel(const __grid_c
       cx.release_bar = (PAIR == 2 && rank != 0) ? mapa_rank(acce0 + 8 * b, 0) : acce0 + 8 * b;
       cx.release_remote = PAIR == 2 && rank != 0;
       if (e == 0) PTRACE(8 + tcount * 8 + 4);                  // epilogue waits for the accumulator
-      mbar_wait(accf0 + 8 * b, (tcount >> 1) & 1u);
+      mbar_wait(accf0 + 8 * b, bph);
       tc_fence_after();
       if (e == 0) PTRACE(8 + tcount * 8 + 5);                  // accumulator complete
       const int m = cx.m_q0 + lane;
       cx.rs = (row_scale && m < M) ? __ldg(row_scale + m) : 1.f;
       const bool full = cx.m_q0 + 32 <= M;
-      if (red) {
-        if (full) epilogue_tile<true, false, true>(cx); else epilogue_tile<true, false, false>(cx);
+      if (grp.deep) {   // (the guarded variants only: a deep launch is MMA-bound, the epilogue is a few per cent of it)
+        if (red) epilogue_tile<true, false, false, true>(cx);
+        else if (cx.bn_acc) epilogue_tile<false, true, false, true>(cx);
+        else epilogue_tile<false, false, false, true>(cx);
+      } else if (red) {
+        if (full) epilogue_tile<true, false, true, false>(cx); else epilogue_tile<true, false, false, false>(cx);
       } else if (cx.bn_acc) {
-        if (full) epilogue_tile<false, true, true>(cx); else epilogue_tile<false, true, false>(cx);
+        if (full) epilogue_tile<false, true, true, false>(cx); else epilogue_tile<false, true, false, false>(cx);
       } else {
-        if (full) epilogue_tile<false, false, true>(cx); else epilogue_tile<false, false, false>(cx);
+        if (full) epilogue_tile<false, false, true, false>(cx); else epilogue_tile<false, false, false, false>(cx);
       }
       if (e == 0) PTRACE(8 + tcount * 8 + 6);                  // tile stored
       ++tcount;
@@ -763,11 +784,11 @@ int gemm_tma_pair() {
 }
 int gemm_tma_b_rows() { return tma::BN / gemm_tma_pair(); }
 
-// shapes the planes kernel takes: full 256-wide column tiles, vector stores, K of a store problem <= 512
+// shapes the planes kernel takes: full 256-wide column tiles, vector stores, K of a store problem <= 2048 (> 512: deep mode)
 bool gemm_tma_supports(const GemmTmaProblem& q) {
   if (q.N < 256 || (q.N % 256) || (q.ldc & 3) || (reinterpret_cast<uintptr_t>(q.C) & 15)) return false;
   if (q.bias && (reinterpret_cast<uintptr_t>(q.bias) & 15)) return false;
-  if (!q.red && (q.K + 31) / 32 > tma::kMaxKbPerItem) return false;
+  if (!q.red && (q.K + 31) / 32 > tma::kMaxKbDeep) return false;
   if (q.bn && (q.red || q.bn->H != q.N)) return false;
   return q.M > 0 && q.K > 0 && q.ta && q.tb;
 }
@@ -802,9 +823,10 @@ int launch_gemm_tma(const GemmTmaProblem* p0, const GemmTmaProblem* p1, cudaStre
     if (ps[k]) items += (int64_t)((q->M + BM * pair - 1) / (BM * pair)) * (q->N / BN) * (q->red ? 148 : 1);
   }
   grp.nprob = p1 ? 2 : 1;
+  for (int k = 0; k < grp.nprob; ++k)
+    if (!grp.g[k].red && (grp.g[k].K + 31) / 32 > kMaxKbPerItem) grp.deep = 1;
   grp.early = dims_early_ref();
   grp.ovh = ovh;
-  { const char* e = getenv("EIMS_GEMM_TMA_DBG"); grp.dbg = e ? atoi(e) : 0; }
   const int units = 148 / pair;
   int grid = (int)(items < units ? items : units) * pair;
   if (grid < pair) grid = pair;

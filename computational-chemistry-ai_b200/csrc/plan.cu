@@ -98,7 +98,7 @@ struct eims_plan {
   eims_step last_step;
   // Planes path of the GraphConv products (csrc/gemm_tma.cu): a_l, q and the GraphConv weights exist as stacked tf32
   // hi / lo planes [2][rows][H] and the GEMMs are fed by the tensor-map copy engine.  planes_cap: the shapes allow it
-  // (H a multiple of 256, <= 512) and the workspace was sized for it; planes_on(): ... and the tensor-core backend is
+  // (H a multiple of 256, <= 1024) and the workspace was sized for it; planes_on(): ... and the tensor-core backend is
   // selected and the path is not switched off (EIMS_GEMM_TMA=0).
   bool planes_cap = false;
   int64_t act_plane = 0;   // floats between the hi and the lo plane of a_l / q ( = rows_alloc * H )
@@ -112,13 +112,17 @@ struct eims_plan {
   const TmaMap* map_q_mn() const { return &maps[4 * (d.num_gcn_layers - 1) + 1]; }
   // Measured on a B200 (profiles/r2_gemm_planes.md): with >= ~4 output tiles per SM (inference batches of 4096) the
   // persistent planes kernel hides every tile's epilogue under the next tile's main loop and runs at the MMA issue rate
-  // (cfg 3: 6.9 -> 7.4 M molecules/s); at a training batch of 512 a launch is ONE tile per SM, nothing overlaps, and
+  // (cfg 3: 6.9 -> 7.4 M molecules/s); at a training batch of 512 with hidden 256 a launch is ONE tile per SM, nothing
+  // overlaps, and
   // what the planes cost (a second plane written by the producers, the weight split, twice the operand bytes from L2)
-  // outweighs the faster main loop: 0.363 against 0.342 ms per step.  So: large batches only, unless EIMS_GEMM_TMA=1.
+  // outweighs the faster main loop: 0.363 against 0.342 ms per step.  At hidden 1024 (cfg 5: 14 tiles per SM, K = 1024) the
+  // planes kernel needs ~12 TB/s of operand bytes out of L2 to keep the tensor cores fed and gets ~7: 7.48 against 7.03 ms
+  // per step - fp32 operands split in the kernel are half the bytes.  So: large batches at hidden <= 512 only, unless
+  // EIMS_GEMM_TMA=1 / eims_plan_set_gemm_planes(EIMS_PLANES_ON).
   bool planes_on() const {
     if (!(planes_cap && gemm_backend == EIMS_GEMM_TCGEN05 && gemm_tma_enabled() && !maps.empty())) return false;
     if (planes_mode >= 0) return planes_mode != 0;
-    return gemm_tma_forced() || Nc >= 4 * 148 * 128;
+    return gemm_tma_forced() || (d.hidden_dim <= 512 && (int64_t)((Nc + 127) / 128) * (d.hidden_dim / 256) >= 4 * 148);
   }
   int planes_mode = -1;  // eims_plan_set_gemm_planes
   int pool_dim() const { return d.pooling == EIMS_POOL_COMBINED ? 2 * d.hidden_dim : d.hidden_dim; }
@@ -466,7 +470,7 @@ int eims_plan_create(const eims_dims* d, int32_t max_graphs, int32_t max_nodes, 
   add(p, "argmax", B * H * 4);
   add(p, "norm", N * 4); add(p, "x", N * F * 4); add(p, "a0", N * F * 4);
   // a_l and q hold two planes (tf32 hi / lo) when the GraphConv GEMMs may take the planes path; rows padded to 32
-  p->planes_cap = gemm_tma_enabled() && H % 256 == 0 && H <= 512 && L > 1;
+  p->planes_cap = gemm_tma_enabled() && H % 256 == 0 && H <= 1024 && L > 1;
   const int64_t Np = (N + 31) & ~(int64_t)31;
   p->act_plane = Np * H;
   p->w_plane = p->planes_cap ? (p->off_gcn_w(L - 1) + H * H - p->off_gcn_w(1)) : 0;
@@ -550,7 +554,7 @@ int eims_plan_set_gemm_backend(eims_plan* p, int32_t backend) {
 int eims_plan_set_gemm_planes(eims_plan* p, int32_t mode) {
   if (!p || mode < -1 || mode > 1) return fail(EIMS_ERR_ARG, "mode must be one of EIMS_PLANES_*");
   if (mode == 1 && !(p->planes_cap && (!p->bound || !p->maps.empty())))
-    return fail(EIMS_ERR_STATE, "the planes GEMM needs hidden_dim %% 256 == 0, hidden_dim <= 512, >= 2 GCN layers and cuTensorMapEncodeTiled");
+    return fail(EIMS_ERR_STATE, "the planes GEMM needs hidden_dim %% 256 == 0, >= 2 GCN layers and cuTensorMapEncodeTiled");
   p->planes_mode = mode;
   return 0;
 }

@@ -173,7 +173,8 @@ int eims_gemm(int32_t backend, const float* A, int32_t lda, int32_t a_mn_major,
  * operands write the planes directly), the planes travel global -> shared by cp.async.bulk.tensor, and one CTA per SM
  * walks over the output tiles of a store problem (accumulate = 0) and / or the k-slices of a split-K problem
  * (accumulate = 1, partial sums added into C), dealt out on the device from the live sizes.  p1 may be NULL; with two
- * problems exactly one must have accumulate = 1.  Needs N % 256 == 0, ldc % 4 == 0, K <= 512 for the store problem, lda /
+ * problems exactly one must have accumulate = 1.  Needs N % 256 == 0, ldc % 4 == 0, K <= 2048 for the store problem (K > 512
+ * keeps the correction products in a second accumulator and gives up the overlap of epilogue and main loop), lda /
  * ldb % 4 == 0; for a split-K problem with a live k_dev < K the operand rows in [k_dev, K) must be finite. */
 typedef struct {
   const float* A; int32_t lda, a_mn_major;
@@ -252,7 +253,7 @@ int eims_plan_set_gemm_backend(eims_plan* p, int32_t backend);
  * EIMS_PLANES_AUTO (default) - the persistent planes kernel (csrc/gemm_tma.cu: operands pre-split into tf32 hi / lo
  * planes by their producers, fed by cp.async.bulk.tensor, CTA pairs) for plans sized for large batches (>= 4 output
  * tiles per SM), the in-kernel-split kernel (csrc/gemm_tc.cu) otherwise; EIMS_PLANES_OFF / EIMS_PLANES_ON force one.
- * EIMS_ERR_STATE if the planes path is asked for but the plan's shapes do not allow it (hidden_dim % 256, > 512). */
+ * EIMS_ERR_STATE if the planes path is asked for but the plan's shapes do not allow it (hidden_dim % 256 != 0). */
 #define EIMS_PLANES_AUTO (-1)
 #define EIMS_PLANES_OFF 0
 #define EIMS_PLANES_ON 1

@@ -227,7 +227,8 @@ def test_batched_inference_equals_single(backend):
     assert rel_err(batched, ref.numpy()) < REL
 
 
-def test_wide_deep_variant_vs_oracle():
+@pytest.mark.parametrize("backend", ["tcgen05", "tcgen05+planes"])
+def test_wide_deep_variant_vs_oracle(backend):
     """BASELINE configs[4] shapes: 6 GCN layers, hidden 1024, molecules up to 128 heavy atoms
     (a small batch so that the CPU oracle finishes in seconds).  Exercises the 8-float4-per-lane
     SpMM split, the 16-slab BatchNorm grids, LayerNorm at width 2048 and the 1024-wide GEMM
@@ -235,7 +236,7 @@ def test_wide_deep_variant_vs_oracle():
     so gradients are held to max(1e-4, 8 x the fp32 oracle's own distance from fp64) - the head
     tensors, which sit behind no such discontinuity, land at ~1e-6."""
     d = ModelDims(hidden_dim=1024, num_gcn_layers=6, max_mz=1000, dropout=0.0)
-    table, targets, plan, ds, fp, sd = setup(d, 24, 128, 77, "tcgen05", wseed=5)
+    table, targets, plan, ds, fp, sd = setup(d, 24, 128, 77, backend, wseed=5)
     graph, feat = O.Graph.from_mols([table.mol(i) for i in range(24)])
     # batched inference at this width (before the training-mode forward moves the running statistics)
     out = plan.infer_batch(ds, None, fp).clone().cpu().numpy()

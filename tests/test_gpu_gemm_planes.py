@@ -36,7 +36,8 @@ def rel(a, b):
     return float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("atoms,cap,H", [(300, 512, 256), (16900, 32768, 256), (1000, 1024, 512), (129, 4096, 256), (4096, 4096, 256)])
+@pytest.mark.parametrize("atoms,cap,H", [(300, 512, 256), (16900, 32768, 256), (1000, 1024, 512), (129, 4096, 256), (4096, 4096, 256),
+                                         (3000, 3072, 1024)])   # hidden 1024: K = 1024, main + correction accumulators
 def test_graphconv_products_vs_fp64(atoms, cap, H):
     g = torch.Generator(device=DEV).manual_seed(atoms + H)
     X = torch.randn(cap, H, device=DEV, generator=g)
@@ -96,9 +97,9 @@ def test_unsupported_shapes_are_refused():
     W = torch.zeros(256, 128, device=DEV)
     Cm = torch.zeros(256, 128, device=DEV)
     assert run(problem(A, 0, W, 1, Cm, 256, 128, 256)) == _lib.ERR_ARG      # N must be a multiple of 256
-    A = torch.zeros(256, 1024, device=DEV)
-    W = torch.zeros(1024, 256, device=DEV)
+    A = torch.zeros(256, 4096, device=DEV)
+    W = torch.zeros(4096, 256, device=DEV)
     Cm = torch.zeros(256, 256, device=DEV)
-    assert run(problem(A, 0, W, 1, Cm, 256, 256, 1024)) == _lib.ERR_ARG     # K of a store problem <= 512
+    assert run(problem(A, 0, W, 1, Cm, 256, 256, 4096)) == _lib.ERR_ARG     # K of a store problem <= 2048
     p0 = problem(A, 0, W, 1, Cm, 256, 256, 256)
     assert run(p0, p0) != 0                                                  # two store problems in one launch
