@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "gemm_persist.cuh"
 #include "launchers.h"
 
 namespace eims {
@@ -142,7 +143,6 @@ struct Args {
 struct Group {
   Args g[2];
   int ctas0;
-  int tiles;  // persistent kernel: tiles of both problems (ctas0 + tiles of g[1])
 };
 
 // Load one 16-byte chunk (4 consecutive floats) with zero fill outside [0, lim) of the
@@ -268,8 +268,14 @@ struct Operand {
   __device__ __forceinline__ void load(TileRegs<ROWS, GT>& r, int k0, int k_lim, int t) {
     constexpr int PER = TileRegs<ROWS, GT>::PER;
     if (full && k0 + BK <= k_lim) {
+      // MN-major with fewer atoms per pass than the tile is wide (8 producer warps on a 256-wide B tile): the passes
+      // walk (mn atoms, then k-groups), two strides instead of one; all compile-time in `it`
+      constexpr int API = GT / 32, MNA = ROWS / 32, R = API < MNA ? MNA / API : 1;
 #pragma unroll
-      for (int it = 0; it < PER; ++it) r.v[it] = ldg4(fast + it * gstride);
+      for (int it = 0; it < PER; ++it) {
+        const int64_t off = (mn_major && API < MNA) ? (int64_t)((it / R) * 4) * ld + (it % R) * API * 32 : it * gstride;
+        r.v[it] = ldg4(fast + off);
+      }
     } else {
 #pragma unroll
       for (int it = 0; it < PER; ++it) {
@@ -559,105 +565,72 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_3xtf32_kernel(const __grid_c
 
 
 // ---------------------------------------------------------------------------------------------
-// Persistent variant for launches with several tiles per SM (inference forwards, the grouped
-// weight- + data-gradient launches).  A kernel that allocates tensor memory runs ONE CTA per SM on this
-// driver (cudaOccupancyMaxActiveBlocksPerMultiprocessor says 1 for any kernel containing tcgen05.alloc,
-// tools/ubench/occ_probe.cu), so a tile's fill (operands in flight, first stage stored) and epilogue
-// (accumulator drained, 128 KB written) cannot hide behind another CTA's main loop; with one CTA per
-// tile they were half of a tile's 26 k cycles.  Here one CTA per SM walks over its tiles
-// (tile = blockIdx.x + n * gridDim.x): the 16 producer warps and the MMA warp run straight
-// through the tile boundaries, the accumulator is double-buffered in TMEM (2 x 256 columns, all three
-// products of a k-step in one accumulator - K <= 512 per tile keeps the accumulate-truncation bias
-// at ~1e-6), and four epilogue warps drain accumulator b (TMEM -> registers -> row scale / bias /
-// ReLU -> global) while the tensor core is already filling accumulator b^1.
-constexpr int kPersistThreads = (kProducerWarps + 1 + 4) * 32;
-constexpr int kPersistPatchBytes = 4 * 32 * 36 * 4;  // one padded 32 x 32 staging patch per epilogue warp
+// Persistent variant: one CTA per SM walks over a list of work items with two 256-column accumulators in TMEM, so the
+// epilogue of item i runs under the main loop of item i + 1.  Used for (a) launches with several 128 x 256 tiles per SM
+// (inference forwards when the planes kernel of gemm_tma.cu is off) and (b) the grouped data-gradient + weight-gradient
+// launch of a GraphConv layer: non-persistent, its 264 live CTAs at BASELINE cfg 2 are two waves of one tile each, i.e.
+// two pipeline fills and two exposed epilogues per SM; here every CTA takes one data-gradient tile and a k-slice of the
+// weight gradient sized ON THE DEVICE from the live atom count so that all CTAs end together (gemm_persist.cuh).
+// A kernel that allocates tensor memory runs ONE CTA per SM on this driver (cudaOccupancyMaxActiveBlocksPerMultiprocessor
+// says 1 for any kernel containing tcgen05.alloc, tools/ubench/occ_probe.cu), so overlap has to come from inside the CTA.
+//   warps 0-7  : A tile of every k-block of the CTA's item sequence, warps 8-15: B tile (global -> registers, prefetched
+//                one k-block ahead across item boundaries -> hi/lo split -> stage n & 1)
+//   warps 16-19: epilogue (pg::epilogue_tile: straight-line, explicit shared-space patch, TMEM loads pipelined; the
+//                first version of this kernel ran a branchy epilogue through generic pointers - LD.E / ST.E instead of
+//                LDS / STS - which took 23 k cycles per tile instead of 5 k and hid the benefit of the overlap)
+//   warp 20    : MMA issuer, all three products of a k-step into ONE accumulator (K <= 512 per item keeps the
+//                accumulate-truncation bias at ~1e-6)
+// (21 warps leave 96 registers per thread: the epilogue runs its rows in two passes of four (VB = 4).  With 8
+// producer warps and the one-pass epilogue the main loop was producer-bound, 2.5 k instead of 1.9 k cycles per k-block;
+// with 16 the epilogue warps starve for issue slots - see use_persistent().)
+constexpr int kPersistProducerWarps = 16, kPersistGroupThreads = kPersistProducerWarps / 2 * 32;
+constexpr int kPersistThreads = (kPersistProducerWarps + 1 + pg::kEpiWarps) * 32;
+constexpr int kPersistStageBytes = 2 * BM * BK * 4 + 2 * 256 * BK * 4;
+constexpr int kPersistOffPatch = 2 * kPersistStageBytes;
+constexpr int kPersistOffStats = kPersistOffPatch + pg::kEpiWarps * pg::kPatchFloats * 4;
+constexpr int kPersistSmem = kPersistOffStats + pg::kEpiWarps * 2 * pg::kStatCols * 8 + 1024;
 
-struct TileInfo {
-  int which, m0, n0, kb0, nkb, bz, M, K;
-  bool live;
-};
-
-__device__ __forceinline__ TileInfo decode_tile(const Group& grp, int tile, const int (&Mv)[2], const int (&Kv)[2]) {
-  TileInfo ti;
-  ti.which = tile >= grp.ctas0 ? 1 : 0;
-  const Args& g = grp.g[ti.which];
-  const int local = tile - (ti.which ? grp.ctas0 : 0);
-  const int bx = local % g.nt, by = (local / g.nt) % g.mt;
-  ti.bz = local / (g.nt * g.mt);
-  ti.M = Mv[ti.which];
-  ti.K = Kv[ti.which];
-  ti.m0 = by * BM;
-  ti.n0 = bx * 256;
-  const int kblocks = (ti.K + BK - 1) / BK;
-  const int per_split = (kblocks + g.splits - 1) / g.splits;
-  ti.kb0 = ti.bz * per_split;
-  ti.nkb = min(kblocks, ti.kb0 + per_split) - ti.kb0;
-  ti.live = ti.m0 < ti.M && ti.n0 < g.N && ti.nkb > 0;
-  return ti;
-}
-
-// Producers of the persistent kernel: warps 0-7 bring the A tile (IS_B = false, ROWS = BM), warps 8-15 the B
-// tile (ROWS = 256) of EVERY k-block of the CTA's flattened (tile, k-block) sequence: global -> registers
-// (prefetched one k-block ahead, across tile boundaries) -> hi/lo split -> stage n & 1.  One operand per
-// thread keeps the prefetched k-block at 16 / 32 registers (21 warps leave 80 registers per thread); all 16
-// warps on both operands (2 + 4 chunks each) measured slower, 124 against 110 us for the cfg-3 forward.
-// `op_off` = byte offset of the operand's hi tile inside a stage; its lo tile follows it.
+// Producers: warps 0-7 bring the A tile (IS_B = false, ROWS = BM), warps 8-15 the B tile (ROWS = 256).  One operand per
+// thread keeps the prefetched k-block at 16 / 32 registers.  `op_off` = byte offset of the operand's hi tile inside a
+// stage; its lo tile follows it.
 template <int ROWS, bool IS_B>
-__device__ __forceinline__ void persistent_producer(const Group& grp, const int (&Mv)[2], const int (&Kv)[2], int T, int G,
-                                                        uint32_t smem_base, uint32_t full0, uint32_t empty0, uint32_t stage_bytes,
-                                                        uint32_t op_off) {
-  const int t = threadIdx.x & (kGroupThreads - 1), lane = threadIdx.x & 31;
-  TileRegs<ROWS> regs;
-  Operand<ROWS> op;
-  int tile = blockIdx.x, i = 0;
-  TileInfo ti;
-  ti.nkb = 0;
-  bool valid = false;
-  auto enter_tile = [&]() -> bool {
-    while (tile < T) {
-      ti = decode_tile(grp, tile, Mv, Kv);
-      if (ti.live) return true;
-      tile += G;
-    }
-    return false;
+__device__ __forceinline__ void persistent_producer(const Group& grp, const pg::Sched& sch, const int (&Mv)[2], const int (&Kv)[2],
+                                                    uint32_t smem_base, uint32_t full0, uint32_t empty0, uint32_t op_off) {
+  const int t = threadIdx.x & (kPersistGroupThreads - 1), lane = threadIdx.x & 31;
+  TileRegs<ROWS, kPersistGroupThreads> regs;
+  Operand<ROWS, kPersistGroupThreads> op;
+  pg::Cursor cur{0, sch.u0};
+  pg::Item it;
+  int i = 0, klim = 0;
+  auto enter = [&]() -> bool {
+    if (!pg::next_item<1>(sch, cur, it)) return false;
+    const Args& g = it.prob ? grp.g[1] : grp.g[0];
+    klim = it.prob ? Kv[1] : Kv[0];
+    if (!IS_B) op.init(g.A, g.lda, g.a_mn, g.vec_a, it.m0, it.prob ? Mv[1] : Mv[0], it.kb0 * BK, t, 1);
+    else op.init(g.B, g.ldb, g.b_mn, g.vec_b, it.n0, g.N, it.kb0 * BK, t, 1);
+    i = 0;
+    return true;
   };
-  auto seek = [&](bool moved) {
-    while (i >= ti.nkb) {
-      tile += G;
-      if (!enter_tile()) { valid = false; return; }
-      i = 0;
-      moved = true;
-    }
-    valid = true;
-    if (moved) {
-      const Args& g = grp.g[ti.which];
-      if (!IS_B) op.init(g.A, g.lda, g.a_mn, g.vec_a, ti.m0, ti.M, (ti.kb0 + i) * BK, t, 1);
-      else op.init(g.B, g.ldb, g.b_mn, g.vec_b, ti.n0, g.N, (ti.kb0 + i) * BK, t, 1);
-    }
-  };
-  if (enter_tile()) seek(true);
-  if (valid) op.load(regs, (ti.kb0 + i) * BK, ti.K, t);
+  bool valid = enter();
+  if (valid) op.load(regs, it.kb0 * BK, klim, t);
   uint32_t n = 0;
   while (valid) {
     const uint32_t sidx = n & 1u;
     mbar_wait(empty0 + 8 * sidx, ((n >> 1) & 1u) ^ 1u);
-    const uint32_t hi = smem_base + sidx * stage_bytes + op_off;
+    const uint32_t hi = smem_base + sidx * kPersistStageBytes + op_off;
     op.store(regs, hi, hi + ROWS * BK * 4);
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) mbar_arrive(full0 + 8 * sidx);
     ++n;
-    ++i;
-    seek(false);
-    if (valid) op.load(regs, (ti.kb0 + i) * BK, ti.K, t);
+    if (++i >= it.nkb) valid = enter();
+    if (valid) op.load(regs, (it.kb0 + i) * BK, klim, t);
   }
 }
 
-__global__ void __launch_bounds__(kPersistThreads, 1) gemm_3xtf32_persistent_kernel(const __grid_constant__ Group grp) {
-  constexpr int BN = 256, STAGES = 2;
+__global__ void __launch_bounds__(kPersistThreads, 1) gemm_3xtf32_persistent_kernel(const __grid_constant__ Group grp, int nprob, int ovh) {
+  constexpr int BN = 256;
   constexpr int A_TILE = BM * BK * 4, B_TILE = BN * BK * 4;
-  constexpr int STAGE_BYTES = 2 * A_TILE + 2 * B_TILE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t bars[8];  // full[2], empty[2], acc_full[2], acc_empty[2]
@@ -666,14 +639,15 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_3xtf32_persistent_ker
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]), accf0 = smem_u32(&bars[4]), acce0 = smem_u32(&bars[6]);
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(full0 + 8 * s, kProducerWarps);
+      mbar_init(full0 + 8 * s, kPersistProducerWarps);
       mbar_init(empty0 + 8 * s, 1);
       mbar_init(accf0 + 8 * s, 1);
-      mbar_init(acce0 + 8 * s, 4);
+      mbar_init(acce0 + 8 * s, pg::kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kProducerWarps) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  constexpr int kMmaWarp = kPersistProducerWarps + pg::kEpiWarps;
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(&tmem_base_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -695,40 +669,43 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_3xtf32_persistent_ker
       if (grp.g[k].k_dev) Kv[k] = __ldcg(grp.g[k].k_dev);
     }
   }
-  const int T = grp.tiles, G = gridDim.x;
+  pg::SchedIn sin;
+  sin.nprob = nprob; sin.ovh = ovh;
+  sin.red[0] = grp.g[0].accumulate; sin.red[1] = grp.g[1].accumulate; sin.N[0] = grp.g[0].N; sin.N[1] = grp.g[1].N;
+  const pg::Sched sch = pg::make_sched<1>(sin, Mv, Kv);
 
-  if (warp < kProducerWarps) {
+  if (warp < kPersistProducerWarps) {
     // ---------------------------------------------------------------- producers
-    if (warp < 8) persistent_producer<BM, false>(grp, Mv, Kv, T, G, smem_base, full0, empty0, STAGE_BYTES, 0u);
-    else persistent_producer<BN, true>(grp, Mv, Kv, T, G, smem_base, full0, empty0, STAGE_BYTES, 2u * A_TILE);
-  } else if (warp == kProducerWarps) {
+    if (warp < kPersistProducerWarps / 2) persistent_producer<BM, false>(grp, sch, Mv, Kv, smem_base, full0, empty0, 0u);
+    else persistent_producer<BN, true>(grp, sch, Mv, Kv, smem_base, full0, empty0, 2u * A_TILE);
+  } else if (warp == kMmaWarp) {
     // ---------------------------------------------------------------- MMA issuer
+    pg::Cursor cur{0, sch.u0};
+    pg::Item it;
     uint32_t n = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < T; tile += G) {
-      const TileInfo ti = decode_tile(grp, tile, Mv, Kv);
-      if (!ti.live) continue;
-      const Args& g = grp.g[ti.which];
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16) |
+    while (pg::next_item<1>(sch, cur, it)) {
+      const int a_mn = it.prob ? grp.g[1].a_mn : grp.g[0].a_mn, b_mn = it.prob ? grp.g[1].b_mn : grp.g[0].b_mn;
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t a_lbo = g.a_mn ? 512u : 16u, a_sbo = g.a_mn ? (uint32_t)(BM / 32 * 512) : 1024u;
-      const uint32_t b_lbo = g.b_mn ? 512u : 16u, b_sbo = g.b_mn ? (uint32_t)(BN / 32 * 512) : 1024u;
-      const uint32_t a_kstep = g.a_mn ? (uint32_t)(BM / 32 * 1024) : 32u;
-      const uint32_t b_kstep = g.b_mn ? (uint32_t)(BN / 32 * 1024) : 32u;
-      const uint32_t a_lt = g.a_mn ? 1u : 2u, b_lt = g.b_mn ? 1u : 2u;
+      const uint32_t a_lbo = a_mn ? 512u : 16u, a_sbo = a_mn ? (uint32_t)(BM / 32 * 512) : 1024u;
+      const uint32_t b_lbo = b_mn ? 512u : 16u, b_sbo = b_mn ? (uint32_t)(BN / 32 * 512) : 1024u;
+      const uint32_t a_kstep = a_mn ? (uint32_t)(BM / 32 * 1024) : 32u;
+      const uint32_t b_kstep = b_mn ? (uint32_t)(BN / 32 * 1024) : 32u;
+      const uint32_t a_lt = a_mn ? 1u : 2u, b_lt = b_mn ? 1u : 2u;
       const uint32_t b = tcount & 1u;
       if (tcount < 8) TRACE(16 + tcount * 8 + 0);
       mbar_wait(acce0 + 8 * b, ((tcount >> 1) & 1u) ^ 1u);  // accumulator b drained by the epilogue warps
       tc_fence_after();
       if (tcount < 8) TRACE(16 + tcount * 8 + 1);
       const uint32_t acc = tmem_base + b * BN;
-      for (int i = 0; i < ti.nkb; ++i, ++n) {
+      for (int i = 0; i < it.nkb; ++i, ++n) {
         const uint32_t s = n & 1u, ph = (n >> 1) & 1u;
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
         if (tcount < 8 && i == 0) TRACE(16 + tcount * 8 + 2);
-        if (tcount < 8 && i == ti.nkb - 1) TRACE(16 + tcount * 8 + 3);
+        if (tcount < 8 && i == it.nkb - 1) TRACE(16 + tcount * 8 + 3);
         if (lane == 0) {
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint32_t sa = smem_base + s * kPersistStageBytes;
           const uint32_t a_hi = sa, a_lo = sa + A_TILE, b_hi = sa + 2 * A_TILE, b_lo = b_hi + B_TILE;
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
@@ -741,7 +718,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_3xtf32_persistent_ker
             umma_tf32(acc, dah, dbh, idesc, 1u);
           }
           umma_commit(empty0 + 8 * s);                        // frees the stage when these MMAs retire
-          if (i == ti.nkb - 1) umma_commit(accf0 + 8 * b);    // accumulator b complete
+          if (i == it.nkb - 1) umma_commit(accf0 + 8 * b);    // accumulator b complete
         }
         __syncwarp();
       }
@@ -750,64 +727,61 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_3xtf32_persistent_ker
     tc_fence_before();
   } else {
     // ---------------------------------------------------------------- epilogue warps
-    const int q = warp & 3;  // the TMEM lane quarter this warp may read
+    const int e = warp - kPersistProducerWarps, q = warp & 3;  // q: the TMEM lane quarter this warp may read
+    pg::EpiCtx cx;
+    cx.patch = smem_base + kPersistOffPatch + e * pg::kPatchFloats * 4;
+    cx.stats = smem_base + kPersistOffStats;
+    cx.e = e; cx.lane = lane; cx.et = threadIdx.x - kPersistProducerWarps * 32;
+    cx.release_remote = false;
+    pg::Cursor cur{0, sch.u0};
+    pg::Item it;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < T; tile += G) {
-      const TileInfo ti = decode_tile(grp, tile, Mv, Kv);
-      if (!ti.live) continue;
-      const Args& g = grp.g[ti.which];
+    while (pg::next_item<1>(sch, cur, it)) {
+      const bool p1 = it.prob != 0;
+      const float* const row_scale = p1 ? grp.g[1].row_scale : grp.g[0].row_scale;
+      const float* const bias = p1 ? grp.g[1].bias : grp.g[0].bias;
+      const bool relu = (p1 ? grp.g[1].relu : grp.g[0].relu) != 0, red = (p1 ? grp.g[1].accumulate : grp.g[0].accumulate) != 0;
+      cx.bn_acc = p1 ? grp.g[1].bn.acc : grp.g[0].bn.acc;
+      cx.bn_H = p1 ? grp.g[1].bn.H : grp.g[0].bn.H;
+      const int ldc = p1 ? grp.g[1].ldc : grp.g[0].ldc;
+      const int M = p1 ? Mv[1] : Mv[0];
       const uint32_t b = tcount & 1u;
+      cx.m_q0 = it.m0 + q * 32;
+      cx.M = M;
+      cx.n0 = it.n0;
+      cx.ldc = ldc;
+      cx.Cq = (p1 ? grp.g[1].C : grp.g[0].C) + (int64_t)cx.m_q0 * ldc + it.n0;
+      cx.bias = (bias && (!red || it.kb0 == 0)) ? bias + it.n0 : nullptr;
+      cx.floor = relu ? 0.f : -INFINITY;
+      cx.taddr = tmem_base + ((uint32_t)(q * 32) << 16) + b * BN;
+      cx.release_bar = acce0 + 8 * b;
       if (tcount < 8 && q == 0) TRACE(16 + tcount * 8 + 4);
       mbar_wait(accf0 + 8 * b, (tcount >> 1) & 1u);
       tc_fence_after();
       if (tcount < 8 && q == 0) TRACE(16 + tcount * 8 + 5);
-      const int row = q * 32 + lane, m = ti.m0 + row;
-      const bool in = m < ti.M;
-      const float rs = (g.row_scale && in) ? __ldg(g.row_scale + m) : 1.f;
-      const bool add_bias = g.bias && (!g.accumulate || ti.bz == 0);
-      // 32 x 32 blocks go through a private, padded shared-memory patch so that every global store
-      // instruction writes four full 128-byte row segments.  (A thread owns a whole row of the accumulator:
-      // stored straight from registers every instruction touches 32 different lines, and the load/store
-      // pipe it shares with the producers became the bottleneck - measured 116 us against 110 us for the
-      // cfg-3 forward, with 16- or 32-byte stores alike.)
-      const uint32_t patch = smem_base + STAGES * STAGE_BYTES + (uint32_t)(warp - kProducerWarps - 1) * (32 * 36 * 4);  // shared-space byte address
-#pragma unroll 1
-      for (int col0 = 0; col0 < BN; col0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + b * BN + (uint32_t)col0, r);
-        __syncwarp();  // the previous block's reads of the patch are done
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          sts_f4(patch + (uint32_t)(lane * 36 + j) * 4u, make_float4(__uint_as_float(r[j]) * rs, __uint_as_float(r[j + 1]) * rs,
-                                                                     __uint_as_float(r[j + 2]) * rs, __uint_as_float(r[j + 3]) * rs));
-        __syncwarp();
-        const int cc = (lane & 7) * 4;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (add_bias) b4 = ldg4(g.bias + ti.n0 + col0 + cc);
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + (lane >> 3);
-          const int mm = ti.m0 + q * 32 + rr;
-          if (mm >= ti.M) continue;
-          float4 v = lds_f4(patch + (uint32_t)(rr * 36 + cc) * 4u);
-          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-          if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-          float* dst = g.C + (int64_t)mm * g.ldc + ti.n0 + col0 + cc;
-          if (g.accumulate) red_add_v4(dst, v);
-          else st4(dst, v);
-        }
+      const int m = cx.m_q0 + lane;
+      cx.rs = (row_scale && m < M) ? __ldg(row_scale + m) : 1.f;
+      const bool full = cx.m_q0 + 32 <= M;
+      if (red) {
+        if (full) pg::epilogue_tile<true, false, true, false, 4>(cx); else pg::epilogue_tile<true, false, false, false, 4>(cx);
+      } else if (cx.bn_acc) {
+        if (full) pg::epilogue_tile<false, true, true, false, 4>(cx); else pg::epilogue_tile<false, true, false, false, 4>(cx);
+      } else {
+        if (full) pg::epilogue_tile<false, false, true, false, 4>(cx); else pg::epilogue_tile<false, false, false, false, 4>(cx);
       }
       if (tcount < 8 && q == 0) TRACE(16 + tcount * 8 + 6);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acce0 + 8 * b);
       ++tcount;
     }
   }
   __syncthreads();
-  if (warp == kProducerWarps) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+  for (int k = 0; k < nprob; ++k) {
+    if (grp.g[k].bn.acc) {  // uniform over the grid: every CTA takes a ticket, the last one finalises the statistics
+      if (last_block_ticket(grp.g[k].bn.ticket, gridDim.x)) bn_finalize(grp.g[k].bn, Mv[k]);
+    }
   }
 }
 
@@ -877,43 +851,54 @@ int set_attrs() {
   if (!attr_done) {
     cudaError_t e1 = cudaFuncSetAttribute(gemm_3xtf32_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (2 * BM * BK * 4 + 2 * 128 * BK * 4) + 1024);
     cudaError_t e2 = cudaFuncSetAttribute(gemm_3xtf32_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * BM * BK * 4 + 2 * 256 * BK * 4) + 1024);
-    cudaError_t e3 = cudaFuncSetAttribute(gemm_3xtf32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * BM * BK * 4 + 2 * 256 * BK * 4) + 1024 + kPersistPatchBytes);
+    cudaError_t e3 = cudaFuncSetAttribute(gemm_3xtf32_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmem);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return EIMS_ERR_CUDA;
     attr_done = true;
   }
   return 0;
 }
 
-// The persistent kernel (one CTA per SM walking over its tiles, double-buffered accumulator) takes
-// the launches with several 128 x 256 tiles per SM whose epilogue it implements: no BatchNorm fusion,
-// vector stores, full column tiles, and K <= 512 per tile (single accumulator, see the kernel).
-bool use_persistent(const tc::Group& grp, int ctas, bool wide) {
+// The persistent kernel takes (a) a single store problem with >= 4 tiles of 128 x 256 per SM and (b) the grouped
+// launch of one store problem + one split-K problem (data gradient + weight gradient of a GraphConv layer), whatever
+// its size: full 256-wide column tiles, vector stores, K <= 512 per store item (single accumulator).
+// EIMS_GEMM_PERSISTENT=0: one CTA per tile everywhere (A/B timing).
+bool use_persistent(const tc::Group& grp, int nprob, bool wide) {
   using namespace tc;
   static int on = -1;
   if (on < 0) { const char* e = getenv("EIMS_GEMM_PERSISTENT"); on = (e && e[0] == '0') ? 0 : 1; }
-  // measured: 13 % faster at ~7 tiles per SM (cfg-3 forward, 127 -> 110 us), no gain at ~2 tiles per SM (the
-  // grouped wgrad + dgrad launches of cfg 2): overlapping a tile's epilogue with the next tile's main loop buys
-  // less than the tile timeline suggests, because both queue in the same load/store / shared-memory pipe
-  if (!on || !wide || ctas < 4 * 148) return false;
-  for (int k = 0; k < 2; ++k) {
+  if (!on || !wide) return false;
+  int reds = 0;
+  for (int k = 0; k < nprob; ++k) {
     const Args& g = grp.g[k];
-    if (g.bn.acc || (g.N % 256) || (g.ldc & 3) || (reinterpret_cast<uintptr_t>(g.C) & 15)) return false;
+    if ((g.N % 256) || (g.ldc & 3) || (reinterpret_cast<uintptr_t>(g.C) & 15)) return false;
     if (g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15)) return false;
-    const int kblocks = (g.K + BK - 1) / BK;  // upper bound when K lives on the device (capacity)
-    if ((kblocks + g.splits - 1) / g.splits > 16) return false;
+    if (g.accumulate) { ++reds; if (g.bn.acc) return false; }
+    else if ((g.K + BK - 1) / BK > pg::kMaxKbPerItem) return false;   // upper bound when K lives on the device (capacity)
+    if ((int64_t)g.mt * g.nt * ((g.K + BK - 1) / BK) * 148 > (int64_t)1 << 30) return false;  // 32-bit schedule arithmetic
   }
-  return true;
+  // (b) is OFF by default.  Measured at BASELINE cfg 2 (B200, stage timing): 44.9 us per grouped launch against 40.0 us
+  // for one CTA per tile in two waves.  The overlap does work - but four epilogue warps share the issue slots with
+  // sixteen producer warps that spend ~500 instructions per k-block on the hi / lo split, and the epilogue (17-20 k
+  // cycles per tile under that load, 5 k alone) becomes the period of the pipeline.  The planes kernel (gemm_tma.cu),
+  // whose producer is one lane driving the copy engine, does not have that problem.  EIMS_GEMM_PERSIST_PAIR=1 for A/B.
+  static int pair_on = -1;
+  if (pair_on < 0) { const char* e = getenv("EIMS_GEMM_PERSIST_PAIR"); pair_on = (e && e[0] == '1') ? 1 : 0; }
+  if (nprob == 2) return pair_on && reds == 1;
+  return reds == 0 && grp.g[0].mt * grp.g[0].nt >= 4 * 148;
 }
 
-int launch_group(const tc::Group& grp_in, int ctas, bool wide, cudaStream_t st) {
+int launch_group(const tc::Group& grp_in, int ctas, bool wide, cudaStream_t st, int nprob) {
   using namespace tc;
   const int BN = wide ? 256 : 128, stages = wide ? 2 : 3;
   const int smem_bytes = stages * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
   cudaError_t e;
-  if (use_persistent(grp_in, ctas, wide)) {
-    Group grp = grp_in;
-    grp.tiles = ctas;
-    e = launch_pdl(gemm_3xtf32_persistent_kernel, dim3(ctas < 148 ? ctas : 148), dim3(kPersistThreads), smem_bytes + kPersistPatchBytes, st, grp);
+  if (use_persistent(grp_in, nprob, wide)) {
+    static int ovh = -1;
+    if (ovh < 0) { const char* v = getenv("EIMS_GEMM_PERSIST_OVH"); ovh = v ? atoi(v) : 4; if (ovh < 0) ovh = 0; }
+    int64_t items = 0;
+    for (int k = 0; k < nprob; ++k) items += grp_in.g[k].accumulate ? 148 : (int64_t)grp_in.g[k].mt * grp_in.g[k].nt;
+    const int grid = items < 148 ? (int)items : 148;
+    e = launch_pdl(gemm_3xtf32_persistent_kernel, dim3(grid < 1 ? 1 : grid), dim3(kPersistThreads), kPersistSmem, st, grp_in, nprob, ovh);
   } else {
     e = wide ? launch_pdl(gemm_3xtf32_kernel<256, 2>, dim3(ctas), dim3(kThreads), smem_bytes, st, grp_in)
              : launch_pdl(gemm_3xtf32_kernel<128, 3>, dim3(ctas), dim3(kThreads), smem_bytes, st, grp_in);
@@ -942,7 +927,7 @@ int launch_gemm_tc(const float* A, int lda, int a_mn, const float* B, int ldb, i
   if (zero && cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st) != cudaSuccess) return EIMS_ERR_CUDA;
   grp.g[1] = grp.g[0];
   grp.ctas0 = grp.g[0].nt * grp.g[0].mt * grp.g[0].splits;
-  return launch_group(grp, grp.ctas0, wide, st);
+  return launch_group(grp, grp.ctas0, wide, st, 1);
 }
 
 // Two independent problems in one launch (the weight gradient and the data gradient of a layer):
@@ -971,7 +956,7 @@ int launch_gemm_tc_pair(const GemmProblem& p0, const GemmProblem& p1, cudaStream
   if (int rc = set_attrs()) return rc;
   grp.ctas0 = grp.g[0].nt * grp.g[0].mt * grp.g[0].splits;
   const int ctas = grp.ctas0 + grp.g[1].nt * grp.g[1].mt * grp.g[1].splits;
-  return launch_group(grp, ctas, w0, st);
+  return launch_group(grp, ctas, w0, st, 2);
 }
 
 }  // namespace eims
