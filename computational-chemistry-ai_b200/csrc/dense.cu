@@ -348,7 +348,12 @@ int launch_bn_bwd_stats_top(const int* dims, const float* dG, const float* zstat
                             float* partials, int max_graphs, cudaStream_t st) {
   if (H % 4 || H > 4096) return EIMS_ERR_ARG;
   const int slabs = (H + kSlab - 1) / kSlab;
-  int rg = (max_graphs + 4 * kRowLanes - 1) / (4 * kRowLanes);  // >= 4 graphs per thread
+  // one graph per thread up to 37 row groups per slab (148 blocks at H = 256): the kernel is a chain of dependent
+  // round trips (sizes -> operands -> shared-memory reduce -> atomics -> ticket -> finalize), so the four graphs a thread
+  // used to walk one after the other were pure latency (EIMS_BN_TOP_GPT = graphs per thread, for A/B)
+  static int gpt = 0;
+  if (!gpt) { const char* e = getenv("EIMS_BN_TOP_GPT"); gpt = e ? atoi(e) : 1; if (gpt < 1) gpt = 1; }
+  int rg = (max_graphs + gpt * kRowLanes - 1) / (gpt * kRowLanes);
   if (rg > 37) rg = 37;
   if (rg < 1) rg = 1;
   launch_pdl(bn_bwd_stats_top_kernel, dim3(slabs, rg), dim3(256), 0, st, dims, dG, zstat, gptr, pooling, H, mean, invstd, dgamma, dbeta,
