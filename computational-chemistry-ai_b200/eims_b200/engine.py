@@ -497,12 +497,17 @@ class Plan:
     def step_block_ptr(self, index: int):
         return C.c_void_p(self._step_block.data_ptr() + int(index) * self._step_block_bytes)
 
-    def step_blocks_upload(self, steps, ids_list, dp_seqs, first: int = 0):
-        """Rewrite blocks [first, first + len(steps)) with one launch (<= 16 blocks)."""
+    def step_blocks_args(self, steps, ids_list, dp_seqs):
+        """The host-side half of step_blocks_upload: the ctypes arrays of one launch (<= 16 blocks)."""
         n = len(steps)
         arr = (Step * n)(*steps)
         pid = (C.c_void_p * n)(*[t.data_ptr() for t in ids_list])
         seq = (C.c_uint32 * n)(*[int(x) & 0xffffffff for x in dp_seqs])
+        return arr, pid, seq, n
+
+    def step_blocks_upload(self, steps, ids_list, dp_seqs, first: int = 0, prepared=None):
+        """Rewrite blocks [first, first + len(steps)) with one launch (<= 16 blocks)."""
+        arr, pid, seq, n = prepared if prepared is not None else self.step_blocks_args(steps, ids_list, dp_seqs)
         check(self.lib.eims_step_blocks_upload(self.h, arr, pid, seq, int(first), n, self.stream))
 
     def step_block_upload(self, step: Step, ids, dp_seq: int = 0):
@@ -566,6 +571,10 @@ class GraphedTrainStep:
         self.group = max(0, min(16, int(os.environ.get("EIMS_GRAPH_GROUP", group)))) // 2 * 2   # even: table parity returns
         self.singles, self.multi, self.k, self.primed = [], None, 0, False
         self.pending = []
+        # hold_next: the next full group is prepared on the host (scalars, sequence numbers, argument arrays) but not
+        # launched; release() launches it.  Lets a timing harness put a start barrier between the two, so that the ranks'
+        # host-side preparation skew is not inside a short timed window (the device work all is).
+        self.hold_next, self.held = False, None
         self.side = torch.cuda.Stream(plan.device)
         # second side branch: the bias gradient of the output layer and the head's AdamW run off the chain (single GPU;
         # in data-parallel runs the fused exchange kernel is the optimiser).  EIMS_STEP_SIDE_BRANCH=0 keeps one chain.
@@ -632,14 +641,28 @@ class GraphedTrainStep:
                 seqs.append(0)
         self._keep = [ids for _, ids in items]
         if self.multi is not None and len(items) == self.group and self.k == 0:
-            self.plan.step_blocks_upload([st for st, _ in items], [ids for _, ids in items], seqs, 0)
-            self.multi.replay()
+            prep = self.plan.step_blocks_args([st for st, _ in items], [ids for _, ids in items], seqs)
+            if self.hold_next:      # everything host-side is done; release() issues the upload kernel and the graph launch
+                self.hold_next, self.held = False, prep
+            else:
+                self.plan.step_blocks_upload(None, None, None, 0, prepared=prep)
+                self.multi.replay()
         else:
             for (st, ids), q in zip(items, seqs):
                 self.plan.step_blocks_upload([st], [ids], [q], 0)
                 self.singles[self.k].replay()
                 self.k ^= 1
         self._bump(len(items))
+
+    def can_hold(self, n_steps: int) -> bool:
+        """A full group can be prepared now and launched later with release() (see hold_next)."""
+        return self.primed and self.multi is not None and self.k == 0 and not self.pending and n_steps >= self.group and self.held is None
+
+    def release(self):
+        """Launch the group that was prepared while hold_next was set: one upload kernel + one graph launch."""
+        prep, self.held = self.held, None
+        self.plan.step_blocks_upload(None, None, None, 0, prepared=prep)
+        self.multi.replay()
 
     def step(self, step: Step, next_ids):
         """Queues the step on the batch built last (and the build of `next_ids`, same length as every batch, for the
