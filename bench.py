@@ -65,7 +65,7 @@ def parse():
                          "event between two steps costs the eager path its kernel-to-kernel launch overlap across the step boundary")
     ap.add_argument("--no-prefetch", action="store_true", help="eager N=1: build each batch inside its own step instead of one step ahead")
     ap.add_argument("--dp", default="fused", choices=["fused", "nccl"], help="N>1: gradient exchange implementation")
-    ap.add_argument("--dp-overlap", action="store_true", help="eager fused path: exchange the head bucket early on a side stream")
+    ap.add_argument("--dp-overlap", action="store_true", help="fused path: exchange the head bucket early on a side stream / graph branch (measured slower, see TrainBench)")
     ap.add_argument("--no-overlap", action="store_true", help="nccl path: one-shot all-reduce after backward instead of two overlapped buckets")
     ap.add_argument("--targets", default="dense", choices=["dense", "peaks"],
                     help="target spectra as dense rows (what the reference's dataset holds, GCN:256) or as the peak lists they are "
@@ -356,7 +356,10 @@ class TrainBench:
             self.dp_note = "NCCL all-reduce (two buckets) + AdamW kernel"
             if args.dp == "fused":
                 try:
-                    self.fused = FusedP2PAdamW(self.fp, cfg["layers"], overlap=args.dp_overlap and args.no_graph)
+                    # --dp-overlap: two buckets, the head's exchange on a side branch under the GraphConv backward.  Measured
+                    # at N=2 under graph replay (same box): 0.3558 ms/step with it, 0.3473 without - a second exchange kernel
+                    # costs its two cross-GPU barriers again and the early one takes SMs from the backward - so it is off.
+                    self.fused = FusedP2PAdamW(self.fp, cfg["layers"], overlap=args.dp_overlap)
                     self.dp_note = ("one fused kernel: all-reduce + AdamW + parameter broadcast over NVLink peer memory ("
                                     + ("NVSwitch multimem" if self.fused.multicast else "peer loads/stores") + ")")
                 except Exception as exc:  # symmetric memory unavailable: say so, use the NCCL path

@@ -967,6 +967,29 @@ int eims_train_step_built_indirect(eims_plan* p, const float* targets, float* pa
   return 0;
 }
 
+// The same step in two parts for a caller that runs its own optimiser between them (data-parallel training: the head
+// bucket of the gradient exchange starts on a side stream when the head gradients are final, i.e. after part 1, and runs
+// under the GraphConv backward of part 2).  No optimiser here.
+int eims_train_step_built_indirect_part(eims_plan* p, const float* targets, float* params, float* grads, float* bn_running,
+                                        int32_t loss_kind, float* metrics, int32_t part, eims_stream_t stream) {
+  if (!p || !p->blk) return fail(EIMS_ERR_STATE, "no step block set (eims_plan_set_step_block)");
+  if (part != 1 && part != 2) return fail(EIMS_ERR_ARG, "part must be 1 (forward, loss, head backward) or 2 (GraphConv backward)");
+  struct Scope {
+    eims_plan* p;
+    ~Scope() { p->indirect = false; p->side = nullptr; }
+  } scope{p};
+  p->indirect = true;
+  p->side = nullptr;
+  if (part == 1) {
+    if (!targets && !p->peak_targets.peak_ptr) return fail(EIMS_ERR_ARG, "training needs target spectra");
+    eims_step dummy{};  // seed / step are not used: the dropout keys come from the step block
+    EIMS_TRY(eims_forward(p, params, bn_running, 1, &dummy, stream));
+    EIMS_TRY(loss_impl(p, targets, p->i("bids"), loss_kind, 1, metrics, stream));
+    return eims_backward_part(p, params, nullptr, grads, EIMS_BWD_HEAD, stream);
+  }
+  return eims_backward_part(p, params, nullptr, grads, EIMS_BWD_GCN, stream);
+}
+
 int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
                      const float* params, const float* bn_running, float* prob_out, eims_stream_t stream) {
   EIMS_TRY(eims_batch_build(p, ds, mol_ids, num_graphs, stream));

@@ -120,6 +120,7 @@ _SIGS = {
     "eims_step_blocks_upload": (C.c_int, [_vp, C.POINTER(Step), C.POINTER(_vp), C.POINTER(C.c_uint32), _i32, _i32, _vp]),
     "eims_batch_build_indirect": (C.c_int, [_vp, C.POINTER(Dataset), _i32, _vp]),
     "eims_train_step_built_indirect": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "eims_train_step_built_indirect_part": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp]),
     "eims_plan_profile": (C.c_int, [_vp, _i32]),
     "eims_plan_profile_read": (C.c_int, [_vp, C.POINTER(_f32), C.POINTER(_i32), _i32, C.POINTER(_i64)]),
     "eims_plan_num_stages": (C.c_int, []),

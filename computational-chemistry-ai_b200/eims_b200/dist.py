@@ -241,14 +241,14 @@ class FusedP2PAdamW:
         synchronous read: call it once per epoch, not per step."""
         return int(self.ticket.view(-1, 4)[:, 1].max().item())
 
-    def head_ready(self, step):
+    def head_ready(self, step, step_block=None):
         """Call when the head gradients are final (between the two parts of backward): exchanges and
         updates the head bucket on a side stream while the GCN layers are differentiated."""
         if self.side is None:
             return
         dev = self.fp.params.device
         self.side.wait_stream(torch.cuda.current_stream(dev))
-        self._launch(1, step, C_stream(self.side))
+        self._launch(1, step, C_stream(self.side), step_block)
         self.side_done = torch.cuda.Event()
         self.side_done.record(self.side)
 

@@ -528,6 +528,11 @@ class Plan:
                                                       ptr(fp.bn_running), _lib.LOSS[loss_kind], ptr(metrics), self.stream,
                                                       C.c_void_p(side.cuda_stream) if side is not None else None))
 
+    def train_step_built_indirect_part(self, ds: DeviceDataset, fp: FlatParams, part: int, metrics=None, loss_kind="mse"):
+        """part 1: forward + loss + head backward; part 2: GraphConv backward (eims_train_step_built_indirect_part)."""
+        check(self.lib.eims_train_step_built_indirect_part(self.h, ptr(self._targets(ds)), ptr(fp.params), ptr(fp.grads),
+                                                           ptr(fp.bn_running), _lib.LOSS[loss_kind], ptr(metrics), int(part), self.stream))
+
     # -- per-stage profiling (bench.py) ------------------------------------------------
     def profile(self, enable: bool):
         check(self.lib.eims_plan_profile(self.h, int(enable)))
@@ -589,9 +594,18 @@ class GraphedTrainStep:
         self.side.wait_stream(cur)                       # fork: the build may start with the step
         if self.fused is not None:
             self.fused.begin_step()
-        plan.train_step_built_indirect(self.ds, self.fp, self.metrics, self.loss_kind, optimizer=self.fused is None, side=self.side2)
-        if self.fused is not None:
-            self.fused.finish(step_for_fused, plan.stream, step_block=plan.step_block_ptr(block))
+        if self.fused is not None and self.fused.side is not None:
+            # two buckets: the head's exchange + AdamW (84 % of the parameters) runs on the exchange's side stream under
+            # the GraphConv backward, only the GraphConv bucket is left for the end of the step
+            blk = plan.step_block_ptr(block)
+            plan.train_step_built_indirect_part(self.ds, self.fp, 1, self.metrics, self.loss_kind)
+            self.fused.head_ready(step_for_fused, step_block=blk)
+            plan.train_step_built_indirect_part(self.ds, self.fp, 2, self.metrics, self.loss_kind)
+            self.fused.finish(step_for_fused, plan.stream, step_block=blk)
+        else:
+            plan.train_step_built_indirect(self.ds, self.fp, self.metrics, self.loss_kind, optimizer=self.fused is None, side=self.side2)
+            if self.fused is not None:
+                self.fused.finish(step_for_fused, plan.stream, step_block=plan.step_block_ptr(block))
         with torch.cuda.stream(self.side):
             plan.batch_build_indirect(self.ds, self.batch)
         cur.wait_stream(self.side)                       # join

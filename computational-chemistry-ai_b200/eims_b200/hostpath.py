@@ -356,12 +356,23 @@ class GraphedHostTrainer:
         plan._peak_targets = None
         fp, opt = self.fp, self.fused is None
         tgt = self._ds[slot].targets
-        check(self.lib.eims_train_step_built_indirect(plan.h, C.c_void_p(tgt) if tgt else None, _lib.ptr(fp.params), _lib.ptr(fp.grads),
-                                                      _lib.ptr(fp.adam_m) if opt else None, _lib.ptr(fp.adam_v) if opt else None,
-                                                      _lib.ptr(fp.bn_running), _lib.LOSS[self.loss_kind], _lib.ptr(self.metrics), plan.stream,
-                                                      C.c_void_p(self.side2.cuda_stream) if self.side2 is not None else None))
-        if self.fused is not None:
-            self.fused.finish(step, plan.stream, step_block=plan.step_block_ptr(block))
+        if self.fused is not None and self.fused.side is not None:
+            # data-parallel, two buckets: the head's exchange runs on the exchange's side stream under the GraphConv backward
+            blk = plan.step_block_ptr(block)
+            for part in (1, 2):
+                check(self.lib.eims_train_step_built_indirect_part(plan.h, C.c_void_p(tgt) if tgt else None, _lib.ptr(fp.params),
+                                                                   _lib.ptr(fp.grads), _lib.ptr(fp.bn_running), _lib.LOSS[self.loss_kind],
+                                                                   _lib.ptr(self.metrics), part, plan.stream))
+                if part == 1:
+                    self.fused.head_ready(step, step_block=blk)
+            self.fused.finish(step, plan.stream, step_block=blk)
+        else:
+            check(self.lib.eims_train_step_built_indirect(plan.h, C.c_void_p(tgt) if tgt else None, _lib.ptr(fp.params), _lib.ptr(fp.grads),
+                                                          _lib.ptr(fp.adam_m) if opt else None, _lib.ptr(fp.adam_v) if opt else None,
+                                                          _lib.ptr(fp.bn_running), _lib.LOSS[self.loss_kind], _lib.ptr(self.metrics), plan.stream,
+                                                          C.c_void_p(self.side2.cuda_stream) if self.side2 is not None else None))
+            if self.fused is not None:
+                self.fused.finish(step, plan.stream, step_block=plan.step_block_ptr(block))
         self.out_host[n_local].copy_(self.metrics, non_blocking=True)      # the step's loss / cosine back to the host
         with torch.cuda.stream(self.copy_stream):
             self.slots[nxt].copy_(self.pinned[(n_local + 1) % (2 * self.G)], non_blocking=True)

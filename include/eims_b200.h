@@ -339,6 +339,11 @@ int eims_batch_build_indirect(eims_plan* p, const eims_dataset* ds, int32_t num_
 int eims_train_step_built_indirect(eims_plan* p, const float* targets, float* params, float* grads, float* adam_m,
                                    float* adam_v, float* bn_running, int32_t loss_kind, float* metrics, eims_stream_t stream,
                                    eims_stream_t side_stream);
+/* The same step in two parts for a caller that runs its own optimiser between them: part 1 = forward, loss and the
+ * backward of the output head (the head gradients are final when it returns: a data-parallel caller starts exchanging
+ * that bucket on a side stream), part 2 = the backward of the GraphConv layers.  No optimiser. */
+int eims_train_step_built_indirect_part(eims_plan* p, const float* targets, float* params, float* grads, float* bn_running,
+                                        int32_t loss_kind, float* metrics, int32_t part, eims_stream_t stream);
 
 /* predict_spectrum (GCN:494-511) for a batch: batch build + eval forward + sigmoid. */
 int eims_infer_batch(eims_plan* p, const eims_dataset* ds, const int32_t* mol_ids, int32_t num_graphs,
