@@ -179,9 +179,6 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {   
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
 // the same load issued by either CTA of a pair: completion bytes go to the LEADER's mbarrier (shared::cluster address)
 __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const void* map, int c0, int c1, int c2, uint32_t leader_bar) {
   asm volatile(
