@@ -133,6 +133,41 @@ def test_graph_replay_equals_eager_steps(dropout):
         np.testing.assert_allclose(float(out[mode][3][0]), float(out["eager"][3][0]), rtol=2e-5)   # the epoch's loss sum
 
 
+def test_two_part_indirect_step_equals_whole_step():
+    """eims_train_step_built_indirect_part (part 1: forward + loss + head backward, part 2: GraphConv backward - what a
+    data-parallel caller runs around its early head-bucket exchange) leaves the gradients of the one-call step."""
+    d = ModelDims(hidden_dim=128, max_mz=200, dropout=0.2)
+    n_mols, batch = 256, 32
+    table = synth_molecules(n_mols, max_atoms=40, seed=21)
+    targets = dense_spectra(*synth_peaks(n_mols, d.max_mz, seed=22), d.max_mz)
+    ds = DeviceDataset(table, targets, DEV)
+    ids = torch.arange(batch, dtype=torch.int32, device=DEV)
+    step = make_step(step=3, seed=5)
+    res = []
+    for parts in (False, True):
+        plan = Plan(d, batch, batch * 40, 2 * (batch * 40 + 3 * batch), DEV)
+        fp = FlatParams(d, DEV)
+        fp.load_state_dict(O.init_params(O.Dims(6, 128, 3, 200, "combined", 0.2), 0))
+        metrics = torch.zeros(8, device=DEV)
+        plan.enable_step_block(1)
+        plan.select_step_block(0)
+        plan.step_block_upload(step, ids, 0)
+        plan.batch_build(ds, ids, batch)
+        fp.grads.zero_()
+        if parts:
+            plan.train_step_built_indirect_part(ds, fp, 1, metrics)
+            plan.train_step_built_indirect_part(ds, fp, 2, metrics)
+        else:
+            plan.train_step_built_indirect(ds, fp, metrics, optimizer=False)
+        plan.check()
+        res.append((fp.grads.clone(), float(metrics[4]), plan.buffer("prob", torch.float32, (batch, d.max_mz)).clone()))
+    (ga, la, pa), (gb, lb, pb) = res
+    assert la == pytest.approx(lb, rel=1e-6)
+    assert float((pa - pb).abs().max()) <= 1e-6 * float(pa.abs().max())
+    # atomics (BatchNorm sums, split-K) fix the gradients up to summation order
+    assert float((ga - gb).abs().max()) <= 2e-5 * float(ga.abs().max())
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run via gpurun --gpus 2)")
 @pytest.mark.parametrize("branch", ["multicast", "peer"])
 def test_two_rank_fused_step_vs_shard_sequential_oracle(branch, tmp_path):
