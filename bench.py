@@ -357,8 +357,9 @@ class TrainBench:
             if args.dp == "fused":
                 try:
                     # --dp-overlap: two buckets, the head's exchange on a side branch under the GraphConv backward.  Measured
-                    # at N=2 under graph replay (same box): 0.3558 ms/step with it, 0.3473 without - a second exchange kernel
-                    # costs its two cross-GPU barriers again and the early one takes SMs from the backward - so it is off.
+                    # at N=2 under graph replay (same box each): 0.3558 vs 0.3473 ms/step with a block of the early kernel
+                    # spinning on every SM, 0.3490 vs 0.3480 with 16 blocks (the default now) - the exchange costs its
+                    # barriers, not its bytes, so hiding 84 % of the bytes buys nothing; one exchange kernel per step stays.
                     self.fused = FusedP2PAdamW(self.fp, cfg["layers"], overlap=args.dp_overlap)
                     self.dp_note = ("one fused kernel: all-reduce + AdamW + parameter broadcast over NVLink peer memory ("
                                     + ("NVSwitch multimem" if self.fused.multicast else "peer loads/stores") + ")")

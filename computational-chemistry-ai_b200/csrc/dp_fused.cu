@@ -200,7 +200,14 @@ extern "C" int eims_dp_adamw_fused_blk(int32_t rank, int32_t world, const uint64
   }
   const int64_t n4 = range_len / 4, per = n4 / world;
   int64_t blocks = (n4 + 255) / 256;   // the zeroing pass covers the whole range
-  if (blocks > 148) blocks = 148;  // one block per SM: the early bucket shares the GPU with the backward pass
+  if (blocks > 148) blocks = 148;  // one block per SM
+  // An early bucket (bucket > 0: exchanged on a side stream while the GraphConv layers are still being differentiated)
+  // runs NEXT TO the backward kernels, and every one of its blocks spins in wait_all until the slowest peer arrives:
+  // with a block on every SM it took more from the backward pass than the overlap gave back (0.3558 vs 0.3473 ms per
+  // step at N=2).  A handful of blocks is plenty for ~0.5 MB per rank with ~130 us of backward to hide under.
+  static int early_blocks = 0;
+  if (!early_blocks) { const char* e = getenv("EIMS_DP_EARLY_BLOCKS"); early_blocks = e ? atoi(e) : 16; if (early_blocks < 1) early_blocks = 1; }
+  if (bucket > 0 && blocks > early_blocks) blocks = early_blocks;
   launch_pdl(dp_adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, pr, rank, world, m_slice, v_slice,
              zero_buf, range_off / 4, n4, per, seq, (int)bucket, ticket, k, reinterpret_cast<const StepBlock*>(step_block),
              timeout_ns);
