@@ -584,6 +584,8 @@ int launch_gemm_tma(const GemmTmaProblem* p0, const GemmTmaProblem* p1, cudaStre
     g.row_scale = q->row_scale; g.bias = q->bias; g.relu = q->relu; g.red = q->red;
     if (q->bn) g.bn = *q->bn;
     if (ps[k]) items += (int64_t)((q->M + BM * pair - 1) / (BM * pair)) * (q->N / BN) * (q->red ? 148 : 1);
+    // the device-side schedule works in 32-bit integers (k-block units times CTAs)
+    if (ps[k] && (int64_t)((q->M + BM - 1) / BM) * (q->N / BN) * ((q->K + BK - 1) / BK) * 148 >= ((int64_t)1 << 31)) return EIMS_ERR_ARG;
   }
   grp.nprob = p1 ? 2 : 1;
   for (int k = 0; k < grp.nprob; ++k)
